@@ -1,0 +1,201 @@
+/*
+ * slacken_gpu.h -- C ABI of libslacken_gpu.so: the B200 (sm_100a) replacement for the Kraken-2-style
+ * build/classify hot path of JNP-Solutions/Slacken.
+ *
+ * The reference has no native seam (it is pure Scala inside Spark closures), so each entry point names the
+ * reference code it replaces; paths are relative to src/main/scala/com/jnpersson/ of the reference.
+ * INTEGRATION.md shows the JNI / Panama binding a Slacken maintainer would add on the Scala side.
+ *
+ * Conventions
+ *  - every call returns 0 (SLK_OK) or a negative SLK_E_* code and never throws or aborts;
+ *    slk_last_error() returns a thread-local message for the last failure on the calling thread;
+ *  - the caller owns all host buffers (ideally pinned: slk_host_alloc / slk_host_register), the library
+ *    owns all device memory behind opaque handles;
+ *  - sequences are ASCII, one byte per base, WITHOUT line breaks (InputFragment "does not contain
+ *    whitespace", kmers/minimizer/MinSplitter.scala:23-32; KeyValueIndex.getSpans requires the same,
+ *    slacken/KeyValueIndex.scala:161-162). A,C,G,T,U in either case are bases, every other byte is ambiguous;
+ *  - sequence i of a batch occupies bases[off[i] .. off[i+1]);
+ *  - taxon ids are the raw ids of the taxonomy (Taxonomy.parents is indexed by them, NONE = 0, ROOT = 1,
+ *    slacken/Taxonomy.scala:30-31,159-160); minimizers are the left-aligned priority words that Slacken stores
+ *    in the Parquet column id1 (kmers/util/NTBitArray.scala:124-125), as signed 64-bit integers;
+ *  - handles are immutable after creation and may be shared by threads; a slk_classifier owns streams and
+ *    scratch and must be used by one thread at a time (create one per Spark task thread).
+ *  There is no CPU fallback: without a CUDA device every call fails with SLK_E_CUDA.
+ */
+#ifndef SLACKEN_GPU_H
+#define SLACKEN_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SLK_API __attribute__((visibility("default")))
+#else
+#define SLK_API
+#endif
+
+#define SLK_OK 0
+#define SLK_E_INVALID (-1)    /* bad argument / unsupported parameter combination */
+#define SLK_E_CUDA (-2)       /* CUDA runtime failure (including: no device) */
+#define SLK_E_NOMEM (-3)      /* host or device allocation failed */
+#define SLK_E_NOSPACE (-4)    /* an output buffer is too small; the required size is reported */
+#define SLK_E_UNSUPPORTED (-5)/* input outside the supported envelope ("limits") */
+
+typedef struct slk_ctx slk_ctx;
+typedef struct slk_tax slk_tax;
+typedef struct slk_index slk_index;
+typedef struct slk_builder slk_builder;
+typedef struct slk_classifier slk_classifier;
+typedef struct slk_counts slk_counts;
+
+/* IndexParams / SplitterFormat of an index (kmers/IndexParams.scala:63-91, kmers/SplitterFormat.scala:55-77):
+ * k, m, minimizerSpaces, XORmask, canonical. Only the `randomXOR` splitter exists in Slacken. */
+typedef struct {
+  int32_t k, m, spaces, canonical;
+  uint64_t toggle_mask;
+} slk_params;
+
+/* One merged hit of a read: TaxonCounts after TaxonCounts.fromHits (slacken/TaxonCounts.scala:31-48).
+ * taxon = raw taxon id, 0 for a minimizer that is not in the library, -1 for an ambiguous span ("A:n"),
+ * -2 for the mate-pair border ("|:|", count = -(k-1)). */
+typedef struct {
+  int32_t taxon;
+  int32_t count;
+} slk_hit;
+
+/* Per-read details needed for ClassifiedRead.outputLine (slacken/Classifier.scala:39-45). */
+typedef struct {
+  uint64_t hit_off;      /* index of the read's first merged hit in hits_out */
+  uint32_t hit_cnt;      /* number of merged hits */
+  uint32_t len1;         /* lengthString part 1: sum of span k-mers + (k-1) (slacken/TaxonCounts.scala:114-121) */
+  uint32_t len2;         /* same for mate 2; 0xFFFFFFFF for single-end */
+  uint32_t num_distinct; /* hit groups: spans with distinct && taxon != NONE (slacken/Classifier.scala:94) */
+} slk_read_detail;
+
+#define SLK_READ_CLASSIFIED 1u /* ClassifiedRead.classified */
+#define SLK_READ_HAS_SPAN 2u   /* 0: the read yields no span, so Slacken emits no line and does not count it */
+
+/* ClassifyParams (slacken/Classifier.scala:47-63), the per-call part. */
+typedef struct {
+  double confidence;      /* one of ClassifyParams.thresholds */
+  int32_t min_hit_groups; /* ClassifyParams.minHitGroups */
+  int32_t reserved;
+} slk_classify_opts;
+
+SLK_API const char* slk_last_error(void);
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+SLK_API int slk_ctx_create(int device, slk_ctx** out);
+SLK_API void slk_ctx_destroy(slk_ctx* ctx);
+SLK_API int slk_ctx_device(const slk_ctx* ctx);
+/* pinned host memory for batch buffers (direct ByteBuffers on the JVM side wrap these) */
+SLK_API int slk_host_alloc(size_t bytes, void** out);
+SLK_API void slk_host_free(void* p);
+SLK_API int slk_host_register(void* p, size_t bytes);
+SLK_API int slk_host_unregister(void* p);
+
+/* ---- parameters: SlackenMinimizerFormats.makeSplitter (slacken/SlackenMinimizerFormats.scala:31-42) ------ */
+SLK_API int slk_params_init(int k, int m, int spaces, uint64_t toggle_mask, int canonical, slk_params* out);
+
+/* ---- taxonomy: the parents array of slacken/Taxonomy.scala:159-160 (broadcast in KeyValueIndex.scala:44-47) - */
+SLK_API int slk_taxonomy_create(slk_ctx* ctx, const int32_t* parents, int32_t n, slk_tax** out);
+SLK_API void slk_taxonomy_destroy(slk_tax* tax);
+
+/* ---- B3: library load, replaces KeyValueIndex.loadRecords + the join side (slacken/KeyValueIndex.scala:150-159,
+ *          slacken/Classifier.scala:84). Columns of the Parquet table: id1:int64, taxon:int32. ------------------ */
+SLK_API int slk_index_from_records(slk_ctx* ctx, slk_tax* tax, const slk_params* params, const int64_t* id1,
+                           const int32_t* taxon, uint64_t n, slk_index** out);
+SLK_API void slk_index_destroy(slk_index* idx);
+SLK_API uint64_t slk_index_size(const slk_index* idx);   /* number of records (distinct minimizers) */
+/* copy the records back (for the Parquet writer, KeyValueIndex.writeRecords :125-139); order unspecified */
+SLK_API int slk_index_records(slk_index* idx, int64_t* id1_out, int32_t* taxon_out, uint64_t cap, uint64_t* n_out);
+
+/* ---- B2: library build, replaces SplitterMinimizers.find + groupBy(id1).agg(TaxonLCA)
+ *          (slacken/Minimizers.scala:43-76, slacken/KeyValueIndex.scala:85-122). -------------------------------- */
+SLK_API int slk_build_begin(slk_ctx* ctx, slk_tax* tax, const slk_params* params, uint64_t expected_bases,
+                    slk_builder** out);
+/* genome fragments with their taxon labels; fragments whose taxon is undefined in the taxonomy are skipped
+ * (KeyValueIndex.scala:118-120). Ambiguous characters split a fragment (InputReader.removeInvalid). */
+SLK_API int slk_build_add(slk_builder* b, const uint8_t* bases, const uint64_t* frag_off, const int32_t* frag_taxon,
+                  uint32_t n_frag);
+/* sort + LCA reduce + hash table construction; the builder is consumed (destroy it afterwards) */
+SLK_API int slk_build_finish(slk_builder* b, slk_index** out);
+SLK_API void slk_build_destroy(slk_builder* b);
+
+/* ---- B1: classify, replaces KeyValueIndex.getSpans + Classifier.spansToGroupedHits + classifyHits
+ *          (slacken/KeyValueIndex.scala:163-185, slacken/Classifier.scala:77-147,439-454). ---------------------- */
+SLK_API int slk_classifier_create(slk_index* idx, slk_classifier** out);
+SLK_API void slk_classifier_destroy(slk_classifier* c);
+/* upper bound of merged hits for a batch: size hits_out with it to make SLK_E_NOSPACE impossible */
+SLK_API uint64_t slk_classify_hits_bound(const slk_params* p, uint32_t n_reads, uint64_t total_bases, int paired);
+/* Host-buffer entry point (what the JVM binding calls from mapPartitions). bases2/off2 = NULL for single-end.
+ * taxon_out[n], flags_out[n] are mandatory; detail_out/hits_out may both be NULL (report-only, the
+ * SQLClassifier path, slacken/Classifier.scala:259-410). hits_used receives the number of hit slots used. */
+SLK_API int slk_classify_batch(slk_classifier* c, const slk_classify_opts* opts,
+                       const uint8_t* bases1, const uint64_t* off1,
+                       const uint8_t* bases2, const uint64_t* off2, uint32_t n_reads,
+                       int32_t* taxon_out, uint8_t* flags_out, slk_read_detail* detail_out,
+                       slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_used);
+/* Same with every pointer in device memory (inputs already resident in HBM; outputs stay there).
+ * hits_used_dev: one uint64 in device memory, zeroed by the call. Runs on the classifier's stream and
+ * returns after the kernel has been enqueued; slk_classifier_sync waits for it. Device base buffers must be
+ * readable up to the next 16-byte boundary past their end (any cudaMalloc allocation is). */
+SLK_API int slk_classify_batch_dev(slk_classifier* c, const slk_classify_opts* opts,
+                           const uint8_t* bases1, const uint64_t* off1,
+                           const uint8_t* bases2, const uint64_t* off2, uint32_t n_reads,
+                           int32_t* taxon_out, uint8_t* flags_out, slk_read_detail* detail_out,
+                           slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_used_dev);
+SLK_API int slk_classifier_sync(slk_classifier* c);
+/* the CUDA stream the classifier launches on (a cudaStream_t), for event timing by the caller */
+SLK_API void* slk_classifier_stream(slk_classifier* c);
+/* kernels launched by this classifier so far */
+SLK_API uint64_t slk_classifier_launches(const slk_classifier* c);
+/* totals over all launches so far: table probes issued (= super-mers looked up) and merged hits produced */
+SLK_API int slk_classifier_stats(slk_classifier* c, uint64_t* probes, uint64_t* merged_hits);
+
+/* CUDA events recorded on the classifier's launch stream, so a caller can time kernels on the device */
+typedef struct slk_event slk_event;
+SLK_API int slk_event_create(slk_ctx* ctx, slk_event** out);
+SLK_API void slk_event_destroy(slk_event* e);
+SLK_API int slk_event_record(slk_event* e, slk_classifier* c);
+SLK_API int slk_event_elapsed_ms(slk_event* start, slk_event* end, float* ms);
+
+/* ---- B4: report counts, replaces groupBy(sampleId, taxon).count (slacken/Classifier.scala:214-217). The host
+ *          feeds the per-read results back (sample ids come from its --sample-regex), or the classifier
+ *          accumulates them on the device when a counts object is attached. --------------------------------- */
+SLK_API int slk_counts_create(slk_ctx* ctx, slk_tax* tax, int32_t n_samples, slk_counts** out);
+SLK_API void slk_counts_destroy(slk_counts* cn);
+/* attach: every following slk_classify_batch* call adds its reads (those with SLK_READ_HAS_SPAN) to sample
+ * `sample` on the device, fused into the classify kernel. NULL detaches. */
+SLK_API int slk_classifier_attach_counts(slk_classifier* c, slk_counts* cn, int32_t sample);
+SLK_API int slk_counts_add(slk_counts* cn, const int32_t* taxon, const uint8_t* flags, const int32_t* sample_id,
+                   uint32_t n);
+/* dense per-taxon vector of one sample: per_taxon_out[t] for t in [0, n_taxa) (n_taxa = taxonomy size) */
+SLK_API int slk_counts_fetch(slk_counts* cn, int32_t sample, int64_t* per_taxon_out, int32_t n_taxa);
+/* device pointer to the [n_samples x n_taxa] int64 counter matrix (for an NCCL all-reduce across ranks) */
+SLK_API void* slk_counts_device_ptr(slk_counts* cn);
+SLK_API int slk_counts_reset(slk_counts* cn);
+
+/* ---- synthetic workloads (bench / tests only; not part of the reference) -------------------------------- */
+SLK_API int slk_synth_genome_dev(slk_ctx* ctx, uint64_t seed, uint64_t start, uint64_t n, uint8_t* out_dev);
+SLK_API int slk_synth_reads_dev(slk_ctx* ctx, uint64_t gseed, uint64_t rseed, uint64_t n_genomes, uint64_t genome_len,
+                        uint64_t first_read, uint64_t n_reads, uint32_t read_len, uint8_t* out_dev);
+/* device-resident variant of slk_build_add (bases/frag_off/frag_taxon in device memory) */
+SLK_API int slk_build_add_dev(slk_builder* b, const uint8_t* bases, const uint64_t* frag_off, const int32_t* frag_taxon,
+                      uint32_t n_frag, uint64_t total_bases);
+/* raw device memory helpers so a harness needs no CUDA binding of its own */
+SLK_API int slk_dev_alloc(slk_ctx* ctx, size_t bytes, void** out);
+SLK_API void slk_dev_free(slk_ctx* ctx, void* p);
+SLK_API int slk_memcpy_h2d(slk_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+SLK_API int slk_memcpy_d2h(slk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+SLK_API int slk_memcpy_d2d(slk_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
+SLK_API int slk_ctx_sync(slk_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLACKEN_GPU_H */

@@ -94,6 +94,8 @@ def lib():
         L.slko_lib_add_records.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.slko_lib_add_fragments.restype = C.c_int
         L.slko_lib_add_fragments.argtypes = [C.c_void_p, P(Params), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.slko_lib_add_sequences.restype = C.c_int
+        L.slko_lib_add_sequences.argtypes = [C.c_void_p, P(Params), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.slko_lib_records.restype = C.c_uint64
         L.slko_lib_records.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.slko_classify_batch.restype = C.c_int
@@ -200,6 +202,24 @@ def pack_sequences(seqs):
     return bases, off
 
 
+_VALID_BASES = None
+
+
+def remove_invalid(seqs, taxa):
+    """InputReader.removeInvalid (kmers/input/InputReader.scala:56-72): split every fragment around characters that
+    are not ACGTU / newlines; each piece keeps the label of its fragment. Returns (pieces, labels)."""
+    import re
+    global _VALID_BASES
+    if _VALID_BASES is None:
+        _VALID_BASES = re.compile(rb"[ACTGUactgu][ACTGUactgu\n\r]*")
+    out, lab = [], []
+    for s, t in zip(seqs, taxa):
+        for m in _VALID_BASES.finditer(_bytes(s)):
+            out.append(m.group(0))
+            lab.append(int(t))
+    return out, np.array(lab, dtype=np.int32)
+
+
 class Library:
     """The minimizer->LCA records of KeyValueIndex.makeRecords (slacken/KeyValueIndex.scala:85-122)."""
 
@@ -222,6 +242,15 @@ class Library:
                                           _ptr(bases), _ptr(off), _ptr(taxa), len(taxa))
         if rc < 0:
             raise ValueError("invalid nucleotide in a genome fragment")
+
+    def add_sequences(self, bases: np.ndarray, off: np.ndarray, taxa: np.ndarray):
+        """Sequences that may still contain ambiguous characters: removeInvalid, then add_fragments."""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        taxa = np.ascontiguousarray(taxa, dtype=np.int32)
+        rc = lib().slko_lib_add_sequences(self.h, C.byref(self.p), _ptr(self.parents), len(self.parents),
+                                          _ptr(bases), _ptr(off), _ptr(taxa), len(taxa))
+        if rc < 0:
+            raise ValueError("add_sequences failed")
 
     def add_records(self, id1: np.ndarray, taxon: np.ndarray):
         id1 = np.ascontiguousarray(id1).view(np.uint64)

@@ -495,7 +495,7 @@ static inline uint64_t mix64(uint64_t x) {
 SLKO_API slko_lib* slko_lib_create(uint64_t expected_keys) {
   slko_lib* L = (slko_lib*)calloc(1, sizeof(slko_lib));
   uint64_t n = 16;
-  while (n < expected_keys * 2 + 16) n <<= 1;
+  while ((double)n * 0.7 < (double)expected_keys + 16.0) n <<= 1;
   L->nslots = n;
   L->keys = (uint64_t*)malloc(sizeof(uint64_t) * n);
   L->taxa = (int32_t*)calloc(n, sizeof(int32_t));
@@ -583,6 +583,36 @@ SLKO_API int slko_lib_add_fragments(slko_lib* L, const slko_params* p, const int
     }
     scratch_free(&sc);
   }
+  return err;
+}
+
+/* InputReader.removeInvalid (kmers/input/InputReader.scala:56-72) + slko_lib_add_fragments: regex
+ * [ACTGUactgu][ACTGUactgu\n\r]* -- every maximal run that starts with a base and continues over bases and
+ * newlines is a fragment of its own with the sequence's label. Used where the sequences still contain N. */
+SLKO_API int slko_lib_add_sequences(slko_lib* L, const slko_params* p, const int32_t* parents, int32_t n_tax,
+                                    const char* bases, const int64_t* off, const int32_t* seq_taxon, int64_t n_seq) {
+  int64_t cap = 1024, n = 0;
+  int64_t* poff = (int64_t*)malloc(sizeof(int64_t) * 2 * (size_t)cap);
+  int32_t* ptax = (int32_t*)malloc(sizeof(int32_t) * (size_t)cap);
+  for (int64_t s = 0; s < n_seq; s++) {
+    int64_t i = off[s], e = off[s + 1];
+    while (i < e) {
+      if (!is_valid_char((unsigned char)bases[i])) { i++; continue; }
+      int64_t j = i + 1;
+      while (j < e && is_nonambiguous_char((unsigned char)bases[j])) j++;
+      if (n == cap) { cap *= 2; poff = (int64_t*)realloc(poff, sizeof(int64_t) * 2 * (size_t)cap); ptax = (int32_t*)realloc(ptax, sizeof(int32_t) * (size_t)cap); }
+      poff[2 * n] = i; poff[2 * n + 1] = j; ptax[n] = seq_taxon[s]; n++;
+      i = j;
+    }
+  }
+  int err = 0;
+  #pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t f = 0; f < n; f++) {
+    int64_t o2[2] = {0, poff[2 * f + 1] - poff[2 * f]};
+    int rc = slko_lib_add_fragments(L, p, parents, n_tax, bases + poff[2 * f], o2, &ptax[f], 1);
+    if (rc < 0) err = rc;
+  }
+  free(poff); free(ptax);
   return err;
 }
 

@@ -1,0 +1,73 @@
+"""Builds libslacken_gpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m slacken_b200.build [--force]
+
+One translation unit per window width W (slk_inst.cu, -DSLK_W=n) plus the host/ABI unit and the sort unit, compiled
+in parallel and linked into slacken_b200/libslacken_gpu.so with a static CUDA runtime.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+SO = os.path.join(HERE, "libslacken_gpu.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ccbin", "/usr/bin/g++",
+         "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]
+WIDTHS = range(1, 9)
+
+
+def _sources():
+    deps = [os.path.join(CSRC, f) for f in ("slk_core.h", "slk_kernels.cuh", "slk_sort.h")]
+    deps.append(os.path.join(HERE, "..", "include", "slacken_gpu.h"))
+    units = [("slacken_gpu", os.path.join(CSRC, "slacken_gpu.cu"), []),
+             ("slk_sort", os.path.join(CSRC, "slk_sort.cu"), [])]
+    units += [(f"slk_inst_w{w}", os.path.join(CSRC, "slk_inst.cu"), [f"-DSLK_W={w}"]) for w in WIDTHS]
+    return units, deps
+
+
+def _stale(target, srcs):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def _compile(unit, deps, force):
+    name, src, extra = unit
+    obj = os.path.join(OBJ, name + ".o")
+    if not force and not _stale(obj, [src] + deps):
+        return obj, ""
+    cmd = [NVCC] + FLAGS + extra + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {name}:\n{r.stdout}\n{r.stderr}")
+    with open(os.path.join(OBJ, name + ".ptxas.log"), "w") as f:
+        f.write(r.stderr)
+    return obj, r.stderr
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    units, deps = _sources()
+    with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(lambda u: _compile(u, deps, force), units))
+    objs = [o for o, _ in results]
+    if verbose:
+        for _, log in results:
+            sys.stderr.write(log)
+    if force or _stale(SO, objs):
+        cmd = [NVCC, "-shared", "-o", SO, "-ccbin", "/usr/bin/g++", "-cudart", "static"] + objs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,1052 @@
+// slacken_gpu.cu -- sm_100a kernels and the C ABI (include/slacken_gpu.h) of the Slacken classify/build hot path.
+// Kernel bodies live in slk_core.h; this file holds the __global__ wrappers, the host-side orchestration
+// (streams, pinned staging, chunked pipelines, dense taxonomy) and the exported entry points.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <string>
+#include <type_traits>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/slacken_gpu.h"
+#include "slk_kernels.cuh"
+#include "slk_sort.h"
+
+static_assert(sizeof(slk_hit) == 8, "slk_hit layout");
+static_assert(sizeof(slk_read_detail) == 24, "slk_read_detail layout");
+
+// ---------------------------------------------------------------------------------------------- errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(e_ == cudaErrorMemoryAllocation ? SLK_E_NOMEM : SLK_E_CUDA, "%s failed: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
+  } while (0)
+#define TRY(call)            \
+  do {                       \
+    int r_ = (call);         \
+    if (r_ != SLK_OK) return r_; \
+  } while (0)
+
+extern "C" const char* slk_last_error(void) { return g_err.c_str(); }
+
+// ---------------------------------------------------------------------------------------------- handles
+struct slk_ctx {
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+};
+struct slk_tax {
+  slk_ctx* ctx;
+  std::vector<int32_t> parents;  // raw-indexed
+};
+struct dense_tax {
+  std::vector<int32_t> raw;       // dense -> raw, raw[0] = 0
+  std::vector<uint16_t> parent;   // dense parent
+  std::vector<uint8_t> depth;
+  std::unordered_map<int32_t, uint32_t> to_dense;
+  uint32_t root = 0;
+  uint16_t* d_parent = nullptr;
+  uint8_t* d_depth = nullptr;
+  int32_t* d_raw = nullptr;
+  slk_tax_view view() const {
+    slk_tax_view v;
+    v.parent = d_parent; v.depth = d_depth; v.raw = d_raw; v.n = (uint32_t)raw.size(); v.root = root;
+    return v;
+  }
+};
+struct slk_index {
+  slk_ctx* ctx;
+  slk_tax* tax;
+  slk_params params;
+  slk_scan_params sp;
+  dense_tax dt;
+  slk_table_view table{nullptr, 0};
+  uint64_t n_records = 0;
+};
+struct slk_builder {
+  slk_ctx* ctx;
+  slk_tax* tax;
+  slk_params params;
+  slk_scan_params sp;
+  dense_tax dt;
+  uint64_t* cells = nullptr;  // emitted (compressed key << 16 | dense taxon)
+  uint64_t cap = 0;
+  unsigned long long* d_count = nullptr;
+  uint64_t count = 0;
+  uint64_t launches = 0;
+};
+struct slk_counts {
+  slk_ctx* ctx;
+  int32_t n_samples, n_taxa;
+  unsigned long long* d;  // [n_samples x n_taxa]
+};
+
+// ---------------------------------------------------------------------------------------------- params
+static int make_scan_params(const slk_params* p, slk_scan_params* sp) {
+  memset(sp, 0, sizeof(*sp));
+  switch (slk_make_scan_params(p->k, p->m, p->spaces, p->toggle_mask, p->canonical, sp)) {
+    case 0: return SLK_OK;
+    case 1: return fail(SLK_E_UNSUPPORTED, "minimizer width m=%d outside 1..31", p->m);
+    case 2: return fail(SLK_E_UNSUPPORTED, "k=%d, m=%d: need m <= k and k-m+1 <= %d", p->k, p->m, SLK_MAX_W);
+    case 3: return fail(SLK_E_INVALID, "spaces=%d outside 0..m/2", p->spaces);
+    default:
+      return fail(SLK_E_UNSUPPORTED, "minimizers with %d significant bits do not fit the 48-bit key of a compact cell",
+                  sp->key_bits);
+  }
+}
+
+extern "C" int slk_params_init(int k, int m, int spaces, uint64_t toggle_mask, int canonical, slk_params* out) {
+  if (!out) return fail(SLK_E_INVALID, "null out");
+  slk_params p;
+  p.k = k; p.m = m; p.spaces = spaces; p.canonical = canonical ? 1 : 0; p.toggle_mask = toggle_mask;
+  slk_scan_params sp;
+  TRY(make_scan_params(&p, &sp));
+  *out = p;
+  return SLK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- context
+extern "C" int slk_ctx_create(int device, slk_ctx** out) {
+  if (!out) return fail(SLK_E_INVALID, "null out");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(SLK_E_CUDA, "no CUDA device available (%s); libslacken_gpu has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(SLK_E_INVALID, "device %d out of range (0..%d)", device, n - 1);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  slk_ctx* c = new (std::nothrow) slk_ctx;
+  if (!c) return fail(SLK_E_NOMEM, "host allocation failed");
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  return SLK_OK;
+}
+extern "C" void slk_ctx_destroy(slk_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+extern "C" int slk_ctx_device(const slk_ctx* c) { return c ? c->device : -1; }
+extern "C" int slk_ctx_sync(slk_ctx* c) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaDeviceSynchronize());
+  return SLK_OK;
+}
+extern "C" int slk_host_alloc(size_t bytes, void** out) {
+  CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return SLK_OK;
+}
+extern "C" void slk_host_free(void* p) { if (p) cudaFreeHost(p); }
+extern "C" int slk_host_register(void* p, size_t bytes) {
+  CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return SLK_OK;
+}
+extern "C" int slk_host_unregister(void* p) {
+  CU(cudaHostUnregister(p));
+  return SLK_OK;
+}
+extern "C" int slk_dev_alloc(slk_ctx* c, size_t bytes, void** out) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaMalloc(out, bytes + 16));
+  return SLK_OK;
+}
+extern "C" void slk_dev_free(slk_ctx* c, void* p) {
+  if (!p) return;
+  cudaSetDevice(c->device);
+  cudaFree(p);
+}
+extern "C" int slk_memcpy_h2d(slk_ctx* c, void* dst, const void* src, size_t bytes) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return SLK_OK;
+}
+extern "C" int slk_memcpy_d2h(slk_ctx* c, void* dst, const void* src, size_t bytes) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return SLK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- taxonomy
+extern "C" int slk_taxonomy_create(slk_ctx* ctx, const int32_t* parents, int32_t n, slk_tax** out) {
+  if (!ctx || !parents || n < 2 || !out) return fail(SLK_E_INVALID, "bad taxonomy arguments");
+  for (int32_t i = 0; i < n; i++)
+    if (parents[i] < 0 || parents[i] >= n) return fail(SLK_E_INVALID, "parents[%d]=%d out of range", i, parents[i]);
+  slk_tax* t = new (std::nothrow) slk_tax;
+  if (!t) return fail(SLK_E_NOMEM, "host allocation failed");
+  t->ctx = ctx;
+  t->parents.assign(parents, parents + n);
+  t->parents[1] = 0;  // parents(ROOT) = NONE (slacken/Taxonomy.scala:105)
+  t->parents[0] = 0;
+  *out = t;
+  return SLK_OK;
+}
+extern "C" void slk_taxonomy_destroy(slk_tax* t) { delete t; }
+
+// dense, ancestor-closed numbering of the taxa a library touches; dense 0 = NONE, ROOT is always present
+static void dense_init(dense_tax& dt) {
+  dt.raw.assign(1, 0); dt.parent.assign(1, 0); dt.depth.assign(1, 0);
+  dt.to_dense.clear(); dt.to_dense[0] = 0;
+}
+static int dense_add(dense_tax& dt, const slk_tax* tax, int32_t raw, uint32_t* out) {
+  auto it = dt.to_dense.find(raw);
+  if (it != dt.to_dense.end()) { if (out) *out = it->second; return SLK_OK; }
+  // walk up until a known node, then number the path top-down
+  std::vector<int32_t> path;
+  int32_t t = raw;
+  while (dt.to_dense.find(t) == dt.to_dense.end()) {
+    path.push_back(t);
+    if (path.size() > 250) return fail(SLK_E_UNSUPPORTED, "taxon %d is deeper than 250 levels (cycle in parents?)", raw);
+    t = tax->parents[t];
+  }
+  uint32_t pd = dt.to_dense[t];
+  for (size_t i = path.size(); i-- > 0;) {
+    if (dt.raw.size() >= 65535) return fail(SLK_E_UNSUPPORTED, "library touches more than 65534 taxonomy nodes (compact 16-bit cells)");
+    if (dt.depth[pd] >= 254) return fail(SLK_E_UNSUPPORTED, "taxonomy deeper than 254 levels");
+    uint32_t id = (uint32_t)dt.raw.size();
+    dt.raw.push_back(path[i]); dt.parent.push_back((uint16_t)pd); dt.depth.push_back((uint8_t)(dt.depth[pd] + 1));
+    dt.to_dense[path[i]] = id;
+    pd = id;
+  }
+  if (out) *out = pd;
+  return SLK_OK;
+}
+static int dense_upload(dense_tax& dt) {
+  size_t n = dt.raw.size();
+  cudaFree(dt.d_parent); cudaFree(dt.d_depth); cudaFree(dt.d_raw);
+  dt.d_parent = nullptr; dt.d_depth = nullptr; dt.d_raw = nullptr;
+  CU(cudaMalloc(&dt.d_parent, n * sizeof(uint16_t)));
+  CU(cudaMalloc(&dt.d_depth, n));
+  CU(cudaMalloc(&dt.d_raw, n * sizeof(int32_t)));
+  CU(cudaMemcpy(dt.d_parent, dt.parent.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dt.d_depth, dt.depth.data(), n, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dt.d_raw, dt.raw.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  return SLK_OK;
+}
+static void dense_free(dense_tax& dt) {
+  cudaFree(dt.d_parent); cudaFree(dt.d_depth); cudaFree(dt.d_raw);
+  dt.d_parent = nullptr; dt.d_depth = nullptr; dt.d_raw = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------- table kernels
+// K4: insert (compressed key << 16 | dense taxon) cells. Equal keys merge by LCA (TaxonLCA.merge,
+// slacken/LowestCommonAncestor.scala:152-170), so the kernel also serves incremental builds.
+__global__ void __launch_bounds__(256) insert_cells_kernel(const uint64_t* __restrict__ in, uint64_t n,
+                                                           slk_table_view tb, slk_tax_view tx,
+                                                           unsigned long long* n_new) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t cell = in[i];
+  uint64_t ckey = cell >> 16;
+  uint32_t taxon = (uint32_t)(cell & 0xffffu);
+  if (taxon == 0) return;  // a record whose taxon is NONE behaves exactly like a missing record
+  uint64_t b = slk_bucket_of(ckey, tb.n_buckets);
+  for (uint64_t tries = 0; tries < tb.n_buckets; tries++) {
+    unsigned long long* slot = reinterpret_cast<unsigned long long*>(tb.cells + b * 4);
+    for (int j = 0; j < 4; j++) {
+      unsigned long long cur = slot[j];
+      if (cur == 0) {
+        unsigned long long old = atomicCAS(&slot[j], 0ull, (unsigned long long)cell);
+        if (old == 0) { atomicAdd(n_new, 1ull); return; }
+        cur = old;
+      }
+      if ((cur >> 16) == ckey) {
+        for (;;) {
+          uint32_t t_old = (uint32_t)(cur & 0xffffu);
+          uint32_t t_new = slk_lca(tx, t_old, taxon);
+          if (t_new == t_old) return;
+          unsigned long long want = (ckey << 16) | t_new;
+          unsigned long long old = atomicCAS(&slot[j], cur, want);
+          if (old == cur) return;
+          cur = old;
+        }
+      }
+    }
+    b = (b + 1 == tb.n_buckets) ? 0 : b + 1;
+  }
+}
+
+// records (id1, raw taxon) -> cells, via the raw->dense lookup table
+__global__ void __launch_bounds__(256) records_to_cells_kernel(const int64_t* __restrict__ id1,
+                                                               const int32_t* __restrict__ taxon, uint64_t n,
+                                                               const uint16_t* __restrict__ raw2dense,
+                                                               slk_scan_params sp, uint64_t* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t key = (uint64_t)id1[i];
+  out[i] = (slk_compress(sp, key) << 16) | raw2dense[taxon[i]];
+}
+__global__ void __launch_bounds__(256) mark_taxa_kernel(const int32_t* __restrict__ taxon, uint64_t n, int32_t n_tax,
+                                                        uint32_t* __restrict__ bitmap, uint32_t* __restrict__ bad) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t t = taxon[i];
+  if (t < 0 || t >= n_tax) { atomicExch(bad, 1u); return; }
+  uint32_t bit = 1u << (t & 31);
+  if (!(bitmap[t >> 5] & bit)) atomicOr(&bitmap[t >> 5], bit);
+}
+// table -> records
+__global__ void __launch_bounds__(256) dump_table_kernel(slk_table_view tb, slk_scan_params sp, const int32_t* __restrict__ raw,
+                                                         int64_t* __restrict__ id1, int32_t* __restrict__ taxon,
+                                                         uint64_t cap, unsigned long long* cursor) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t ncell = tb.n_buckets * 4;
+  uint64_t cell = i < ncell ? tb.cells[i] : 0;
+  uint64_t o = warp_agg_alloc(cursor, cell != 0 ? 1u : 0u);
+  if (cell != 0 && o < cap) {
+    id1[o] = (int64_t)slk_expand(sp, cell >> 16);
+    taxon[o] = raw[cell & 0xffffu];
+  }
+}
+
+// K3b: segmented LCA reduce over the sorted cells. The head of every run of equal keys folds the run's taxa
+// (duplicates are adjacent because all 64 bits are sorted) and appends one cell.
+__global__ void __launch_bounds__(256) reduce_cells_kernel(const uint64_t* __restrict__ in, uint64_t n, slk_tax_view tx,
+                                                           uint64_t* __restrict__ out, unsigned long long* cursor) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t cell = 0;
+  bool head = false;
+  if (i < n) {
+    cell = in[i];
+    head = (i == 0) || ((in[i - 1] >> 16) != (cell >> 16));
+  }
+  uint64_t res = 0;
+  if (head) {
+    uint64_t key = cell >> 16;
+    uint32_t acc = (uint32_t)(cell & 0xffffu), last = acc;
+    for (uint64_t j = i + 1; j < n; j++) {
+      uint64_t c = in[j];
+      if ((c >> 16) != key) break;
+      uint32_t t = (uint32_t)(c & 0xffffu);
+      if (t != last) { acc = slk_lca(tx, acc, t); last = t; }
+    }
+    res = (key << 16) | acc;
+  }
+  uint64_t o = warp_agg_alloc(cursor, head ? 1u : 0u);
+  if (head) out[o] = res;
+}
+
+__global__ void snapshot_kernel(const unsigned long long* src, unsigned long long* dst) { *dst = *src; }
+
+__global__ void __launch_bounds__(256) counts_add_kernel(const int32_t* __restrict__ taxon, const uint8_t* __restrict__ flags,
+                                                         const int32_t* __restrict__ sample, uint32_t n, int32_t n_samples,
+                                                         int32_t n_taxa, unsigned long long* counts, uint32_t* bad) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!(flags[i] & SLK_READ_HAS_SPAN)) return;
+  int32_t s = sample ? sample[i] : 0, t = taxon[i];
+  if (s < 0 || s >= n_samples || t < 0 || t >= n_taxa) { atomicExch(bad, 1u); return; }
+  atomicAdd(&counts[(uint64_t)s * n_taxa + t], 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------- synthetic data kernels
+__global__ void __launch_bounds__(256) synth_genome_kernel(uint64_t seed, uint64_t start, uint64_t n, uint8_t* out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = slk_synth_genome_base(seed, start + i);
+}
+__global__ void __launch_bounds__(256) synth_reads_kernel(uint64_t gseed, uint64_t rseed, uint64_t n_genomes,
+                                                          uint64_t genome_len, uint64_t first, uint64_t n_reads,
+                                                          uint32_t L, uint8_t* out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_reads * L) return;
+  uint64_t r = i / L;
+  uint32_t j = (uint32_t)(i - r * L);
+  out[i] = slk_synth_read_base(gseed, rseed, n_genomes, genome_len, first + r, L, j);
+}
+
+extern "C" int slk_synth_genome_dev(slk_ctx* ctx, uint64_t seed, uint64_t start, uint64_t n, uint8_t* out) {
+  CU(cudaSetDevice(ctx->device));
+  if (n == 0) return SLK_OK;
+  synth_genome_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(seed, start, n, out);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SLK_OK;
+}
+extern "C" int slk_synth_reads_dev(slk_ctx* ctx, uint64_t gseed, uint64_t rseed, uint64_t n_genomes, uint64_t genome_len,
+                                   uint64_t first_read, uint64_t n_reads, uint32_t read_len, uint8_t* out) {
+  CU(cudaSetDevice(ctx->device));
+  if (n_reads == 0) return SLK_OK;
+  if (read_len == 0 || genome_len < read_len) return fail(SLK_E_INVALID, "bad read/genome length");
+  uint64_t n = n_reads * read_len;
+  synth_reads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(gseed, rseed, n_genomes, genome_len, first_read,
+                                                                            n_reads, read_len, out);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SLK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- index construction
+static uint64_t buckets_for(uint64_t n_keys) {
+  // 4 cells per 32-byte bucket, load factor <= 0.70
+  uint64_t cells = (uint64_t)((double)n_keys / 0.70) + 64;
+  return (cells + 3) / 4;
+}
+static int table_alloc(slk_table_view* tb, uint64_t n_keys) {
+  tb->n_buckets = buckets_for(n_keys);
+  CU(cudaMalloc(&tb->cells, tb->n_buckets * 32));
+  CU(cudaMemset(tb->cells, 0, tb->n_buckets * 32));
+  return SLK_OK;
+}
+static int insert_cells(slk_ctx* ctx, slk_index* idx, const uint64_t* d_cells, uint64_t n, unsigned long long* d_new) {
+  if (n == 0) return SLK_OK;
+  insert_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_cells, n, idx->table, idx->dt.view(), d_new);
+  CU(cudaGetLastError());
+  return SLK_OK;
+}
+
+extern "C" int slk_index_from_records(slk_ctx* ctx, slk_tax* tax, const slk_params* params, const int64_t* id1,
+                                      const int32_t* taxon, uint64_t n, slk_index** out) {
+  if (!ctx || !tax || !params || !out || (n && (!id1 || !taxon))) return fail(SLK_E_INVALID, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  slk_index* idx = new (std::nothrow) slk_index;
+  if (!idx) return fail(SLK_E_NOMEM, "host allocation failed");
+  idx->ctx = ctx; idx->tax = tax; idx->params = *params;
+  int rc = make_scan_params(params, &idx->sp);
+  if (rc != SLK_OK) { delete idx; return rc; }
+  dense_init(idx->dt);
+  int32_t n_tax = (int32_t)tax->parents.size();
+  // 1) which taxa occur: device bitmap over raw ids, records streamed in chunks
+  const uint64_t CH = 1ull << 26;
+  uint64_t chunk = std::min<uint64_t>(n ? n : 1, CH);
+  int64_t* d_id = nullptr; int32_t* d_tx = nullptr; uint64_t* d_cells = nullptr;
+  uint32_t *d_bitmap = nullptr, *d_bad = nullptr; uint16_t* d_r2d = nullptr; unsigned long long* d_new = nullptr;
+  size_t words = ((size_t)n_tax + 31) / 32;
+  auto cleanup = [&]() {
+    cudaFree(d_id); cudaFree(d_tx); cudaFree(d_cells); cudaFree(d_bitmap); cudaFree(d_bad); cudaFree(d_r2d); cudaFree(d_new);
+  };
+#define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); slk_index_destroy(idx); \
+    return fail(e_ == cudaErrorMemoryAllocation ? SLK_E_NOMEM : SLK_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+  CUX(cudaMalloc(&d_id, chunk * 8)); CUX(cudaMalloc(&d_tx, chunk * 4)); CUX(cudaMalloc(&d_cells, chunk * 8));
+  CUX(cudaMalloc(&d_bitmap, words * 4)); CUX(cudaMalloc(&d_bad, 4)); CUX(cudaMalloc(&d_new, 8));
+  CUX(cudaMemset(d_bitmap, 0, words * 4)); CUX(cudaMemset(d_bad, 0, 4)); CUX(cudaMemset(d_new, 0, 8));
+  for (uint64_t s = 0; s < n; s += chunk) {
+    uint64_t c = std::min(chunk, n - s);
+    CUX(cudaMemcpyAsync(d_tx, taxon + s, c * 4, cudaMemcpyHostToDevice, ctx->stream));
+    mark_taxa_kernel<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(d_tx, c, n_tax, d_bitmap, d_bad);
+    CUX(cudaGetLastError());
+    CUX(cudaStreamSynchronize(ctx->stream));
+  }
+  uint32_t bad = 0;
+  CUX(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost));
+  if (bad) { cleanup(); slk_index_destroy(idx); return fail(SLK_E_INVALID, "a record's taxon is outside the taxonomy (0..%d)", n_tax - 1); }
+  std::vector<uint32_t> bitmap(words);
+  CUX(cudaMemcpy(bitmap.data(), d_bitmap, words * 4, cudaMemcpyDeviceToHost));
+  rc = dense_add(idx->dt, tax, 1, &idx->dt.root);
+  for (int32_t t = 1; t < n_tax && rc == SLK_OK; t++)
+    if (bitmap[t >> 5] & (1u << (t & 31))) rc = dense_add(idx->dt, tax, t, nullptr);
+  if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
+  rc = dense_upload(idx->dt);
+  if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
+  std::vector<uint16_t> r2d((size_t)n_tax, 0);
+  for (auto& kv : idx->dt.to_dense) r2d[kv.first] = (uint16_t)kv.second;
+  CUX(cudaMalloc(&d_r2d, (size_t)n_tax * 2));
+  CUX(cudaMemcpy(d_r2d, r2d.data(), (size_t)n_tax * 2, cudaMemcpyHostToDevice));
+  // 2) table + insert
+  rc = table_alloc(&idx->table, n);
+  if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
+  for (uint64_t s = 0; s < n; s += chunk) {
+    uint64_t c = std::min(chunk, n - s);
+    CUX(cudaMemcpyAsync(d_id, id1 + s, c * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUX(cudaMemcpyAsync(d_tx, taxon + s, c * 4, cudaMemcpyHostToDevice, ctx->stream));
+    records_to_cells_kernel<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(d_id, d_tx, c, d_r2d, idx->sp, d_cells);
+    CUX(cudaGetLastError());
+    rc = insert_cells(ctx, idx, d_cells, c, d_new);
+    if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
+    CUX(cudaStreamSynchronize(ctx->stream));
+  }
+  unsigned long long nn = 0;
+  CUX(cudaMemcpy(&nn, d_new, 8, cudaMemcpyDeviceToHost));
+  idx->n_records = nn;
+  cleanup();
+#undef CUX
+  *out = idx;
+  return SLK_OK;
+}
+extern "C" void slk_index_destroy(slk_index* idx) {
+  if (!idx) return;
+  cudaSetDevice(idx->ctx->device);
+  cudaFree(idx->table.cells);
+  dense_free(idx->dt);
+  delete idx;
+}
+extern "C" uint64_t slk_index_size(const slk_index* idx) { return idx ? idx->n_records : 0; }
+
+extern "C" int slk_index_records(slk_index* idx, int64_t* id1_out, int32_t* taxon_out, uint64_t cap, uint64_t* n_out) {
+  if (!idx || !n_out) return fail(SLK_E_INVALID, "bad arguments");
+  slk_ctx* ctx = idx->ctx;
+  CU(cudaSetDevice(ctx->device));
+  *n_out = idx->n_records;
+  if (cap < idx->n_records) return fail(SLK_E_NOSPACE, "records need room for %llu rows", (unsigned long long)idx->n_records);
+  if (idx->n_records == 0) return SLK_OK;
+  int64_t* d_id = nullptr; int32_t* d_tx = nullptr; unsigned long long* d_cur = nullptr;
+  CU(cudaMalloc(&d_id, idx->n_records * 8));
+  CU(cudaMalloc(&d_tx, idx->n_records * 4));
+  CU(cudaMalloc(&d_cur, 8));
+  CU(cudaMemset(d_cur, 0, 8));
+  uint64_t ncell = idx->table.n_buckets * 4;
+  dump_table_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, ctx->stream>>>(idx->table, idx->sp, idx->dt.d_raw, d_id, d_tx,
+                                                                              idx->n_records, d_cur);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(id1_out, d_id, idx->n_records * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(taxon_out, d_tx, idx->n_records * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_id); cudaFree(d_tx); cudaFree(d_cur);
+  return SLK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- builder
+extern "C" int slk_build_begin(slk_ctx* ctx, slk_tax* tax, const slk_params* params, uint64_t expected_bases,
+                               slk_builder** out) {
+  if (!ctx || !tax || !params || !out) return fail(SLK_E_INVALID, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  slk_builder* b = new (std::nothrow) slk_builder;
+  if (!b) return fail(SLK_E_NOMEM, "host allocation failed");
+  b->ctx = ctx; b->tax = tax; b->params = *params;
+  int rc = make_scan_params(params, &b->sp);
+  if (rc != SLK_OK) { delete b; return rc; }
+  dense_init(b->dt);
+  rc = dense_add(b->dt, tax, 1, &b->dt.root);
+  if (rc != SLK_OK) { delete b; return rc; }
+  b->cap = expected_bases / 2 + (1u << 20);
+  cudaError_t e = cudaMalloc(&b->cells, b->cap * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_count, 8);
+  if (e == cudaSuccess) e = cudaMemset(b->d_count, 0, 8);
+  if (e != cudaSuccess) { slk_build_destroy(b); return fail(SLK_E_NOMEM, "builder allocation failed: %s", cudaGetErrorString(e)); }
+  *out = b;
+  return SLK_OK;
+}
+extern "C" void slk_build_destroy(slk_builder* b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaFree(b->cells); cudaFree(b->d_count);
+  dense_free(b->dt);
+  delete b;
+}
+static int builder_reserve(slk_builder* b, uint64_t extra) {
+  if (b->count + extra <= b->cap) return SLK_OK;
+  uint64_t ncap = std::max(b->count + extra, b->cap + b->cap / 2);
+  uint64_t* n = nullptr;
+  CU(cudaMalloc(&n, ncap * 8));
+  CU(cudaMemcpyAsync(n, b->cells, b->count * 8, cudaMemcpyDeviceToDevice, b->ctx->stream));
+  CU(cudaStreamSynchronize(b->ctx->stream));
+  cudaFree(b->cells);
+  b->cells = n; b->cap = ncap;
+  return SLK_OK;
+}
+
+#define DISPATCH_W(w, FN, ARGS)          \
+  switch (w) {                           \
+    case 1: FN##1(ARGS); break;          \
+    case 2: FN##2(ARGS); break;          \
+    case 3: FN##3(ARGS); break;          \
+    case 4: FN##4(ARGS); break;          \
+    case 5: FN##5(ARGS); break;          \
+    case 6: FN##6(ARGS); break;          \
+    case 7: FN##7(ARGS); break;          \
+    default: FN##8(ARGS); break;         \
+  }
+
+// shared by the host- and device-buffer entry points; off_host: fragment offsets on the host (always needed)
+static int build_add_impl(slk_builder* b, const uint8_t* d_bases, const uint64_t* d_off, uint64_t shift,
+                          const uint64_t* off_host, const int32_t* taxon_host, uint32_t n_frag) {
+  slk_ctx* ctx = b->ctx;
+  int32_t n_tax = (int32_t)b->tax->parents.size();
+  std::vector<uint32_t> dense(n_frag, 0);
+  std::vector<uint64_t> prefix((size_t)n_frag + 1, 0);
+  uint64_t windows = 0;
+  for (uint32_t f = 0; f < n_frag; f++) {
+    int32_t t = taxon_host[f];
+    uint64_t len = off_host[f + 1] - off_host[f];
+    uint64_t nw = len >= (uint64_t)b->sp.k ? len - b->sp.k + 1 : 0;
+    // Taxonomy.isDefined (slacken/Taxonomy.scala:175-176): undefined labels are dropped (KeyValueIndex.scala:118-120)
+    bool defined = t > 0 && t < n_tax && (b->tax->parents[t] != 0 || t == 1);
+    if (!defined) nw = 0;
+    else TRY(dense_add(b->dt, b->tax, t, &dense[f]));
+    prefix[f + 1] = prefix[f] + (nw + BUILD_WPT - 1) / BUILD_WPT;
+    windows += nw;
+  }
+  uint64_t n_items = prefix[n_frag];
+  if (n_items == 0) return SLK_OK;
+  TRY(builder_reserve(b, windows));
+  uint32_t* d_dense = nullptr; uint64_t* d_prefix = nullptr;
+  CU(cudaMalloc(&d_dense, (size_t)n_frag * 4));
+  CU(cudaMalloc(&d_prefix, ((size_t)n_frag + 1) * 8));
+  CU(cudaMemcpyAsync(d_dense, dense.data(), (size_t)n_frag * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_prefix, prefix.data(), ((size_t)n_frag + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  slk_emit_args ea;
+  ea.sp = b->sp; ea.bases = d_bases; ea.frag_off = d_off; ea.off_shift = shift; ea.frag_dense = d_dense;
+  ea.item_prefix = d_prefix; ea.n_frag = n_frag; ea.n_items = n_items; ea.out = b->cells; ea.cap = b->cap;
+  ea.cursor = b->d_count; ea.stream = ctx->stream;
+  DISPATCH_W(b->sp.w, slk_launch_emit_w, ea);
+  b->launches++;
+  CU(cudaGetLastError());
+  unsigned long long cnt = 0;
+  CU(cudaMemcpyAsync(&cnt, b->d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  b->count = cnt;
+  cudaFree(d_dense); cudaFree(d_prefix);
+  return SLK_OK;
+}
+
+extern "C" int slk_build_add(slk_builder* b, const uint8_t* bases, const uint64_t* frag_off, const int32_t* frag_taxon,
+                             uint32_t n_frag) {
+  if (!b || !bases || !frag_off || !frag_taxon) return fail(SLK_E_INVALID, "bad arguments");
+  if (n_frag == 0) return SLK_OK;
+  slk_ctx* ctx = b->ctx;
+  CU(cudaSetDevice(ctx->device));
+  uint64_t s = frag_off[0], total = frag_off[n_frag] - s;
+  uint8_t* d_bases = nullptr; uint64_t* d_off = nullptr;
+  CU(cudaMalloc(&d_bases, total + 16));
+  CU(cudaMalloc(&d_off, ((size_t)n_frag + 1) * 8));
+  CU(cudaMemcpyAsync(d_bases, bases + s, total, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_off, frag_off, ((size_t)n_frag + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = build_add_impl(b, d_bases, d_off, s, frag_off, frag_taxon, n_frag);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_bases); cudaFree(d_off);
+  return rc;
+}
+extern "C" int slk_build_add_dev(slk_builder* b, const uint8_t* bases, const uint64_t* frag_off, const int32_t* frag_taxon,
+                                 uint32_t n_frag, uint64_t total_bases) {
+  if (!b || !bases || !frag_off || !frag_taxon) return fail(SLK_E_INVALID, "bad arguments");
+  (void)total_bases;
+  if (n_frag == 0) return SLK_OK;
+  CU(cudaSetDevice(b->ctx->device));
+  std::vector<uint64_t> off((size_t)n_frag + 1);
+  std::vector<int32_t> tx(n_frag);
+  CU(cudaMemcpy(off.data(), frag_off, ((size_t)n_frag + 1) * 8, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(tx.data(), frag_taxon, (size_t)n_frag * 4, cudaMemcpyDeviceToHost));
+  // device offsets index `bases` directly (no shift)
+  return build_add_impl(b, bases, frag_off, 0, off.data(), tx.data(), n_frag);
+}
+
+extern "C" int slk_build_finish(slk_builder* b, slk_index** out) {
+  if (!b || !out) return fail(SLK_E_INVALID, "bad arguments");
+  slk_ctx* ctx = b->ctx;
+  CU(cudaSetDevice(ctx->device));
+  slk_index* idx = new (std::nothrow) slk_index;
+  if (!idx) return fail(SLK_E_NOMEM, "host allocation failed");
+  idx->ctx = ctx; idx->tax = b->tax; idx->params = b->params; idx->sp = b->sp;
+  idx->dt = b->dt;  // host vectors copied; device arrays created below
+  idx->dt.d_parent = nullptr; idx->dt.d_depth = nullptr; idx->dt.d_raw = nullptr;
+  int rc = dense_upload(idx->dt);
+  if (rc != SLK_OK) { slk_index_destroy(idx); return rc; }
+  uint64_t n = b->count;
+  uint64_t* d_sorted = nullptr; uint64_t* d_unique = nullptr; unsigned long long* d_cur = nullptr;
+  auto cleanup = [&]() { cudaFree(d_sorted); cudaFree(d_unique); cudaFree(d_cur); };
+#define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); slk_index_destroy(idx); \
+    return fail(e_ == cudaErrorMemoryAllocation ? SLK_E_NOMEM : SLK_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+  unsigned long long n_unique = 0;
+  if (n > 0) {
+    // K3a: radix sort of the cells (all 64 bits, so equal (key, taxon) pairs become adjacent)
+    CUX(cudaMalloc(&d_sorted, n * 8));
+    uint64_t* sorted_ptr = nullptr;
+    rc = slk_sort_u64(b->cells, d_sorted, n, 0, 16 + b->sp.key_bits, ctx->stream, &sorted_ptr);
+    if (rc != 0) { cleanup(); slk_index_destroy(idx); return fail(SLK_E_CUDA, "radix sort failed (%d)", rc); }
+    b->launches += 8;
+    // K3b: segmented LCA reduce; the other buffer receives the unique cells
+    uint64_t* other = sorted_ptr == d_sorted ? b->cells : d_sorted;
+    CUX(cudaMalloc(&d_cur, 8));
+    CUX(cudaMemsetAsync(d_cur, 0, 8, ctx->stream));
+    reduce_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(sorted_ptr, n, idx->dt.view(), other, d_cur);
+    CUX(cudaGetLastError());
+    CUX(cudaMemcpyAsync(&n_unique, d_cur, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUX(cudaStreamSynchronize(ctx->stream));
+    b->launches++;
+    // K4: hash table
+    rc = table_alloc(&idx->table, n_unique);
+    if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
+    CUX(cudaMemsetAsync(d_cur, 0, 8, ctx->stream));
+    rc = insert_cells(ctx, idx, other, n_unique, d_cur);
+    if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
+    CUX(cudaStreamSynchronize(ctx->stream));
+    b->launches++;
+  } else {
+    rc = table_alloc(&idx->table, 0);
+    if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
+  }
+#undef CUX
+  idx->n_records = n_unique;
+  cleanup();
+  cudaFree(b->cells); b->cells = nullptr; b->cap = 0; b->count = 0;
+  *out = idx;
+  return SLK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- counts
+extern "C" int slk_counts_create(slk_ctx* ctx, slk_tax* tax, int32_t n_samples, slk_counts** out) {
+  if (!ctx || !tax || n_samples < 1 || !out) return fail(SLK_E_INVALID, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  slk_counts* c = new (std::nothrow) slk_counts;
+  if (!c) return fail(SLK_E_NOMEM, "host allocation failed");
+  c->ctx = ctx; c->n_samples = n_samples; c->n_taxa = (int32_t)tax->parents.size(); c->d = nullptr;
+  size_t bytes = (size_t)n_samples * c->n_taxa * 8;
+  cudaError_t e = cudaMalloc(&c->d, bytes);
+  if (e == cudaSuccess) e = cudaMemset(c->d, 0, bytes);
+  if (e != cudaSuccess) { delete c; return fail(SLK_E_NOMEM, "counts allocation failed: %s", cudaGetErrorString(e)); }
+  *out = c;
+  return SLK_OK;
+}
+extern "C" void slk_counts_destroy(slk_counts* c) {
+  if (!c) return;
+  cudaSetDevice(c->ctx->device);
+  cudaFree(c->d);
+  delete c;
+}
+extern "C" int slk_counts_reset(slk_counts* c) {
+  CU(cudaSetDevice(c->ctx->device));
+  CU(cudaMemset(c->d, 0, (size_t)c->n_samples * c->n_taxa * 8));
+  return SLK_OK;
+}
+extern "C" void* slk_counts_device_ptr(slk_counts* c) { return c ? c->d : nullptr; }
+extern "C" int slk_counts_add(slk_counts* c, const int32_t* taxon, const uint8_t* flags, const int32_t* sample_id, uint32_t n) {
+  if (!c || !taxon || !flags) return fail(SLK_E_INVALID, "bad arguments");
+  if (n == 0) return SLK_OK;
+  slk_ctx* ctx = c->ctx;
+  CU(cudaSetDevice(ctx->device));
+  int32_t *d_t = nullptr, *d_s = nullptr; uint8_t* d_f = nullptr; uint32_t* d_bad = nullptr;
+  CU(cudaMalloc(&d_t, (size_t)n * 4)); CU(cudaMalloc(&d_f, n)); CU(cudaMalloc(&d_bad, 4));
+  CU(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+  CU(cudaMemcpyAsync(d_t, taxon, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_f, flags, n, cudaMemcpyHostToDevice, ctx->stream));
+  if (sample_id) {
+    CU(cudaMalloc(&d_s, (size_t)n * 4));
+    CU(cudaMemcpyAsync(d_s, sample_id, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  counts_add_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_t, d_f, d_s, n, c->n_samples, c->n_taxa, c->d, d_bad);
+  CU(cudaGetLastError());
+  uint32_t bad = 0;
+  CU(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_t); cudaFree(d_f); cudaFree(d_s); cudaFree(d_bad);
+  if (bad) return fail(SLK_E_INVALID, "a sample id or taxon is out of range");
+  return SLK_OK;
+}
+extern "C" int slk_counts_fetch(slk_counts* c, int32_t sample, int64_t* per_taxon_out, int32_t n_taxa) {
+  if (!c || !per_taxon_out || sample < 0 || sample >= c->n_samples) return fail(SLK_E_INVALID, "bad arguments");
+  if (n_taxa < c->n_taxa) return fail(SLK_E_NOSPACE, "per_taxon_out needs %d entries", c->n_taxa);
+  CU(cudaSetDevice(c->ctx->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(per_taxon_out, c->d + (size_t)sample * c->n_taxa, (size_t)c->n_taxa * 8, cudaMemcpyDeviceToHost));
+  return SLK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- classifier
+#define NSLOT 3
+struct cls_slot {
+  uint8_t *bases1 = nullptr, *bases2 = nullptr;
+  uint64_t *off1 = nullptr, *off2 = nullptr;
+  int32_t* taxon = nullptr; uint8_t* flags = nullptr; slk_read_detail* detail = nullptr;
+  slk_hit* hits = nullptr; uint64_t hits_cap = 0;
+  unsigned long long* d_range = nullptr;   // [0] = cursor value before the kernel, [1] = after
+  unsigned long long* h_range = nullptr;   // pinned copy
+  cudaEvent_t h2d_done, k_done, d2h_done;
+  bool busy = false;
+  uint32_t r0 = 0, n = 0;
+};
+struct slk_classifier {
+  slk_index* idx;
+  slk_ctx* ctx;
+  cudaStream_t s_h2d, s_k, s_d2h;
+  cls_slot slot[NSLOT];
+  size_t cap_reads = 0, cap_bases = 0;
+  bool cap_paired = false, cap_hits = false;
+  unsigned long long* d_cursor = nullptr;
+  uint32_t* d_err = nullptr;
+  unsigned long long* d_stats = nullptr;  // [0] probes, [1] merged hits, accumulated over launches
+  slk_counts* counts = nullptr;
+  int32_t counts_sample = 0;
+  uint64_t launches = 0;
+};
+static const uint32_t CH_READS = 1u << 19;
+static const uint64_t CH_BASES = 96ull << 20;
+
+extern "C" int slk_classifier_create(slk_index* idx, slk_classifier** out) {
+  if (!idx || !out) return fail(SLK_E_INVALID, "bad arguments");
+  slk_ctx* ctx = idx->ctx;
+  CU(cudaSetDevice(ctx->device));
+  slk_classifier* c = new (std::nothrow) slk_classifier;
+  if (!c) return fail(SLK_E_NOMEM, "host allocation failed");
+  c->idx = idx; c->ctx = ctx;
+  CU(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < NSLOT; i++) {
+    CU(cudaEventCreateWithFlags(&c->slot[i].h2d_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->slot[i].k_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->slot[i].d2h_done, cudaEventDisableTiming));
+    CU(cudaMalloc(&c->slot[i].d_range, 16));
+    CU(cudaHostAlloc(&c->slot[i].h_range, 16, cudaHostAllocDefault));
+  }
+  CU(cudaMalloc(&c->d_cursor, 8));
+  CU(cudaMalloc(&c->d_err, 4));
+  CU(cudaMemset(c->d_err, 0, 4));
+  CU(cudaMalloc(&c->d_stats, 16));
+  CU(cudaMemset(c->d_stats, 0, 16));
+  *out = c;
+  return SLK_OK;
+}
+static void slot_free(cls_slot& s) {
+  cudaFree(s.bases1); cudaFree(s.bases2); cudaFree(s.off1); cudaFree(s.off2); cudaFree(s.taxon); cudaFree(s.flags);
+  cudaFree(s.detail); cudaFree(s.hits);
+  s.bases1 = s.bases2 = nullptr; s.off1 = s.off2 = nullptr; s.taxon = nullptr; s.flags = nullptr; s.detail = nullptr; s.hits = nullptr;
+}
+extern "C" void slk_classifier_destroy(slk_classifier* c) {
+  if (!c) return;
+  cudaSetDevice(c->ctx->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < NSLOT; i++) {
+    slot_free(c->slot[i]);
+    cudaFree(c->slot[i].d_range); cudaFreeHost(c->slot[i].h_range);
+    cudaEventDestroy(c->slot[i].h2d_done); cudaEventDestroy(c->slot[i].k_done); cudaEventDestroy(c->slot[i].d2h_done);
+  }
+  cudaFree(c->d_cursor); cudaFree(c->d_err); cudaFree(c->d_stats);
+  cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_k); cudaStreamDestroy(c->s_d2h);
+  delete c;
+}
+extern "C" int slk_classifier_sync(slk_classifier* c) {
+  CU(cudaSetDevice(c->ctx->device));
+  CU(cudaStreamSynchronize(c->s_k));
+  return SLK_OK;
+}
+extern "C" void* slk_classifier_stream(slk_classifier* c) { return c ? (void*)c->s_k : nullptr; }
+extern "C" uint64_t slk_classifier_launches(const slk_classifier* c) { return c ? c->launches : 0; }
+extern "C" int slk_classifier_stats(slk_classifier* c, uint64_t* probes, uint64_t* merged_hits) {
+  if (!c) return fail(SLK_E_INVALID, "bad arguments");
+  CU(cudaSetDevice(c->ctx->device));
+  CU(cudaStreamSynchronize(c->s_k));
+  unsigned long long v[2];
+  CU(cudaMemcpy(v, c->d_stats, 16, cudaMemcpyDeviceToHost));
+  if (probes) *probes = v[0];
+  if (merged_hits) *merged_hits = v[1];
+  return SLK_OK;
+}
+// CUDA-event timing on the classifier's launch stream (bench / profiling helpers)
+struct slk_event { cudaEvent_t ev; int device; };
+extern "C" int slk_event_create(slk_ctx* ctx, slk_event** out) {
+  if (!ctx || !out) return fail(SLK_E_INVALID, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  slk_event* e = new (std::nothrow) slk_event;
+  if (!e) return fail(SLK_E_NOMEM, "host allocation failed");
+  e->device = ctx->device;
+  CU(cudaEventCreate(&e->ev));
+  *out = e;
+  return SLK_OK;
+}
+extern "C" void slk_event_destroy(slk_event* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaEventDestroy(e->ev);
+  delete e;
+}
+extern "C" int slk_event_record(slk_event* e, slk_classifier* c) {
+  if (!e || !c) return fail(SLK_E_INVALID, "bad arguments");
+  CU(cudaSetDevice(e->device));
+  CU(cudaEventRecord(e->ev, c->s_k));
+  return SLK_OK;
+}
+extern "C" int slk_event_elapsed_ms(slk_event* start, slk_event* end, float* ms) {
+  if (!start || !end || !ms) return fail(SLK_E_INVALID, "bad arguments");
+  CU(cudaSetDevice(start->device));
+  CU(cudaEventSynchronize(end->ev));
+  CU(cudaEventElapsedTime(ms, start->ev, end->ev));
+  return SLK_OK;
+}
+extern "C" int slk_memcpy_d2d(slk_ctx* c, void* dst, const void* src, size_t bytes) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+  return SLK_OK;
+}
+extern "C" int slk_classifier_attach_counts(slk_classifier* c, slk_counts* cn, int32_t sample) {
+  if (!c) return fail(SLK_E_INVALID, "bad arguments");
+  if (cn && (sample < 0 || sample >= cn->n_samples)) return fail(SLK_E_INVALID, "sample %d out of range", sample);
+  c->counts = cn; c->counts_sample = sample;
+  return SLK_OK;
+}
+extern "C" uint64_t slk_classify_hits_bound(const slk_params* p, uint32_t n_reads, uint64_t total_bases, int paired) {
+  (void)p;
+  return total_bases + (uint64_t)n_reads * (paired ? 5ull : 3ull);
+}
+
+static void launch_classify(slk_classifier* c, bool hits, const slk_classify_opts* o, const uint8_t* b1, const uint64_t* o1,
+                            uint64_t sh1, const uint8_t* b2, const uint64_t* o2, uint64_t sh2, uint32_t n, int32_t* taxon,
+                            uint8_t* flags, slk_read_detail* detail, slk_hit* hbase, const unsigned long long* hshift,
+                            uint64_t hcap, unsigned long long* cursor) {
+  slk_index* idx = c->idx;
+  slk_classify_args a;
+  a.sp = idx->sp; a.tb = idx->table; a.tx = idx->dt.view();
+  a.bases1 = b1; a.off1 = o1; a.shift1 = sh1; a.bases2 = b2; a.off2 = o2; a.shift2 = sh2; a.n_reads = n;
+  a.confidence = o->confidence; a.min_hit_groups = o->min_hit_groups;
+  a.taxon_out = taxon; a.flags_out = flags; a.detail_out = detail;
+  a.hits_base = hbase; a.hits_shift_ptr = hshift; a.hits_cap = hcap; a.hits_cursor = cursor;
+  a.counts = c->counts ? c->counts->d + (size_t)c->counts_sample * c->counts->n_taxa : nullptr;
+  a.error_flag = c->d_err; a.stats = c->d_stats; a.hits = hits; a.stream = c->s_k;
+  DISPATCH_W(idx->sp.w, slk_launch_classify_w, a);
+  c->launches++;
+}
+
+static int check_error_flag(slk_classifier* c) {
+  uint32_t err = 0;
+  CU(cudaMemcpy(&err, c->d_err, 4, cudaMemcpyDeviceToHost));
+  if (err) {
+    CU(cudaMemset(c->d_err, 0, 4));
+    return fail(SLK_E_UNSUPPORTED, "a fragment hit more than %d distinct taxa (per-read histogram limit)", SLK_KMAX);
+  }
+  return SLK_OK;
+}
+
+extern "C" int slk_classify_batch_dev(slk_classifier* c, const slk_classify_opts* opts, const uint8_t* bases1,
+                                      const uint64_t* off1, const uint8_t* bases2, const uint64_t* off2, uint32_t n_reads,
+                                      int32_t* taxon_out, uint8_t* flags_out, slk_read_detail* detail_out, slk_hit* hits_out,
+                                      uint64_t hits_cap, uint64_t* hits_used_dev) {
+  if (!c || !opts || !bases1 || !off1 || !taxon_out || !flags_out) return fail(SLK_E_INVALID, "bad arguments");
+  if ((bases2 == nullptr) != (off2 == nullptr)) return fail(SLK_E_INVALID, "bases2/off2 must both be given or both be NULL");
+  bool hits = hits_out != nullptr;
+  if (hits && (!detail_out || !hits_used_dev)) return fail(SLK_E_INVALID, "hits_out needs detail_out and hits_used_dev");
+  CU(cudaSetDevice(c->ctx->device));
+  if (n_reads == 0) return SLK_OK;
+  if (hits) CU(cudaMemsetAsync(hits_used_dev, 0, 8, c->s_k));
+  launch_classify(c, hits, opts, bases1, off1, 0, bases2, off2, 0, n_reads, taxon_out, flags_out, detail_out, hits_out, nullptr,
+                  hits_cap, reinterpret_cast<unsigned long long*>(hits_used_dev));
+  CU(cudaGetLastError());
+  return SLK_OK;
+}
+
+static int ensure_slots(slk_classifier* c, bool paired, bool hits) {
+  bool need = c->cap_reads == 0 || (paired && !c->cap_paired) || (hits && !c->cap_hits);
+  if (!need) return SLK_OK;
+  CU(cudaDeviceSynchronize());
+  for (int i = 0; i < NSLOT; i++) {
+    cls_slot& s = c->slot[i];
+    slot_free(s);
+    CU(cudaMalloc(&s.bases1, CH_BASES + 64));
+    CU(cudaMalloc(&s.off1, ((size_t)CH_READS + 1) * 8));
+    if (paired) {
+      CU(cudaMalloc(&s.bases2, CH_BASES + 64));
+      CU(cudaMalloc(&s.off2, ((size_t)CH_READS + 1) * 8));
+    }
+    CU(cudaMalloc(&s.taxon, (size_t)CH_READS * 4));
+    CU(cudaMalloc(&s.flags, CH_READS));
+    CU(cudaMalloc(&s.detail, (size_t)CH_READS * sizeof(slk_read_detail)));
+    if (hits) {
+      s.hits_cap = (paired ? 2 : 1) * CH_BASES + 5ull * CH_READS;
+      CU(cudaMalloc(&s.hits, s.hits_cap * sizeof(slk_hit)));
+    }
+  }
+  c->cap_reads = CH_READS; c->cap_bases = CH_BASES; c->cap_paired = paired; c->cap_hits = hits;
+  return SLK_OK;
+}
+
+// finish one chunk: wait for its kernel, then copy its results into the caller's arrays
+static int finalize_slot(slk_classifier* c, cls_slot& s, bool hits, int32_t* taxon_out, uint8_t* flags_out,
+                         slk_read_detail* detail_out, slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_total, bool* nospace) {
+  CU(cudaEventSynchronize(s.k_done));
+  CU(cudaMemcpyAsync(taxon_out + s.r0, s.taxon, (size_t)s.n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+  CU(cudaMemcpyAsync(flags_out + s.r0, s.flags, s.n, cudaMemcpyDeviceToHost, c->s_d2h));
+  if (detail_out)
+    CU(cudaMemcpyAsync(detail_out + s.r0, s.detail, (size_t)s.n * sizeof(slk_read_detail), cudaMemcpyDeviceToHost, c->s_d2h));
+  if (hits) {
+    uint64_t lo = s.h_range[0], hi = s.h_range[1];
+    *hits_total = hi;
+    if (hi > hits_cap) *nospace = true;
+    uint64_t end = std::min<uint64_t>(hi, hits_cap);
+    if (end > lo)
+      CU(cudaMemcpyAsync(hits_out + lo, s.hits, (size_t)(end - lo) * sizeof(slk_hit), cudaMemcpyDeviceToHost, c->s_d2h));
+  }
+  CU(cudaEventRecord(s.d2h_done, c->s_d2h));
+  return SLK_OK;
+}
+
+extern "C" int slk_classify_batch(slk_classifier* c, const slk_classify_opts* opts, const uint8_t* bases1, const uint64_t* off1,
+                                  const uint8_t* bases2, const uint64_t* off2, uint32_t n_reads, int32_t* taxon_out,
+                                  uint8_t* flags_out, slk_read_detail* detail_out, slk_hit* hits_out, uint64_t hits_cap,
+                                  uint64_t* hits_used) {
+  if (!c || !opts || !bases1 || !off1 || !taxon_out || !flags_out) return fail(SLK_E_INVALID, "bad arguments");
+  if ((bases2 == nullptr) != (off2 == nullptr)) return fail(SLK_E_INVALID, "bases2/off2 must both be given or both be NULL");
+  bool hits = hits_out != nullptr, paired = bases2 != nullptr;
+  if (hits && !detail_out) return fail(SLK_E_INVALID, "hits_out needs detail_out");
+  if (hits_used) *hits_used = 0;
+  CU(cudaSetDevice(c->ctx->device));
+  if (n_reads == 0) return SLK_OK;
+  TRY(ensure_slots(c, paired, hits));
+  CU(cudaMemsetAsync(c->d_cursor, 0, 8, c->s_k));
+  uint64_t hits_total = 0;
+  bool nospace = false;
+  int prev = -1, ci = 0;
+  uint32_t r0 = 0;
+  while (r0 < n_reads) {
+    // chunk [r0, r1): bounded by reads and by bases of either mate
+    uint32_t r1 = std::min<uint64_t>(n_reads, (uint64_t)r0 + CH_READS);
+    auto fits = [&](uint32_t e) {
+      if (off1[e] - off1[r0] > CH_BASES) return false;
+      if (paired && off2[e] - off2[r0] > CH_BASES) return false;
+      return true;
+    };
+    if (!fits(r1)) {
+      uint32_t lo = r0, hi = r1;  // fits(lo) holds
+      while (hi - lo > 1) { uint32_t mid = lo + (hi - lo) / 2; if (fits(mid)) lo = mid; else hi = mid; }
+      r1 = lo;
+      if (r1 == r0) return fail(SLK_E_UNSUPPORTED, "read %u is longer than %llu bases", r0, (unsigned long long)CH_BASES);
+    }
+    cls_slot& s = c->slot[ci % NSLOT];
+    if (s.busy) { CU(cudaEventSynchronize(s.d2h_done)); s.busy = false; }
+    s.r0 = r0; s.n = r1 - r0;
+    uint64_t b1 = off1[r1] - off1[r0];
+    CU(cudaMemcpyAsync(s.bases1, bases1 + off1[r0], b1, cudaMemcpyHostToDevice, c->s_h2d));
+    CU(cudaMemcpyAsync(s.off1, off1 + r0, ((size_t)s.n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d));
+    if (paired) {
+      uint64_t b2 = off2[r1] - off2[r0];
+      CU(cudaMemcpyAsync(s.bases2, bases2 + off2[r0], b2, cudaMemcpyHostToDevice, c->s_h2d));
+      CU(cudaMemcpyAsync(s.off2, off2 + r0, ((size_t)s.n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d));
+    }
+    CU(cudaEventRecord(s.h2d_done, c->s_h2d));
+    CU(cudaStreamWaitEvent(c->s_k, s.h2d_done, 0));
+    if (hits) snapshot_kernel<<<1, 1, 0, c->s_k>>>(c->d_cursor, s.d_range);
+    launch_classify(c, hits, opts, s.bases1, s.off1, off1[r0], s.bases2, s.off2, paired ? off2[r0] : 0, s.n, s.taxon, s.flags,
+                    s.detail, s.hits, s.d_range, s.hits_cap, c->d_cursor);
+    CU(cudaGetLastError());
+    if (hits) {
+      snapshot_kernel<<<1, 1, 0, c->s_k>>>(c->d_cursor, s.d_range + 1);
+      CU(cudaMemcpyAsync(s.h_range, s.d_range, 16, cudaMemcpyDeviceToHost, c->s_k));
+      c->launches += 2;
+    }
+    CU(cudaEventRecord(s.k_done, c->s_k));
+    s.busy = true;
+    if (prev >= 0)
+      TRY(finalize_slot(c, c->slot[prev], hits, taxon_out, flags_out, detail_out, hits_out, hits_cap, &hits_total, &nospace));
+    prev = ci % NSLOT;
+    ci++;
+    r0 = r1;
+  }
+  if (prev >= 0)
+    TRY(finalize_slot(c, c->slot[prev], hits, taxon_out, flags_out, detail_out, hits_out, hits_cap, &hits_total, &nospace));
+  CU(cudaStreamSynchronize(c->s_d2h));
+  for (int i = 0; i < NSLOT; i++) c->slot[i].busy = false;
+  if (hits_used) *hits_used = hits_total;
+  TRY(check_error_flag(c));
+  if (nospace) return fail(SLK_E_NOSPACE, "hits_out needs room for %llu hits", (unsigned long long)hits_total);
+  return SLK_OK;
+}

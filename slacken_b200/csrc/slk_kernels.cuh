@@ -1,0 +1,192 @@
+// slk_kernels.cuh -- the two W-templated kernels (classify, build-side emit) and their launch descriptors.
+// Each window width W = k-m+1 is instantiated in its own translation unit (slk_inst.cu with -DSLK_W=n) so the
+// library builds in parallel; slacken_gpu.cu dispatches on the index's W at run time.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "../../include/slacken_gpu.h"
+#include "slk_core.h"
+
+#define BUILD_WPT 96  // k-mer windows scanned per thread of the build-side emit kernel
+
+struct slk_classify_args {
+  slk_scan_params sp; slk_table_view tb; slk_tax_view tx;
+  const uint8_t* bases1; const uint64_t* off1; uint64_t shift1;
+  const uint8_t* bases2; const uint64_t* off2; uint64_t shift2;
+  uint32_t n_reads; double confidence; int32_t min_hit_groups;
+  int32_t* taxon_out; uint8_t* flags_out; slk_read_detail* detail_out;
+  slk_hit* hits_base; const unsigned long long* hits_shift_ptr; uint64_t hits_cap; unsigned long long* hits_cursor;
+  unsigned long long* counts; uint32_t* error_flag; unsigned long long* stats;
+  bool hits; cudaStream_t stream;
+};
+struct slk_emit_args {
+  slk_scan_params sp; const uint8_t* bases; const uint64_t* frag_off; uint64_t off_shift; const uint32_t* frag_dense;
+  const uint64_t* item_prefix; uint32_t n_frag; uint64_t n_items; uint64_t* out; uint64_t cap; unsigned long long* cursor;
+  cudaStream_t stream;
+};
+#define SLK_DECL_W(w) void slk_launch_classify_w##w(const slk_classify_args&); void slk_launch_emit_w##w(const slk_emit_args&);
+SLK_DECL_W(1) SLK_DECL_W(2) SLK_DECL_W(3) SLK_DECL_W(4) SLK_DECL_W(5) SLK_DECL_W(6) SLK_DECL_W(7) SLK_DECL_W(8)
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint64_t warp_agg_alloc(unsigned long long* cursor, uint32_t n) {
+  // all 32 lanes must call; returns each lane's offset in a warp-wide contiguous allocation
+  uint32_t lane = threadIdx.x & 31, incl = n;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= (uint32_t)d) incl += v;
+  }
+  uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned long long base = 0;
+  if (lane == 0 && total) base = atomicAdd(cursor, (unsigned long long)total);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  return base + incl - n;
+}
+
+// ---------------------------------------------------------------------------------------------- build kernels
+// K2 (build side) + K3a emit: one thread scans BUILD_WPT k-mer windows of one fragment and appends its cells.
+template <int W>
+__global__ void __launch_bounds__(128) emit_cells_kernel(slk_scan_params sp, const uint8_t* __restrict__ bases,
+                                                         const uint64_t* __restrict__ frag_off, uint64_t off_shift,
+                                                         const uint32_t* __restrict__ frag_dense,
+                                                         const uint64_t* __restrict__ item_prefix, uint32_t n_frag,
+                                                         uint64_t n_items, uint64_t* __restrict__ out,
+                                                         uint64_t cap, unsigned long long* cursor) {
+  uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t local[BUILD_WPT];
+  uint32_t nl = 0;
+  if (it < n_items) {
+    // fragment of this item: last f with item_prefix[f] <= it
+    uint32_t lo = 0, hi = n_frag;
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (item_prefix[mid] <= it) lo = mid; else hi = mid;
+    }
+    uint32_t f = lo;
+    uint32_t dense = frag_dense[f];
+    if (dense != 0) {
+      uint64_t fs = frag_off[f] - off_shift, fe = frag_off[f + 1] - off_shift;
+      uint64_t w0 = (it - item_prefix[f]) * BUILD_WPT;
+      uint64_t nb = fe - fs - w0;
+      uint64_t want = (uint64_t)BUILD_WPT + sp.k - 1;
+      if (nb > want) nb = want;
+      auto emit = [&](uint64_t cell) { local[nl++] = cell; };
+      slk_emit_cells<W>(sp, bases + fs + w0, nb, dense, emit);
+    }
+  }
+  uint64_t o = warp_agg_alloc(cursor, nl);
+  for (uint32_t j = 0; j < nl; j++)
+    if (o + j < cap) out[o + j] = local[j];
+}
+
+// ---------------------------------------------------------------------------------------------- classify kernel
+struct dev_hit_sink {
+  slk_hit buf[SLK_HCAP];
+  uint32_t n;
+  bool spilled;
+  uint64_t goff;
+  slk_hit* gbase;         // scratch, indexed by (absolute index - gshift)
+  uint64_t gshift, gcap;  // gcap: capacity of gbase in hits
+  unsigned long long* cursor;
+  __device__ __forceinline__ void put(uint64_t abs_idx, slk_hit h) {
+    uint64_t rel = abs_idx - gshift;
+    if (rel < gcap) gbase[rel] = h;
+  }
+  __device__ __forceinline__ void push(int32_t taxon, int32_t count, uint32_t windows_left) {
+    slk_hit h;
+    h.taxon = taxon; h.count = count;
+    if (!spilled) {
+      if (n < SLK_HCAP) { buf[n++] = h; return; }
+      goff = atomicAdd(cursor, (unsigned long long)n + windows_left + 2ull);
+      for (uint32_t i = 0; i < n; i++) put(goff + i, buf[i]);
+      spilled = true;
+    }
+    put(goff + n, h);
+    n++;
+  }
+};
+
+template <int W, bool HITS>
+__global__ void __launch_bounds__(128) classify_kernel(slk_scan_params sp, slk_table_view tb, slk_tax_view tx,
+                                                       const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ off1,
+                                                       uint64_t shift1, const uint8_t* __restrict__ bases2,
+                                                       const uint64_t* __restrict__ off2, uint64_t shift2, uint32_t n_reads,
+                                                       double confidence, int32_t min_hit_groups,
+                                                       int32_t* __restrict__ taxon_out, uint8_t* __restrict__ flags_out,
+                                                       slk_read_detail* __restrict__ detail_out, slk_hit* hits_base,
+                                                       const unsigned long long* hits_shift_ptr, uint64_t hits_cap,
+                                                       unsigned long long* hits_cursor, unsigned long long* counts,
+                                                       uint32_t* error_flag, unsigned long long* stats) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = r < n_reads;
+  slk_frag_result res;
+  res.taxon = 0; res.flags = 0; res.kmers1 = 0; res.kmers2 = 0; res.num_distinct = 0; res.n_hits = 0; res.n_probes = 0;
+  typedef typename std::conditional<HITS, dev_hit_sink, slk_null_sink>::type sink_t;
+  sink_t sink;
+  if constexpr (HITS) {
+    sink.n = 0; sink.spilled = false; sink.goff = 0; sink.gbase = hits_base;
+    sink.gshift = hits_shift_ptr ? *hits_shift_ptr : 0ull;
+    sink.gcap = hits_cap; sink.cursor = hits_cursor;
+  }
+  if (active) {
+    uint64_t s1 = off1[r], e1 = off1[r + 1];
+    const uint8_t* p2 = nullptr;
+    uint32_t l2 = 0;
+    if (bases2) {
+      uint64_t s2 = off2[r], e2 = off2[r + 1];
+      p2 = bases2 + (s2 - shift2);
+      l2 = (uint32_t)(e2 - s2);
+    }
+    slk_frag_classifier<W, sink_t> cl(sp, tb, tx, sink);
+    cl.run(bases1 + (s1 - shift1), (uint32_t)(e1 - s1), p2, l2, confidence, min_hit_groups, res);
+    taxon_out[r] = res.taxon;
+    flags_out[r] = (uint8_t)(res.flags & 3u);
+    if (res.flags & SLK_F_OVERFLOW) atomicExch(error_flag, 1u);
+  }
+  if constexpr (HITS) {
+    // compact allocation of the (non-spilled) merged hits, one atomic per warp
+    uint32_t need = (active && !sink.spilled) ? sink.n : 0u;
+    uint64_t o = warp_agg_alloc(hits_cursor, need);
+    if (active) {
+      if (!sink.spilled) {
+        sink.goff = o;
+        for (uint32_t i = 0; i < sink.n; i++) sink.put(o + i, sink.buf[i]);
+      }
+      slk_read_detail d;
+      d.hit_off = sink.goff; d.hit_cnt = sink.n;
+      d.len1 = res.kmers1 + (uint32_t)(sp.k - 1);
+      d.len2 = bases2 ? res.kmers2 + (uint32_t)(sp.k - 1) : 0xFFFFFFFFu;
+      d.num_distinct = res.num_distinct;
+      detail_out[r] = d;
+    }
+  } else if (detail_out != nullptr && active) {
+    slk_read_detail d;
+    d.hit_off = 0; d.hit_cnt = 0;
+    d.len1 = res.kmers1 + (uint32_t)(sp.k - 1);
+    d.len2 = bases2 ? res.kmers2 + (uint32_t)(sp.k - 1) : 0xFFFFFFFFu;
+    d.num_distinct = res.num_distinct;
+    detail_out[r] = d;
+  }
+  if (stats != nullptr) {  // probes and merged hits of this launch (the S and H of the roofline arithmetic)
+    uint32_t np = __reduce_add_sync(0xffffffffu, active ? res.n_probes : 0u);
+    uint32_t nh = __reduce_add_sync(0xffffffffu, active ? res.n_hits : 0u);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&stats[0], (unsigned long long)np);
+      atomicAdd(&stats[1], (unsigned long long)nh);
+    }
+  }
+  // K7: per-taxon report counters (groupBy(sampleId, taxon).count, slacken/Classifier.scala:214-217),
+  // aggregated per warp with match_any so a hot taxon costs one atomic per warp
+  if (counts != nullptr) {
+    bool cnt = active && (res.flags & SLK_F_HAS_SPAN);
+    uint32_t key = cnt ? (uint32_t)res.taxon : 0xFFFFFFFFu;
+    uint32_t peers = __match_any_sync(0xffffffffu, key);
+    if (cnt && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1))
+      atomicAdd(&counts[(uint32_t)res.taxon], (unsigned long long)__popc(peers));
+  }
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,389 @@
+"""Host-side mirror of the reference's classes for the hot path (the part of the Scala driver that would call the
+C ABI). Citations are relative to /root/reference/src/main/scala/com/jnpersson/."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import ClassifyOpts, Params, check
+
+DEFAULT_TOGGLE_MASK = 0xE37E28C4271B5A2D  # kmers/minimizer/package.scala:32
+NONE, ROOT = 0, 1  # slacken/Taxonomy.scala:30-31
+AMBIGUOUS_SPAN, MATE_PAIR_BORDER = -1, -2  # slacken/package.scala:28-29
+
+HIT_DTYPE = np.dtype([("taxon", "<i4"), ("count", "<i4")])
+DETAIL_DTYPE = np.dtype([("hit_off", "<u8"), ("hit_cnt", "<u4"), ("len1", "<u4"), ("len2", "<u4"), ("num_distinct", "<u4")])
+assert DETAIL_DTYPE.itemsize == 24
+
+
+def _ptr(a) -> Optional[C.c_void_p]:
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class GpuContext:
+    """One CUDA device (slk_ctx). One process per GPU is the deployment model."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        check(self._L.slk_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.slk_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        check(self._L.slk_ctx_sync(self.h))
+
+    # pinned host arrays ------------------------------------------------------------
+    def pinned(self, shape, dtype) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        check(self._L.slk_host_alloc(max(n, 1), C.byref(p)))
+        buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
+        _PINNED[arr.ctypes.data] = (p, self._L)
+        return arr
+
+    def free_pinned(self, arr: np.ndarray):
+        ent = _PINNED.pop(arr.ctypes.data, None)
+        if ent:
+            ent[1].slk_host_free(ent[0])
+
+    # raw device memory (for device-resident benchmarks) ------------------------------
+    def dev_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        check(self._L.slk_dev_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def dev_free(self, p: int):
+        self._L.slk_dev_free(self.h, C.c_void_p(p))
+
+    def h2d(self, dst: int, src: np.ndarray):
+        src = np.ascontiguousarray(src)
+        check(self._L.slk_memcpy_h2d(self.h, C.c_void_p(dst), _ptr(src), src.nbytes))
+
+    def d2h(self, dst: np.ndarray, src: int):
+        assert dst.flags["C_CONTIGUOUS"]
+        check(self._L.slk_memcpy_d2h(self.h, _ptr(dst), C.c_void_p(src), dst.nbytes))
+
+
+_PINNED: dict = {}
+
+
+@dataclass
+class IndexParams:
+    """kmers/IndexParams.scala:63-91 + kmers/SplitterFormat.scala:55-77 (splitter = randomXOR)."""
+    k: int = 35
+    m: int = 31
+    spaces: int = 7
+    canonical: bool = True
+    toggle_mask: int = DEFAULT_TOGGLE_MASK
+    buckets: int = 200
+
+    def c_params(self) -> Params:
+        p = Params()
+        check(_lib.load().slk_params_init(self.k, self.m, self.spaces, self.toggle_mask, 1 if self.canonical else 0,
+                                          C.byref(p)))
+        return p
+
+
+class Taxonomy:
+    """slacken/Taxonomy.scala:159-160: parents[] indexed by raw taxon id (NONE = 0, ROOT = 1), plus the rank titles
+    and scientific names the report needs (host only)."""
+
+    def __init__(self, ctx: GpuContext, parents: np.ndarray, ranks: Optional[Sequence[Optional[str]]] = None,
+                 names: Optional[Sequence[Optional[str]]] = None):
+        self.ctx = ctx
+        self.parents = np.ascontiguousarray(parents, dtype=np.int32).copy()
+        self.parents[ROOT] = NONE  # Taxonomy.fromNodesAndNames, slacken/Taxonomy.scala:105
+        self.ranks = list(ranks) if ranks is not None else [None] * len(self.parents)
+        self.names = list(names) if names is not None else [None] * len(self.parents)
+        h = C.c_void_p()
+        check(ctx._L.slk_taxonomy_create(ctx.h, _ptr(self.parents), len(self.parents), C.byref(h)))
+        self.h = h
+
+    @property
+    def size(self) -> int:
+        return len(self.parents)
+
+    def is_defined(self, t: int) -> bool:  # slacken/Taxonomy.scala:175-176
+        return bool(self.parents[t] != NONE or t == ROOT)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx._L.slk_taxonomy_destroy(self.h)
+            self.h = None
+
+
+class KeyValueIndex:
+    """slacken/KeyValueIndex.scala: the minimizer -> LCA taxon library, resident in HBM as an open-addressing table."""
+
+    def __init__(self, ctx: GpuContext, taxonomy: Taxonomy, params: IndexParams, handle):
+        self.ctx, self.taxonomy, self.params, self.h = ctx, taxonomy, params, handle
+
+    # KeyValueIndex.loadRecords (slacken/KeyValueIndex.scala:150-159)
+    @classmethod
+    def from_records(cls, ctx: GpuContext, taxonomy: Taxonomy, params: IndexParams, id1: np.ndarray, taxon: np.ndarray):
+        id1 = np.ascontiguousarray(id1).view(np.int64)
+        taxon = np.ascontiguousarray(taxon, dtype=np.int32)
+        assert len(id1) == len(taxon)
+        p = params.c_params()
+        h = C.c_void_p()
+        check(ctx._L.slk_index_from_records(ctx.h, taxonomy.h, C.byref(p), _ptr(id1), _ptr(taxon), len(id1), C.byref(h)))
+        return cls(ctx, taxonomy, params, h)
+
+    # KeyValueIndex.makeRecords (slacken/KeyValueIndex.scala:85-122): genomes -> records, on the GPU
+    @classmethod
+    def build(cls, ctx: GpuContext, taxonomy: Taxonomy, params: IndexParams, batches, expected_bases: int = 0):
+        """batches: iterable of (bases uint8[], frag_off uint64[n+1], frag_taxon int32[n])."""
+        b = LibraryBuilder(ctx, taxonomy, params, expected_bases)
+        try:
+            for bases, off, taxa in batches:
+                b.add(bases, off, taxa)
+            return b.finish()
+        finally:
+            b.close()
+
+    def __len__(self) -> int:
+        return int(self.ctx._L.slk_index_size(self.h))
+
+    def records(self, sort: bool = True):
+        """(id1 uint64[], taxon int32[]) -- the rows KeyValueIndex.writeRecords stores; sorted by id1 on request
+        (the table itself has no order)."""
+        n = len(self)
+        id1 = np.zeros(n, dtype=np.int64)
+        taxon = np.zeros(n, dtype=np.int32)
+        got = C.c_uint64()
+        check(self.ctx._L.slk_index_records(self.h, _ptr(id1), _ptr(taxon), n, C.byref(got)))
+        if not sort:
+            return id1.view(np.uint64), taxon
+        o = np.argsort(id1.view(np.uint64), kind="stable")
+        return id1.view(np.uint64)[o], taxon[o]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx._L.slk_index_destroy(self.h)
+            self.h = None
+
+
+class LibraryBuilder:
+    """Incremental form of KeyValueIndex.makeRecords: feed (taxon, genome fragment) batches, then finish()."""
+
+    def __init__(self, ctx: GpuContext, taxonomy: Taxonomy, params: IndexParams, expected_bases: int = 0):
+        self.ctx, self.taxonomy, self.params = ctx, taxonomy, params
+        p = params.c_params()
+        b = C.c_void_p()
+        check(ctx._L.slk_build_begin(ctx.h, taxonomy.h, C.byref(p), int(expected_bases), C.byref(b)))
+        self.h = b
+
+    def add(self, bases: np.ndarray, frag_off: np.ndarray, frag_taxon: np.ndarray):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        off = np.ascontiguousarray(frag_off, dtype=np.uint64)
+        taxa = np.ascontiguousarray(frag_taxon, dtype=np.int32)
+        check(self.ctx._L.slk_build_add(self.h, _ptr(bases), _ptr(off), _ptr(taxa), len(taxa)))
+
+    def add_dev(self, bases_dev: int, frag_off_dev: int, frag_taxon_dev: int, n_frag: int, total_bases: int):
+        """Fragments already resident in HBM (offsets index bases_dev directly)."""
+        check(self.ctx._L.slk_build_add_dev(self.h, C.c_void_p(bases_dev), C.c_void_p(frag_off_dev),
+                                            C.c_void_p(frag_taxon_dev), n_frag, total_bases))
+
+    def finish(self) -> "KeyValueIndex":
+        h = C.c_void_p()
+        check(self.ctx._L.slk_build_finish(self.h, C.byref(h)))
+        return KeyValueIndex(self.ctx, self.taxonomy, self.params, h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx._L.slk_build_destroy(self.h)
+            self.h = None
+
+
+class DeviceTimer:
+    """CUDA events on a classifier's launch stream."""
+
+    def __init__(self, classifier: "Classifier"):
+        self.c, self.L = classifier, classifier.ctx._L
+        self.a, self.b = C.c_void_p(), C.c_void_p()
+        check(self.L.slk_event_create(classifier.ctx.h, C.byref(self.a)))
+        check(self.L.slk_event_create(classifier.ctx.h, C.byref(self.b)))
+
+    def start(self):
+        check(self.L.slk_event_record(self.a, self.c.h))
+
+    def stop(self):
+        check(self.L.slk_event_record(self.b, self.c.h))
+
+    def elapsed_ms(self) -> float:
+        ms = C.c_float()
+        check(self.L.slk_event_elapsed_ms(self.a, self.b, C.byref(ms)))
+        return float(ms.value)
+
+    def close(self):
+        self.L.slk_event_destroy(self.a)
+        self.L.slk_event_destroy(self.b)
+
+
+@dataclass
+class ClassifyParams:
+    """slacken/Classifier.scala:47-63"""
+    min_hit_groups: int = 2
+    with_unclassified: bool = True
+    thresholds: List[float] = field(default_factory=lambda: [0.0])
+    sample_regex: Optional[str] = None
+    per_read_output: bool = True
+
+
+class ReportCounts:
+    """Device-resident per-(sample, taxon) read counters: groupBy(sampleId, taxon).count, slacken/Classifier.scala:214-217."""
+
+    def __init__(self, ctx: GpuContext, taxonomy: Taxonomy, n_samples: int = 1):
+        self.ctx, self.taxonomy, self.n_samples = ctx, taxonomy, n_samples
+        h = C.c_void_p()
+        check(ctx._L.slk_counts_create(ctx.h, taxonomy.h, n_samples, C.byref(h)))
+        self.h = h
+
+    def add(self, taxon: np.ndarray, flags: np.ndarray, sample_id: Optional[np.ndarray] = None):
+        taxon = np.ascontiguousarray(taxon, dtype=np.int32)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        sid = np.ascontiguousarray(sample_id, dtype=np.int32) if sample_id is not None else None
+        check(self.ctx._L.slk_counts_add(self.h, _ptr(taxon), _ptr(flags), _ptr(sid), len(taxon)))
+
+    def fetch(self, sample: int = 0) -> np.ndarray:
+        out = np.zeros(self.taxonomy.size, dtype=np.int64)
+        check(self.ctx._L.slk_counts_fetch(self.h, sample, _ptr(out), len(out)))
+        return out
+
+    def pairs(self, sample: int = 0):
+        """[(taxon, count)] with count > 0, the input of KrakenReport."""
+        v = self.fetch(sample)
+        nz = np.nonzero(v)[0]
+        return [(int(t), int(v[t])) for t in nz]
+
+    def device_ptr(self) -> int:
+        return self.ctx._L.slk_counts_device_ptr(self.h)
+
+    def reset(self):
+        check(self.ctx._L.slk_counts_reset(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx._L.slk_counts_destroy(self.h)
+            self.h = None
+
+
+@dataclass
+class ClassifiedBatch:
+    """Arrays behind a batch of ClassifiedRead (slacken/Classifier.scala:27-45)."""
+    taxon: np.ndarray
+    flags: np.ndarray
+    detail: Optional[np.ndarray]
+    hits: Optional[np.ndarray]
+    hits_used: int = 0
+
+    @property
+    def classified(self) -> np.ndarray:
+        return (self.flags & _lib.READ_CLASSIFIED) != 0
+
+    @property
+    def has_span(self) -> np.ndarray:
+        return (self.flags & _lib.READ_HAS_SPAN) != 0
+
+    def hits_of(self, i: int) -> np.ndarray:
+        d = self.detail[i]
+        return self.hits[int(d["hit_off"]):int(d["hit_off"]) + int(d["hit_cnt"])]
+
+
+class Classifier:
+    """slacken/Classifier.scala: classify batches of reads against a KeyValueIndex."""
+
+    def __init__(self, index: KeyValueIndex):
+        self.index, self.ctx = index, index.ctx
+        h = C.c_void_p()
+        check(self.ctx._L.slk_classifier_create(index.h, C.byref(h)))
+        self.h = h
+
+    def attach_counts(self, counts: Optional[ReportCounts], sample: int = 0):
+        check(self.ctx._L.slk_classifier_attach_counts(self.h, counts.h if counts else None, sample))
+
+    def hits_bound(self, n_reads: int, total_bases: int, paired: bool) -> int:
+        p = self.index.params.c_params()
+        return int(self.ctx._L.slk_classify_hits_bound(C.byref(p), n_reads, total_bases, 1 if paired else 0))
+
+    def classify(self, bases1: np.ndarray, off1: np.ndarray, bases2: Optional[np.ndarray] = None,
+                 off2: Optional[np.ndarray] = None, confidence: float = 0.0, min_hit_groups: int = 2,
+                 per_read_output: bool = True, out: Optional[ClassifiedBatch] = None) -> ClassifiedBatch:
+        """Classifier.classify (slacken/Classifier.scala:114-122) for one batch held in host arrays."""
+        n = len(off1) - 1
+        assert bases1.dtype == np.uint8 and off1.dtype == np.uint64
+        paired = bases2 is not None
+        if out is None:
+            taxon = np.zeros(n, dtype=np.int32)
+            flags = np.zeros(n, dtype=np.uint8)
+            detail = np.zeros(n, dtype=DETAIL_DTYPE)
+            hits = None
+            if per_read_output:
+                total = int(off1[-1] - off1[0]) + (int(off2[-1] - off2[0]) if paired else 0)
+                hits = np.zeros(self.hits_bound(n, total, paired), dtype=HIT_DTYPE)
+            out = ClassifiedBatch(taxon, flags, detail, hits)
+        opts = ClassifyOpts(float(confidence), int(min_hit_groups), 0)
+        used = C.c_uint64(0)
+        hits = out.hits if per_read_output else None
+        check(self.ctx._L.slk_classify_batch(self.h, C.byref(opts), _ptr(bases1), _ptr(off1), _ptr(bases2), _ptr(off2), n,
+                                             _ptr(out.taxon), _ptr(out.flags), _ptr(out.detail), _ptr(hits),
+                                             len(hits) if hits is not None else 0, C.byref(used)))
+        out.hits_used = int(used.value)
+        return out
+
+    def classify_dev(self, bases1: int, off1: int, bases2: int, off2: int, n_reads: int, taxon_out: int, flags_out: int,
+                     detail_out: int, hits_out: int, hits_cap: int, hits_used_dev: int, confidence: float = 0.0,
+                     min_hit_groups: int = 2):
+        """Device-resident variant: every argument is a device address (0 = NULL); asynchronous on self.stream."""
+        opts = ClassifyOpts(float(confidence), int(min_hit_groups), 0)
+        v = lambda p: C.c_void_p(p) if p else None
+        check(self.ctx._L.slk_classify_batch_dev(self.h, C.byref(opts), v(bases1), v(off1), v(bases2), v(off2), n_reads,
+                                                 v(taxon_out), v(flags_out), v(detail_out), v(hits_out), hits_cap,
+                                                 v(hits_used_dev)))
+
+    @property
+    def stream(self) -> int:
+        return self.ctx._L.slk_classifier_stream(self.h)
+
+    def sync(self):
+        check(self.ctx._L.slk_classifier_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.ctx._L.slk_classifier_launches(self.h))
+
+    def stats(self):
+        """(table probes, merged hits) accumulated over every launch of this classifier."""
+        a, b = C.c_uint64(), C.c_uint64()
+        check(self.ctx._L.slk_classifier_stats(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx._L.slk_classifier_destroy(self.h)
+            self.h = None
+
+
+def pack_sequences(seqs):
+    """list of bytes/str -> (uint8 bases, uint64 offsets[n+1]): what the JVM side assembles in a pinned buffer."""
+    bs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    joined = b"".join(bs)
+    bases = np.frombuffer(joined, dtype=np.uint8).copy() if joined else np.zeros(16, dtype=np.uint8)[:0]
+    return bases, off

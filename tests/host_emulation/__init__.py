@@ -1,0 +1,148 @@
+"""TEST-ONLY host emulation of the CUDA kernel bodies (slacken_b200/csrc/slk_core.h compiled with g++).
+Never imported by the product package; see emu.cpp."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libslk_emu.so")
+_CORE = os.path.join(_HERE, "..", "..", "slacken_b200", "csrc", "slk_core.h")
+BUILD_WPT = 96
+
+
+class ScanParams(C.Structure):
+    _fields_ = [("k", C.c_int32), ("m", C.c_int32), ("w", C.c_int32), ("canonical", C.c_int32), ("fshift", C.c_int32),
+                ("key_bits", C.c_int32), ("xor_mask", C.c_uint64), ("sig_mask", C.c_uint64), ("mmask", C.c_uint64),
+                ("cmv", C.c_uint64 * 6)]
+
+
+RESULT_DTYPE = np.dtype([("taxon", "<i4"), ("flags", "<u4"), ("kmers1", "<u4"), ("kmers2", "<u4"),
+                         ("num_distinct", "<u4"), ("n_hits", "<u4")])
+HIT_DTYPE = np.dtype([("taxon", "<i4"), ("count", "<i4")])
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src = os.path.join(_HERE, "emu.cpp")
+        newest = max(os.path.getmtime(src), os.path.getmtime(_CORE))
+        if not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
+            subprocess.check_call(["/usr/bin/g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
+                                   "-o", _SO, src])
+        L = C.CDLL(_SO)
+        L.emu_scan_params.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(ScanParams)]
+        L.emu_compress.restype = C.c_uint64
+        L.emu_compress.argtypes = [C.POINTER(ScanParams), C.c_uint64]
+        L.emu_expand.restype = C.c_uint64
+        L.emu_expand.argtypes = [C.POINTER(ScanParams), C.c_uint64]
+        L.emu_code.restype = C.c_uint32
+        L.emu_code.argtypes = [C.c_uint32]
+        L.emu_buckets_for.restype = C.c_uint64
+        L.emu_buckets_for.argtypes = [C.c_uint64]
+        L.emu_insert_cells.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
+        L.emu_classify.restype = C.c_int64
+        L.emu_classify.argtypes = [C.POINTER(ScanParams), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                   C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.emu_emit_cells.restype = C.c_int64
+        L.emu_emit_cells.argtypes = [C.POINTER(ScanParams), C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]
+        L.emu_synth_genome.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.emu_synth_reads.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def scan_params(k, m, spaces, mask, canonical) -> ScanParams:
+    sp = ScanParams()
+    rc = lib().emu_scan_params(k, m, spaces, mask, 1 if canonical else 0, C.byref(sp))
+    if rc:
+        raise ValueError(f"unsupported parameters ({rc})")
+    return sp
+
+
+class DenseTax:
+    """Python twin of the host-side dense taxonomy (dense_add in slacken_gpu.cu), test use only."""
+
+    def __init__(self, parents: np.ndarray, taxa):
+        self.raw = [0]
+        self.parent = [0]
+        self.depth = [0]
+        self.to_dense = {0: 0}
+        self.parents = parents
+        self.root = self.add(1)
+        for t in sorted(set(int(x) for x in taxa)):
+            if t > 0:
+                self.add(t)
+
+    def add(self, raw: int) -> int:
+        path = []
+        t = raw
+        while t not in self.to_dense:
+            path.append(t)
+            t = int(self.parents[t])
+        pd = self.to_dense[t]
+        for x in reversed(path):
+            self.raw.append(x)
+            self.parent.append(pd)
+            self.depth.append(self.depth[pd] + 1)
+            pd = len(self.raw) - 1
+            self.to_dense[x] = pd
+        return pd
+
+    def arrays(self):
+        return (np.array(self.parent, dtype=np.uint16), np.array(self.depth, dtype=np.uint8),
+                np.array(self.raw, dtype=np.int32))
+
+
+class EmuIndex:
+    def __init__(self, sp: ScanParams, parents: np.ndarray, id1: np.ndarray, taxon: np.ndarray):
+        self.sp = sp
+        self.dt = DenseTax(parents, taxon)
+        self.parent, self.depth, self.raw = self.dt.arrays()
+        self.n_buckets = int(lib().emu_buckets_for(len(id1)))
+        self.cells = np.zeros(self.n_buckets * 4, dtype=np.uint64)
+        cells_in = np.array([(lib().emu_compress(C.byref(sp), int(k)) << 16) | self.dt.to_dense[int(t)]
+                             for k, t in zip(id1.view(np.uint64), taxon)], dtype=np.uint64)
+        lib().emu_insert_cells(_p(self.cells), self.n_buckets, _p(self.parent), _p(self.depth), self.dt.root,
+                               _p(cells_in), len(cells_in))
+
+    def classify(self, bases1, off1, bases2=None, off2=None, confidence=0.0, min_hit_groups=2):
+        n = len(off1) - 1
+        off1 = np.ascontiguousarray(off1, dtype=np.uint64)
+        if bases2 is not None:
+            off2 = np.ascontiguousarray(off2, dtype=np.uint64)
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        cap = int(off1[-1]) + (int(off2[-1]) if bases2 is not None else 0) + 5 * n + 8
+        hits = np.zeros(cap, dtype=HIT_DTYPE)
+        hit_off = np.zeros(n + 1, dtype=np.uint64)
+        used = lib().emu_classify(C.byref(self.sp), _p(self.cells), self.n_buckets, _p(self.parent), _p(self.depth),
+                                  _p(self.raw), len(self.raw), self.dt.root, _p(bases1), _p(off1), _p(bases2), _p(off2), n,
+                                  float(confidence), int(min_hit_groups), _p(res), _p(hit_off), _p(hits), cap)
+        assert used >= 0
+        hit_off[n] = used
+        return res, hit_off, hits[:used]
+
+
+def emit_cells(sp: ScanParams, seq: bytes, dense_taxon: int, wpt: int = BUILD_WPT) -> np.ndarray:
+    b = np.frombuffer(seq, dtype=np.uint8)
+    out = np.zeros(len(b) + 1, dtype=np.uint64)
+    n = lib().emu_emit_cells(C.byref(sp), _p(b), len(b), dense_taxon, wpt, _p(out), len(out))
+    assert n >= 0
+    return out[:n]
+
+
+def expand(sp: ScanParams, x: int) -> int:
+    return lib().emu_expand(C.byref(sp), x)
+
+
+def compress(sp: ScanParams, x: int) -> int:
+    return lib().emu_compress(C.byref(sp), x)

@@ -1,0 +1,118 @@
+// emu.cpp -- TEST-ONLY host emulation of the kernel bodies in slacken_b200/csrc/slk_core.h.
+// It runs the per-thread functions of the CUDA kernels one "thread" at a time on the CPU so that the device
+// logic can be checked against the oracle on machines without a GPU (pytest -m "not gpu").
+// It is NOT a fallback: nothing in slacken_b200/ loads it, and the product library refuses to run without CUDA.
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../slacken_b200/csrc/slk_core.h"
+
+#define EMU_API extern "C" __attribute__((visibility("default")))
+
+EMU_API int emu_scan_params(int k, int m, int spaces, uint64_t mask, int canonical, slk_scan_params* sp) {
+  memset(sp, 0, sizeof(*sp));
+  return slk_make_scan_params(k, m, spaces, mask, canonical, sp);
+}
+EMU_API uint64_t emu_compress(const slk_scan_params* sp, uint64_t x) { return slk_compress(*sp, x); }
+EMU_API uint64_t emu_expand(const slk_scan_params* sp, uint64_t x) { return slk_expand(*sp, x); }
+EMU_API uint32_t emu_code(uint32_t c) { return slk_code(c); }
+EMU_API uint64_t emu_buckets_for(uint64_t n_keys) { return ((uint64_t)((double)n_keys / 0.70) + 64 + 3) / 4; }
+
+// sequential twin of insert_cells_kernel (no atomics needed with one "thread")
+EMU_API void emu_insert_cells(uint64_t* cells, uint64_t n_buckets, const uint16_t* parent, const uint8_t* depth,
+                              uint32_t root, const uint64_t* in, uint64_t n) {
+  slk_tax_view tx{parent, depth, nullptr, 0, root};
+  for (uint64_t i = 0; i < n; i++) {
+    uint64_t cell = in[i], ckey = cell >> 16;
+    uint32_t taxon = (uint32_t)(cell & 0xffff);
+    if (!taxon) continue;
+    uint64_t b = slk_bucket_of(ckey, n_buckets);
+    bool done = false;
+    while (!done) {
+      for (int j = 0; j < 4 && !done; j++) {
+        uint64_t& c = cells[b * 4 + j];
+        if (c == 0) { c = cell; done = true; }
+        else if ((c >> 16) == ckey) { c = (ckey << 16) | slk_lca(tx, (uint32_t)(c & 0xffff), taxon); done = true; }
+      }
+      b = (b + 1 == n_buckets) ? 0 : b + 1;
+    }
+  }
+}
+
+struct vec_sink {
+  std::vector<slk_hit>* v;
+  void push(int32_t taxon, int32_t count, uint32_t) { v->push_back(slk_hit{taxon, count}); }
+};
+
+struct emu_result { int32_t taxon; uint32_t flags, kmers1, kmers2, num_distinct, n_hits; };
+
+// one classify "thread" per read; hits are appended to hits_out (cap entries), hit_off[i] = first hit of read i
+template <int W>
+static int64_t classify_w(const slk_scan_params* sp, uint64_t* cells, uint64_t n_buckets, const uint16_t* parent,
+                          const uint8_t* depth, const int32_t* raw, uint32_t n_dense, uint32_t root, const uint8_t* b1,
+                          const uint64_t* o1, const uint8_t* b2, const uint64_t* o2, uint32_t n, double confidence,
+                          int min_hit_groups, emu_result* res, uint64_t* hit_off, slk_hit* hits_out, uint64_t cap) {
+  slk_table_view tb{cells, n_buckets};
+  slk_tax_view tx{parent, depth, raw, n_dense, root};
+  std::vector<slk_hit> hv;
+  uint64_t used = 0;
+  for (uint32_t r = 0; r < n; r++) {
+    hv.clear();
+    vec_sink sink{&hv};
+    slk_frag_classifier<W, vec_sink> cl(*sp, tb, tx, sink);
+    slk_frag_result fr;
+    const uint8_t* p2 = b2 ? b2 + o2[r] : nullptr;
+    cl.run(b1 + o1[r], (uint32_t)(o1[r + 1] - o1[r]), p2, b2 ? (uint32_t)(o2[r + 1] - o2[r]) : 0, confidence,
+           min_hit_groups, fr);
+    res[r] = emu_result{fr.taxon, fr.flags, fr.kmers1, fr.kmers2, fr.num_distinct, fr.n_hits};
+    hit_off[r] = used;
+    if (used + hv.size() > cap) return -1;
+    std::copy(hv.begin(), hv.end(), hits_out + used);
+    used += hv.size();
+  }
+  return (int64_t)used;
+}
+
+#define DISPATCH_W(w, CALL)                                                                                       \
+  switch (w) {                                                                                                    \
+    case 1: { constexpr int W_ = 1; CALL; break; } case 2: { constexpr int W_ = 2; CALL; break; }                 \
+    case 3: { constexpr int W_ = 3; CALL; break; } case 4: { constexpr int W_ = 4; CALL; break; }                 \
+    case 5: { constexpr int W_ = 5; CALL; break; } case 6: { constexpr int W_ = 6; CALL; break; }                 \
+    case 7: { constexpr int W_ = 7; CALL; break; } default: { constexpr int W_ = 8; CALL; break; }                \
+  }
+
+EMU_API int64_t emu_classify(const slk_scan_params* sp, uint64_t* cells, uint64_t n_buckets, const uint16_t* parent,
+                             const uint8_t* depth, const int32_t* raw, uint32_t n_dense, uint32_t root, const uint8_t* b1,
+                             const uint64_t* o1, const uint8_t* b2, const uint64_t* o2, uint32_t n, double confidence,
+                             int min_hit_groups, emu_result* res, uint64_t* hit_off, slk_hit* hits_out, uint64_t cap) {
+  int64_t r = -2;
+  DISPATCH_W(sp->w, r = classify_w<W_>(sp, cells, n_buckets, parent, depth, raw, n_dense, root, b1, o1, b2, o2, n,
+                                       confidence, min_hit_groups, res, hit_off, hits_out, cap));
+  return r;
+}
+
+// the emit "threads" of one fragment, BUILD_WPT windows each, exactly like emit_cells_kernel partitions the work
+EMU_API int64_t emu_emit_cells(const slk_scan_params* sp, const uint8_t* bases, uint64_t len, uint32_t dense_taxon,
+                               uint32_t wpt, uint64_t* out, uint64_t cap) {
+  uint64_t n = 0;
+  bool overflow = false;
+  auto emit = [&](uint64_t cell) { if (n < cap) out[n++] = cell; else overflow = true; };
+  uint64_t nw = len >= (uint64_t)sp->k ? len - sp->k + 1 : 0;
+  for (uint64_t w0 = 0; w0 < nw; w0 += wpt) {
+    uint64_t nb = std::min<uint64_t>(len - w0, (uint64_t)wpt + sp->k - 1);
+    DISPATCH_W(sp->w, (slk_emit_cells<W_>(*sp, bases + w0, nb, dense_taxon, emit)));
+  }
+  return overflow ? -1 : (int64_t)n;
+}
+
+EMU_API void emu_synth_genome(uint64_t seed, uint64_t start, uint64_t n, uint8_t* out) {
+  for (uint64_t i = 0; i < n; i++) out[i] = slk_synth_genome_base(seed, start + i);
+}
+EMU_API void emu_synth_reads(uint64_t gseed, uint64_t rseed, uint64_t n_genomes, uint64_t genome_len, uint64_t first,
+                             uint64_t n_reads, uint32_t L, uint8_t* out) {
+  for (uint64_t r = 0; r < n_reads; r++)
+    for (uint32_t j = 0; j < L; j++) out[r * L + j] = slk_synth_read_base(gseed, rseed, n_genomes, genome_len, first + r, L, j);
+}
