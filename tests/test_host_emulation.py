@@ -1,0 +1,130 @@
+"""The CUDA kernel bodies (slk_core.h), run thread by thread on the CPU by tests/host_emulation, against the oracle.
+This is the no-GPU half of the parity suite; tests/test_gpu_parity.py runs the same comparisons on the device."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import oracle
+from tests import host_emulation as emu
+from tests.util import leaf_taxa, make_taxonomy, random_dna, simulate_reads
+
+
+def world(seed, k=35, m=31, s=7, canonical=True, n_genomes=16, glen=2500):
+    rng = np.random.default_rng(seed)
+    parents, ranks, names = make_taxonomy(100, seed)
+    leaves = leaf_taxa(parents)
+    genomes = [random_dna(rng, glen) for _ in range(n_genomes)]
+    for i in range(n_genomes // 2, n_genomes):
+        g = bytearray(genomes[i - n_genomes // 2])
+        for j in range(0, len(g), 53):
+            g[j] = ord("ACGT"[int(rng.integers(4))])
+        genomes[i] = bytes(g)
+    taxa = np.array([leaves[int(rng.integers(len(leaves)))] for _ in genomes], dtype=np.int32)
+    p = oracle.params(k=k, m=m, spaces=s, canonical=canonical)
+    lib = oracle.Library(p, parents, 1 << 17)
+    b, off = oracle.pack_sequences(genomes)
+    lib.add_fragments(b, off, taxa)
+    sp = emu.scan_params(k, m, s, oracle.DEFAULT_TOGGLE_MASK, canonical)
+    return rng, parents, genomes, taxa, p, lib, sp
+
+
+def compare(lib, ix, rb, ro, rb2=None, ro2=None, confidence=0.0, k=35):
+    res, _, _, per = lib.classify(rb, ro, rb2, ro2, confidence=confidence)
+    eres, ehoff, ehits = ix.classify(rb, ro, rb2, ro2, confidence=confidence)
+    assert np.array_equal(res["taxon"], eres["taxon"])
+    assert np.array_equal(res["classified"], eres["flags"] & 1)
+    assert np.array_equal(res["has_span"], (eres["flags"] >> 1) & 1)
+    hs = res["has_span"].astype(bool)
+    assert np.array_equal(res["num_distinct"][hs], eres["num_distinct"][hs].astype(np.int32))
+    assert np.array_equal(res["len1"][hs], eres["kmers1"][hs].astype(np.int32) + (k - 1))
+    if rb2 is not None:
+        assert np.array_equal(res["len2"][hs], eres["kmers2"][hs].astype(np.int32) + (k - 1))
+    for i in range(len(per)):
+        h = ehits[int(ehoff[i]):int(ehoff[i + 1])]
+        assert np.array_equal(h["taxon"], per[i]["taxon"]) and np.array_equal(h["count"], per[i]["count"]), i
+
+
+@pytest.mark.parametrize("confidence", [0.0, 0.15, 0.7])
+def test_classify_body_single_end(confidence):
+    rng, parents, genomes, taxa, p, lib, sp = world(5)
+    id1, tx = lib.records()
+    ix = emu.EmuIndex(sp, parents, id1, tx)
+    reads = simulate_reads(rng, genomes, 1200, (10, 230), n_rate=0.2) + [b"", b"ACGT", b"N" * 90, b"A" * 120]
+    rb, ro = oracle.pack_sequences(reads)
+    compare(lib, ix, rb, ro, confidence=confidence)
+
+
+def test_classify_body_paired_end():
+    rng, parents, genomes, taxa, p, lib, sp = world(6)
+    id1, tx = lib.records()
+    ix = emu.EmuIndex(sp, parents, id1, tx)
+    r1 = simulate_reads(rng, genomes, 600, (20, 160), n_rate=0.15)
+    r2 = simulate_reads(rng, genomes, 600, (20, 160), n_rate=0.15)
+    r1[0], r2[0] = b"AC", b"GT"
+    b1, o1 = oracle.pack_sequences(r1)
+    b2, o2 = oracle.pack_sequences(r2)
+    for c in (0.0, 0.3):
+        compare(lib, ix, b1, o1, b2, o2, confidence=c)
+
+
+@pytest.mark.parametrize("k,m,s,canonical", [(31, 24, 0, True), (25, 20, 3, False), (28, 28, 4, True), (22, 15, 0, True),
+                                             (12, 5, 1, True)])
+def test_classify_and_emit_other_parameters(k, m, s, canonical):
+    rng, parents, genomes, taxa, p, lib, sp = world(10 + k, k, m, s, canonical, n_genomes=8, glen=1500)
+    id1, tx = lib.records()
+    ix = emu.EmuIndex(sp, parents, id1, tx)
+    reads = simulate_reads(rng, genomes, 400, (k - 2, 140), n_rate=0.1)
+    rb, ro = oracle.pack_sequences(reads)
+    compare(lib, ix, rb, ro, confidence=0.1, k=k)
+    # build side: the cells the emit threads produce = the oracle's super-mer minimizers (as a set)
+    for g in genomes[:3]:
+        cells = emu.emit_cells(sp, g, 7)
+        assert set(int(c) & 0xFFFF for c in cells) == {7}
+        got = {emu.expand(sp, int(c) >> 16) for c in cells}
+        want = {r for _, r, _ in oracle.superkmers(p, g)}
+        assert got == want
+
+
+def test_emit_cells_break_at_ambiguous_characters():
+    rng, parents, genomes, taxa, p, lib, sp = world(3)
+    g = bytearray(genomes[0])
+    g[500:520] = b"N" * 20
+    g[1200] = ord("x")
+    pieces, _ = oracle.remove_invalid([bytes(g)], [1])
+    want = set()
+    for piece in pieces:
+        want |= {r for _, r, _ in oracle.superkmers(p, piece)}
+    for wpt in (96, 7, 1000):
+        cells = emu.emit_cells(sp, bytes(g), 3, wpt)
+        assert {emu.expand(sp, int(c) >> 16) for c in cells} == want
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(0, 2**64 - 1), st.sampled_from([(31, 7), (24, 0), (20, 3), (28, 4), (15, 0), (31, 15)]))
+def test_key_compression_round_trip(x, ms):
+    m, s = ms
+    sp = emu.scan_params(m + 4, m, s, oracle.DEFAULT_TOGGLE_MASK, True)
+    key = x & sp.sig_mask
+    c = emu.compress(sp, key)
+    assert c < (1 << sp.key_bits)
+    assert emu.expand(sp, c) == key
+    # order preserving
+    y = (x * 0x9E3779B97F4A7C15 + 12345) & ((1 << 64) - 1) & sp.sig_mask
+    assert (key < y) == (c < emu.compress(sp, y)) or key == y
+
+
+def test_unsupported_parameters_are_rejected():
+    for k, m, s in [(35, 31, 0), (40, 31, 7), (35, 32, 8), (30, 31, 7)]:
+        with pytest.raises(ValueError):
+            emu.scan_params(k, m, s, oracle.DEFAULT_TOGGLE_MASK, True)
+
+
+def test_synthetic_generators_agree_with_the_oracle_copy():
+    n = 200_000
+    a = np.zeros(n, dtype=np.uint8)
+    emu.lib().emu_synth_genome(7, 60_000, n, emu._p(a))
+    assert np.array_equal(a, oracle.synth_genome(7, 60_000, n))
+    assert (a == ord("N")).sum() > 0
+    r = np.zeros(3000 * 150, dtype=np.uint8)
+    emu.lib().emu_synth_reads(7, 8, 4, 70_000, 11, 3000, 150, emu._p(r))
+    assert np.array_equal(r, oracle.synth_reads(7, 8, 4, 70_000, 11, 3000, 150))
