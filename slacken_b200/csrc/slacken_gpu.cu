@@ -400,9 +400,16 @@ extern "C" int slk_synth_reads_dev(slk_ctx* ctx, uint64_t gseed, uint64_t rseed,
 }
 
 // ---------------------------------------------------------------------------------------------- index construction
+static double table_load_factor() {
+  // Default 0.5: at 4 cells per bucket 86% of the buckets still have a free cell, so most probes (hits and misses)
+  // end in their first 32-byte sector. SLK_TABLE_LOAD_FACTOR (0.3 .. 0.9) trades probe length for memory when a
+  // library would not fit otherwise.
+  const char* e = getenv("SLK_TABLE_LOAD_FACTOR");
+  double lf = e ? atof(e) : 0.5;
+  return lf < 0.3 ? 0.3 : lf > 0.9 ? 0.9 : lf;
+}
 static uint64_t buckets_for(uint64_t n_keys) {
-  // 4 cells per 32-byte bucket, load factor <= 0.70
-  uint64_t cells = (uint64_t)((double)n_keys / 0.70) + 64;
+  uint64_t cells = (uint64_t)((double)n_keys / table_load_factor()) + 64;
   return (cells + 3) / 4;
 }
 static int table_alloc(slk_table_view* tb, uint64_t n_keys) {

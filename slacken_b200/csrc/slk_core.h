@@ -19,13 +19,16 @@
 
 #if defined(__CUDACC__)
 #define SLK_HD __host__ __device__ __forceinline__
+#define SLK_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define SLK_HD inline
+#define SLK_HD_NOINLINE __attribute__((noinline))
 #endif
 
 #define SLK_MAX_W 8      // k - m + 1 supported by the kernels (35 - 31 + 1 = 5 for the Kraken 2 defaults)
-#define SLK_ECAP 64      // span entries buffered per thread between scan and probe
-#define SLK_HCAP 64      // merged hits buffered per thread before spilling to a worst-case global block
+#define SLK_ECAP 16      // span entries buffered per thread between scan and probe (shared memory on the device)
+#define SLK_SHITS 8      // merged hits of a fragment kept in the fast store (shared memory on the device)
+#define SLK_XHITS 56     // further merged hits kept in a per-thread overflow array before spilling to global memory
 #define SLK_KMAX 128     // distinct taxa per fragment held in the per-thread histogram
 
 // labels of merged hits (slacken/package.scala:28-29)
@@ -41,6 +44,8 @@ struct slk_scan_params {
   int32_t k, m, w, canonical;
   int32_t fshift;      // 64 - 2m: position of the last base of a left-aligned m-mer
   int32_t key_bits;    // popcount(sig_mask) <= 48
+  int32_t fast_compress;  // sig_mask == 0xffffffffcccccccc (m=31, s=7): 11-instruction compress
+  int32_t pad_;
   uint64_t xor_mask;   // toggle mask aligned to the m-mer (RandomXOR.mask)
   uint64_t sig_mask;   // bits of a priority that can be non-zero: the space mask, or the m-mer fill mask
   uint64_t mmask;      // fill mask of an m-mer
@@ -70,6 +75,8 @@ SLK_HD int slk_make_scan_params(int k, int m, int spaces, uint64_t toggle_mask, 
   for (uint64_t x = sp->sig_mask; x; x &= x - 1) bits++;
   sp->key_bits = bits;
   if (bits > 48) return 4;
+  sp->fast_compress = sp->sig_mask == 0xffffffffccccccccull ? 1 : 0;
+  sp->pad_ = 0;
   // parallel-suffix move masks (Hacker's Delight 7-4) for sig_mask
   uint64_t mm = sp->sig_mask, mk = ~mm << 1;
   for (int i = 0; i < 6; i++) {
@@ -106,10 +113,10 @@ struct slk_hit {
 // ------------------------------------------------------------------------------------------------ encode
 // A=0 C=1 G=2 T=U=3, anything else (including whitespace: the boundary contract is whitespace-free input) = 4.
 SLK_HD uint32_t slk_code(uint32_t c) {
-  uint32_t u = c | 0x20u;
+  uint32_t u = (c | 0x20u) - 'a';   // a=0 c=2 g=6 t=19 u=20
   uint32_t code = (c >> 1) & 3u;
   code ^= code >> 1;
-  bool ok = (u == 'a') | (u == 'c') | (u == 'g') | (u == 't') | (u == 'u');
+  bool ok = u < 32u && ((0x00180045u >> (u & 31u)) & 1u);
   return ok ? code : 4u;
 }
 
@@ -143,6 +150,13 @@ SLK_HD void slk_for_each_byte(const uint8_t* s, uint64_t len, F&& f) {
 // ------------------------------------------------------------------------------------------------ key compression
 // Hacker's-Delight style compress: gathers the bits of x selected by sig_mask at the low end, keeping their order.
 SLK_HD uint64_t slk_compress(const slk_scan_params& sp, uint64_t x) {
+  if (sp.fast_compress) {  // the Kraken 2 default mask: keep the high word, gather bit pairs 2-3 of every low nibble
+    uint32_t y = ((uint32_t)x >> 2) & 0x33333333u;
+    y = (y | (y >> 2)) & 0x0f0f0f0fu;
+    y = (y | (y >> 4)) & 0x00ff00ffu;
+    y = (y | (y >> 8)) & 0x0000ffffu;
+    return ((x >> 32) << 16) | y;
+  }
   x &= sp.sig_mask;
 #pragma unroll
   for (int i = 0; i < 6; i++) {
@@ -171,29 +185,43 @@ SLK_HD uint64_t slk_mulhi64(uint64_t a, uint64_t b) {
 }
 SLK_HD uint64_t slk_bucket_of(uint64_t ckey, uint64_t n_buckets) {
   uint64_t h = ckey * 0x9E3779B97F4A7C15ull;
-  h ^= h >> 32;
-  h *= 0xD6E8FEB86659FD93ull;
-  h ^= h >> 32;
-  return slk_mulhi64(h, n_buckets);
+  h ^= h >> 29;
+  return slk_mulhi64(h * 0xD6E8FEB86659FD93ull, n_buckets);
+}
+SLK_HD void slk_prefetch_bucket(const slk_table_view& tb, uint64_t ckey) {
+#if defined(__CUDA_ARCH__)
+  const uint64_t* p = tb.cells + slk_bucket_of(ckey, tb.n_buckets) * 4;
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)tb; (void)ckey;
+#endif
+}
+
+// One bucket (= one 32-byte sector) of a probe: both halves are loaded before anything is compared.
+// Returns true when the probe is decided: *dense = the key's taxon, or 0 if an empty cell proves its absence
+// (cells of a bucket fill in order and are never deleted, so nothing can follow an empty cell).
+SLK_HD bool slk_probe_bucket(const slk_table_view& tb, uint64_t b, uint64_t ckey, uint32_t* dense) {
+  uint64_t c0, c1, c2, c3;
+#if defined(__CUDA_ARCH__)
+  const ulonglong2* p = reinterpret_cast<const ulonglong2*>(tb.cells + b * 4);
+  const ulonglong2 v0 = __ldg(p), v1 = __ldg(p + 1);
+  c0 = v0.x; c1 = v0.y; c2 = v1.x; c3 = v1.y;
+#else
+  c0 = tb.cells[b * 4]; c1 = tb.cells[b * 4 + 1]; c2 = tb.cells[b * 4 + 2]; c3 = tb.cells[b * 4 + 3];
+#endif
+  const bool m0 = c0 != 0 && (c0 >> 16) == ckey, m1 = c1 != 0 && (c1 >> 16) == ckey;
+  const bool m2 = c2 != 0 && (c2 >> 16) == ckey, m3 = c3 != 0 && (c3 >> 16) == ckey;
+  const uint64_t hit = m0 ? c0 : m1 ? c1 : m2 ? c2 : m3 ? c3 : 0ull;
+  *dense = (uint32_t)(hit & 0xffffu);
+  return hit != 0 || c3 == 0;   // c3 == 0 <=> the bucket has an empty cell
 }
 
 // Probe: returns the dense taxon of the key, 0 when absent (a left join miss -> Taxonomy.NONE).
 SLK_HD uint32_t slk_probe(const slk_table_view& tb, uint64_t ckey) {
   uint64_t b = slk_bucket_of(ckey, tb.n_buckets);
   for (uint64_t tries = 0; tries < tb.n_buckets; tries++) {
-    uint64_t c[4];
-#if defined(__CUDA_ARCH__)
-    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(tb.cells + b * 4);
-    ulonglong2 v0 = __ldg(p), v1 = __ldg(p + 1);
-    c[0] = v0.x; c[1] = v0.y; c[2] = v1.x; c[3] = v1.y;
-#else
-    for (int i = 0; i < 4; i++) c[i] = tb.cells[b * 4 + i];
-#endif
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      if (c[i] == 0) return 0;
-      if ((c[i] >> 16) == ckey) return (uint32_t)(c[i] & 0xffffu);
-    }
+    uint32_t dense;
+    if (slk_probe_bucket(tb, b, ckey, &dense)) return dense;
     b = (b + 1 == tb.n_buckets) ? 0 : b + 1;
   }
   return 0;
@@ -218,35 +246,44 @@ SLK_HD bool slk_has_ancestor(const slk_tax_view& tx, uint32_t t, uint32_t anc) {
 }
 
 // ------------------------------------------------------------------------------------------------ scanner
+SLK_HD uint64_t slk_min64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
 // Rolling m-mer (forward and reverse complement, both left-aligned), its priority, and the minimum over the
-// last W priorities = the minimizer of the k-mer window that ends at the base just pushed.
+// last W priorities = the minimizer of the k-mer window that ends at the base just pushed (the monotone deque of
+// PosRankWindow.scala:47-74 collapses to this for a fixed, small W; ties do not matter because super-mers merge
+// on equal VALUE, MinSplitter.scala:200-201). The window minimum is kept as suffix minima: sfx[j] = min of the
+// last j+1 priorities, updated in place, so no ring buffer has to be shifted.
+// Branch-free by design: an invalid character only resets `nvalid`; stale bits in fwd/rc/sfx are flushed by the
+// k valid bases that must follow before the next window is reported.
 template <int W>
 struct slk_scanner {
   uint64_t fwd, rc;
-  uint64_t ring[W];
+  uint64_t sfx[W > 1 ? W - 1 : 1];
   uint32_t nvalid;  // consecutive valid bases seen
 
   SLK_HD void reset() {
     fwd = 0; rc = 0; nvalid = 0;
 #pragma unroll
-    for (int i = 0; i < W; i++) ring[i] = 0;
+    for (int i = 0; i < (W > 1 ? W - 1 : 1); i++) sfx[i] = 0;
   }
-  // push one valid base (0..3); true when a full k-mer window ends here, *minv = its minimizer priority
-  SLK_HD bool push(const slk_scan_params& sp, uint32_t c, uint64_t* minv) {
-    fwd = (fwd << 2) | ((uint64_t)c << sp.fshift);
-    rc = ((rc >> 2) | ((uint64_t)(3u - c) << 62)) & sp.mmask;
-    nvalid++;
-    uint64_t x = (sp.canonical && rc < fwd) ? rc : fwd;
-    x = (x ^ sp.xor_mask) & sp.sig_mask;
+  // c: 0..3 for a base, 4 for anything else. Returns true when a full k-mer window of valid bases ends here.
+  SLK_HD bool push(uint32_t c, uint32_t k, int fshift, uint64_t mmask, uint64_t xor_mask, uint64_t sig_mask,
+                   bool canonical, uint64_t* minv) {
+    uint32_t b = c & 3u;
+    fwd = (fwd << 2) | ((uint64_t)b << fshift);
+    rc = ((rc >> 2) | ((uint64_t)(3u - b) << 62)) & mmask;
+    nvalid = c < 4u ? nvalid + 1 : 0;
+    uint64_t x = canonical ? slk_min64(fwd, rc) : fwd;
+    x = (x ^ xor_mask) & sig_mask;
+    uint64_t mn = x;
+    if (W > 1) {
+      mn = slk_min64(x, sfx[W > 1 ? W - 2 : 0]);
 #pragma unroll
-    for (int i = 0; i + 1 < W; i++) ring[i] = ring[i + 1];
-    ring[W - 1] = x;
-    if (nvalid < (uint32_t)sp.k) return false;
-    uint64_t mn = ring[0];
-#pragma unroll
-    for (int i = 1; i < W; i++) mn = ring[i] < mn ? ring[i] : mn;
+      for (int j = W - 2; j >= 1; j--) sfx[j] = slk_min64(x, sfx[j - 1]);
+      sfx[0] = x;
+    }
     *minv = mn;
-    return true;
+    return nvalid >= k;
   }
 };
 
@@ -254,6 +291,7 @@ struct slk_scanner {
 #define SLK_E_SEQ 0u
 #define SLK_E_AMB 1u
 #define SLK_E_BORDER 2u
+#define SLK_E_CNT_MAX 0x3fffu   // longer runs are split, which no output can see (equal labels merge again)
 
 struct slk_frag_result {
   int32_t taxon;          // raw taxon reported (0 when unclassified)
@@ -264,37 +302,52 @@ struct slk_frag_result {
   uint32_t n_probes;      // table probes issued (= SEQ spans)
 };
 
-// A sink for merged hits. The device kernel's sink buffers SLK_HCAP hits per thread and spills to a global block.
+// A sink for merged hits that no longer fit the per-thread buffers (device: a worst-case block of the global hit
+// buffer; emulation: a vector). `need` = upper bound of the hits this fragment can still produce.
 struct slk_null_sink {
   SLK_HD void push(int32_t, int32_t, uint32_t) {}
 };
 
-template <int W, class Sink>
+// Per-thread fast store: span entries key[j]/meta[j] (count | type << 14) for j < SLK_ECAP and the first SLK_SHITS
+// merged hits. On the device these are columns of shared-memory tiles; the emulation uses plain arrays.
+struct slk_store_local {
+  uint64_t key[SLK_ECAP];
+  uint16_t meta[SLK_ECAP];
+  int32_t hl[SLK_SHITS], hc[SLK_SHITS];
+  SLK_HD void set(uint32_t j, uint64_t k, uint32_t m) { key[j] = k; meta[j] = (uint16_t)m; }
+  SLK_HD uint64_t get_key(uint32_t j) const { return key[j]; }
+  SLK_HD uint32_t get_meta(uint32_t j) const { return meta[j]; }
+  SLK_HD void set_hit(uint32_t i, int32_t label, int32_t count) { hl[i] = label; hc[i] = count; }
+  SLK_HD void get_hit(uint32_t i, int32_t* label, int32_t* count) const { *label = hl[i]; *count = hc[i]; }
+};
+
+template <int W, class Sink, class Entries>
 struct slk_frag_classifier {
-  const slk_scan_params& sp;
   const slk_table_view& tb;
   const slk_tax_view& tx;
   Sink& sink;
+  Entries& ent;
 
-  // span entries waiting for their probe
-  uint64_t ekey[SLK_ECAP];
-  uint32_t emeta[SLK_ECAP];  // count | type << 30
-  uint32_t ne;
-  // per-fragment state
+  // per-fragment state of the drain side
   uint64_t last_seq_key;
   bool have_last_seq;
   int32_t cur_label, cur_count;
   bool have_cur;
-  uint32_t mate, kmers[2], nd, nhits, total_entries, nprobes;
+  uint32_t mate, kmers[2], nd, nprobes;
   uint32_t windows_left;  // upper bound of merged hits still to come (for the sink's spill allocation)
+  // merged hits (dense labels): the first SLK_SHITS in the fast store, then xh_*, then spilled through the sink
+  uint32_t nh;            // buffered
+  uint32_t nh_spilled;    // already pushed to the sink (0 for all but very long reads)
+  int32_t xh_label[SLK_XHITS];
+  int32_t xh_count[SLK_XHITS];
   // histogram: dense taxon -> k-mer count, insertion ordered (fastutil Int2IntArrayMap)
   uint32_t hk[SLK_KMAX];
   int32_t hv[SLK_KMAX];
   uint32_t nk;
   bool overflow;
 
-  SLK_HD slk_frag_classifier(const slk_scan_params& sp_, const slk_table_view& tb_, const slk_tax_view& tx_, Sink& s)
-      : sp(sp_), tb(tb_), tx(tx_), sink(s) {}
+  SLK_HD slk_frag_classifier(const slk_table_view& tb_, const slk_tax_view& tx_, Sink& s, Entries& e)
+      : tb(tb_), tx(tx_), sink(s), ent(e) {}
 
   SLK_HD void hist_add(uint32_t t, int32_t c) {
     for (uint32_t i = 0; i < nk; i++)
@@ -307,107 +360,116 @@ struct slk_frag_classifier {
       if (hk[i] == t) return hv[i];
     return 0;
   }
-
-  // TaxonCounts.fromHits: adjacent hits with the same taxon merge (slacken/TaxonCounts.scala:31-48)
-  SLK_HD void flush_hit() {
-    if (!have_cur) return;
-    int32_t out_taxon = cur_label >= 0 ? tx.raw[cur_label] : cur_label;
-    sink.push(out_taxon, cur_count, windows_left);
-    nhits++;
-    if (cur_label >= 0) hist_add((uint32_t)cur_label, cur_count);  // toMap skips AMBIGUOUS / MATE_PAIR_BORDER
-    have_cur = false;
+  SLK_HD void buffered_hit(uint32_t i, int32_t* label, int32_t* count) const {
+    if (i < SLK_SHITS) ent.get_hit(i, label, count);
+    else { *label = xh_label[i - SLK_SHITS]; *count = xh_count[i - SLK_SHITS]; }
   }
-  SLK_HD void add_hit(int32_t label, int32_t count) {
-    if (have_cur && label == cur_label) { cur_count += count; return; }
-    flush_hit();
-    cur_label = label; cur_count = count; have_cur = true;
+  // TaxonCounts.toMap (slacken/TaxonCounts.scala:70-81) over the buffered merged hits, in order
+  SLK_HD void fold_hits() {
+    for (uint32_t i = 0; i < nh; i++) {
+      int32_t l, c;
+      buffered_hit(i, &l, &c);
+      if (l >= 0) hist_add((uint32_t)l, c);  // skips AMBIGUOUS / MATE_PAIR_BORDER
+    }
+  }
+  // only reads with more than SLK_SHITS + SLK_XHITS merged hits come here
+  SLK_HD_NOINLINE void spill(uint32_t need) {
+    fold_hits();
+    for (uint32_t i = 0; i < nh; i++) {
+      int32_t l, c;
+      buffered_hit(i, &l, &c);
+      sink.push(l >= 0 ? tx.raw[l] : l, c, need + nh);
+    }
+    nh_spilled += nh;
+    nh = 0;
+  }
+  // TaxonCounts.fromHits (slacken/TaxonCounts.scala:31-48) has already merged adjacent equal taxa: one store
+  SLK_HD void push_hit(int32_t label, int32_t count, uint32_t need) {
+    if (nh == SLK_SHITS + SLK_XHITS) spill(need);
+    if (nh < SLK_SHITS) ent.set_hit(nh, label, count);
+    else { xh_label[nh - SLK_SHITS] = label; xh_count[nh - SLK_SHITS] = count; }
+    nh++;
   }
 
-  // spanToHit (slacken/KeyValueIndex.scala:176-185) + numDistinct (slacken/Classifier.scala:94)
-  SLK_HD void drain() {
-    for (uint32_t j = 0; j < ne; j++) {
-      uint32_t type = emeta[j] >> 30, cnt = emeta[j] & 0x3fffffffu;
+  // spanToHit (slacken/KeyValueIndex.scala:176-185) + numDistinct (slacken/Classifier.scala:94) for the first
+  // `ne` buffered entries. Out of line on purpose (the scan loop stays small); every lane of a warp calls it at the
+  // same time. Its running state is copied into registers for the duration of the call, because stores through
+  // the entry/sink pointers could otherwise alias the members and force a reload per entry.
+  SLK_HD_NOINLINE void drain(const slk_scan_params& sp, uint32_t ne) {
+    // all buckets of this batch are requested from HBM first, so the probes below find them in L2
+    for (uint32_t j = 0; j < ne; j++)
+      if ((ent.get_meta(j) >> 14) == SLK_E_SEQ) slk_prefetch_bucket(tb, slk_compress(sp, ent.get_key(j)));
+    uint64_t l_last = last_seq_key;
+    bool l_have_last = have_last_seq, l_have_cur = have_cur;
+    int32_t l_label = cur_label, l_count = cur_count;
+    uint32_t l_mate = mate, l_k0 = kmers[0], l_k1 = kmers[1], l_nd = nd, l_np = nprobes, l_wl = windows_left;
+    const int32_t border_cnt = -(sp.k - 1);
+    // One loop for "next entry" and "next bucket of the current probe": every lane walks its own entries and its
+    // own collision chains at its own pace, so a long chain in one lane does not hold back the other 31.
+    uint32_t j = 0;
+    bool probing = false;
+    uint64_t key = 0, ckey = 0, bucket = 0;
+    while (probing || j < ne) {
+      const uint32_t meta = ent.get_meta(j), type = meta >> 14, cnt = meta & SLK_E_CNT_MAX;
+      int32_t label, hcnt = (int32_t)cnt;
       if (type == SLK_E_SEQ) {
-        uint64_t key = ekey[j];
-        uint32_t dense = slk_probe(tb, slk_compress(sp, key));
-        nprobes++;
-        bool distinct = !have_last_seq || key != last_seq_key;
-        if (distinct && dense != 0) nd++;
-        last_seq_key = key; have_last_seq = true;
-        kmers[mate] += cnt;
-        add_hit((int32_t)dense, (int32_t)cnt);
-      } else if (type == SLK_E_AMB) {
-        kmers[mate] += cnt;
-        add_hit(SLK_AMBIGUOUS_SPAN, (int32_t)cnt);
-      } else {
-        add_hit(SLK_MATE_PAIR_BORDER, -(sp.k - 1));
-        mate = 1;
-      }
-      windows_left = windows_left > cnt ? windows_left - cnt : 0;
-    }
-    ne = 0;
-  }
-  SLK_HD void emit(uint32_t type, uint64_t key, uint32_t cnt) {
-    if (ne == SLK_ECAP) drain();
-    ekey[ne] = key; emeta[ne] = cnt | (type << 30); ne++;
-    total_entries++;
-  }
-
-  struct mate_state {
-    slk_scanner<W> sc;
-    uint64_t run_key;
-    uint32_t run_cnt, ninv, amb_cnt;
-    bool in_run;
-  };
-  SLK_HD void mate_begin(mate_state& st) {
-    st.sc.reset(); st.run_key = 0; st.run_cnt = 0; st.ninv = 0; st.amb_cnt = 0; st.in_run = false;
-  }
-  // one character of a read. Supermers.splitByAmbiguity/splitFragment: valid runs >= k are scanned for
-  // super-mers, runs of >= k ambiguous characters become one AMBIGUOUS span of len-(k-1), anything shorter vanishes.
-  SLK_HD void step(mate_state& st, uint32_t ch) {
-    uint32_t c = slk_code(ch);
-    if (c < 4u) {
-      if (st.amb_cnt) { emit(SLK_E_AMB, 0, st.amb_cnt); st.amb_cnt = 0; }
-      st.ninv = 0;
-      uint64_t mn;
-      if (st.sc.push(sp, c, &mn)) {
-        if (st.in_run && mn == st.run_key && st.run_cnt < 0x3fffffffu) st.run_cnt++;
-        else {
-          if (st.in_run) emit(SLK_E_SEQ, st.run_key, st.run_cnt);
-          st.run_key = mn; st.run_cnt = 1; st.in_run = true;
+        if (!probing) {
+          key = ent.get_key(j);
+          ckey = slk_compress(sp, key);
+          bucket = slk_bucket_of(ckey, tb.n_buckets);
+          probing = true;
+          l_np++;
         }
+        uint32_t dense;
+        if (!slk_probe_bucket(tb, bucket, ckey, &dense)) {
+          bucket = (bucket + 1 == tb.n_buckets) ? 0 : bucket + 1;
+          continue;
+        }
+        probing = false;
+        l_nd += ((!l_have_last || key != l_last) && dense != 0) ? 1u : 0u;
+        l_last = key; l_have_last = true;
+        label = (int32_t)dense;
+      } else if (type == SLK_E_AMB) {
+        label = SLK_AMBIGUOUS_SPAN;
+      } else {
+        label = SLK_MATE_PAIR_BORDER; hcnt = border_cnt;
       }
-    } else {
-      if (st.in_run) { emit(SLK_E_SEQ, st.run_key, st.run_cnt); st.in_run = false; }
-      st.sc.nvalid = 0;
-      st.ninv++;
-      if (st.ninv >= (uint32_t)sp.k) st.amb_cnt++;
+      if (type != SLK_E_BORDER) { if (l_mate) l_k1 += cnt; else l_k0 += cnt; }
+      // TaxonCounts.fromHits: adjacent hits with the same taxon merge (slacken/TaxonCounts.scala:31-48)
+      if (l_have_cur && label == l_label) l_count += hcnt;
+      else {
+        if (l_have_cur) push_hit(l_label, l_count, l_wl + 2);
+        l_label = label; l_count = hcnt; l_have_cur = true;
+      }
+      if (type == SLK_E_BORDER) l_mate = 1;
+      l_wl = l_wl > cnt ? l_wl - cnt : 0;
+      j++;
     }
-  }
-  SLK_HD void mate_end(mate_state& st) {
-    if (st.in_run) { emit(SLK_E_SEQ, st.run_key, st.run_cnt); st.in_run = false; }
-    if (st.amb_cnt) { emit(SLK_E_AMB, 0, st.amb_cnt); st.amb_cnt = 0; }
-  }
-
-  SLK_HD void scan_mate(const uint8_t* s, uint32_t len) {
-    mate_state st;
-    mate_begin(st);
-    slk_for_each_byte(s, len, [&](uint32_t ch) { step(st, ch); });
-    mate_end(st);
+    last_seq_key = l_last; have_last_seq = l_have_last; have_cur = l_have_cur; cur_label = l_label; cur_count = l_count;
+    mate = l_mate; kmers[0] = l_k0; kmers[1] = l_k1; nd = l_nd; nprobes = l_np; windows_left = l_wl;
   }
 
   // LowestCommonAncestor.resolveTree (slacken/LowestCommonAncestor.scala:91-146)
-  SLK_HD uint32_t resolve(double confidence) {
+  SLK_HD_NOINLINE uint32_t resolve(double confidence) {
+    fold_hits();   // the buffered hits (a fragment that spilled has none left and was folded on the way)
     int32_t total = (int32_t)(kmers[0] + kmers[1]);  // totalKmers: ambiguous spans count, the border does not
     double required = ceil(confidence * (double)total);
     uint32_t max_taxon = 0;
     int32_t max_score = 0;
-    for (uint32_t i = 0; i < nk; i++) {
-      uint32_t taxon = hk[i], node = taxon;
-      int32_t score = 0;
-      while (node != 0) { score += hist_get(node); node = tx.parent[node]; }
-      if (score > max_score) { max_taxon = taxon; max_score = score; }
-      else if (score == max_score) max_taxon = slk_lca(tx, max_taxon, taxon);
+    // one hit taxon (plus, possibly, misses): its path score is its own count, nothing to walk
+    uint32_t nz = 0, only = 0;
+    for (uint32_t i = 0; i < nk; i++)
+      if (hk[i] != 0) { nz++; only = hk[i]; }
+    if (nz == 1) {
+      max_taxon = only;
+    } else if (nz > 1) {
+      for (uint32_t i = 0; i < nk; i++) {
+        uint32_t taxon = hk[i], node = taxon;
+        int32_t score = 0;
+        while (node != 0) { score += hist_get(node); node = tx.parent[node]; }
+        if (score > max_score) { max_taxon = taxon; max_score = score; }
+        else if (score == max_score) max_taxon = slk_lca(tx, max_taxon, taxon);
+      }
     }
     max_score = hist_get(max_taxon);
     while (max_taxon != 0 && (double)max_score < required) {
@@ -421,25 +483,113 @@ struct slk_frag_classifier {
   }
 
   // One fragment end to end. s2 == nullptr for single-end reads.
-  SLK_HD void run(const uint8_t* s1, uint32_t len1, const uint8_t* s2, uint32_t len2, double confidence,
-                  int32_t min_hit_groups, slk_frag_result& r) {
-    ne = 0; have_last_seq = false; last_seq_key = 0; have_cur = false; cur_label = 0; cur_count = 0;
-    mate = 0; kmers[0] = 0; kmers[1] = 0; nd = 0; nhits = 0; total_entries = 0; nk = 0; overflow = false; nprobes = 0;
-    uint32_t km1 = (uint32_t)(sp.k - 1);
+  // Scan: Supermers.splitByAmbiguity/splitFragment (slacken/Supermers.scala:113-189): valid runs >= k are cut into
+  // super-mers (runs of k-mer windows with equal minimizer), runs of >= k ambiguous characters become one
+  // AMBIGUOUS span of len-(k-1), anything shorter vanishes; the mates are separated by a MATE_PAIR_BORDER span.
+  SLK_HD void run(const slk_scan_params& sp, const uint8_t* s1, uint32_t len1, const uint8_t* s2, uint32_t len2,
+                  double confidence, int32_t min_hit_groups, slk_frag_result& r) {
+    have_last_seq = false; last_seq_key = 0; have_cur = false; cur_label = 0; cur_count = 0; nh = 0; nh_spilled = 0;
+    mate = 0; kmers[0] = 0; kmers[1] = 0; nd = 0; nk = 0; overflow = false; nprobes = 0;
+    const uint32_t k = (uint32_t)sp.k, km1 = k - 1;
+    const int fshift = sp.fshift;
+    const uint64_t mmask = sp.mmask, xor_mask = sp.xor_mask, sig_mask = sp.sig_mask;
+    const bool canonical = sp.canonical != 0;
     windows_left = (len1 > km1 ? len1 - km1 : 0) + (s2 ? (len2 > km1 ? len2 - km1 : 0) + 1 : 0);
-    scan_mate(s1, len1);
-    if (s2) {
-      emit(SLK_E_BORDER, 0, 0);
-      scan_mate(s2, len2);
+    uint32_t ne = 0;       // buffered entries (register)
+    bool any = false;      // did the fragment yield any span at all
+#pragma unroll 1
+    for (int mt = 0; mt < (s2 ? 2 : 1); mt++) {  // one copy of the scan loop serves both mates
+      if (mt) {
+#if defined(__CUDA_ARCH__)
+        const bool full = __any_sync(0xffffffffu, ne > SLK_ECAP - 5);
+#else
+        const bool full = ne > SLK_ECAP - 5;
+#endif
+        if (full) { any = any || ne != 0; drain(sp, ne); ne = 0; }
+        ent.set(ne, 0, SLK_E_BORDER << 14); ne++;
+      }
+      const uint8_t* s = mt ? s2 : s1;
+      const uint32_t len = mt ? len2 : len1;
+      slk_scanner<W> sc;
+      sc.reset();
+      uint64_t run_key = 0;
+      uint32_t run_cnt = 0, ninv = 0, amb_cnt = 0;
+      bool in_run = false;
+      // One character. Straight-line code: at most one entry is stored per character.
+      auto step = [&](uint32_t ch) {
+        const uint32_t c = slk_code(ch);
+        const bool valid = c < 4u;
+        uint64_t mn;
+        const bool window_ok = sc.push(c, k, fshift, mmask, xor_mask, sig_mask, canonical, &mn);
+        ninv = valid ? 0u : ninv + 1u;
+        const bool same = in_run && mn == run_key && run_cnt < SLK_E_CNT_MAX;
+        const bool start_new = window_ok && !same;
+        const bool emit_seq = in_run && (start_new || !valid);  // the open super-mer ends here
+        const bool emit_amb = amb_cnt != 0 && (valid || amb_cnt == SLK_E_CNT_MAX);  // an ambiguous stretch ended
+        if (emit_seq || emit_amb) {
+          ent.set(ne, emit_seq ? run_key : 0ull, emit_seq ? run_cnt : (amb_cnt | (SLK_E_AMB << 14)));
+          ne++;
+        }
+        amb_cnt = (valid || emit_amb) ? 0u : amb_cnt;
+        amb_cnt += (!valid && ninv >= k) ? 1u : 0u;
+        run_cnt = start_new ? 1u : run_cnt + ((window_ok && same) ? 1u : 0u);
+        run_key = start_new ? mn : run_key;
+        in_run = valid && (in_run || start_new);
+      };
+#if defined(__CUDA_ARCH__)
+      // 16-byte aligned vector loads over [s, s+len). The buffer is readable up to the next 16-byte boundary
+      // (library-owned and cudaMalloc'ed buffers are); bytes outside the read are skipped in the edge chunks.
+      // All 32 lanes of the warp run the same number of iterations (the longest read of the warp decides) and
+      // drain together as soon as one lane's entry tile is nearly full, so the warp never splits around drain().
+      const uintptr_t a0 = reinterpret_cast<uintptr_t>(s);
+      const uintptr_t abase = a0 & ~(uintptr_t)15;
+      const int32_t lo0 = (int32_t)(a0 - abase), total = lo0 + (int32_t)len;  // byte range [lo0, total) from abase
+      const int32_t total_w = (int32_t)__reduce_max_sync(0xffffffffu, (uint32_t)total);
+      for (int32_t cb = 0; cb < total_w; cb += 16) {
+        const bool have = cb < total;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (have) v = __ldg(reinterpret_cast<const uint4*>(abase + cb));
+        const bool interior = cb >= lo0 && cb + 16 <= total;
+#pragma unroll 1
+        for (int wi = 0; wi < 4; wi++) {
+          if (__any_sync(0xffffffffu, ne > SLK_ECAP - 5)) {   // 4 characters add at most 4 entries
+            any = any || ne != 0;
+            drain(sp, ne);
+            ne = 0;
+          }
+          const uint32_t word = wi == 0 ? v.x : wi == 1 ? v.y : wi == 2 ? v.z : v.w;
+          if (interior) {
+#pragma unroll
+            for (int bi = 0; bi < 4; bi++) step((word >> (8 * bi)) & 0xffu);
+          } else if (have) {
+#pragma unroll 1
+            for (int bi = 0; bi < 4; bi++) {
+              const int32_t pos = cb + 4 * wi + bi;
+              if (pos >= lo0 && pos < total) step((word >> (8 * bi)) & 0xffu);
+            }
+          }
+        }
+      }
+#else
+      for (uint32_t i = 0; i < len; i++) {
+        if ((i & 3) == 0 && ne > SLK_ECAP - 5) { any = true; drain(sp, ne); ne = 0; }
+        step(s[i]);
+      }
+#endif
+      // mate end: at most one pending entry (a run and an ambiguous stretch cannot both be open)
+      if (in_run) { ent.set(ne, run_key, run_cnt); ne++; }
+      if (amb_cnt) { ent.set(ne, 0, amb_cnt | (SLK_E_AMB << 14)); ne++; }
     }
-    drain();
-    flush_hit();
+    if (ne) any = true;
+    drain(sp, ne);
+    if (have_cur) { push_hit(cur_label, cur_count, 2); have_cur = false; }
+    if (nh_spilled) spill(0);   // a fragment that went to the sink keeps all its hits there
     uint32_t taxon = resolve(confidence);
     bool classified = taxon != 0 && nd >= (uint32_t)min_hit_groups;  // slacken/Classifier.scala:446
     r.taxon = classified ? tx.raw[taxon] : 0;
-    r.flags = (classified ? SLK_F_CLASSIFIED : 0u) | (total_entries ? SLK_F_HAS_SPAN : 0u) | (overflow ? SLK_F_OVERFLOW : 0u);
+    r.flags = (classified ? SLK_F_CLASSIFIED : 0u) | (any ? SLK_F_HAS_SPAN : 0u) | (overflow ? SLK_F_OVERFLOW : 0u);
     r.kmers1 = kmers[0]; r.kmers2 = kmers[1];
-    r.num_distinct = nd; r.n_hits = nhits; r.n_probes = nprobes;
+    r.num_distinct = nd; r.n_hits = nh + nh_spilled; r.n_probes = nprobes;
   }
 };
 
@@ -454,21 +604,21 @@ SLK_HD void slk_emit_cells(const slk_scan_params& sp, const uint8_t* s, uint64_t
                            Emit& out) {
   slk_scanner<W> sc;
   sc.reset();
+  const uint32_t k = (uint32_t)sp.k;
+  const int fshift = sp.fshift;
+  const uint64_t mmask = sp.mmask, xor_mask = sp.xor_mask, sig_mask = sp.sig_mask;
+  const bool canonical = sp.canonical != 0;
   uint64_t run_key = 0;
   bool in_run = false;
   slk_for_each_byte(s, nbases, [&](uint32_t ch) {
-    uint32_t c = slk_code(ch);
-    if (c < 4u) {
-      uint64_t mn;
-      if (sc.push(sp, c, &mn)) {
-        if (!in_run || mn != run_key) {
-          out((slk_compress(sp, mn) << 16) | dense_taxon);
-          run_key = mn; in_run = true;
-        }
-      }
-    } else {
-      sc.nvalid = 0; in_run = false;
+    const uint32_t c = slk_code(ch);
+    uint64_t mn;
+    const bool window_ok = sc.push(c, k, fshift, mmask, xor_mask, sig_mask, canonical, &mn);
+    if (window_ok && (!in_run || mn != run_key)) {
+      out((slk_compress(sp, mn) << 16) | dense_taxon);
+      run_key = mn;
     }
+    in_run = window_ok;
   });
 }
 

@@ -49,7 +49,7 @@ __device__ __forceinline__ uint64_t warp_agg_alloc(unsigned long long* cursor, u
 // ---------------------------------------------------------------------------------------------- build kernels
 // K2 (build side) + K3a emit: one thread scans BUILD_WPT k-mer windows of one fragment and appends its cells.
 template <int W>
-__global__ void __launch_bounds__(128) emit_cells_kernel(slk_scan_params sp, const uint8_t* __restrict__ bases,
+__global__ void __launch_bounds__(128) emit_cells_kernel(const __grid_constant__ slk_scan_params sp, const uint8_t* __restrict__ bases,
                                                          const uint64_t* __restrict__ frag_off, uint64_t off_shift,
                                                          const uint32_t* __restrict__ frag_dense,
                                                          const uint64_t* __restrict__ item_prefix, uint32_t n_frag,
@@ -83,34 +83,52 @@ __global__ void __launch_bounds__(128) emit_cells_kernel(slk_scan_params sp, con
 }
 
 // ---------------------------------------------------------------------------------------------- classify kernel
+// Per-thread fast store: columns of shared-memory tiles [*][128] (conflict-free for a warp whose lanes use the
+// same row, never evicted, and -- unlike local memory -- one 4-byte access by a lone lane costs 4 bytes, not a sector).
+struct dev_store {
+  uint64_t* key;   // &skey[0][threadIdx.x]
+  uint16_t* meta;  // &smeta[0][threadIdx.x]
+  int2* hit;       // &shit[0][threadIdx.x]
+  __device__ __forceinline__ void set(uint32_t j, uint64_t k, uint32_t m) { key[j * 128] = k; meta[j * 128] = (uint16_t)m; }
+  __device__ __forceinline__ uint64_t get_key(uint32_t j) const { return key[j * 128]; }
+  __device__ __forceinline__ uint32_t get_meta(uint32_t j) const { return meta[j * 128]; }
+  __device__ __forceinline__ void set_hit(uint32_t i, int32_t label, int32_t count) { hit[i * 128] = make_int2(label, count); }
+  __device__ __forceinline__ void get_hit(uint32_t i, int32_t* label, int32_t* count) const {
+    int2 h = hit[i * 128];
+    *label = h.x; *count = h.y;
+  }
+};
+
+// Spill path for a read with more merged hits than the per-thread buffers hold: it takes a worst-case block of the
+// global hit buffer for itself (one atomic) and appends there. Ordinary reads never touch it; their hits are
+// written from the buffers to a compact, warp-allocated block at the end of the kernel.
 struct dev_hit_sink {
-  slk_hit buf[SLK_HCAP];
   uint32_t n;
   bool spilled;
   uint64_t goff;
   slk_hit* gbase;         // scratch, indexed by (absolute index - gshift)
   uint64_t gshift, gcap;  // gcap: capacity of gbase in hits
   unsigned long long* cursor;
-  __device__ __forceinline__ void put(uint64_t abs_idx, slk_hit h) {
+  __device__ __forceinline__ void put(uint64_t abs_idx, int32_t taxon, int32_t count) {
     uint64_t rel = abs_idx - gshift;
-    if (rel < gcap) gbase[rel] = h;
-  }
-  __device__ __forceinline__ void push(int32_t taxon, int32_t count, uint32_t windows_left) {
     slk_hit h;
     h.taxon = taxon; h.count = count;
+    if (rel < gcap) gbase[rel] = h;
+  }
+  __device__ __forceinline__ void push(int32_t taxon, int32_t count, uint32_t need) {
     if (!spilled) {
-      if (n < SLK_HCAP) { buf[n++] = h; return; }
-      goff = atomicAdd(cursor, (unsigned long long)n + windows_left + 2ull);
-      for (uint32_t i = 0; i < n; i++) put(goff + i, buf[i]);
+      goff = atomicAdd(cursor, (unsigned long long)need + 2ull);
       spilled = true;
     }
-    put(goff + n, h);
+    put(goff + n, taxon, count);
     n++;
   }
 };
 
 template <int W, bool HITS>
-__global__ void __launch_bounds__(128) classify_kernel(slk_scan_params sp, slk_table_view tb, slk_tax_view tx,
+__global__ void __launch_bounds__(128) classify_kernel(const __grid_constant__ slk_scan_params sp,
+                                                       const __grid_constant__ slk_table_view tb,
+                                                       const __grid_constant__ slk_tax_view tx,
                                                        const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ off1,
                                                        uint64_t shift1, const uint8_t* __restrict__ bases2,
                                                        const uint64_t* __restrict__ off2, uint64_t shift2, uint32_t n_reads,
@@ -125,38 +143,54 @@ __global__ void __launch_bounds__(128) classify_kernel(slk_scan_params sp, slk_t
   slk_frag_result res;
   res.taxon = 0; res.flags = 0; res.kmers1 = 0; res.kmers2 = 0; res.num_distinct = 0; res.n_hits = 0; res.n_probes = 0;
   typedef typename std::conditional<HITS, dev_hit_sink, slk_null_sink>::type sink_t;
+  __shared__ uint64_t skey[SLK_ECAP][128];
+  __shared__ uint16_t smeta[SLK_ECAP][128];
+  __shared__ int2 shit[SLK_SHITS][128];
+  dev_store ent;
+  ent.key = &skey[0][threadIdx.x]; ent.meta = &smeta[0][threadIdx.x]; ent.hit = &shit[0][threadIdx.x];
   sink_t sink;
   if constexpr (HITS) {
     sink.n = 0; sink.spilled = false; sink.goff = 0; sink.gbase = hits_base;
     sink.gshift = hits_shift_ptr ? *hits_shift_ptr : 0ull;
     sink.gcap = hits_cap; sink.cursor = hits_cursor;
   }
-  if (active) {
-    uint64_t s1 = off1[r], e1 = off1[r + 1];
-    const uint8_t* p2 = nullptr;
-    uint32_t l2 = 0;
-    if (bases2) {
-      uint64_t s2 = off2[r], e2 = off2[r + 1];
-      p2 = bases2 + (s2 - shift2);
-      l2 = (uint32_t)(e2 - s2);
+  slk_frag_classifier<W, sink_t, dev_store> cl(tb, tx, sink, ent);
+  {
+    // every lane runs the classifier (lanes past the end of the batch get an empty read) so that the warp-wide
+    // votes inside run() always see 32 participants
+    const uint8_t* p1 = bases1;
+    const uint8_t* p2 = bases2;
+    uint32_t l1 = 0, l2 = 0;
+    if (active) {
+      uint64_t s1 = off1[r], e1 = off1[r + 1];
+      p1 = bases1 + (s1 - shift1); l1 = (uint32_t)(e1 - s1);
+      if (bases2) {
+        uint64_t s2 = off2[r], e2 = off2[r + 1];
+        p2 = bases2 + (s2 - shift2); l2 = (uint32_t)(e2 - s2);
+      }
     }
-    slk_frag_classifier<W, sink_t> cl(sp, tb, tx, sink);
-    cl.run(bases1 + (s1 - shift1), (uint32_t)(e1 - s1), p2, l2, confidence, min_hit_groups, res);
-    taxon_out[r] = res.taxon;
-    flags_out[r] = (uint8_t)(res.flags & 3u);
-    if (res.flags & SLK_F_OVERFLOW) atomicExch(error_flag, 1u);
+    cl.run(sp, p1, l1, p2, l2, confidence, min_hit_groups, res);
+    if (active) {
+      taxon_out[r] = res.taxon;
+      flags_out[r] = (uint8_t)(res.flags & 3u);
+      if (res.flags & SLK_F_OVERFLOW) atomicExch(error_flag, 1u);
+    }
   }
   if constexpr (HITS) {
-    // compact allocation of the (non-spilled) merged hits, one atomic per warp
-    uint32_t need = (active && !sink.spilled) ? sink.n : 0u;
+    // compact allocation of the buffered merged hits, one atomic per warp; dense labels become raw taxon ids here
+    uint32_t need = (active && !sink.spilled) ? cl.nh : 0u;
     uint64_t o = warp_agg_alloc(hits_cursor, need);
     if (active) {
       if (!sink.spilled) {
-        sink.goff = o;
-        for (uint32_t i = 0; i < sink.n; i++) sink.put(o + i, sink.buf[i]);
+        for (uint32_t i = 0; i < cl.nh; i++) {
+          int32_t l, c;
+          cl.buffered_hit(i, &l, &c);
+          sink.put(o + i, l >= 0 ? tx.raw[l] : l, c);
+        }
       }
       slk_read_detail d;
-      d.hit_off = sink.goff; d.hit_cnt = sink.n;
+      d.hit_off = sink.spilled ? sink.goff : o;
+      d.hit_cnt = res.n_hits;
       d.len1 = res.kmers1 + (uint32_t)(sp.k - 1);
       d.len2 = bases2 ? res.kmers2 + (uint32_t)(sp.k - 1) : 0xFFFFFFFFu;
       d.num_distinct = res.num_distinct;

@@ -16,7 +16,7 @@ BUILD_WPT = 96
 
 class ScanParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("m", C.c_int32), ("w", C.c_int32), ("canonical", C.c_int32), ("fshift", C.c_int32),
-                ("key_bits", C.c_int32), ("xor_mask", C.c_uint64), ("sig_mask", C.c_uint64), ("mmask", C.c_uint64),
+                ("key_bits", C.c_int32), ("fast_compress", C.c_int32), ("pad_", C.c_int32), ("xor_mask", C.c_uint64), ("sig_mask", C.c_uint64), ("mmask", C.c_uint64),
                 ("cmv", C.c_uint64 * 6)]
 
 
@@ -35,6 +35,7 @@ def lib():
             subprocess.check_call(["/usr/bin/g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
                                    "-o", _SO, src])
         L = C.CDLL(_SO)
+        assert L.emu_sizeof_scan_params() == C.sizeof(ScanParams), "ScanParams mirror out of date"
         L.emu_scan_params.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(ScanParams)]
         L.emu_compress.restype = C.c_uint64
         L.emu_compress.argtypes = [C.POINTER(ScanParams), C.c_uint64]

@@ -16,6 +16,7 @@ EMU_API int emu_scan_params(int k, int m, int spaces, uint64_t mask, int canonic
   memset(sp, 0, sizeof(*sp));
   return slk_make_scan_params(k, m, spaces, mask, canonical, sp);
 }
+EMU_API int emu_sizeof_scan_params() { return (int)sizeof(slk_scan_params); }
 EMU_API uint64_t emu_compress(const slk_scan_params* sp, uint64_t x) { return slk_compress(*sp, x); }
 EMU_API uint64_t emu_expand(const slk_scan_params* sp, uint64_t x) { return slk_expand(*sp, x); }
 EMU_API uint32_t emu_code(uint32_t c) { return slk_code(c); }
@@ -62,12 +63,19 @@ static int64_t classify_w(const slk_scan_params* sp, uint64_t* cells, uint64_t n
   for (uint32_t r = 0; r < n; r++) {
     hv.clear();
     vec_sink sink{&hv};
-    slk_frag_classifier<W, vec_sink> cl(*sp, tb, tx, sink);
+    slk_store_local ent;
+    slk_frag_classifier<W, vec_sink, slk_store_local> cl(tb, tx, sink, ent);
     slk_frag_result fr;
     const uint8_t* p2 = b2 ? b2 + o2[r] : nullptr;
-    cl.run(b1 + o1[r], (uint32_t)(o1[r + 1] - o1[r]), p2, b2 ? (uint32_t)(o2[r + 1] - o2[r]) : 0, confidence,
+    cl.run(*sp, b1 + o1[r], (uint32_t)(o1[r + 1] - o1[r]), p2, b2 ? (uint32_t)(o2[r + 1] - o2[r]) : 0, confidence,
            min_hit_groups, fr);
     res[r] = emu_result{fr.taxon, fr.flags, fr.kmers1, fr.kmers2, fr.num_distinct, fr.n_hits};
+    if (cl.nh_spilled == 0)   // the kernel epilogue: buffered hits leave with raw taxon ids
+      for (uint32_t i = 0; i < cl.nh; i++) {
+        int32_t l, c;
+        cl.buffered_hit(i, &l, &c);
+        hv.push_back(slk_hit{l >= 0 ? raw[l] : l, c});
+      }
     hit_off[r] = used;
     if (used + hv.size() > cap) return -1;
     std::copy(hv.begin(), hv.end(), hits_out + used);

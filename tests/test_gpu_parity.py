@@ -7,7 +7,7 @@ from oracle import oracle
 from slacken_b200 import Classifier, IndexParams, KeyValueIndex, KrakenReport, ReportCounts, Taxonomy
 from slacken_b200.host import pack_sequences
 from slacken_b200.report import output_line
-from tests.util import leaf_taxa, make_taxonomy, random_dna, simulate_reads
+from tests.util import chimeric_reads, leaf_taxa, make_taxonomy, random_dna, simulate_reads
 
 pytestmark = pytest.mark.gpu
 
@@ -77,6 +77,31 @@ def test_classify_single_end(gpu, confidence):
             a = oracle.output_line(f"r{i}", res[i], [(int(h["taxon"]), int(h["count"])) for h in per[i]])
             b = output_line(f"r{i}", got.taxon[i], got.classified[i], got.detail[i], got.hits_of(i))
             assert a == b
+    cls.close(); index.close(); tax.close()
+
+
+def test_classify_long_reads_with_many_hits(gpu):
+    """Reads of several kb whose merged hit lists outgrow the per-thread buffers (spill to a worst-case global block),
+    mixed with ordinary reads in the same warps."""
+    rng, parents, ranks, names, genomes, taxa = make_world(44)
+    p = oracle.params()
+    olib = oracle_lib(p, parents, genomes, taxa)
+    id1, tx = olib.records()
+    tax = Taxonomy(gpu, parents, ranks, names)
+    index = KeyValueIndex.from_records(gpu, tax, IndexParams(), id1, tx)
+    reads = chimeric_reads(rng, genomes, 40, 150) + simulate_reads(rng, genomes, 300, (30, 150)) + chimeric_reads(rng, genomes, 60, 25)
+    order = rng.permutation(len(reads))
+    reads = [reads[i] for i in order]
+    rb, ro = pack_sequences(reads)
+    cls = Classifier(index)
+    for conf in (0.0, 0.25):
+        got = cls.classify(rb, ro, confidence=conf)
+        res, _, _, per = olib.classify(rb, ro.astype(np.int64), confidence=conf)
+        assert max(len(h) for h in per) > 70
+        assert_batch_equal(res, per, got, 35)
+    got = cls.classify(rb, ro, rb, ro, confidence=0.1)
+    res, _, _, per = olib.classify(rb, ro.astype(np.int64), rb, ro.astype(np.int64), confidence=0.1)
+    assert_batch_equal(res, per, got, 35)
     cls.close(); index.close(); tax.close()
 
 

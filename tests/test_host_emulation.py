@@ -6,7 +6,7 @@ from hypothesis import given, settings, strategies as st
 
 from oracle import oracle
 from tests import host_emulation as emu
-from tests.util import leaf_taxa, make_taxonomy, random_dna, simulate_reads
+from tests.util import chimeric_reads, leaf_taxa, make_taxonomy, random_dna, simulate_reads
 
 
 def world(seed, k=35, m=31, s=7, canonical=True, n_genomes=16, glen=2500):
@@ -52,6 +52,18 @@ def test_classify_body_single_end(confidence):
     reads = simulate_reads(rng, genomes, 1200, (10, 230), n_rate=0.2) + [b"", b"ACGT", b"N" * 90, b"A" * 120]
     rb, ro = oracle.pack_sequences(reads)
     compare(lib, ix, rb, ro, confidence=confidence)
+
+
+def test_classify_body_long_reads_with_many_hits():
+    rng, parents, genomes, taxa, p, lib, sp = world(8)
+    id1, tx = lib.records()
+    ix = emu.EmuIndex(sp, parents, id1, tx)
+    reads = chimeric_reads(rng, genomes, 12, 150) + chimeric_reads(rng, genomes, 20, 30) + simulate_reads(rng, genomes, 50, 100)
+    rb, ro = oracle.pack_sequences(reads)
+    res, _, _, per = lib.classify(rb, ro, confidence=0.02)
+    assert max(len(h) for h in per) > 70          # beyond SLK_SHITS + SLK_XHITS: the spill path runs
+    compare(lib, ix, rb, ro, confidence=0.02)
+    compare(lib, ix, rb, ro, rb, ro, confidence=0.3)
 
 
 def test_classify_body_paired_end():

@@ -77,3 +77,18 @@ def simulate_reads(rng, genomes, n: int, length, sub_rate=0.01, n_rate=0.02, ran
             r = bytearray(bytes(r).replace(b"T", b"U", 3))
         out.append(bytes(r))
     return out
+
+
+def chimeric_reads(rng, genomes, n: int, pieces: int, piece_len=(40, 90)):
+    """Long reads stitched from many short genome slices: dozens of merged hits per read (exercises the paths for
+    reads whose hit list outgrows the per-thread buffers)."""
+    out = []
+    for _ in range(n):
+        parts = []
+        for _ in range(pieces):
+            g = genomes[int(rng.integers(len(genomes)))]
+            L = int(rng.integers(piece_len[0], piece_len[1] + 1))
+            p = int(rng.integers(0, len(g) - L))
+            parts.append(g[p:p + L])
+        out.append(b"".join(parts))
+    return out
