@@ -40,7 +40,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -52,7 +52,7 @@ class ClockSampler:
             self.lines.append((time.perf_counter(), line.strip()))
 
     def window(self, t0, t1):
-        return [l for t, l in self.lines if t0 <= t <= t1 + 0.15]
+        return [l for t, l in self.lines if t0 - 0.03 <= t <= t1 + 0.05]
 
     def stop(self):
         if self.proc:
@@ -168,7 +168,7 @@ def run_ours(args, w):
     import ctypes as C
     from slacken_b200 import Classifier, DeviceTimer, GpuContext, IndexParams, ReportCounts, Taxonomy
     from slacken_b200._lib import check
-    from slacken_b200.host import DETAIL_DTYPE, HIT_DTYPE, ClassifiedBatch
+    from slacken_b200.host import DETAIL_DTYPE, HIT_DTYPE, ClassifiedBatch, PackedReads, block_offsets
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -211,6 +211,15 @@ def run_ours(args, w):
     off = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
     d_off = ctx.dev_alloc(off.nbytes)
     ctx.h2d(d_off, off)
+    # stage 1 on the device: the same reads as 2-bit packed blocks + ambiguity masks (the input form the north star names)
+    boff = block_offsets(off)
+    n_blocks = int(boff[-1])
+    d_boff, d_codes, d_mask, d_len = ctx.dev_alloc(boff.nbytes), ctx.dev_alloc(n_blocks * 8), ctx.dev_alloc(n_blocks * 4), ctx.dev_alloc(n * 4)
+    ctx.h2d(d_boff, boff)
+    ctx.pack_reads_dev(d_reads, d_off, n, d_boff, d_codes, d_mask, d_len)
+    t0 = time.perf_counter()
+    ctx.pack_reads_dev(d_reads, d_off, n, d_boff, d_codes, d_mask, d_len)
+    t_pack = time.perf_counter() - t0
     cls = Classifier(index)
     counts = ReportCounts(ctx, tax, 1)
     cls.attach_counts(counts, 0)
@@ -226,9 +235,13 @@ def run_ours(args, w):
             __cuda_array_interface__ = {"shape": (tax.size,), "typestr": "<i8", "data": (counts.device_ptr(), False), "version": 2}
         counts_t = torch.as_tensor(_Wrap(), device=f"cuda:{local}")
 
-    def device_step():
+    def device_step_ascii():
         cls.classify_dev(d_reads, d_off, 0, 0, n, d_taxon, d_flags, d_detail, d_hits, hits_cap, d_used,
                          confidence=w.confidence, min_hit_groups=w.min_hit_groups)
+
+    def device_step():
+        cls.classify_packed_dev(d_codes, d_mask, d_boff, d_len, 0, 0, 0, 0, n, d_taxon, d_flags, d_detail, d_hits, hits_cap,
+                                d_used, confidence=w.confidence, min_hit_groups=w.min_hit_groups)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -270,13 +283,26 @@ def run_ours(args, w):
 
     # roofline of the dominant (only) kernel of the step: the fused classify kernel
     S, H = probes_per_read, hits_per_read
-    bytes_per_read = L + 8 + 32.0 * S + (4 + 1 + 24) + 8.0 * H
+    bytes_per_read = 12.0 * n_blocks / n + 8 + 4 + 32.0 * S + (4 + 1 + 24) + 8.0 * H   # packed input
     achieved = bytes_per_read * n * args.steps / (ms / 1e3) / 1e9 / 1.0  # per GPU: every rank runs the same launch
     peak, peak_src = measured_peak()
-    roofline = {"bound": "hbm", "kernel": "classify_kernel<5,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    # the same launch on ASCII-resident input (stage 1 fused into the kernel), for comparison
+    for _ in range(2):
+        device_step_ascii()
+    cls.sync()
+    t_a = DeviceTimer(cls)
+    t_a.start()
+    for _ in range(args.steps):
+        device_step_ascii()
+    t_a.stop()
+    ms_ascii = max_over_ranks(t_a.elapsed_ms())
+    cls.attach_counts(None)
+    roofline = {"bound": "hbm", "kernel": "classify_kernel<5,true,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src, "traffic": args.traffic,
                 "bytes_per_read": bytes_per_read, "probes_per_read": S, "merged_hits_per_read": H,
-                "probe_sectors_gbs": 32.0 * S * n * args.steps / (ms / 1e3) / 1e9}
+                "probe_sectors_gbs": 32.0 * S * n * args.steps / (ms / 1e3) / 1e9,
+                "random_gather_ceiling": "35 G 32-byte gathers/s measured on this GPU for a 20 GB table (profiles/r01_probe_microbench.md): "
+                                         "the probe stage cannot exceed 0.17 of the copy-bandwidth roofline"}
 
     # ---- e2e: the host-buffer entry point, pinned host memory, H2D + D2H inside the timed region
     h_reads = ctx.pinned(n * L, np.uint8)
@@ -285,32 +311,47 @@ def run_ours(args, w):
     h_off[:] = off
     e2e_cap = 16 * n
     out = ClassifiedBatch(ctx.pinned(n, np.int32), ctx.pinned(n, np.uint8), ctx.pinned(n, DETAIL_DTYPE), ctx.pinned(e2e_cap, HIT_DTYPE))
-    for _ in range(max(1, min(args.warmup, 2))):
-        cls.classify(h_reads, h_off, confidence=w.confidence, min_hit_groups=w.min_hit_groups, out=out)
-    barrier()
-    te0 = time.perf_counter()
-    for _ in range(args.steps):
-        cls.classify(h_reads, h_off, confidence=w.confidence, min_hit_groups=w.min_hit_groups, out=out)
-    e2e_s = time.perf_counter() - te0
-    barrier()
-    te1 = time.perf_counter()
-    e2e_s = max_over_ranks(e2e_s)
+    hp = PackedReads(ctx.pinned(n_blocks, np.uint64), ctx.pinned(n_blocks, np.uint32), ctx.pinned(n + 1, np.uint64), ctx.pinned(n, np.uint32))
+    ctx.d2h(hp.codes, d_codes); ctx.d2h(hp.mask, d_mask); ctx.d2h(hp.len, d_len)
+    hp.boff[:] = boff
+
+    def timed_e2e(fn):
+        for _ in range(max(1, min(args.warmup, 2))):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        dt = time.perf_counter() - t0
+        barrier()
+        return max_over_ranks(dt), t0, time.perf_counter()
+
+    e2e_s, te0, te1 = timed_e2e(lambda: cls.classify_packed(hp, confidence=w.confidence, min_hit_groups=w.min_hit_groups, out=out))
     clocks_e2e = ClockSampler.summarize(sampler.window(te0, te1))
-    sampler.stop()
-    e2e = {"value": world * n * args.steps / e2e_s, "unit": "reads/s",
-           "h2d_bytes_per_step": int(h_reads.nbytes + h_off.nbytes),
+    e2e = {"value": world * n * args.steps / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": int(hp.nbytes),
            "d2h_bytes_per_step": int(out.taxon.nbytes + out.flags.nbytes + out.detail.nbytes + out.hits_used * 8),
-           "ms_per_step": 1e3 * e2e_s / args.steps, "api": "slk_classify_batch (pinned host buffers, per-read hit lists on)",
+           "ms_per_step": 1e3 * e2e_s / args.steps,
+           "api": "slk_classify_batch_packed: pinned HOST buffers holding 2-bit packed reads + ambiguity masks (the host-side "
+                  "packing is the Scala driver's batching work and is outside the timed region), per-read hit lists on",
            "clocks": clocks_e2e}
+    a_s, _, _ = timed_e2e(lambda: cls.classify(h_reads, h_off, confidence=w.confidence, min_hit_groups=w.min_hit_groups, out=out))
+    e2e_ascii = {"value": world * n * args.steps / a_s, "unit": "reads/s", "h2d_bytes_per_step": int(h_reads.nbytes + h_off.nbytes),
+                 "ms_per_step": 1e3 * a_s / args.steps, "api": "slk_classify_batch: pinned HOST buffers holding ASCII reads"}
+    sampler.stop()
 
     line = {"metric": "reads/sec classified (150bp)", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": w.name, "reads_per_gpu_per_step": n, "library_records": len(index),
-                       "library": "replicated per GPU", "l2": "inputs (reads 1.5 GB + table) are far larger than L2; no flush needed",
+                       "library": "replicated per GPU", "input": "2-bit packed reads + ambiguity mask (72 B/read)", "l2": "inputs (reads 1.5 GB + table) are far larger than L2; no flush needed",
                        "classified_fraction": float((rep.sum() - rep[0]) / max(1, rep.sum())),
                        "reads_counted_in_report": total_reads_counted},
-            "probes_per_s": value * S, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "probes_per_s": value * S, "clocks": clocks, "e2e": e2e, "e2e_ascii_input": e2e_ascii,
+            "value_ascii_input": {"value": world * n * args.steps / (ms_ascii / 1e3), "unit": "reads/s", "ms_per_step": ms_ascii / args.steps,
+                                  "note": "same launch with ASCII reads resident in HBM (stage 1 fused into the kernel)"},
+            "encode_kernel": {"ms": 1e3 * t_pack, "reads_per_s": n / t_pack, "gbs": (L + 8 + 12.0 * n_blocks / n + 4) * n / t_pack / 1e9,
+                              "note": "stage 1 alone (pack_reads_kernel: ASCII -> 2-bit blocks + mask), wall clock around a synchronous call"},
+            "gpu_launches": int(launches), "roofline": roofline,
             "build": {"seconds": t_build, "gbases_per_s": w.total_bases / t_build / 1e9, "records": len(index)}}
 
     # ---- cpu_baseline: the oracle on the host cores, bounded sample, rank 0 at N=1 only

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libslacken_gpu.so")
+SO_PATH = os.path.join(_HERE, os.environ.get("SLK_SO", "libslacken_gpu.so"))
 
 SLK_OK, SLK_E_INVALID, SLK_E_CUDA, SLK_E_NOMEM, SLK_E_NOSPACE, SLK_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 READ_CLASSIFIED, READ_HAS_SPAN = 1, 2
@@ -59,6 +59,11 @@ SIGNATURES = {
                                   C.POINTER(_U64)]),
     "slk_classify_batch_dev": (_INT, [_VP, C.POINTER(ClassifyOpts), _VP, _VP, _VP, _VP, _U32, _VP, _VP, _VP, _VP, _U64,
                                       _VP]),
+    "slk_classify_batch_packed": (_INT, [_VP, C.POINTER(ClassifyOpts), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP, _VP,
+                                         _VP, _VP, _U64, C.POINTER(_U64)]),
+    "slk_classify_packed_dev": (_INT, [_VP, C.POINTER(ClassifyOpts), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP, _VP,
+                                       _VP, _VP, _U64, _VP]),
+    "slk_pack_reads_dev": (_INT, [_VP, _VP, _VP, _U32, _VP, _VP, _VP, _VP]),
     "slk_classifier_sync": (_INT, [_VP]),
     "slk_classifier_stream": (_VP, [_VP]),
     "slk_classifier_launches": (_U64, [_VP]),

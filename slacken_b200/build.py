@@ -20,6 +20,10 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ccbin", "/usr/bin/g++",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]
 WIDTHS = range(1, 9)
+if os.environ.get("SLK_CLS_MINB"):
+    FLAGS = FLAGS + ["-DSLK_CLS_MINB=" + os.environ["SLK_CLS_MINB"]]
+    SO = os.path.join(HERE, "libslacken_gpu_minb" + os.environ["SLK_CLS_MINB"] + ".so")
+    OBJ = OBJ + "_minb" + os.environ["SLK_CLS_MINB"]
 
 
 def _sources():

@@ -80,7 +80,7 @@ struct slk_index {
   slk_params params;
   slk_scan_params sp;
   dense_tax dt;
-  slk_table_view table{nullptr, 0};
+  slk_table_view table{nullptr, 0, 0, 0};
   uint64_t n_records = 0;
 };
 struct slk_builder {
@@ -142,6 +142,9 @@ extern "C" int slk_ctx_create(int device, slk_ctx** out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  // The probes are random 32-byte sectors: ask L2 to fetch single sectors from HBM instead of the default 64 bytes.
+  if (!getenv("SLK_L2_FETCH_DEFAULT")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+  cudaGetLastError();
   *out = c;
   return SLK_OK;
 }
@@ -350,6 +353,18 @@ __global__ void __launch_bounds__(256) reduce_cells_kernel(const uint64_t* __res
   if (head) out[o] = res;
 }
 
+// K1: 2-bit encode + ambiguity mask, one read per thread, into the packed block layout (slk_read_src)
+__global__ void __launch_bounds__(128) pack_reads_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ off,
+                                                         uint32_t n_reads, const uint64_t* __restrict__ boff,
+                                                         uint64_t* __restrict__ codes, uint32_t* __restrict__ mask,
+                                                         uint32_t* __restrict__ len_out) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const uint64_t s = off[r], e = off[r + 1], b0 = boff[r];
+  len_out[r] = (uint32_t)(e - s);
+  slk_pack_read(bases + s, (uint32_t)(e - s), [&](uint32_t b, uint64_t cw, uint32_t mw) { codes[b0 + b] = cw; mask[b0 + b] = mw; });
+}
+
 __global__ void snapshot_kernel(const unsigned long long* src, unsigned long long* dst) { *dst = *src; }
 
 __global__ void __launch_bounds__(256) counts_add_kernel(const int32_t* __restrict__ taxon, const uint8_t* __restrict__ flags,
@@ -414,6 +429,8 @@ static uint64_t buckets_for(uint64_t n_keys) {
 }
 static int table_alloc(slk_table_view* tb, uint64_t n_keys) {
   tb->n_buckets = buckets_for(n_keys);
+  tb->prefetch = getenv("SLK_PREFETCH") ? 1u : 0u;   // measured on B200: the L2 prefetch pass costs more than it hides
+  tb->pad_ = 0;
   CU(cudaMalloc(&tb->cells, tb->n_buckets * 32));
   CU(cudaMemset(tb->cells, 0, tb->n_buckets * 32));
   return SLK_OK;
@@ -764,8 +781,9 @@ extern "C" int slk_counts_fetch(slk_counts* c, int32_t sample, int64_t* per_taxo
 // ---------------------------------------------------------------------------------------------- classifier
 #define NSLOT 3
 struct cls_slot {
-  uint8_t *bases1 = nullptr, *bases2 = nullptr;
+  uint8_t *bases1 = nullptr, *bases2 = nullptr;   // ASCII bases, or the uint64 code blocks of packed input
   uint64_t *off1 = nullptr, *off2 = nullptr;
+  uint32_t *mask1 = nullptr, *mask2 = nullptr, *len1 = nullptr, *len2 = nullptr;   // packed input only
   int32_t* taxon = nullptr; uint8_t* flags = nullptr; slk_read_detail* detail = nullptr;
   slk_hit* hits = nullptr; uint64_t hits_cap = 0;
   unsigned long long* d_range = nullptr;   // [0] = cursor value before the kernel, [1] = after
@@ -780,7 +798,7 @@ struct slk_classifier {
   cudaStream_t s_h2d, s_k, s_d2h;
   cls_slot slot[NSLOT];
   size_t cap_reads = 0, cap_bases = 0;
-  bool cap_paired = false, cap_hits = false;
+  bool cap_paired = false, cap_hits = false, cap_packed = false;
   unsigned long long* d_cursor = nullptr;
   uint32_t* d_err = nullptr;
   unsigned long long* d_stats = nullptr;  // [0] probes, [1] merged hits, accumulated over launches
@@ -818,8 +836,9 @@ extern "C" int slk_classifier_create(slk_index* idx, slk_classifier** out) {
 }
 static void slot_free(cls_slot& s) {
   cudaFree(s.bases1); cudaFree(s.bases2); cudaFree(s.off1); cudaFree(s.off2); cudaFree(s.taxon); cudaFree(s.flags);
-  cudaFree(s.detail); cudaFree(s.hits);
+  cudaFree(s.detail); cudaFree(s.hits); cudaFree(s.mask1); cudaFree(s.mask2); cudaFree(s.len1); cudaFree(s.len2);
   s.bases1 = s.bases2 = nullptr; s.off1 = s.off2 = nullptr; s.taxon = nullptr; s.flags = nullptr; s.detail = nullptr; s.hits = nullptr;
+  s.mask1 = s.mask2 = s.len1 = s.len2 = nullptr;
 }
 extern "C" void slk_classifier_destroy(slk_classifier* c) {
   if (!c) return;
@@ -898,14 +917,23 @@ extern "C" uint64_t slk_classify_hits_bound(const slk_params* p, uint32_t n_read
   return total_bases + (uint64_t)n_reads * (paired ? 5ull : 3ull);
 }
 
-static void launch_classify(slk_classifier* c, bool hits, const slk_classify_opts* o, const uint8_t* b1, const uint64_t* o1,
-                            uint64_t sh1, const uint8_t* b2, const uint64_t* o2, uint64_t sh2, uint32_t n, int32_t* taxon,
-                            uint8_t* flags, slk_read_detail* detail, slk_hit* hbase, const unsigned long long* hshift,
-                            uint64_t hcap, unsigned long long* cursor) {
+// one mate of a batch as the kernel sees it (device pointers)
+struct mate_dev {
+  const uint8_t* bases = nullptr;    // ASCII bases or code blocks
+  const uint64_t* off = nullptr;     // byte offsets (ASCII) or block offsets (packed)
+  uint64_t shift = 0;                // value of off[] that corresponds to the start of `bases`
+  const uint32_t* mask = nullptr;    // packed only
+  const uint32_t* len = nullptr;     // packed only
+};
+static void launch_classify(slk_classifier* c, bool hits, bool packed, const slk_classify_opts* o, const mate_dev& m1,
+                            const mate_dev& m2, uint32_t n, int32_t* taxon, uint8_t* flags, slk_read_detail* detail,
+                            slk_hit* hbase, const unsigned long long* hshift, uint64_t hcap, unsigned long long* cursor) {
   slk_index* idx = c->idx;
   slk_classify_args a;
   a.sp = idx->sp; a.tb = idx->table; a.tx = idx->dt.view();
-  a.bases1 = b1; a.off1 = o1; a.shift1 = sh1; a.bases2 = b2; a.off2 = o2; a.shift2 = sh2; a.n_reads = n;
+  a.bases1 = m1.bases; a.off1 = m1.off; a.shift1 = m1.shift; a.mask1 = m1.mask; a.len1 = m1.len;
+  a.bases2 = m2.bases; a.off2 = m2.off; a.shift2 = m2.shift; a.mask2 = m2.mask; a.len2 = m2.len;
+  a.packed = packed; a.n_reads = n;
   a.confidence = o->confidence; a.min_hit_groups = o->min_hit_groups;
   a.taxon_out = taxon; a.flags_out = flags; a.detail_out = detail;
   a.hits_base = hbase; a.hits_shift_ptr = hshift; a.hits_cap = hcap; a.hits_cursor = cursor;
@@ -925,25 +953,59 @@ static int check_error_flag(slk_classifier* c) {
   return SLK_OK;
 }
 
-extern "C" int slk_classify_batch_dev(slk_classifier* c, const slk_classify_opts* opts, const uint8_t* bases1,
-                                      const uint64_t* off1, const uint8_t* bases2, const uint64_t* off2, uint32_t n_reads,
-                                      int32_t* taxon_out, uint8_t* flags_out, slk_read_detail* detail_out, slk_hit* hits_out,
-                                      uint64_t hits_cap, uint64_t* hits_used_dev) {
-  if (!c || !opts || !bases1 || !off1 || !taxon_out || !flags_out) return fail(SLK_E_INVALID, "bad arguments");
-  if ((bases2 == nullptr) != (off2 == nullptr)) return fail(SLK_E_INVALID, "bases2/off2 must both be given or both be NULL");
+static int classify_dev_common(slk_classifier* c, const slk_classify_opts* opts, bool packed, const mate_dev& m1,
+                               const mate_dev& m2, uint32_t n_reads, int32_t* taxon_out, uint8_t* flags_out,
+                               slk_read_detail* detail_out, slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_used_dev) {
+  if (!c || !opts || !m1.bases || !m1.off || !taxon_out || !flags_out) return fail(SLK_E_INVALID, "bad arguments");
+  if ((m2.bases == nullptr) != (m2.off == nullptr)) return fail(SLK_E_INVALID, "mate 2 needs both its data and its offsets");
+  if (packed && (!m1.mask || !m1.len || (m2.bases && (!m2.mask || !m2.len))))
+    return fail(SLK_E_INVALID, "packed input needs mask and len arrays");
   bool hits = hits_out != nullptr;
   if (hits && (!detail_out || !hits_used_dev)) return fail(SLK_E_INVALID, "hits_out needs detail_out and hits_used_dev");
   CU(cudaSetDevice(c->ctx->device));
   if (n_reads == 0) return SLK_OK;
   if (hits) CU(cudaMemsetAsync(hits_used_dev, 0, 8, c->s_k));
-  launch_classify(c, hits, opts, bases1, off1, 0, bases2, off2, 0, n_reads, taxon_out, flags_out, detail_out, hits_out, nullptr,
-                  hits_cap, reinterpret_cast<unsigned long long*>(hits_used_dev));
+  launch_classify(c, hits, packed, opts, m1, m2, n_reads, taxon_out, flags_out, detail_out, hits_out, nullptr, hits_cap,
+                  reinterpret_cast<unsigned long long*>(hits_used_dev));
   CU(cudaGetLastError());
   return SLK_OK;
 }
+extern "C" int slk_classify_batch_dev(slk_classifier* c, const slk_classify_opts* opts, const uint8_t* bases1,
+                                      const uint64_t* off1, const uint8_t* bases2, const uint64_t* off2, uint32_t n_reads,
+                                      int32_t* taxon_out, uint8_t* flags_out, slk_read_detail* detail_out, slk_hit* hits_out,
+                                      uint64_t hits_cap, uint64_t* hits_used_dev) {
+  mate_dev m1, m2;
+  m1.bases = bases1; m1.off = off1; m2.bases = bases2; m2.off = off2;
+  return classify_dev_common(c, opts, false, m1, m2, n_reads, taxon_out, flags_out, detail_out, hits_out, hits_cap, hits_used_dev);
+}
+extern "C" int slk_classify_packed_dev(slk_classifier* c, const slk_classify_opts* opts, const uint64_t* codes1,
+                                       const uint32_t* mask1, const uint64_t* boff1, const uint32_t* len1,
+                                       const uint64_t* codes2, const uint32_t* mask2, const uint64_t* boff2,
+                                       const uint32_t* len2, uint32_t n_reads, int32_t* taxon_out, uint8_t* flags_out,
+                                       slk_read_detail* detail_out, slk_hit* hits_out, uint64_t hits_cap,
+                                       uint64_t* hits_used_dev) {
+  mate_dev m1, m2;
+  m1.bases = reinterpret_cast<const uint8_t*>(codes1); m1.off = boff1; m1.mask = mask1; m1.len = len1;
+  m2.bases = reinterpret_cast<const uint8_t*>(codes2); m2.off = boff2; m2.mask = mask2; m2.len = len2;
+  return classify_dev_common(c, opts, true, m1, m2, n_reads, taxon_out, flags_out, detail_out, hits_out, hits_cap, hits_used_dev);
+}
+// K1 as an entry point: ASCII reads already in HBM -> packed blocks (boff_dev = exclusive prefix of ceil(len/32))
+extern "C" int slk_pack_reads_dev(slk_ctx* ctx, const uint8_t* bases_dev, const uint64_t* off_dev, uint32_t n_reads,
+                                  const uint64_t* boff_dev, uint64_t* codes_dev, uint32_t* mask_dev, uint32_t* len_dev) {
+  if (!ctx || !bases_dev || !off_dev || !boff_dev || !codes_dev || !mask_dev || !len_dev) return fail(SLK_E_INVALID, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  if (n_reads == 0) return SLK_OK;
+  pack_reads_kernel<<<(n_reads + 127) / 128, 128, 0, ctx->stream>>>(bases_dev, off_dev, n_reads, boff_dev, codes_dev, mask_dev, len_dev);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SLK_OK;
+}
 
-static int ensure_slots(slk_classifier* c, bool paired, bool hits) {
-  bool need = c->cap_reads == 0 || (paired && !c->cap_paired) || (hits && !c->cap_hits);
+static const uint64_t CH_BLOCKS = CH_BASES / 8;   // packed input: the same buffer holds CH_BLOCKS code blocks
+
+static int ensure_slots(slk_classifier* c, bool paired, bool hits, bool packed) {
+  bool need = c->cap_reads == 0 || (paired && !c->cap_paired) || (hits && !c->cap_hits) || (packed && !c->cap_packed);
+  paired = paired || c->cap_paired; hits = hits || c->cap_hits; packed = packed || c->cap_packed;
   if (!need) return SLK_OK;
   CU(cudaDeviceSynchronize());
   for (int i = 0; i < NSLOT; i++) {
@@ -955,6 +1017,10 @@ static int ensure_slots(slk_classifier* c, bool paired, bool hits) {
       CU(cudaMalloc(&s.bases2, CH_BASES + 64));
       CU(cudaMalloc(&s.off2, ((size_t)CH_READS + 1) * 8));
     }
+    if (packed) {
+      CU(cudaMalloc(&s.mask1, CH_BLOCKS * 4)); CU(cudaMalloc(&s.len1, (size_t)CH_READS * 4));
+      if (paired) { CU(cudaMalloc(&s.mask2, CH_BLOCKS * 4)); CU(cudaMalloc(&s.len2, (size_t)CH_READS * 4)); }
+    }
     CU(cudaMalloc(&s.taxon, (size_t)CH_READS * 4));
     CU(cudaMalloc(&s.flags, CH_READS));
     CU(cudaMalloc(&s.detail, (size_t)CH_READS * sizeof(slk_read_detail)));
@@ -963,7 +1029,7 @@ static int ensure_slots(slk_classifier* c, bool paired, bool hits) {
       CU(cudaMalloc(&s.hits, s.hits_cap * sizeof(slk_hit)));
     }
   }
-  c->cap_reads = CH_READS; c->cap_bases = CH_BASES; c->cap_paired = paired; c->cap_hits = hits;
+  c->cap_reads = CH_READS; c->cap_bases = CH_BASES; c->cap_paired = paired; c->cap_hits = hits; c->cap_packed = packed;
   return SLK_OK;
 }
 
@@ -987,29 +1053,40 @@ static int finalize_slot(slk_classifier* c, cls_slot& s, bool hits, int32_t* tax
   return SLK_OK;
 }
 
-extern "C" int slk_classify_batch(slk_classifier* c, const slk_classify_opts* opts, const uint8_t* bases1, const uint64_t* off1,
-                                  const uint8_t* bases2, const uint64_t* off2, uint32_t n_reads, int32_t* taxon_out,
-                                  uint8_t* flags_out, slk_read_detail* detail_out, slk_hit* hits_out, uint64_t hits_cap,
-                                  uint64_t* hits_used) {
-  if (!c || !opts || !bases1 || !off1 || !taxon_out || !flags_out) return fail(SLK_E_INVALID, "bad arguments");
-  if ((bases2 == nullptr) != (off2 == nullptr)) return fail(SLK_E_INVALID, "bases2/off2 must both be given or both be NULL");
-  bool hits = hits_out != nullptr, paired = bases2 != nullptr;
+// one mate of a batch in HOST memory, either input form
+struct mate_host {
+  const uint8_t* bases = nullptr;    // ASCII
+  const uint64_t* codes = nullptr;   // packed
+  const uint32_t* mask = nullptr;
+  const uint32_t* len = nullptr;
+  const uint64_t* off = nullptr;     // byte offsets (ASCII) or block offsets (packed), n+1 entries
+};
+
+// The chunked, triple-buffered H2D -> kernel -> D2H pipeline behind both host-buffer entry points.
+static int classify_host_common(slk_classifier* c, const slk_classify_opts* opts, bool packed, const mate_host& h1,
+                                const mate_host& h2, uint32_t n_reads, int32_t* taxon_out, uint8_t* flags_out,
+                                slk_read_detail* detail_out, slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_used) {
+  if (!c || !opts || !h1.off || !taxon_out || !flags_out) return fail(SLK_E_INVALID, "bad arguments");
+  const bool paired = h2.off != nullptr, hits = hits_out != nullptr;
+  if (packed ? (!h1.codes || !h1.mask || !h1.len || (paired && (!h2.codes || !h2.mask || !h2.len))) : (!h1.bases || (paired && !h2.bases)))
+    return fail(SLK_E_INVALID, "missing input arrays");
   if (hits && !detail_out) return fail(SLK_E_INVALID, "hits_out needs detail_out");
   if (hits_used) *hits_used = 0;
   CU(cudaSetDevice(c->ctx->device));
   if (n_reads == 0) return SLK_OK;
-  TRY(ensure_slots(c, paired, hits));
+  TRY(ensure_slots(c, paired, hits, packed));
   CU(cudaMemsetAsync(c->d_cursor, 0, 8, c->s_k));
+  const uint64_t unit_cap = packed ? CH_BLOCKS : CH_BASES;   // offsets count blocks or bytes
   uint64_t hits_total = 0;
   bool nospace = false;
   int prev = -1, ci = 0;
   uint32_t r0 = 0;
   while (r0 < n_reads) {
-    // chunk [r0, r1): bounded by reads and by bases of either mate
-    uint32_t r1 = std::min<uint64_t>(n_reads, (uint64_t)r0 + CH_READS);
+    // chunk [r0, r1): bounded by reads and by the data volume of either mate
+    uint32_t r1 = (uint32_t)std::min<uint64_t>(n_reads, (uint64_t)r0 + CH_READS);
     auto fits = [&](uint32_t e) {
-      if (off1[e] - off1[r0] > CH_BASES) return false;
-      if (paired && off2[e] - off2[r0] > CH_BASES) return false;
+      if (h1.off[e] - h1.off[r0] > unit_cap) return false;
+      if (paired && h2.off[e] - h2.off[r0] > unit_cap) return false;
       return true;
     };
     if (!fits(r1)) {
@@ -1021,19 +1098,30 @@ extern "C" int slk_classify_batch(slk_classifier* c, const slk_classify_opts* op
     cls_slot& s = c->slot[ci % NSLOT];
     if (s.busy) { CU(cudaEventSynchronize(s.d2h_done)); s.busy = false; }
     s.r0 = r0; s.n = r1 - r0;
-    uint64_t b1 = off1[r1] - off1[r0];
-    CU(cudaMemcpyAsync(s.bases1, bases1 + off1[r0], b1, cudaMemcpyHostToDevice, c->s_h2d));
-    CU(cudaMemcpyAsync(s.off1, off1 + r0, ((size_t)s.n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d));
-    if (paired) {
-      uint64_t b2 = off2[r1] - off2[r0];
-      CU(cudaMemcpyAsync(s.bases2, bases2 + off2[r0], b2, cudaMemcpyHostToDevice, c->s_h2d));
-      CU(cudaMemcpyAsync(s.off2, off2 + r0, ((size_t)s.n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d));
+    mate_dev d1, d2;
+    for (int mt = 0; mt < (paired ? 2 : 1); mt++) {
+      const mate_host& h = mt ? h2 : h1;
+      mate_dev& d = mt ? d2 : d1;
+      uint8_t* dbases = mt ? s.bases2 : s.bases1;
+      uint64_t* doff = mt ? s.off2 : s.off1;
+      const uint64_t u0 = h.off[r0], units = h.off[r1] - u0;
+      if (packed) {
+        uint32_t* dmask = mt ? s.mask2 : s.mask1;
+        uint32_t* dlen = mt ? s.len2 : s.len1;
+        CU(cudaMemcpyAsync(dbases, h.codes + u0, units * 8, cudaMemcpyHostToDevice, c->s_h2d));
+        CU(cudaMemcpyAsync(dmask, h.mask + u0, units * 4, cudaMemcpyHostToDevice, c->s_h2d));
+        CU(cudaMemcpyAsync(dlen, h.len + r0, (size_t)s.n * 4, cudaMemcpyHostToDevice, c->s_h2d));
+        d.mask = dmask; d.len = dlen;
+      } else {
+        CU(cudaMemcpyAsync(dbases, h.bases + u0, units, cudaMemcpyHostToDevice, c->s_h2d));
+      }
+      CU(cudaMemcpyAsync(doff, h.off + r0, ((size_t)s.n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d));
+      d.bases = dbases; d.off = doff; d.shift = u0;
     }
     CU(cudaEventRecord(s.h2d_done, c->s_h2d));
     CU(cudaStreamWaitEvent(c->s_k, s.h2d_done, 0));
     if (hits) snapshot_kernel<<<1, 1, 0, c->s_k>>>(c->d_cursor, s.d_range);
-    launch_classify(c, hits, opts, s.bases1, s.off1, off1[r0], s.bases2, s.off2, paired ? off2[r0] : 0, s.n, s.taxon, s.flags,
-                    s.detail, s.hits, s.d_range, s.hits_cap, c->d_cursor);
+    launch_classify(c, hits, packed, opts, d1, d2, s.n, s.taxon, s.flags, s.detail, s.hits, s.d_range, s.hits_cap, c->d_cursor);
     CU(cudaGetLastError());
     if (hits) {
       snapshot_kernel<<<1, 1, 0, c->s_k>>>(c->d_cursor, s.d_range + 1);
@@ -1056,4 +1144,25 @@ extern "C" int slk_classify_batch(slk_classifier* c, const slk_classify_opts* op
   TRY(check_error_flag(c));
   if (nospace) return fail(SLK_E_NOSPACE, "hits_out needs room for %llu hits", (unsigned long long)hits_total);
   return SLK_OK;
+}
+
+extern "C" int slk_classify_batch(slk_classifier* c, const slk_classify_opts* opts, const uint8_t* bases1, const uint64_t* off1,
+                                  const uint8_t* bases2, const uint64_t* off2, uint32_t n_reads, int32_t* taxon_out,
+                                  uint8_t* flags_out, slk_read_detail* detail_out, slk_hit* hits_out, uint64_t hits_cap,
+                                  uint64_t* hits_used) {
+  if ((bases2 == nullptr) != (off2 == nullptr)) return fail(SLK_E_INVALID, "bases2/off2 must both be given or both be NULL");
+  mate_host h1, h2;
+  h1.bases = bases1; h1.off = off1; h2.bases = bases2; h2.off = off2;
+  return classify_host_common(c, opts, false, h1, h2, n_reads, taxon_out, flags_out, detail_out, hits_out, hits_cap, hits_used);
+}
+extern "C" int slk_classify_batch_packed(slk_classifier* c, const slk_classify_opts* opts, const uint64_t* codes1,
+                                         const uint32_t* mask1, const uint64_t* boff1, const uint32_t* len1,
+                                         const uint64_t* codes2, const uint32_t* mask2, const uint64_t* boff2,
+                                         const uint32_t* len2, uint32_t n_reads, int32_t* taxon_out, uint8_t* flags_out,
+                                         slk_read_detail* detail_out, slk_hit* hits_out, uint64_t hits_cap,
+                                         uint64_t* hits_used) {
+  mate_host h1, h2;
+  h1.codes = codes1; h1.mask = mask1; h1.off = boff1; h1.len = len1;
+  h2.codes = codes2; h2.mask = mask2; h2.off = boff2; h2.len = len2;
+  return classify_host_common(c, opts, true, h1, h2, n_reads, taxon_out, flags_out, detail_out, hits_out, hits_cap, hits_used);
 }

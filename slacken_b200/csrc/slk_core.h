@@ -93,6 +93,8 @@ SLK_HD int slk_make_scan_params(int k, int m, int spaces, uint64_t toggle_mask, 
 struct slk_table_view {
   uint64_t* cells;     // n_buckets * 4 cells of (compressed key << 16 | dense taxon); 0 = empty
   uint64_t n_buckets;  // one bucket = one 32-byte sector
+  uint32_t prefetch;   // issue an L2 prefetch for every bucket of a batch before probing it
+  uint32_t pad_;
 };
 
 struct slk_tax_view {
@@ -287,6 +289,18 @@ struct slk_scanner {
   }
 };
 
+// One mate of a fragment, in either of the two input forms of the C ABI:
+//  * ASCII: `ascii[0..len)`, one byte per base;
+//  * packed: 32-base blocks, block b = bases 32b..32b+31 of the read; base i of a block sits in bits [2i, 2i+1] of
+//    codes[b] (A=0 C=1 G=2 T/U=3) and bit i of mask[b] is set when that character is ambiguous (its code bits are 0).
+//    Every read starts a new block, so a batch is three flat arrays plus block offsets and lengths.
+struct slk_read_src {
+  const uint8_t* ascii;
+  const uint64_t* codes;
+  const uint32_t* mask;
+  uint32_t len;
+};
+
 // Span entries: one per super-mer (SEQ), per run of >= k ambiguous bases (AMB) and per mate border.
 #define SLK_E_SEQ 0u
 #define SLK_E_AMB 1u
@@ -323,10 +337,10 @@ struct slk_store_local {
 
 template <int W, class Sink, class Entries>
 struct slk_frag_classifier {
-  const slk_table_view& tb;
-  const slk_tax_view& tx;
+  const slk_table_view tb;   // by value: the hot loops copy what they need into registers anyway
+  const slk_tax_view tx;
   Sink& sink;
-  Entries& ent;
+  Entries ent;
 
   // per-fragment state of the drain side
   uint64_t last_seq_key;
@@ -346,7 +360,7 @@ struct slk_frag_classifier {
   uint32_t nk;
   bool overflow;
 
-  SLK_HD slk_frag_classifier(const slk_table_view& tb_, const slk_tax_view& tx_, Sink& s, Entries& e)
+  SLK_HD slk_frag_classifier(const slk_table_view& tb_, const slk_tax_view& tx_, Sink& s, const Entries& e)
       : tb(tb_), tx(tx_), sink(s), ent(e) {}
 
   SLK_HD void hist_add(uint32_t t, int32_t c) {
@@ -396,9 +410,15 @@ struct slk_frag_classifier {
   // same time. Its running state is copied into registers for the duration of the call, because stores through
   // the entry/sink pointers could otherwise alias the members and force a reload per entry.
   SLK_HD_NOINLINE void drain(const slk_scan_params& sp, uint32_t ne) {
+    const slk_table_view tb = this->tb;   // registers, not members behind `this`
+#if defined(__CUDA_ARCH__)
+    const Entries ent = this->ent;
+#else
+    const Entries& ent = this->ent;
+#endif
     // all buckets of this batch are requested from HBM first, so the probes below find them in L2
     for (uint32_t j = 0; j < ne; j++)
-      if ((ent.get_meta(j) >> 14) == SLK_E_SEQ) slk_prefetch_bucket(tb, slk_compress(sp, ent.get_key(j)));
+      if (tb.prefetch && (ent.get_meta(j) >> 14) == SLK_E_SEQ) slk_prefetch_bucket(tb, slk_compress(sp, ent.get_key(j)));
     uint64_t l_last = last_seq_key;
     bool l_have_last = have_last_seq, l_have_cur = have_cur;
     int32_t l_label = cur_label, l_count = cur_count;
@@ -482,11 +502,12 @@ struct slk_frag_classifier {
     return max_taxon;
   }
 
-  // One fragment end to end. s2 == nullptr for single-end reads.
+  // One fragment end to end (paired == false: r2 is ignored).
   // Scan: Supermers.splitByAmbiguity/splitFragment (slacken/Supermers.scala:113-189): valid runs >= k are cut into
   // super-mers (runs of k-mer windows with equal minimizer), runs of >= k ambiguous characters become one
   // AMBIGUOUS span of len-(k-1), anything shorter vanishes; the mates are separated by a MATE_PAIR_BORDER span.
-  SLK_HD void run(const slk_scan_params& sp, const uint8_t* s1, uint32_t len1, const uint8_t* s2, uint32_t len2,
+  template <bool PACKED>
+  SLK_HD void run(const slk_scan_params& sp, const slk_read_src& r1, const slk_read_src& r2, bool paired,
                   double confidence, int32_t min_hit_groups, slk_frag_result& r) {
     have_last_seq = false; last_seq_key = 0; have_cur = false; cur_label = 0; cur_count = 0; nh = 0; nh_spilled = 0;
     mate = 0; kmers[0] = 0; kmers[1] = 0; nd = 0; nk = 0; overflow = false; nprobes = 0;
@@ -494,30 +515,33 @@ struct slk_frag_classifier {
     const int fshift = sp.fshift;
     const uint64_t mmask = sp.mmask, xor_mask = sp.xor_mask, sig_mask = sp.sig_mask;
     const bool canonical = sp.canonical != 0;
-    windows_left = (len1 > km1 ? len1 - km1 : 0) + (s2 ? (len2 > km1 ? len2 - km1 : 0) + 1 : 0);
+    windows_left = (r1.len > km1 ? r1.len - km1 : 0) + (paired ? (r2.len > km1 ? r2.len - km1 : 0) + 1 : 0);
     uint32_t ne = 0;       // buffered entries (register)
     bool any = false;      // did the fragment yield any span at all
-#pragma unroll 1
-    for (int mt = 0; mt < (s2 ? 2 : 1); mt++) {  // one copy of the scan loop serves both mates
-      if (mt) {
 #if defined(__CUDA_ARCH__)
-        const bool full = __any_sync(0xffffffffu, ne > SLK_ECAP - 5);
+    const Entries ent = this->ent;   // the three shared-space addresses, in registers
+#define SLK_WARP_ANY(p) __any_sync(0xffffffffu, (p))
+#define SLK_WARP_MAX(x) __reduce_max_sync(0xffffffffu, (x))
 #else
-        const bool full = ne > SLK_ECAP - 5;
+    Entries& ent = this->ent;
+#define SLK_WARP_ANY(p) (p)
+#define SLK_WARP_MAX(x) (x)
 #endif
-        if (full) { any = any || ne != 0; drain(sp, ne); ne = 0; }
+#pragma unroll 1
+    for (int mt = 0; mt < (paired ? 2 : 1); mt++) {  // one copy of the scan loop serves both mates
+      if (mt) {
+        if (SLK_WARP_ANY(ne > SLK_ECAP - 5)) { any = any || ne != 0; drain(sp, ne); ne = 0; }
         ent.set(ne, 0, SLK_E_BORDER << 14); ne++;
       }
-      const uint8_t* s = mt ? s2 : s1;
-      const uint32_t len = mt ? len2 : len1;
+      const slk_read_src& src = mt ? r2 : r1;
+      const uint32_t len = src.len;
       slk_scanner<W> sc;
       sc.reset();
       uint64_t run_key = 0;
       uint32_t run_cnt = 0, ninv = 0, amb_cnt = 0;
       bool in_run = false;
-      // One character. Straight-line code: at most one entry is stored per character.
-      auto step = [&](uint32_t ch) {
-        const uint32_t c = slk_code(ch);
+      // One character (c = 0..3 for a base, 4 for anything else). Straight-line code: at most one entry is stored.
+      auto step = [&](uint32_t c) {
         const bool valid = c < 4u;
         uint64_t mn;
         const bool window_ok = sc.push(c, k, fshift, mmask, xor_mask, sig_mask, canonical, &mn);
@@ -536,46 +560,72 @@ struct slk_frag_classifier {
         run_key = start_new ? mn : run_key;
         in_run = valid && (in_run || start_new);
       };
+      // All lanes of a warp run the same number of iterations (the longest read of the warp decides) and drain
+      // together as soon as one lane's entry tile is nearly full, so the warp never splits around drain().
+      if (PACKED) {
+        const uint32_t nblk = (len + 31u) >> 5;
+        const uint32_t nblk_w = SLK_WARP_MAX(nblk);
+        for (uint32_t b = 0; b < nblk_w; b++) {
+          uint64_t cw = 0;
+          uint32_t mw = 0, nb = 0;
+          if (b < nblk) {
 #if defined(__CUDA_ARCH__)
-      // 16-byte aligned vector loads over [s, s+len). The buffer is readable up to the next 16-byte boundary
-      // (library-owned and cudaMalloc'ed buffers are); bytes outside the read are skipped in the edge chunks.
-      // All 32 lanes of the warp run the same number of iterations (the longest read of the warp decides) and
-      // drain together as soon as one lane's entry tile is nearly full, so the warp never splits around drain().
-      const uintptr_t a0 = reinterpret_cast<uintptr_t>(s);
-      const uintptr_t abase = a0 & ~(uintptr_t)15;
-      const int32_t lo0 = (int32_t)(a0 - abase), total = lo0 + (int32_t)len;  // byte range [lo0, total) from abase
-      const int32_t total_w = (int32_t)__reduce_max_sync(0xffffffffu, (uint32_t)total);
-      for (int32_t cb = 0; cb < total_w; cb += 16) {
-        const bool have = cb < total;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (have) v = __ldg(reinterpret_cast<const uint4*>(abase + cb));
-        const bool interior = cb >= lo0 && cb + 16 <= total;
-#pragma unroll 1
-        for (int wi = 0; wi < 4; wi++) {
-          if (__any_sync(0xffffffffu, ne > SLK_ECAP - 5)) {   // 4 characters add at most 4 entries
-            any = any || ne != 0;
-            drain(sp, ne);
-            ne = 0;
+            cw = __ldg(src.codes + b); mw = __ldg(src.mask + b);
+#else
+            cw = src.codes[b]; mw = src.mask[b];
+#endif
+            nb = len - 32u * b; nb = nb > 32u ? 32u : nb;
           }
-          const uint32_t word = wi == 0 ? v.x : wi == 1 ? v.y : wi == 2 ? v.z : v.w;
-          if (interior) {
-#pragma unroll
-            for (int bi = 0; bi < 4; bi++) step((word >> (8 * bi)) & 0xffu);
-          } else if (have) {
 #pragma unroll 1
-            for (int bi = 0; bi < 4; bi++) {
-              const int32_t pos = cb + 4 * wi + bi;
-              if (pos >= lo0 && pos < total) step((word >> (8 * bi)) & 0xffu);
+          for (uint32_t q = 0; q < 8; q++) {
+            if (SLK_WARP_ANY(ne > SLK_ECAP - 5)) { any = any || ne != 0; drain(sp, ne); ne = 0; }  // 4 chars: <= 4 entries
+            const uint32_t g = (uint32_t)(cw >> (8u * q)) & 0xffu, gm = (mw >> (4u * q)) & 0xfu;
+            const uint32_t left = nb > 4u * q ? nb - 4u * q : 0u;
+            if (left >= 4u) {
+#pragma unroll
+              for (uint32_t i = 0; i < 4; i++) step(((g >> (2u * i)) & 3u) | (((gm >> i) & 1u) << 2));
+            } else {
+#pragma unroll 1
+              for (uint32_t i = 0; i < left; i++) step(((g >> (2u * i)) & 3u) | (((gm >> i) & 1u) << 2));
             }
           }
         }
-      }
+      } else {
+#if defined(__CUDA_ARCH__)
+        // 16-byte aligned vector loads over [s, s+len). The buffer is readable up to the next 16-byte boundary
+        // (library-owned and cudaMalloc'ed buffers are); bytes outside the read are skipped in the edge chunks.
+        const uintptr_t a0 = reinterpret_cast<uintptr_t>(src.ascii);
+        const uintptr_t abase = a0 & ~(uintptr_t)15;
+        const int32_t lo0 = (int32_t)(a0 - abase), total = lo0 + (int32_t)len;  // byte range [lo0, total) from abase
+        const int32_t total_w = (int32_t)SLK_WARP_MAX((uint32_t)total);
+        for (int32_t cb = 0; cb < total_w; cb += 16) {
+          const bool have = cb < total;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (have) v = __ldg(reinterpret_cast<const uint4*>(abase + cb));
+          const bool interior = cb >= lo0 && cb + 16 <= total;
+#pragma unroll 1
+          for (int wi = 0; wi < 4; wi++) {
+            if (SLK_WARP_ANY(ne > SLK_ECAP - 5)) { any = any || ne != 0; drain(sp, ne); ne = 0; }
+            const uint32_t word = wi == 0 ? v.x : wi == 1 ? v.y : wi == 2 ? v.z : v.w;
+            if (interior) {
+#pragma unroll
+              for (int bi = 0; bi < 4; bi++) step(slk_code((word >> (8 * bi)) & 0xffu));
+            } else if (have) {
+#pragma unroll 1
+              for (int bi = 0; bi < 4; bi++) {
+                const int32_t pos = cb + 4 * wi + bi;
+                if (pos >= lo0 && pos < total) step(slk_code((word >> (8 * bi)) & 0xffu));
+              }
+            }
+          }
+        }
 #else
-      for (uint32_t i = 0; i < len; i++) {
-        if ((i & 3) == 0 && ne > SLK_ECAP - 5) { any = true; drain(sp, ne); ne = 0; }
-        step(s[i]);
-      }
+        for (uint32_t i = 0; i < len; i++) {
+          if ((i & 3) == 0 && ne > SLK_ECAP - 5) { any = true; drain(sp, ne); ne = 0; }
+          step(slk_code(src.ascii[i]));
+        }
 #endif
+      }
       // mate end: at most one pending entry (a run and an ambiguous stretch cannot both be open)
       if (in_run) { ent.set(ne, run_key, run_cnt); ne++; }
       if (amb_cnt) { ent.set(ne, 0, amb_cnt | (SLK_E_AMB << 14)); ne++; }
@@ -590,8 +640,25 @@ struct slk_frag_classifier {
     r.flags = (classified ? SLK_F_CLASSIFIED : 0u) | (any ? SLK_F_HAS_SPAN : 0u) | (overflow ? SLK_F_OVERFLOW : 0u);
     r.kmers1 = kmers[0]; r.kmers2 = kmers[1];
     r.num_distinct = nd; r.n_hits = nh + nh_spilled; r.n_probes = nprobes;
+#undef SLK_WARP_ANY
+#undef SLK_WARP_MAX
   }
 };
+
+// K1 as a stand-alone step: ASCII -> 2-bit codes + ambiguity mask in the packed block layout of slk_read_src.
+// `emit(block index, codes, mask)` is called for every 32-base block of the read.
+template <class Emit>
+SLK_HD void slk_pack_read(const uint8_t* s, uint32_t len, Emit&& emit) {
+  uint64_t cw = 0;
+  uint32_t mw = 0, i = 0, b = 0;
+  slk_for_each_byte(s, len, [&](uint32_t ch) {
+    const uint32_t c = slk_code(ch);
+    cw |= (uint64_t)(c & 3u) << (2u * i);
+    mw |= (c >> 2) << i;
+    if (++i == 32u) { emit(b, cw, mw); b++; cw = 0; mw = 0; i = 0; }
+  });
+  if (i) emit(b, cw, mw);
+}
 
 // ------------------------------------------------------------------------------------------------ build side
 // SplitterMinimizers.find (slacken/Minimizers.scala:43-76): every super-mer of a genome fragment contributes

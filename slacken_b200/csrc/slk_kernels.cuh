@@ -12,10 +12,14 @@
 
 #define BUILD_WPT 96  // k-mer windows scanned per thread of the build-side emit kernel
 
+// ASCII input: bases*/off* (+shift: offsets are absolute in the caller's buffer, the device buffer starts at `shift`).
+// Packed input: bases* point at the uint64 code blocks, mask* at the uint32 masks, off* are block offsets, len* the
+// read lengths in bases.
 struct slk_classify_args {
   slk_scan_params sp; slk_table_view tb; slk_tax_view tx;
   const uint8_t* bases1; const uint64_t* off1; uint64_t shift1;
   const uint8_t* bases2; const uint64_t* off2; uint64_t shift2;
+  const uint32_t* mask1; const uint32_t* len1; const uint32_t* mask2; const uint32_t* len2; bool packed;
   uint32_t n_reads; double confidence; int32_t min_hit_groups;
   int32_t* taxon_out; uint8_t* flags_out; slk_read_detail* detail_out;
   slk_hit* hits_base; const unsigned long long* hits_shift_ptr; uint64_t hits_cap; unsigned long long* hits_cursor;
@@ -85,17 +89,31 @@ __global__ void __launch_bounds__(128) emit_cells_kernel(const __grid_constant__
 // ---------------------------------------------------------------------------------------------- classify kernel
 // Per-thread fast store: columns of shared-memory tiles [*][128] (conflict-free for a warp whose lanes use the
 // same row, never evicted, and -- unlike local memory -- one 4-byte access by a lone lane costs 4 bytes, not a sector).
+// It holds 32-bit shared-space addresses and uses ld.shared / st.shared explicitly: with generic pointers the
+// compiler must assume that every store may alias the pointers themselves and reloads them around each access.
 struct dev_store {
-  uint64_t* key;   // &skey[0][threadIdx.x]
-  uint16_t* meta;  // &smeta[0][threadIdx.x]
-  int2* hit;       // &shit[0][threadIdx.x]
-  __device__ __forceinline__ void set(uint32_t j, uint64_t k, uint32_t m) { key[j * 128] = k; meta[j * 128] = (uint16_t)m; }
-  __device__ __forceinline__ uint64_t get_key(uint32_t j) const { return key[j * 128]; }
-  __device__ __forceinline__ uint32_t get_meta(uint32_t j) const { return meta[j * 128]; }
-  __device__ __forceinline__ void set_hit(uint32_t i, int32_t label, int32_t count) { hit[i * 128] = make_int2(label, count); }
+  uint32_t key, meta, hit;   // shared-space byte addresses of this thread's columns
+  __device__ __forceinline__ void set(uint32_t j, uint64_t k, uint32_t m) const {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(key + j * 1024u), "l"(k));
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(meta + j * 256u), "h"((uint16_t)m));
+  }
+  __device__ __forceinline__ uint64_t get_key(uint32_t j) const {
+    uint64_t k;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(k) : "r"(key + j * 1024u));
+    return k;
+  }
+  __device__ __forceinline__ uint32_t get_meta(uint32_t j) const {
+    uint16_t m;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(m) : "r"(meta + j * 256u));
+    return m;
+  }
+  __device__ __forceinline__ void set_hit(uint32_t i, int32_t label, int32_t count) const {
+    asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(hit + i * 1024u), "r"(label), "r"(count));
+  }
   __device__ __forceinline__ void get_hit(uint32_t i, int32_t* label, int32_t* count) const {
-    int2 h = hit[i * 128];
-    *label = h.x; *count = h.y;
+    int32_t l, c;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(l), "=r"(c) : "r"(hit + i * 1024u));
+    *label = l; *count = c;
   }
 };
 
@@ -125,14 +143,19 @@ struct dev_hit_sink {
   }
 };
 
-template <int W, bool HITS>
-__global__ void __launch_bounds__(128) classify_kernel(const __grid_constant__ slk_scan_params sp,
+#ifndef SLK_CLS_MINB
+#define SLK_CLS_MINB 6   // 80 registers: measured best on B200 (96 regs/5 blocks: +4% time, 64 regs: spills, 3.5x slower)
+#endif
+template <int W, bool HITS, bool PACKED>
+__global__ void __launch_bounds__(128, SLK_CLS_MINB) classify_kernel(const __grid_constant__ slk_scan_params sp,
                                                        const __grid_constant__ slk_table_view tb,
                                                        const __grid_constant__ slk_tax_view tx,
                                                        const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ off1,
                                                        uint64_t shift1, const uint8_t* __restrict__ bases2,
-                                                       const uint64_t* __restrict__ off2, uint64_t shift2, uint32_t n_reads,
-                                                       double confidence, int32_t min_hit_groups,
+                                                       const uint64_t* __restrict__ off2, uint64_t shift2,
+                                                       const uint32_t* __restrict__ mask1, const uint32_t* __restrict__ len1,
+                                                       const uint32_t* __restrict__ mask2, const uint32_t* __restrict__ len2,
+                                                       uint32_t n_reads, double confidence, int32_t min_hit_groups,
                                                        int32_t* __restrict__ taxon_out, uint8_t* __restrict__ flags_out,
                                                        slk_read_detail* __restrict__ detail_out, slk_hit* hits_base,
                                                        const unsigned long long* hits_shift_ptr, uint64_t hits_cap,
@@ -147,7 +170,9 @@ __global__ void __launch_bounds__(128) classify_kernel(const __grid_constant__ s
   __shared__ uint16_t smeta[SLK_ECAP][128];
   __shared__ int2 shit[SLK_SHITS][128];
   dev_store ent;
-  ent.key = &skey[0][threadIdx.x]; ent.meta = &smeta[0][threadIdx.x]; ent.hit = &shit[0][threadIdx.x];
+  ent.key = (uint32_t)__cvta_generic_to_shared(&skey[0][threadIdx.x]);
+  ent.meta = (uint32_t)__cvta_generic_to_shared(&smeta[0][threadIdx.x]);
+  ent.hit = (uint32_t)__cvta_generic_to_shared(&shit[0][threadIdx.x]);
   sink_t sink;
   if constexpr (HITS) {
     sink.n = 0; sink.spilled = false; sink.goff = 0; sink.gbase = hits_base;
@@ -158,18 +183,27 @@ __global__ void __launch_bounds__(128) classify_kernel(const __grid_constant__ s
   {
     // every lane runs the classifier (lanes past the end of the batch get an empty read) so that the warp-wide
     // votes inside run() always see 32 participants
-    const uint8_t* p1 = bases1;
-    const uint8_t* p2 = bases2;
-    uint32_t l1 = 0, l2 = 0;
+    slk_read_src r1, r2;
+    r1.ascii = bases1; r1.codes = reinterpret_cast<const uint64_t*>(bases1); r1.mask = mask1; r1.len = 0;
+    r2.ascii = bases2; r2.codes = reinterpret_cast<const uint64_t*>(bases2); r2.mask = mask2; r2.len = 0;
     if (active) {
-      uint64_t s1 = off1[r], e1 = off1[r + 1];
-      p1 = bases1 + (s1 - shift1); l1 = (uint32_t)(e1 - s1);
-      if (bases2) {
-        uint64_t s2 = off2[r], e2 = off2[r + 1];
-        p2 = bases2 + (s2 - shift2); l2 = (uint32_t)(e2 - s2);
+      if (PACKED) {
+        const uint64_t b1 = off1[r] - shift1;
+        r1.codes += b1; r1.mask += b1; r1.len = len1[r];
+        if (bases2) {
+          const uint64_t b2 = off2[r] - shift2;
+          r2.codes += b2; r2.mask += b2; r2.len = len2[r];
+        }
+      } else {
+        const uint64_t s1 = off1[r], e1 = off1[r + 1];
+        r1.ascii = bases1 + (s1 - shift1); r1.len = (uint32_t)(e1 - s1);
+        if (bases2) {
+          const uint64_t s2 = off2[r], e2 = off2[r + 1];
+          r2.ascii = bases2 + (s2 - shift2); r2.len = (uint32_t)(e2 - s2);
+        }
       }
     }
-    cl.run(sp, p1, l1, p2, l2, confidence, min_hit_groups, res);
+    cl.template run<PACKED>(sp, r1, r2, bases2 != nullptr, confidence, min_hit_groups, res);
     if (active) {
       taxon_out[r] = res.taxon;
       flags_out[r] = (uint8_t)(res.flags & 3u);

@@ -73,6 +73,13 @@ class GpuContext:
         src = np.ascontiguousarray(src)
         check(self._L.slk_memcpy_h2d(self.h, C.c_void_p(dst), _ptr(src), src.nbytes))
 
+    def pack_reads_dev(self, bases_dev: int, off_dev: int, n_reads: int, boff_dev: int, codes_dev: int, mask_dev: int,
+                       len_dev: int):
+        """Stage 1 on the device: ASCII reads in HBM -> packed blocks in HBM."""
+        v = C.c_void_p
+        check(self._L.slk_pack_reads_dev(self.h, v(bases_dev), v(off_dev), n_reads, v(boff_dev), v(codes_dev), v(mask_dev),
+                                         v(len_dev)))
+
     def d2h(self, dst: np.ndarray, src: int):
         assert dst.flags["C_CONTIGUOUS"]
         check(self._L.slk_memcpy_d2h(self.h, _ptr(dst), C.c_void_p(src), dst.nbytes))
@@ -345,6 +352,38 @@ class Classifier:
         out.hits_used = int(used.value)
         return out
 
+    def classify_packed(self, r1: PackedReads, r2: Optional[PackedReads] = None, confidence: float = 0.0,
+                        min_hit_groups: int = 2, per_read_output: bool = True,
+                        out: Optional[ClassifiedBatch] = None) -> ClassifiedBatch:
+        """The packed-input twin of classify(): 2-bit blocks + ambiguity masks in host memory."""
+        n = len(r1.len)
+        if out is None:
+            hits = None
+            if per_read_output:
+                total = int(r1.len.sum()) + (int(r2.len.sum()) if r2 is not None else 0)
+                hits = np.zeros(self.hits_bound(n, total, r2 is not None), dtype=HIT_DTYPE)
+            out = ClassifiedBatch(np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=DETAIL_DTYPE), hits)
+        opts = ClassifyOpts(float(confidence), int(min_hit_groups), 0)
+        used = C.c_uint64(0)
+        hits = out.hits if per_read_output else None
+        m2 = (r2.codes, r2.mask, r2.boff, r2.len) if r2 is not None else (None, None, None, None)
+        check(self.ctx._L.slk_classify_batch_packed(self.h, C.byref(opts), _ptr(r1.codes), _ptr(r1.mask), _ptr(r1.boff),
+                                                    _ptr(r1.len), _ptr(m2[0]), _ptr(m2[1]), _ptr(m2[2]), _ptr(m2[3]), n,
+                                                    _ptr(out.taxon), _ptr(out.flags), _ptr(out.detail), _ptr(hits),
+                                                    len(hits) if hits is not None else 0, C.byref(used)))
+        out.hits_used = int(used.value)
+        return out
+
+    def classify_packed_dev(self, codes1: int, mask1: int, boff1: int, len1: int, codes2: int, mask2: int, boff2: int,
+                            len2: int, n_reads: int, taxon_out: int, flags_out: int, detail_out: int, hits_out: int,
+                            hits_cap: int, hits_used_dev: int, confidence: float = 0.0, min_hit_groups: int = 2):
+        """Device-resident packed input; every argument is a device address (0 = NULL); asynchronous."""
+        opts = ClassifyOpts(float(confidence), int(min_hit_groups), 0)
+        v = lambda p: C.c_void_p(p) if p else None
+        check(self.ctx._L.slk_classify_packed_dev(self.h, C.byref(opts), v(codes1), v(mask1), v(boff1), v(len1), v(codes2),
+                                                  v(mask2), v(boff2), v(len2), n_reads, v(taxon_out), v(flags_out),
+                                                  v(detail_out), v(hits_out), hits_cap, v(hits_used_dev)))
+
     def classify_dev(self, bases1: int, off1: int, bases2: int, off2: int, n_reads: int, taxon_out: int, flags_out: int,
                      detail_out: int, hits_out: int, hits_cap: int, hits_used_dev: int, confidence: float = 0.0,
                      min_hit_groups: int = 2):
@@ -376,6 +415,57 @@ class Classifier:
         if getattr(self, "h", None):
             self.ctx._L.slk_classifier_destroy(self.h)
             self.h = None
+
+
+_CODE = np.full(256, 4, dtype=np.uint8)
+for _ch, _c in ((b"Aa", 0), (b"Cc", 1), (b"Gg", 2), (b"TtUu", 3)):
+    for _b in _ch:
+        _CODE[_b] = _c
+
+
+@dataclass
+class PackedReads:
+    """2-bit packed batch (include/slacken_gpu.h, "Packed input"): what the Scala host would fill while it copies the
+    nucleotides of a partition into its pinned buffers."""
+    codes: np.ndarray   # uint64[n_blocks]
+    mask: np.ndarray    # uint32[n_blocks]
+    boff: np.ndarray    # uint64[n+1]
+    len: np.ndarray     # uint32[n]
+
+    @property
+    def nbytes(self) -> int:
+        return self.codes.nbytes + self.mask.nbytes + self.boff.nbytes + self.len.nbytes
+
+
+def block_offsets(off: np.ndarray) -> np.ndarray:
+    """Block offsets of a packed batch: exclusive prefix of ceil(len / 32)."""
+    ln = np.diff(off.astype(np.int64))
+    boff = np.zeros(len(off), dtype=np.uint64)
+    boff[1:] = np.cumsum((ln + 31) // 32)
+    return boff
+
+
+def pack_reads(bases: np.ndarray, off: np.ndarray) -> PackedReads:
+    """Host-side packer (numpy): ASCII bases + offsets -> PackedReads. The JVM binding does the same per character."""
+    off = off.astype(np.int64)
+    n = len(off) - 1
+    ln = np.diff(off)
+    boff = block_offsets(off)
+    nblk = int(boff[-1])
+    code = _CODE[bases[off[0]:off[-1]]]
+    # position of every base inside the padded block layout
+    read_of = np.repeat(np.arange(n), ln)
+    pos_in_read = np.arange(len(code)) - np.repeat(off[:-1] - off[0], ln)
+    slot = boff[:-1].astype(np.int64)[read_of] * 32 + pos_in_read
+    padded_code = np.zeros(nblk * 32, dtype=np.uint64)
+    padded_mask = np.zeros(nblk * 32, dtype=np.uint32)
+    padded_code[slot] = code & 3
+    padded_mask[slot] = code >> 2
+    sh = (2 * np.arange(32, dtype=np.uint64))[None, :]
+    codes = np.bitwise_or.reduce(padded_code.reshape(nblk, 32) << sh, axis=1) if nblk else np.zeros(0, dtype=np.uint64)
+    msh = np.arange(32, dtype=np.uint32)[None, :]
+    mask = np.bitwise_or.reduce(padded_mask.reshape(nblk, 32) << msh, axis=1).astype(np.uint32) if nblk else np.zeros(0, dtype=np.uint32)
+    return PackedReads(np.ascontiguousarray(codes), np.ascontiguousarray(mask), boff, ln.astype(np.uint32))
 
 
 def pack_sequences(seqs):

@@ -49,7 +49,7 @@ def lib():
         L.emu_classify.restype = C.c_int64
         L.emu_classify.argtypes = [C.POINTER(ScanParams), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
-                                   C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+                                   C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
         L.emu_emit_cells.restype = C.c_int64
         L.emu_emit_cells.argtypes = [C.POINTER(ScanParams), C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]
         L.emu_synth_genome.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
@@ -116,7 +116,7 @@ class EmuIndex:
         lib().emu_insert_cells(_p(self.cells), self.n_buckets, _p(self.parent), _p(self.depth), self.dt.root,
                                _p(cells_in), len(cells_in))
 
-    def classify(self, bases1, off1, bases2=None, off2=None, confidence=0.0, min_hit_groups=2):
+    def classify(self, bases1, off1, bases2=None, off2=None, confidence=0.0, min_hit_groups=2, packed=False):
         n = len(off1) - 1
         off1 = np.ascontiguousarray(off1, dtype=np.uint64)
         if bases2 is not None:
@@ -127,7 +127,7 @@ class EmuIndex:
         hit_off = np.zeros(n + 1, dtype=np.uint64)
         used = lib().emu_classify(C.byref(self.sp), _p(self.cells), self.n_buckets, _p(self.parent), _p(self.depth),
                                   _p(self.raw), len(self.raw), self.dt.root, _p(bases1), _p(off1), _p(bases2), _p(off2), n,
-                                  float(confidence), int(min_hit_groups), _p(res), _p(hit_off), _p(hits), cap)
+                                  float(confidence), int(min_hit_groups), _p(res), _p(hit_off), _p(hits), cap, 1 if packed else 0)
         assert used >= 0
         hit_off[n] = used
         return res, hit_off, hits[:used]

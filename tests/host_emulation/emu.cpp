@@ -55,8 +55,8 @@ template <int W>
 static int64_t classify_w(const slk_scan_params* sp, uint64_t* cells, uint64_t n_buckets, const uint16_t* parent,
                           const uint8_t* depth, const int32_t* raw, uint32_t n_dense, uint32_t root, const uint8_t* b1,
                           const uint64_t* o1, const uint8_t* b2, const uint64_t* o2, uint32_t n, double confidence,
-                          int min_hit_groups, emu_result* res, uint64_t* hit_off, slk_hit* hits_out, uint64_t cap) {
-  slk_table_view tb{cells, n_buckets};
+                          int min_hit_groups, emu_result* res, uint64_t* hit_off, slk_hit* hits_out, uint64_t cap, bool packed) {
+  slk_table_view tb{cells, n_buckets, 0, 0};
   slk_tax_view tx{parent, depth, raw, n_dense, root};
   std::vector<slk_hit> hv;
   uint64_t used = 0;
@@ -66,9 +66,21 @@ static int64_t classify_w(const slk_scan_params* sp, uint64_t* cells, uint64_t n
     slk_store_local ent;
     slk_frag_classifier<W, vec_sink, slk_store_local> cl(tb, tx, sink, ent);
     slk_frag_result fr;
-    const uint8_t* p2 = b2 ? b2 + o2[r] : nullptr;
-    cl.run(*sp, b1 + o1[r], (uint32_t)(o1[r + 1] - o1[r]), p2, b2 ? (uint32_t)(o2[r + 1] - o2[r]) : 0, confidence,
-           min_hit_groups, fr);
+    slk_read_src r1{b1 + o1[r], nullptr, nullptr, (uint32_t)(o1[r + 1] - o1[r])};
+    slk_read_src r2{b2 ? b2 + o2[r] : nullptr, nullptr, nullptr, b2 ? (uint32_t)(o2[r + 1] - o2[r]) : 0u};
+    std::vector<uint64_t> c1, c2;
+    std::vector<uint32_t> m1, m2;
+    if (packed) {   // the same read through the packed input form: pack it with the K1 body first
+      slk_pack_read(r1.ascii, r1.len, [&](uint32_t, uint64_t cw, uint32_t mw) { c1.push_back(cw); m1.push_back(mw); });
+      r1.codes = c1.data(); r1.mask = m1.data();
+      if (b2) {
+        slk_pack_read(r2.ascii, r2.len, [&](uint32_t, uint64_t cw, uint32_t mw) { c2.push_back(cw); m2.push_back(mw); });
+        r2.codes = c2.data(); r2.mask = m2.data();
+      }
+      cl.template run<true>(*sp, r1, r2, b2 != nullptr, confidence, min_hit_groups, fr);
+    } else {
+      cl.template run<false>(*sp, r1, r2, b2 != nullptr, confidence, min_hit_groups, fr);
+    }
     res[r] = emu_result{fr.taxon, fr.flags, fr.kmers1, fr.kmers2, fr.num_distinct, fr.n_hits};
     if (cl.nh_spilled == 0)   // the kernel epilogue: buffered hits leave with raw taxon ids
       for (uint32_t i = 0; i < cl.nh; i++) {
@@ -95,10 +107,11 @@ static int64_t classify_w(const slk_scan_params* sp, uint64_t* cells, uint64_t n
 EMU_API int64_t emu_classify(const slk_scan_params* sp, uint64_t* cells, uint64_t n_buckets, const uint16_t* parent,
                              const uint8_t* depth, const int32_t* raw, uint32_t n_dense, uint32_t root, const uint8_t* b1,
                              const uint64_t* o1, const uint8_t* b2, const uint64_t* o2, uint32_t n, double confidence,
-                             int min_hit_groups, emu_result* res, uint64_t* hit_off, slk_hit* hits_out, uint64_t cap) {
+                             int min_hit_groups, emu_result* res, uint64_t* hit_off, slk_hit* hits_out, uint64_t cap,
+                             int packed) {
   int64_t r = -2;
   DISPATCH_W(sp->w, r = classify_w<W_>(sp, cells, n_buckets, parent, depth, raw, n_dense, root, b1, o1, b2, o2, n,
-                                       confidence, min_hit_groups, res, hit_off, hits_out, cap));
+                                       confidence, min_hit_groups, res, hit_off, hits_out, cap, packed != 0));
   return r;
 }
 

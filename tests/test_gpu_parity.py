@@ -5,7 +5,7 @@ import pytest
 
 from oracle import oracle
 from slacken_b200 import Classifier, IndexParams, KeyValueIndex, KrakenReport, ReportCounts, Taxonomy
-from slacken_b200.host import pack_sequences
+from slacken_b200.host import block_offsets, pack_reads, pack_sequences
 from slacken_b200.report import output_line
 from tests.util import chimeric_reads, leaf_taxa, make_taxonomy, random_dna, simulate_reads
 
@@ -102,6 +102,46 @@ def test_classify_long_reads_with_many_hits(gpu):
     got = cls.classify(rb, ro, rb, ro, confidence=0.1)
     res, _, _, per = olib.classify(rb, ro.astype(np.int64), rb, ro.astype(np.int64), confidence=0.1)
     assert_batch_equal(res, per, got, 35)
+    cls.close(); index.close(); tax.close()
+
+
+def test_packed_input_and_device_packer(gpu):
+    """The packed input form (2-bit blocks + ambiguity mask) gives the same results as ASCII, single and paired, and
+    the device-side stage-1 kernel packs exactly like the host packer."""
+    rng, parents, ranks, names, genomes, taxa = make_world(55)
+    p = oracle.params()
+    olib = oracle_lib(p, parents, genomes, taxa)
+    id1, tx = olib.records()
+    tax = Taxonomy(gpu, parents, ranks, names)
+    index = KeyValueIndex.from_records(gpu, tax, IndexParams(), id1, tx)
+    r1 = simulate_reads(rng, genomes, 2000, (1, 200), n_rate=0.2) + [b"", b"N" * 70, b"acgu" * 20]
+    r2 = simulate_reads(rng, genomes, len(r1), (20, 180), n_rate=0.1)
+    b1, o1 = pack_sequences(r1)
+    b2, o2 = pack_sequences(r2)
+    p1, p2 = pack_reads(b1, o1), pack_reads(b2, o2)
+    # device packer == host packer
+    d_b, d_o = gpu.dev_alloc(max(len(b1), 16)), gpu.dev_alloc(o1.nbytes)
+    gpu.h2d(d_b, b1); gpu.h2d(d_o, o1)
+    boff = block_offsets(o1)
+    d_boff, d_codes = gpu.dev_alloc(boff.nbytes), gpu.dev_alloc(max(p1.codes.nbytes, 16))
+    d_mask, d_len = gpu.dev_alloc(max(p1.mask.nbytes, 16)), gpu.dev_alloc(p1.len.nbytes)
+    gpu.h2d(d_boff, boff)
+    gpu.pack_reads_dev(d_b, d_o, len(r1), d_boff, d_codes, d_mask, d_len)
+    codes, mask, ln = np.zeros_like(p1.codes), np.zeros_like(p1.mask), np.zeros_like(p1.len)
+    gpu.d2h(codes, d_codes); gpu.d2h(mask, d_mask); gpu.d2h(ln, d_len)
+    assert np.array_equal(codes, p1.codes) and np.array_equal(mask, p1.mask) and np.array_equal(ln, p1.len)
+    for d in (d_b, d_o, d_boff, d_codes, d_mask, d_len):
+        gpu.dev_free(d)
+    cls = Classifier(index)
+    for conf in (0.0, 0.2):
+        got = cls.classify_packed(p1, confidence=conf)
+        res, _, _, per = olib.classify(b1, o1.astype(np.int64), confidence=conf)
+        assert_batch_equal(res, per, got, 35)
+        got = cls.classify_packed(p1, p2, confidence=conf)
+        res, _, _, per = olib.classify(b1, o1.astype(np.int64), b2, o2.astype(np.int64), confidence=conf)
+        assert_batch_equal(res, per, got, 35)
+    got2 = cls.classify_packed(p1, p2, confidence=0.2, per_read_output=False)
+    assert np.array_equal(got2.taxon, got.taxon) and np.array_equal(got2.flags, got.flags)
     cls.close(); index.close(); tax.close()
 
 

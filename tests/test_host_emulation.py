@@ -29,8 +29,13 @@ def world(seed, k=35, m=31, s=7, canonical=True, n_genomes=16, glen=2500):
 
 
 def compare(lib, ix, rb, ro, rb2=None, ro2=None, confidence=0.0, k=35):
+    for packed in (False, True):   # both input forms of the ABI must give the same answer
+        _compare(lib, ix, rb, ro, rb2, ro2, confidence, k, packed)
+
+
+def _compare(lib, ix, rb, ro, rb2, ro2, confidence, k, packed):
     res, _, _, per = lib.classify(rb, ro, rb2, ro2, confidence=confidence)
-    eres, ehoff, ehits = ix.classify(rb, ro, rb2, ro2, confidence=confidence)
+    eres, ehoff, ehits = ix.classify(rb, ro, rb2, ro2, confidence=confidence, packed=packed)
     assert np.array_equal(res["taxon"], eres["taxon"])
     assert np.array_equal(res["classified"], eres["flags"] & 1)
     assert np.array_equal(res["has_span"], (eres["flags"] >> 1) & 1)
