@@ -214,6 +214,8 @@ SLK_API int slk_memcpy_h2d(slk_ctx* ctx, void* dst_dev, const void* src_host, si
 SLK_API int slk_memcpy_d2h(slk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 SLK_API int slk_memcpy_d2d(slk_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
 SLK_API int slk_ctx_sync(slk_ctx* ctx);
+/* test hook: the library's radix sort (K3a) on a host array, bits [begin_bit, end_bit), stable */
+SLK_API int slk_debug_sort_u64(slk_ctx* ctx, uint64_t* keys, uint64_t n, int begin_bit, int end_bit);
 
 #ifdef __cplusplus
 }

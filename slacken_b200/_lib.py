@@ -85,6 +85,7 @@ SIGNATURES = {
     "slk_dev_free": (None, [_VP, _VP]),
     "slk_memcpy_h2d": (_INT, [_VP, _VP, _VP, C.c_size_t]),
     "slk_memcpy_d2h": (_INT, [_VP, _VP, _VP, C.c_size_t]),
+    "slk_debug_sort_u64": (_INT, [_VP, _VP, _U64, _INT, _INT]),
     "slk_memcpy_d2d": (_INT, [_VP, _VP, _VP, C.c_size_t]),
 }
 

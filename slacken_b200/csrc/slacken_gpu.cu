@@ -326,8 +326,8 @@ __global__ void __launch_bounds__(256) dump_table_kernel(slk_table_view tb, slk_
   }
 }
 
-// K3b: segmented LCA reduce over the sorted cells. The head of every run of equal keys folds the run's taxa
-// (duplicates are adjacent because all 64 bits are sorted) and appends one cell.
+// K3b: segmented LCA reduce over the sorted cells. The head of every run of equal keys folds the run's taxa (in
+// whatever order the stable sort left them: LCA is associative and commutative) and appends one cell.
 __global__ void __launch_bounds__(256) reduce_cells_kernel(const uint64_t* __restrict__ in, uint64_t n, slk_tax_view tx,
                                                            uint64_t* __restrict__ out, unsigned long long* cursor) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -685,12 +685,13 @@ extern "C" int slk_build_finish(slk_builder* b, slk_index** out) {
     return fail(e_ == cudaErrorMemoryAllocation ? SLK_E_NOMEM : SLK_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
   unsigned long long n_unique = 0;
   if (n > 0) {
-    // K3a: radix sort of the cells (all 64 bits, so equal (key, taxon) pairs become adjacent)
+    // K3a: radix sort of the cells
     CUX(cudaMalloc(&d_sorted, n * 8));
     uint64_t* sorted_ptr = nullptr;
-    rc = slk_sort_u64(b->cells, d_sorted, n, 0, 16 + b->sp.key_bits, ctx->stream, &sorted_ptr);
+    // bits [16, 16+key_bits): only the minimizer has to be ordered, the reduce folds the taxa of a run in any order
+    rc = slk_sort_u64(b->cells, d_sorted, n, 16, 16 + b->sp.key_bits, ctx->stream, &sorted_ptr);
     if (rc != 0) { cleanup(); slk_index_destroy(idx); return fail(SLK_E_CUDA, "radix sort failed (%d)", rc); }
-    b->launches += 8;
+    b->launches += 3 * ((b->sp.key_bits + 7) / 8);
     // K3b: segmented LCA reduce; the other buffer receives the unique cells
     uint64_t* other = sorted_ptr == d_sorted ? b->cells : d_sorted;
     CUX(cudaMalloc(&d_cur, 8));
@@ -899,6 +900,21 @@ extern "C" int slk_event_elapsed_ms(slk_event* start, slk_event* end, float* ms)
   CU(cudaSetDevice(start->device));
   CU(cudaEventSynchronize(end->ev));
   CU(cudaEventElapsedTime(ms, start->ev, end->ev));
+  return SLK_OK;
+}
+// test hook: sort a host array of 64-bit keys on bits [begin_bit, end_bit) with the library's radix sort (stable)
+extern "C" int slk_debug_sort_u64(slk_ctx* ctx, uint64_t* keys, uint64_t n, int begin_bit, int end_bit) {
+  if (!ctx || (!keys && n)) return fail(SLK_E_INVALID, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  if (n == 0) return SLK_OK;
+  uint64_t *a = nullptr, *b = nullptr, *res = nullptr;
+  CU(cudaMalloc(&a, n * 8));
+  CU(cudaMalloc(&b, n * 8));
+  CU(cudaMemcpy(a, keys, n * 8, cudaMemcpyHostToDevice));
+  int rc = slk_sort_u64(a, b, n, begin_bit, end_bit, ctx->stream, &res);
+  if (rc == 0) rc = (int)cudaMemcpy(keys, res, n * 8, cudaMemcpyDeviceToHost);
+  cudaFree(a); cudaFree(b);
+  if (rc != 0) return fail(SLK_E_CUDA, "radix sort failed (%d)", rc);
   return SLK_OK;
 }
 extern "C" int slk_memcpy_d2d(slk_ctx* c, void* dst, const void* src, size_t bytes) {

@@ -268,3 +268,26 @@ def test_chunked_pipeline_many_reads(gpu):
             h = got.hits_of(rep * n + i)
             assert np.array_equal(h["taxon"], per[i]["taxon"]) and np.array_equal(h["count"], per[i]["count"])
     cls.close(); index.close(); tax.close()
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 4096, 4097, 100_003, 3_000_000])
+def test_radix_sort_matches_numpy(gpu, n):
+    """K3a: the hand-written LSD radix sort against numpy, including stability on a partial bit range."""
+    import ctypes as C
+    from slacken_b200._lib import check
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 2**63, n, dtype=np.int64).astype(np.uint64) ^ (rng.integers(0, 2, n).astype(np.uint64) << np.uint64(63))
+    if n > 10:
+        keys[: n // 3] = keys[n // 3: 2 * (n // 3)]          # duplicates
+        keys[-5:] = [0, 2**64 - 1, 0, 2**64 - 1, 1 << 16]
+    a = keys.copy()
+    check(gpu._L.slk_debug_sort_u64(gpu.h, a.ctypes.data_as(C.c_void_p), n, 0, 64))
+    assert np.array_equal(a, np.sort(keys))
+    b = keys.copy()
+    check(gpu._L.slk_debug_sort_u64(gpu.h, b.ctypes.data_as(C.c_void_p), n, 16, 64))
+    want = keys[np.argsort(keys >> np.uint64(16), kind="stable")]   # low 16 bits keep their input order
+    assert np.array_equal(b, want)
+    c = keys.copy()
+    check(gpu._L.slk_debug_sort_u64(gpu.h, c.ctypes.data_as(C.c_void_p), n, 16, 56))
+    want = keys[np.argsort((keys >> np.uint64(16)) & np.uint64((1 << 40) - 1), kind="stable")]
+    assert np.array_equal(c, want)
