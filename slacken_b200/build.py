@@ -20,10 +20,12 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ccbin", "/usr/bin/g++",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]
 WIDTHS = range(1, 9)
-if os.environ.get("SLK_CLS_MINB"):
-    FLAGS = FLAGS + ["-DSLK_CLS_MINB=" + os.environ["SLK_CLS_MINB"]]
-    SO = os.path.join(HERE, "libslacken_gpu_minb" + os.environ["SLK_CLS_MINB"] + ".so")
-    OBJ = OBJ + "_minb" + os.environ["SLK_CLS_MINB"]
+# tuning variants for A/B runs on the GPU box: SLK_VARIANT=name SLK_DEFS="-DSLK_CLS_MINB=5 -DSLK_LOOKUP_ILP=2"
+# builds libslacken_gpu_<name>.so next to the default library; SLK_SO=libslacken_gpu_<name>.so selects it at load time
+if os.environ.get("SLK_VARIANT"):
+    FLAGS = FLAGS + os.environ.get("SLK_DEFS", "").split()
+    SO = os.path.join(HERE, "libslacken_gpu_" + os.environ["SLK_VARIANT"] + ".so")
+    OBJ = OBJ + "_" + os.environ["SLK_VARIANT"]
 
 
 def _sources():

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(256) insert_cells_kernel(const uint64_t* __res
   uint32_t taxon = (uint32_t)(cell & 0xffffu);
   if (taxon == 0) return;  // a record whose taxon is NONE behaves exactly like a missing record
   uint64_t b = slk_bucket_of(ckey, tb.n_buckets);
-  for (uint64_t tries = 0; tries < tb.n_buckets; tries++) {
+  for (uint64_t tries = 1; tries <= tb.n_buckets; tries++) {
     unsigned long long* slot = reinterpret_cast<unsigned long long*>(tb.cells + b * 4);
     for (int j = 0; j < 4; j++) {
       unsigned long long cur = slot[j];
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256) insert_cells_kernel(const uint64_t* __res
         }
       }
     }
-    b = (b + 1 == tb.n_buckets) ? 0 : b + 1;
+    b = slk_next_bucket(b, tries, tb.n_buckets);   // the lookup's probe sequence: own 128-byte line first
   }
 }
 
@@ -425,11 +425,11 @@ static double table_load_factor() {
 }
 static uint64_t buckets_for(uint64_t n_keys) {
   uint64_t cells = (uint64_t)((double)n_keys / table_load_factor()) + 64;
-  return (cells + 3) / 4;
+  return ((cells + 15) / 16) * 4;   // whole 128-byte lines of four buckets
 }
 static int table_alloc(slk_table_view* tb, uint64_t n_keys) {
   tb->n_buckets = buckets_for(n_keys);
-  tb->prefetch = getenv("SLK_PREFETCH") ? 1u : 0u;   // measured on B200: the L2 prefetch pass costs more than it hides
+  tb->prefetch = 0;
   tb->pad_ = 0;
   CU(cudaMalloc(&tb->cells, tb->n_buckets * 32));
   CU(cudaMemset(tb->cells, 0, tb->n_buckets * 32));

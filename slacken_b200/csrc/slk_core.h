@@ -26,7 +26,10 @@
 #endif
 
 #define SLK_MAX_W 8      // k - m + 1 supported by the kernels (35 - 31 + 1 = 5 for the Kraken 2 defaults)
-#define SLK_ECAP 16      // span entries buffered per thread between scan and probe (shared memory on the device)
+#ifndef SLK_POOL
+#define SLK_POOL 128     // span entries per tile; a WARP owns two tiles (filling / in flight) in shared memory
+#endif
+#define SLK_SHIST (SLK_POOL / 8)  // (taxon, k-mers) histogram pairs per lane that fit the idle staging area of a tile
 #define SLK_SHITS 8      // merged hits of a fragment kept in the fast store (shared memory on the device)
 #define SLK_XHITS 56     // further merged hits kept in a per-thread overflow array before spilling to global memory
 #define SLK_KMAX 128     // distinct taxa per fragment held in the per-thread histogram
@@ -91,9 +94,9 @@ SLK_HD int slk_make_scan_params(int k, int m, int spaces, uint64_t toggle_mask, 
 }
 
 struct slk_table_view {
-  uint64_t* cells;     // n_buckets * 4 cells of (compressed key << 16 | dense taxon); 0 = empty
-  uint64_t n_buckets;  // one bucket = one 32-byte sector
-  uint32_t prefetch;   // issue an L2 prefetch for every bucket of a batch before probing it
+  uint64_t* cells;     // n_buckets * 4 cells of (compressed key << 16 | dense taxon); 0 = empty; 128-byte aligned
+  uint64_t n_buckets;  // one bucket = one 32-byte sector; always a multiple of 4 (four buckets = one 128-byte line)
+  uint32_t prefetch;   // unused (kept for layout): the L2 prefetch pass cost more than it hid on B200
   uint32_t pad_;
 };
 
@@ -151,14 +154,15 @@ SLK_HD void slk_for_each_byte(const uint8_t* s, uint64_t len, F&& f) {
 
 // ------------------------------------------------------------------------------------------------ key compression
 // Hacker's-Delight style compress: gathers the bits of x selected by sig_mask at the low end, keeping their order.
-SLK_HD uint64_t slk_compress(const slk_scan_params& sp, uint64_t x) {
-  if (sp.fast_compress) {  // the Kraken 2 default mask: keep the high word, gather bit pairs 2-3 of every low nibble
-    uint32_t y = ((uint32_t)x >> 2) & 0x33333333u;
-    y = (y | (y >> 2)) & 0x0f0f0f0fu;
-    y = (y | (y >> 4)) & 0x00ff00ffu;
-    y = (y | (y >> 8)) & 0x0000ffffu;
-    return ((x >> 32) << 16) | y;
-  }
+// the Kraken 2 default mask 0xffffffffcccccccc: keep the high word, gather bit pairs 2-3 of every low nibble
+SLK_HD uint64_t slk_compress_fast(uint64_t x) {
+  uint32_t y = ((uint32_t)x >> 2) & 0x33333333u;
+  y = (y | (y >> 2)) & 0x0f0f0f0fu;
+  y = (y | (y >> 4)) & 0x00ff00ffu;
+  y = (y | (y >> 8)) & 0x0000ffffu;
+  return ((x >> 32) << 16) | y;
+}
+SLK_HD uint64_t slk_compress_generic(const slk_scan_params& sp, uint64_t x) {
   x &= sp.sig_mask;
 #pragma unroll
   for (int i = 0; i < 6; i++) {
@@ -166,6 +170,9 @@ SLK_HD uint64_t slk_compress(const slk_scan_params& sp, uint64_t x) {
     x = (x ^ t) | (t >> (1 << i));
   }
   return x;
+}
+SLK_HD uint64_t slk_compress(const slk_scan_params& sp, uint64_t x) {
+  return sp.fast_compress ? slk_compress_fast(x) : slk_compress_generic(sp, x);
 }
 SLK_HD uint64_t slk_expand(const slk_scan_params& sp, uint64_t x) {
 #pragma unroll
@@ -185,48 +192,82 @@ SLK_HD uint64_t slk_mulhi64(uint64_t a, uint64_t b) {
   return (uint64_t)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
 #endif
 }
-SLK_HD uint64_t slk_bucket_of(uint64_t ckey, uint64_t n_buckets) {
-  uint64_t h = ckey * 0x9E3779B97F4A7C15ull;
-  h ^= h >> 29;
-  return slk_mulhi64(h * 0xD6E8FEB86659FD93ull, n_buckets);
-}
-SLK_HD void slk_prefetch_bucket(const slk_table_view& tb, uint64_t ckey) {
+SLK_HD uint32_t slk_mulhi32(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
-  const uint64_t* p = tb.cells + slk_bucket_of(ckey, tb.n_buckets) * 4;
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  return __umulhi(a, b);
 #else
-  (void)tb; (void)ckey;
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
 #endif
+}
+// Home bucket of a compressed key: a 128-byte line (n_buckets / 4 of them, fewer than 2^32 for any table that fits
+// 180 GB) and one of its four 32-byte buckets. 32-bit arithmetic throughout (a 64-bit multiply is four instructions
+// on the device): x, a murmur3-finalizer mix of all 48 key bits, picks the line by multiply-shift; y, a further
+// mix that also separates keys with equal x, picks the bucket.
+SLK_HD uint64_t slk_bucket_of(uint64_t ckey, uint64_t n_buckets) {
+  const uint32_t lo = (uint32_t)ckey, hi = (uint32_t)(ckey >> 32);
+  uint32_t x = lo ^ (hi * 0x9E3779B1u);
+  x *= 0x85EBCA6Bu; x ^= x >> 15;
+  x *= 0xC2B2AE35u; x ^= x >> 13;
+  const uint32_t y = (x ^ hi) * 0x27D4EB2Fu;
+  return (uint64_t)slk_mulhi32(x, (uint32_t)(n_buckets >> 2)) * 4u + (y >> 30);
+}
+// Probe sequence. B200 answers a random 32-byte sector miss with the whole 128-byte line (measured: 127 B of DRAM
+// traffic per random 32-byte gather, profiles/r01_probe_microbench.md) and is limited by the NUMBER of random
+// line requests (~36 G/s), not by their bytes. So a collision chain first walks the other three buckets of its own
+// line (cache hits), and only then moves on to the next line. `tries` = buckets already examined (>= 1).
+SLK_HD uint64_t slk_next_bucket(uint64_t b, uint64_t tries, uint64_t n_buckets) {
+  uint64_t nb = (b & ~3ull) | ((b + 1) & 3ull);
+  if ((tries & 3ull) == 0) { nb += 4; if (nb >= n_buckets) nb -= n_buckets; }
+  return nb;
 }
 
 // One bucket (= one 32-byte sector) of a probe: both halves are loaded before anything is compared.
 // Returns true when the probe is decided: *dense = the key's taxon, or 0 if an empty cell proves its absence
 // (cells of a bucket fill in order and are never deleted, so nothing can follow an empty cell).
-SLK_HD bool slk_probe_bucket(const slk_table_view& tb, uint64_t b, uint64_t ckey, uint32_t* dense) {
-  uint64_t c0, c1, c2, c3;
+struct slk_bucket { uint64_t c0, c1, c2, c3; };
+SLK_HD void slk_load_bucket(const slk_table_view& tb, uint64_t b, slk_bucket* o) {
 #if defined(__CUDA_ARCH__)
   const ulonglong2* p = reinterpret_cast<const ulonglong2*>(tb.cells + b * 4);
   const ulonglong2 v0 = __ldg(p), v1 = __ldg(p + 1);
-  c0 = v0.x; c1 = v0.y; c2 = v1.x; c3 = v1.y;
+  o->c0 = v0.x; o->c1 = v0.y; o->c2 = v1.x; o->c3 = v1.y;
 #else
-  c0 = tb.cells[b * 4]; c1 = tb.cells[b * 4 + 1]; c2 = tb.cells[b * 4 + 2]; c3 = tb.cells[b * 4 + 3];
+  o->c0 = tb.cells[b * 4]; o->c1 = tb.cells[b * 4 + 1]; o->c2 = tb.cells[b * 4 + 2]; o->c3 = tb.cells[b * 4 + 3];
 #endif
-  const bool m0 = c0 != 0 && (c0 >> 16) == ckey, m1 = c1 != 0 && (c1 >> 16) == ckey;
-  const bool m2 = c2 != 0 && (c2 >> 16) == ckey, m3 = c3 != 0 && (c3 >> 16) == ckey;
-  const uint64_t hit = m0 ? c0 : m1 ? c1 : m2 ? c2 : m3 ? c3 : 0ull;
-  *dense = (uint32_t)(hit & 0xffffu);
-  return hit != 0 || c3 == 0;   // c3 == 0 <=> the bucket has an empty cell
 }
-
-// Probe: returns the dense taxon of the key, 0 when absent (a left join miss -> Taxonomy.NONE).
-SLK_HD uint32_t slk_probe(const slk_table_view& tb, uint64_t ckey) {
-  uint64_t b = slk_bucket_of(ckey, tb.n_buckets);
-  for (uint64_t tries = 0; tries < tb.n_buckets; tries++) {
+// A stored cell is (ckey << 16 | taxon) with taxon != 0, an empty cell is 0. Cell c holds the key iff its high word
+// equals the key's and the low words differ in the taxon bits only; an empty cell that "matches" key 0 contributes
+// taxon 0. At most one cell of a table holds a given key, so the taxa of the matching cells can simply be OR-ed.
+SLK_HD bool slk_match_bucket(const slk_bucket& k, uint64_t ckey, uint32_t* dense) {
+  const uint32_t khi = (uint32_t)(ckey >> 16), klo = (uint32_t)ckey << 16;
+  const uint32_t l0 = (uint32_t)k.c0, l1 = (uint32_t)k.c1, l2 = (uint32_t)k.c2, l3 = (uint32_t)k.c3;
+  const bool m0 = (uint32_t)(k.c0 >> 32) == khi && (l0 ^ klo) < 0x10000u;
+  const bool m1 = (uint32_t)(k.c1 >> 32) == khi && (l1 ^ klo) < 0x10000u;
+  const bool m2 = (uint32_t)(k.c2 >> 32) == khi && (l2 ^ klo) < 0x10000u;
+  const bool m3 = (uint32_t)(k.c3 >> 32) == khi && (l3 ^ klo) < 0x10000u;
+  const uint32_t d = ((m0 ? l0 : 0u) | (m1 ? l1 : 0u) | (m2 ? l2 : 0u) | (m3 ? l3 : 0u)) & 0xffffu;
+  *dense = d;
+  return d != 0 || k.c3 == 0;   // c3 == 0 <=> the bucket has an empty cell: cells fill in order, nothing is deleted
+}
+SLK_HD bool slk_probe_bucket(const slk_table_view& tb, uint64_t b, uint64_t ckey, uint32_t* dense) {
+  slk_bucket k;
+  slk_load_bucket(tb, b, &k);
+  return slk_match_bucket(k, ckey, dense);
+}
+// Continues a probe whose first `tries` buckets (the last of them `b`) were full without a match.
+static SLK_HD_NOINLINE uint32_t slk_probe_rest(const slk_table_view& tb, uint64_t b, uint64_t tries, uint64_t ckey) {
+  for (; tries < tb.n_buckets; tries++) {
+    b = slk_next_bucket(b, tries, tb.n_buckets);
     uint32_t dense;
     if (slk_probe_bucket(tb, b, ckey, &dense)) return dense;
-    b = (b + 1 == tb.n_buckets) ? 0 : b + 1;
   }
   return 0;
+}
+// Probe: returns the dense taxon of the key, 0 when absent (a left join miss -> Taxonomy.NONE).
+SLK_HD uint32_t slk_probe(const slk_table_view& tb, uint64_t ckey) {
+  const uint64_t b = slk_bucket_of(ckey, tb.n_buckets);
+  uint32_t dense;
+  if (slk_probe_bucket(tb, b, ckey, &dense)) return dense;
+  return slk_probe_rest(tb, b, 1, ckey);
 }
 
 // ------------------------------------------------------------------------------------------------ taxonomy
@@ -273,7 +314,7 @@ struct slk_scanner {
                    bool canonical, uint64_t* minv) {
     uint32_t b = c & 3u;
     fwd = (fwd << 2) | ((uint64_t)b << fshift);
-    rc = ((rc >> 2) | ((uint64_t)(3u - b) << 62)) & mmask;
+    rc = ((rc >> 2) | ((uint64_t)(b ^ 3u) << 62)) & mmask;
     nvalid = c < 4u ? nvalid + 1 : 0;
     uint64_t x = canonical ? slk_min64(fwd, rc) : fwd;
     x = (x ^ xor_mask) & sig_mask;
@@ -306,6 +347,7 @@ struct slk_read_src {
 #define SLK_E_AMB 1u
 #define SLK_E_BORDER 2u
 #define SLK_E_CNT_MAX 0x3fffu   // longer runs are split, which no output can see (equal labels merge again)
+#define SLK_LABEL_PENDING 0xffffu  // a SEQ entry whose first bucket was full without a match (dense taxa are <= 65534)
 
 struct slk_frag_result {
   int32_t taxon;          // raw taxon reported (0 when unclassified)
@@ -313,7 +355,7 @@ struct slk_frag_result {
   uint32_t kmers1, kmers2;  // sum of span k-mer counts per mate (lengthString = kmers + k - 1)
   uint32_t num_distinct;
   uint32_t n_hits;        // merged hits
-  uint32_t n_probes;      // table probes issued (= SEQ spans)
+  uint32_t n_probes;      // table lookups issued (= SEQ spans)
 };
 
 // A sink for merged hits that no longer fit the per-thread buffers (device: a worst-case block of the global hit
@@ -322,39 +364,133 @@ struct slk_null_sink {
   SLK_HD void push(int32_t, int32_t, uint32_t) {}
 };
 
-// Per-thread fast store: span entries key[j]/meta[j] (count | type << 14) for j < SLK_ECAP and the first SLK_SHITS
-// merged hits. On the device these are columns of shared-memory tiles; the emulation uses plain arrays.
-struct slk_store_local {
-  uint64_t key[SLK_ECAP];
-  uint16_t meta[SLK_ECAP];
-  int32_t hl[SLK_SHITS], hc[SLK_SHITS];
-  SLK_HD void set(uint32_t j, uint64_t k, uint32_t m) { key[j] = k; meta[j] = (uint16_t)m; }
-  SLK_HD uint64_t get_key(uint32_t j) const { return key[j]; }
-  SLK_HD uint32_t get_meta(uint32_t j) const { return meta[j]; }
-  SLK_HD void set_hit(uint32_t i, int32_t label, int32_t count) { hl[i] = label; hc[i] = count; }
-  SLK_HD void get_hit(uint32_t i, int32_t* label, int32_t* count) const { *label = hl[i]; *count = hc[i]; }
+// LowestCommonAncestor.resolveTree (slacken/LowestCommonAncestor.scala:91-146) over a histogram H of
+// (dense taxon -> k-mers) pairs in insertion order (fastutil Int2IntArrayMap): size(), at(i, &taxon, &count), count(taxon).
+template <class H>
+SLK_HD uint32_t slk_resolve_tree(const H& h, const slk_tax_view& tx, double confidence, int32_t total) {
+  const double required = ceil(confidence * (double)total);
+  const uint32_t n = h.size();
+  uint32_t max_taxon = 0;
+  int32_t max_score = 0;
+  // one hit taxon (plus, possibly, misses): its path score is its own count, nothing to walk
+  uint32_t nz = 0, only = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t t; int32_t v;
+    h.at(i, &t, &v);
+    if (t != 0) { nz++; only = t; }
+  }
+  if (nz == 1) {
+    max_taxon = only;
+  } else if (nz > 1) {
+    for (uint32_t i = 0; i < n; i++) {
+      uint32_t taxon; int32_t v;
+      h.at(i, &taxon, &v);
+      uint32_t node = taxon;
+      int32_t score = 0;
+      while (node != 0) { score += h.count(node); node = tx.parent[node]; }
+      if (score > max_score) { max_taxon = taxon; max_score = score; }
+      else if (score == max_score) max_taxon = slk_lca(tx, max_taxon, taxon);
+    }
+  }
+  max_score = h.count(max_taxon);
+  while (max_taxon != 0 && (double)max_score < required) {
+    max_score = 0;
+    for (uint32_t i = 0; i < n; i++) {
+      uint32_t t; int32_t v;
+      h.at(i, &t, &v);
+      if (slk_has_ancestor(tx, t, max_taxon)) max_score += v;
+    }
+    if ((double)max_score >= required) return max_taxon;
+    max_taxon = tx.parent[max_taxon];
+  }
+  return max_taxon;
+}
+// the first SLK_SHIST pairs of a lane's histogram, in the idle bucket staging area of the fast store
+template <class Entries>
+struct slk_fast_hist {
+  Entries& ent;
+  uint32_t n;
+  SLK_HD uint32_t size() const { return n; }
+  SLK_HD void at(uint32_t i, uint32_t* t, int32_t* v) const { ent.hist_get(i, t, v); }
+  SLK_HD int32_t count(uint32_t t) const {
+    for (uint32_t i = 0; i < n; i++) {
+      uint32_t ti; int32_t vi;
+      ent.hist_get(i, &ti, &vi);
+      if (ti == t) return vi;
+    }
+    return 0;
+  }
+  SLK_HD bool add(uint32_t t, int32_t c) {   // false: no room (the caller falls back to the per-thread arrays)
+    for (uint32_t i = 0; i < n; i++) {
+      uint32_t ti; int32_t vi;
+      ent.hist_get(i, &ti, &vi);
+      if (ti == t) { ent.hist_set(i, t, vi + c); return true; }
+    }
+    if (n == SLK_SHIST) return false;
+    ent.hist_set(n, t, c); n++;
+    return true;
+  }
 };
 
+// Fast store of a WARP (shared memory on the device, plain arrays in the one-lane emulation):
+//  * two tiles (one being filled, one whose lookups are in flight) of SLK_POOL span entries each. The lanes of a warp
+//    append to the tile in step order; an entry is key (64 bit), meta (count | type << 14), the slot of the same
+//    lane's next entry, and a 32-byte staging area that receives the entry's table bucket through an ASYNCHRONOUS copy;
+//  * per lane, the first SLK_SHITS merged hits of its fragment;
+//  * once the scan is over, the staging areas are reused as each lane's first SLK_SHIST (taxon, k-mers) histogram pairs.
+struct slk_store_local {
+  uint64_t keys[2][SLK_POOL];
+  uint16_t metas[2][SLK_POOL];
+  uint8_t nexts[2][SLK_POOL], pend[2][SLK_POOL];
+  uint64_t stage[2][SLK_POOL][4];
+  int32_t hl[SLK_SHITS], hc[SLK_SHITS];
+  SLK_HD uint32_t tile(uint32_t t) const { return t; }   // tile handle (the device's is a shared-space address)
+  SLK_HD void put(uint32_t t, uint32_t s, uint64_t k, uint32_t m) { keys[t][s] = k; metas[t][s] = (uint16_t)m; }
+  SLK_HD uint64_t key(uint32_t t, uint32_t s) const { return keys[t][s]; }
+  SLK_HD void set_key(uint32_t t, uint32_t s, uint64_t k) { keys[t][s] = k; }
+  SLK_HD uint32_t meta(uint32_t t, uint32_t s) const { return metas[t][s]; }
+  SLK_HD void set_next(uint32_t t, uint32_t s, uint32_t n) { nexts[t][s] = (uint8_t)n; }
+  SLK_HD uint32_t next(uint32_t t, uint32_t s) const { return nexts[t][s]; }
+  SLK_HD void set_pending(uint32_t t, uint32_t q, uint32_t s) { pend[t][q] = (uint8_t)s; }
+  SLK_HD uint32_t pending(uint32_t t, uint32_t q) const { return pend[t][q]; }
+  SLK_HD void fetch(uint32_t t, uint32_t s, const uint64_t* src) { for (int i = 0; i < 4; i++) stage[t][s][i] = src[i]; }
+  SLK_HD void bucket(uint32_t t, uint32_t s, slk_bucket* o) const {
+    o->c0 = stage[t][s][0]; o->c1 = stage[t][s][1]; o->c2 = stage[t][s][2]; o->c3 = stage[t][s][3];
+  }
+  SLK_HD void commit() const {}
+  SLK_HD void wait_all() const {}
+  SLK_HD void wait_prev() const {}
+  SLK_HD void set_hit(uint32_t i, int32_t label, int32_t count) { hl[i] = label; hc[i] = count; }
+  SLK_HD void get_hit(uint32_t i, int32_t* label, int32_t* count) const { *label = hl[i]; *count = hc[i]; }
+  SLK_HD void hist_set(uint32_t i, uint32_t t, int32_t v) { (&stage[0][0][0])[i] = ((uint64_t)(uint32_t)v << 32) | t; }
+  SLK_HD void hist_get(uint32_t i, uint32_t* t, int32_t* v) const { uint64_t x = (&stage[0][0][0])[i]; *t = (uint32_t)x; *v = (int32_t)(x >> 32); }
+};
+
+// One fragment (a read or a read pair) per thread, end to end: scan -> span entries -> table lookups -> merged
+// hits -> resolveTree, with the lookups decoupled from the thread that needs them:
+//  * the lanes of a warp append their span entries to a tile of the warp. When the tile is full the warp closes it:
+//    the buckets of all its SEQ entries are requested with asynchronous global->shared copies (32 entries per
+//    round, every lane busy whatever its own fragment looks like) and are only examined when the NEXT tile closes,
+//    after the warp has scanned on. A warp keeps up to SLK_POOL random line requests in flight without holding a
+//    register for them and without waiting, and the B200's random-request ceiling (~36 G lines/s,
+//    profiles/r01_probe_microbench.md) is reached with 12-16 warps per SM;
+//  * matching a landed bucket against its key is again done 32 entries per round; only the merge of a lane's own
+//    hits (adjacent equal taxa, numDistinct, k-mer totals) walks that lane's entries in order.
 template <int W, class Sink, class Entries>
 struct slk_frag_classifier {
-  const slk_table_view tb;   // by value: the hot loops copy what they need into registers anyway
+  const slk_table_view tb;
   const slk_tax_view tx;
   Sink& sink;
   Entries ent;
 
-  // per-fragment state of the drain side
-  uint64_t last_seq_key;
-  bool have_last_seq;
-  int32_t cur_label, cur_count;
-  bool have_cur;
-  uint32_t mate, kmers[2], nd, nprobes;
-  uint32_t windows_left;  // upper bound of merged hits still to come (for the sink's spill allocation)
+  // totals of the fragment (written once, at the end of the scan; resolve() and the kernel epilogue read them)
+  uint32_t kmers[2], nd, nprobes;
   // merged hits (dense labels): the first SLK_SHITS in the fast store, then xh_*, then spilled through the sink
   uint32_t nh;            // buffered
   uint32_t nh_spilled;    // already pushed to the sink (0 for all but very long reads)
   int32_t xh_label[SLK_XHITS];
   int32_t xh_count[SLK_XHITS];
-  // histogram: dense taxon -> k-mer count, insertion ordered (fastutil Int2IntArrayMap)
+  // histogram of the slow path (a fragment that spilled hits while its tiles were busy, or hit > SLK_SHIST taxa)
   uint32_t hk[SLK_KMAX];
   int32_t hv[SLK_KMAX];
   uint32_t nk;
@@ -363,16 +499,18 @@ struct slk_frag_classifier {
   SLK_HD slk_frag_classifier(const slk_table_view& tb_, const slk_tax_view& tx_, Sink& s, const Entries& e)
       : tb(tb_), tx(tx_), sink(s), ent(e) {}
 
+  SLK_HD uint32_t size() const { return nk; }
+  SLK_HD void at(uint32_t i, uint32_t* t, int32_t* v) const { *t = hk[i]; *v = hv[i]; }
+  SLK_HD int32_t count(uint32_t t) const {
+    for (uint32_t i = 0; i < nk; i++)
+      if (hk[i] == t) return hv[i];
+    return 0;
+  }
   SLK_HD void hist_add(uint32_t t, int32_t c) {
     for (uint32_t i = 0; i < nk; i++)
       if (hk[i] == t) { hv[i] += c; return; }
     if (nk == SLK_KMAX) { overflow = true; return; }
     hk[nk] = t; hv[nk] = c; nk++;
-  }
-  SLK_HD int32_t hist_get(uint32_t t) const {
-    for (uint32_t i = 0; i < nk; i++)
-      if (hk[i] == t) return hv[i];
-    return 0;
   }
   SLK_HD void buffered_hit(uint32_t i, int32_t* label, int32_t* count) const {
     if (i < SLK_SHITS) ent.get_hit(i, label, count);
@@ -397,142 +535,184 @@ struct slk_frag_classifier {
     nh_spilled += nh;
     nh = 0;
   }
-  // TaxonCounts.fromHits (slacken/TaxonCounts.scala:31-48) has already merged adjacent equal taxa: one store
-  SLK_HD void push_hit(int32_t label, int32_t count, uint32_t need) {
-    if (nh == SLK_SHITS + SLK_XHITS) spill(need);
-    if (nh < SLK_SHITS) ent.set_hit(nh, label, count);
-    else { xh_label[nh - SLK_SHITS] = label; xh_count[nh - SLK_SHITS] = count; }
-    nh++;
-  }
-
-  // spanToHit (slacken/KeyValueIndex.scala:176-185) + numDistinct (slacken/Classifier.scala:94) for the first
-  // `ne` buffered entries. Out of line on purpose (the scan loop stays small); every lane of a warp calls it at the
-  // same time. Its running state is copied into registers for the duration of the call, because stores through
-  // the entry/sink pointers could otherwise alias the members and force a reload per entry.
-  SLK_HD_NOINLINE void drain(const slk_scan_params& sp, uint32_t ne) {
-    const slk_table_view tb = this->tb;   // registers, not members behind `this`
-#if defined(__CUDA_ARCH__)
-    const Entries ent = this->ent;
-#else
-    const Entries& ent = this->ent;
-#endif
-    // all buckets of this batch are requested from HBM first, so the probes below find them in L2
-    for (uint32_t j = 0; j < ne; j++)
-      if (tb.prefetch && (ent.get_meta(j) >> 14) == SLK_E_SEQ) slk_prefetch_bucket(tb, slk_compress(sp, ent.get_key(j)));
-    uint64_t l_last = last_seq_key;
-    bool l_have_last = have_last_seq, l_have_cur = have_cur;
-    int32_t l_label = cur_label, l_count = cur_count;
-    uint32_t l_mate = mate, l_k0 = kmers[0], l_k1 = kmers[1], l_nd = nd, l_np = nprobes, l_wl = windows_left;
-    const int32_t border_cnt = -(sp.k - 1);
-    // One loop for "next entry" and "next bucket of the current probe": every lane walks its own entries and its
-    // own collision chains at its own pace, so a long chain in one lane does not hold back the other 31.
-    uint32_t j = 0;
-    bool probing = false;
-    uint64_t key = 0, ckey = 0, bucket = 0;
-    while (probing || j < ne) {
-      const uint32_t meta = ent.get_meta(j), type = meta >> 14, cnt = meta & SLK_E_CNT_MAX;
-      int32_t label, hcnt = (int32_t)cnt;
-      if (type == SLK_E_SEQ) {
-        if (!probing) {
-          key = ent.get_key(j);
-          ckey = slk_compress(sp, key);
-          bucket = slk_bucket_of(ckey, tb.n_buckets);
-          probing = true;
-          l_np++;
-        }
-        uint32_t dense;
-        if (!slk_probe_bucket(tb, bucket, ckey, &dense)) {
-          bucket = (bucket + 1 == tb.n_buckets) ? 0 : bucket + 1;
-          continue;
-        }
-        probing = false;
-        l_nd += ((!l_have_last || key != l_last) && dense != 0) ? 1u : 0u;
-        l_last = key; l_have_last = true;
-        label = (int32_t)dense;
-      } else if (type == SLK_E_AMB) {
-        label = SLK_AMBIGUOUS_SPAN;
-      } else {
-        label = SLK_MATE_PAIR_BORDER; hcnt = border_cnt;
-      }
-      if (type != SLK_E_BORDER) { if (l_mate) l_k1 += cnt; else l_k0 += cnt; }
-      // TaxonCounts.fromHits: adjacent hits with the same taxon merge (slacken/TaxonCounts.scala:31-48)
-      if (l_have_cur && label == l_label) l_count += hcnt;
-      else {
-        if (l_have_cur) push_hit(l_label, l_count, l_wl + 2);
-        l_label = label; l_count = hcnt; l_have_cur = true;
-      }
-      if (type == SLK_E_BORDER) l_mate = 1;
-      l_wl = l_wl > cnt ? l_wl - cnt : 0;
-      j++;
-    }
-    last_seq_key = l_last; have_last_seq = l_have_last; have_cur = l_have_cur; cur_label = l_label; cur_count = l_count;
-    mate = l_mate; kmers[0] = l_k0; kmers[1] = l_k1; nd = l_nd; nprobes = l_np; windows_left = l_wl;
-  }
-
-  // LowestCommonAncestor.resolveTree (slacken/LowestCommonAncestor.scala:91-146)
-  SLK_HD_NOINLINE uint32_t resolve(double confidence) {
+  // the slow path of the final step: histogram in the per-thread arrays
+  SLK_HD_NOINLINE uint32_t resolve_slow(double confidence) {
     fold_hits();   // the buffered hits (a fragment that spilled has none left and was folded on the way)
-    int32_t total = (int32_t)(kmers[0] + kmers[1]);  // totalKmers: ambiguous spans count, the border does not
-    double required = ceil(confidence * (double)total);
-    uint32_t max_taxon = 0;
-    int32_t max_score = 0;
-    // one hit taxon (plus, possibly, misses): its path score is its own count, nothing to walk
-    uint32_t nz = 0, only = 0;
-    for (uint32_t i = 0; i < nk; i++)
-      if (hk[i] != 0) { nz++; only = hk[i]; }
-    if (nz == 1) {
-      max_taxon = only;
-    } else if (nz > 1) {
-      for (uint32_t i = 0; i < nk; i++) {
-        uint32_t taxon = hk[i], node = taxon;
-        int32_t score = 0;
-        while (node != 0) { score += hist_get(node); node = tx.parent[node]; }
-        if (score > max_score) { max_taxon = taxon; max_score = score; }
-        else if (score == max_score) max_taxon = slk_lca(tx, max_taxon, taxon);
-      }
-    }
-    max_score = hist_get(max_taxon);
-    while (max_taxon != 0 && (double)max_score < required) {
-      max_score = 0;
-      for (uint32_t i = 0; i < nk; i++)
-        if (slk_has_ancestor(tx, hk[i], max_taxon)) max_score += hv[i];
-      if ((double)max_score >= required) return max_taxon;
-      max_taxon = tx.parent[max_taxon];
-    }
-    return max_taxon;
+    return slk_resolve_tree(*this, tx, confidence, (int32_t)(kmers[0] + kmers[1]));
   }
 
-  // One fragment end to end (paired == false: r2 is ignored).
+  // One fragment end to end (paired == false: r2 is ignored). Every lane of a warp must call it (lanes without a
+  // fragment pass empty reads): tiles are filled, closed and matched by the warp as a whole.
   // Scan: Supermers.splitByAmbiguity/splitFragment (slacken/Supermers.scala:113-189): valid runs >= k are cut into
   // super-mers (runs of k-mer windows with equal minimizer), runs of >= k ambiguous characters become one
   // AMBIGUOUS span of len-(k-1), anything shorter vanishes; the mates are separated by a MATE_PAIR_BORDER span.
-  template <bool PACKED>
+  template <bool PACKED, bool CANON>
   SLK_HD void run(const slk_scan_params& sp, const slk_read_src& r1, const slk_read_src& r2, bool paired,
                   double confidence, int32_t min_hit_groups, slk_frag_result& r) {
-    have_last_seq = false; last_seq_key = 0; have_cur = false; cur_label = 0; cur_count = 0; nh = 0; nh_spilled = 0;
-    mate = 0; kmers[0] = 0; kmers[1] = 0; nd = 0; nk = 0; overflow = false; nprobes = 0;
+    // The running state of the merge side lives in registers for the whole scan; the members (which sit in local
+    // memory because spill() and resolve() are out of line) are only written at the end and around a spill.
+    uint64_t l_last = 0;
+    bool l_have_last = false, l_have_cur = false;
+    int32_t l_label = 0, l_count = 0;
+    uint32_t l_mate = 0, l_k0 = 0, l_k1 = 0, l_nd = 0, l_np = 0, l_nh = 0;
+    nh = 0; nh_spilled = 0; nk = 0; overflow = false;
+    bool l_spilled = false;
     const uint32_t k = (uint32_t)sp.k, km1 = k - 1;
     const int fshift = sp.fshift;
     const uint64_t mmask = sp.mmask, xor_mask = sp.xor_mask, sig_mask = sp.sig_mask;
-    const bool canonical = sp.canonical != 0;
-    windows_left = (r1.len > km1 ? r1.len - km1 : 0) + (paired ? (r2.len > km1 ? r2.len - km1 : 0) + 1 : 0);
-    uint32_t ne = 0;       // buffered entries (register)
-    bool any = false;      // did the fragment yield any span at all
+    const bool fast = sp.fast_compress != 0;
+    const int32_t border_cnt = -(sp.k - 1);
+    // upper bound of the merged hits of the fragment (for the sink's spill allocation)
+    const uint32_t max_hits = (r1.len > km1 ? r1.len - km1 : 0) + (paired ? (r2.len > km1 ? r2.len - km1 : 0) + 1 : 0) + 2;
+    uint32_t n_cur = 0, n_prev = 0;        // entries of the warp in the tile being filled / in flight (warp-uniform)
+    uint32_t head_cur = 0, tail_cur = 0, cnt_cur = 0;   // this lane's own entries in the tile being filled
+    uint32_t head_prev = 0, cnt_prev = 0;               // ... and in the tile in flight
+    bool any = false;                      // did the fragment yield any span at all
 #if defined(__CUDA_ARCH__)
-    const Entries ent = this->ent;   // the three shared-space addresses, in registers
+    const Entries ent = this->ent;   // shared-space addresses, in registers
+    const slk_table_view tb = this->tb;
+    const uint32_t lane = threadIdx.x & 31u, lanes_below = (1u << lane) - 1u;
+#define SLK_LANES 32u
 #define SLK_WARP_ANY(p) __any_sync(0xffffffffu, (p))
+#define SLK_WARP_ALL(p) __all_sync(0xffffffffu, (p))
 #define SLK_WARP_MAX(x) __reduce_max_sync(0xffffffffu, (x))
+#define SLK_BALLOT(p) __ballot_sync(0xffffffffu, (p))
+#define SLK_POPC(x) ((uint32_t)__popc(x))
+#define SLK_SYNCWARP() __syncwarp()
 #else
     Entries& ent = this->ent;
+    const slk_table_view& tb = this->tb;
+    const uint32_t lane = 0, lanes_below = 0;
+#define SLK_LANES 1u
 #define SLK_WARP_ANY(p) (p)
+#define SLK_WARP_ALL(p) (p)
 #define SLK_WARP_MAX(x) (x)
+#define SLK_BALLOT(p) ((p) ? 1u : 0u)
+#define SLK_POPC(x) ((uint32_t)__builtin_popcount(x))
+#define SLK_SYNCWARP() do {} while (0)
 #endif
+    const uint32_t pool_limit = SLK_POOL - SLK_LANES;   // a tile with more entries cannot take another step
+    const uint32_t ent_tile0 = ent.tile(0), ent_tile1 = ent.tile(1);
+    uint32_t cur = ent_tile0;              // handle of the tile being filled
+
+    // TaxonCounts.fromHits (slacken/TaxonCounts.scala:31-48) has already merged adjacent equal taxa: one store
+    auto push_hit = [&](int32_t label, int32_t count) {
+      if (l_nh == SLK_SHITS + SLK_XHITS) { nh = l_nh; spill(max_hits - l_nh); l_nh = 0; l_spilled = true; }   // spill allocates need + nh + 2
+      if (l_nh < SLK_SHITS) ent.set_hit(l_nh, label, count);
+      else { xh_label[l_nh - SLK_SHITS] = label; xh_count[l_nh - SLK_SHITS] = count; }
+      l_nh++;
+    };
+    // Closes the tile being filled. The whole warp comes here together.
+    //  1. the buckets of the PREVIOUS tile, requested one tile ago, have landed in the staging areas;
+    //  2. match pass over the previous tile, 32 entries per round: spanToHit's join (slacken/KeyValueIndex.scala:
+    //     176-185). The dense taxon (0 = miss -> Taxonomy.NONE) goes to the top 16 bits of the entry's key slot.
+    //     The few entries whose bucket was full without a match are collected in the tile's pending list; they
+    //     then request the next bucket of their chain (same 128-byte line: a cache hit), 32 per round;
+    //  3. issue pass over the tile just filled, 32 entries per round: compress the key, request its bucket;
+    //  4. the chain buckets of step 2 have landed (the requests of step 3 stay in flight): pending pass;
+    //  5. merge pass: every lane walks ITS entries of the previous tile in span order: numDistinct
+    //     (slacken/Classifier.scala:94), k-mer totals, TaxonCounts.fromHits.
+    // A lane only ever waits for copies it issued itself: slot s is requested and matched by lane s % 32, pending
+    // entry q by lane q % 32.
+    auto close = [&]() {
+      any = any || cnt_cur != 0;
+      const uint32_t prev = cur ^ ent_tile0 ^ ent_tile1;
+      SLK_SYNCWARP();   // the entries other lanes appended are visible
+      ent.wait_all();
+      uint32_t n_pend = 0;
+      for (uint32_t s0 = 0; s0 < n_prev; s0 += SLK_LANES) {
+        const uint32_t s = s0 + lane;
+        bool pend = false;
+        if (s < n_prev && (ent.meta(prev, s) >> 14) == SLK_E_SEQ) {
+          const uint64_t ck = ent.key(prev, s);
+          slk_bucket bk;
+          ent.bucket(prev, s, &bk);
+          uint32_t dense;
+          pend = !slk_match_bucket(bk, ck, &dense);
+          if (!pend) ent.set_key(prev, s, ck | ((uint64_t)dense << 48));
+        }
+        const uint32_t bal = SLK_BALLOT(pend);
+        if (pend) ent.set_pending(prev, n_pend + SLK_POPC(bal & lanes_below), s);
+        n_pend += SLK_POPC(bal);
+      }
+      SLK_SYNCWARP();   // the pending list is complete, and nobody reads a first bucket any more
+      for (uint32_t q = lane; q < n_pend; q += SLK_LANES) {
+        const uint32_t s = ent.pending(prev, q);
+        const uint64_t nb = slk_next_bucket(slk_bucket_of(ent.key(prev, s), tb.n_buckets), 1, tb.n_buckets);
+        ent.fetch(prev, s, tb.cells + nb * 4);
+      }
+      ent.commit();
+      for (uint32_t s = lane; s < n_cur; s += SLK_LANES) {
+        if ((ent.meta(cur, s) >> 14) == SLK_E_SEQ) {
+          const uint64_t key = ent.key(cur, s);
+          const uint64_t ck = fast ? slk_compress_fast(key) : slk_compress_generic(sp, key);
+          ent.set_key(cur, s, ck);
+          ent.fetch(cur, s, tb.cells + slk_bucket_of(ck, tb.n_buckets) * 4);
+        }
+      }
+      ent.commit();
+      ent.wait_prev();
+      for (uint32_t q = lane; q < n_pend; q += SLK_LANES) {
+        const uint32_t s = ent.pending(prev, q);
+        const uint64_t ck = ent.key(prev, s);
+        slk_bucket bk;
+        ent.bucket(prev, s, &bk);
+        uint32_t dense;
+        if (!slk_match_bucket(bk, ck, &dense)) {
+          const uint64_t b2 = slk_next_bucket(slk_bucket_of(ck, tb.n_buckets), 1, tb.n_buckets);
+          dense = slk_probe_rest(tb, b2, 2, ck);
+        }
+        ent.set_key(prev, s, ck | ((uint64_t)dense << 48));
+      }
+      SLK_SYNCWARP();   // all labels of the previous tile are visible to the lanes that own the entries
+      uint32_t s = head_prev;
+      for (uint32_t q = 0; q < cnt_prev; q++) {
+        const uint32_t meta = ent.meta(prev, s), type = meta >> 14, cnt = meta & SLK_E_CNT_MAX;
+        int32_t label, hcnt = (int32_t)cnt;
+        if (type == SLK_E_SEQ) {
+          const uint64_t kl = ent.key(prev, s), ck = kl & 0xffffffffffffull;
+          const uint32_t dense = (uint32_t)(kl >> 48);
+          l_np++;
+          l_nd += ((!l_have_last || ck != l_last) && dense != 0) ? 1u : 0u;
+          l_last = ck; l_have_last = true;
+          label = (int32_t)dense;
+        } else if (type == SLK_E_AMB) {
+          label = SLK_AMBIGUOUS_SPAN;
+        } else {
+          label = SLK_MATE_PAIR_BORDER; hcnt = border_cnt;
+        }
+        if (type != SLK_E_BORDER) { if (l_mate) l_k1 += cnt; else l_k0 += cnt; }
+        // TaxonCounts.fromHits: adjacent hits with the same taxon merge (slacken/TaxonCounts.scala:31-48)
+        if (l_have_cur && label == l_label) l_count += hcnt;
+        else {
+          if (l_have_cur) push_hit(l_label, l_count);
+          l_label = label; l_count = hcnt; l_have_cur = true;
+        }
+        if (type == SLK_E_BORDER) l_mate = 1;
+        s = ent.next(prev, s);
+      }
+      SLK_SYNCWARP();   // nobody appends to the previous tile before everybody has left it
+      n_prev = n_cur; head_prev = head_cur; cnt_prev = cnt_cur;
+      n_cur = 0; cnt_cur = 0; cur = prev;
+    };
+    // Appends one entry per lane with `emit` set, in lane order. All lanes call it; the tile has room for all of
+    // them (n_cur <= pool_limit). The caller closes the tile when the return value says it is full.
+    auto append = [&](bool emit, uint64_t key, uint32_t meta) -> bool {
+      const uint32_t bal = SLK_BALLOT(emit);
+      if (emit) {
+        const uint32_t s = n_cur + SLK_POPC(bal & lanes_below);
+        ent.put(cur, s, key, meta);
+        ent.set_next(cur, cnt_cur ? tail_cur : s, s);   // the first entry links to itself; its link is set by the second
+        head_cur = cnt_cur ? head_cur : s;
+        tail_cur = s; cnt_cur++;
+      }
+      n_cur += SLK_POPC(bal);
+      return n_cur > pool_limit;
+    };
+
 #pragma unroll 1
     for (int mt = 0; mt < (paired ? 2 : 1); mt++) {  // one copy of the scan loop serves both mates
-      if (mt) {
-        if (SLK_WARP_ANY(ne > SLK_ECAP - 5)) { any = any || ne != 0; drain(sp, ne); ne = 0; }
-        ent.set(ne, 0, SLK_E_BORDER << 14); ne++;
-      }
+      if (mt && append(true, 0, SLK_E_BORDER << 14)) close();
       const slk_read_src& src = mt ? r2 : r1;
       const uint32_t len = src.len;
       slk_scanner<W> sc;
@@ -540,28 +720,79 @@ struct slk_frag_classifier {
       uint64_t run_key = 0;
       uint32_t run_cnt = 0, ninv = 0, amb_cnt = 0;
       bool in_run = false;
-      // One character (c = 0..3 for a base, 4 for anything else). Straight-line code: at most one entry is stored.
-      auto step = [&](uint32_t c) {
-        const bool valid = c < 4u;
-        uint64_t mn;
-        const bool window_ok = sc.push(c, k, fshift, mmask, xor_mask, sig_mask, canonical, &mn);
-        ninv = valid ? 0u : ninv + 1u;
+      // One character (c = 0..3 for a base, 4 for anything else) of the lanes with `act` set; at most one entry
+      // each. Returns true when the tile is full.
+      auto step = [&](uint32_t c, bool act) -> bool {
+        bool valid = true, window_ok = false;
+        uint64_t mn = 0;
+        if (act) {
+          valid = c < 4u;
+          window_ok = sc.push(c, k, fshift, mmask, xor_mask, sig_mask, CANON, &mn);
+          ninv = valid ? 0u : ninv + 1u;
+        }
         const bool same = in_run && mn == run_key && run_cnt < SLK_E_CNT_MAX;
         const bool start_new = window_ok && !same;
         const bool emit_seq = in_run && (start_new || !valid);  // the open super-mer ends here
-        const bool emit_amb = amb_cnt != 0 && (valid || amb_cnt == SLK_E_CNT_MAX);  // an ambiguous stretch ended
-        if (emit_seq || emit_amb) {
-          ent.set(ne, emit_seq ? run_key : 0ull, emit_seq ? run_cnt : (amb_cnt | (SLK_E_AMB << 14)));
-          ne++;
+        const bool emit_amb = act && amb_cnt != 0 && (valid || amb_cnt == SLK_E_CNT_MAX);  // an ambiguous stretch ended
+        const uint32_t amb_meta = amb_cnt | (SLK_E_AMB << 14);
+        if (act) {
+          amb_cnt = (valid || emit_amb) ? 0u : amb_cnt;
+          amb_cnt += (!valid && ninv >= k) ? 1u : 0u;
         }
-        amb_cnt = (valid || emit_amb) ? 0u : amb_cnt;
-        amb_cnt += (!valid && ninv >= k) ? 1u : 0u;
+        const uint64_t ek = emit_seq ? run_key : 0ull;
+        const uint32_t em = emit_seq ? run_cnt : amb_meta;
         run_cnt = start_new ? 1u : run_cnt + ((window_ok && same) ? 1u : 0u);
         run_key = start_new ? mn : run_key;
         in_run = valid && (in_run || start_new);
+        return append(emit_seq || emit_amb, ek, em);
       };
-      // All lanes of a warp run the same number of iterations (the longest read of the warp decides) and drain
-      // together as soon as one lane's entry tile is nearly full, so the warp never splits around drain().
+      // The same for a base (b = 0..3) of a block in which no lane of the warp has an ambiguous character or an
+      // open ambiguous stretch: no validity bookkeeping at all. GUARD: some lanes may be outside their read.
+      auto fstep = [&](uint32_t b, bool act) -> bool {
+        bool window_ok = false;
+        uint64_t mn = 0;
+        if (act) window_ok = sc.push(b, k, fshift, mmask, xor_mask, sig_mask, CANON, &mn);
+        const bool same = in_run && mn == run_key && run_cnt < SLK_E_CNT_MAX;
+        const bool start_new = window_ok && !same;
+        const bool emit = in_run && start_new;
+        const uint64_t ek = run_key;
+        const uint32_t em = run_cnt;
+        run_cnt = start_new ? 1u : run_cnt + (window_ok ? 1u : 0u);
+        run_key = start_new ? mn : run_key;
+        in_run = in_run || start_new;
+        return append(emit, ek, em);
+      };
+      // Bases [i0, i1) of a block of 2-bit codes `cw` (base i in bits 2i, 2i+1) with ambiguity bits `mw`. All lanes
+      // of a warp run the same number of iterations. The scan loops leave when the tile is full, so that there is
+      // one copy of close() here, and come back to where they were.
+      auto scan_block = [&](uint64_t cw, uint32_t mw, uint32_t i0, uint32_t i1) {
+        const bool dirty = SLK_WARP_ANY(mw != 0u || ninv != 0u || amb_cnt != 0u);
+        const uint32_t i1w = SLK_WARP_MAX(i1);
+        const bool whole = !dirty && SLK_WARP_ALL(i0 == 0u && i1 == i1w);   // every lane has all i1w bases
+        uint32_t i = 0;
+        while (i < i1w) {
+          bool full = false;
+          if (whole) {
+            while (i + 4u <= i1w && !full) {   // four bases per round, no per-lane guards
+              const uint32_t g = (uint32_t)(cw >> (2u * i)) & 0xffu;
+              if (fstep(g & 3u, true)) { i += 1u; full = true; continue; }
+              if (fstep((g >> 2) & 3u, true)) { i += 2u; full = true; continue; }
+              if (fstep((g >> 4) & 3u, true)) { i += 3u; full = true; continue; }
+              full = fstep(g >> 6, true);
+              i += 4u;
+            }
+            while (i < i1w && !full) { full = fstep((uint32_t)(cw >> (2u * i)) & 3u, true); i++; }
+          } else if (!dirty) {
+            while (i < i1w && !full) { full = fstep((uint32_t)(cw >> (2u * i)) & 3u, i >= i0 && i < i1); i++; }
+          } else {
+            while (i < i1w && !full) {
+              full = step(((uint32_t)(cw >> (2u * i)) & 3u) | (((mw >> i) & 1u) << 2), i >= i0 && i < i1);
+              i++;
+            }
+          }
+          if (full) close();
+        }
+      };
       if (PACKED) {
         const uint32_t nblk = (len + 31u) >> 5;
         const uint32_t nblk_w = SLK_WARP_MAX(nblk);
@@ -576,72 +807,77 @@ struct slk_frag_classifier {
 #endif
             nb = len - 32u * b; nb = nb > 32u ? 32u : nb;
           }
-#pragma unroll 1
-          for (uint32_t q = 0; q < 8; q++) {
-            if (SLK_WARP_ANY(ne > SLK_ECAP - 5)) { any = any || ne != 0; drain(sp, ne); ne = 0; }  // 4 chars: <= 4 entries
-            const uint32_t g = (uint32_t)(cw >> (8u * q)) & 0xffu, gm = (mw >> (4u * q)) & 0xfu;
-            const uint32_t left = nb > 4u * q ? nb - 4u * q : 0u;
-            if (left >= 4u) {
-#pragma unroll
-              for (uint32_t i = 0; i < 4; i++) step(((g >> (2u * i)) & 3u) | (((gm >> i) & 1u) << 2));
-            } else {
-#pragma unroll 1
-              for (uint32_t i = 0; i < left; i++) step(((g >> (2u * i)) & 3u) | (((gm >> i) & 1u) << 2));
-            }
-          }
+          scan_block(cw, mw, 0u, nb);
         }
       } else {
-#if defined(__CUDA_ARCH__)
-        // 16-byte aligned vector loads over [s, s+len). The buffer is readable up to the next 16-byte boundary
-        // (library-owned and cudaMalloc'ed buffers are); bytes outside the read are skipped in the edge chunks.
+        // 16-byte chunks over [s, s+len), aligned for the device's vector loads. The buffer is readable up to the
+        // next 16-byte boundary (library-owned and cudaMalloc'ed buffers are); bytes outside the read are skipped.
         const uintptr_t a0 = reinterpret_cast<uintptr_t>(src.ascii);
         const uintptr_t abase = a0 & ~(uintptr_t)15;
         const int32_t lo0 = (int32_t)(a0 - abase), total = lo0 + (int32_t)len;  // byte range [lo0, total) from abase
-        const int32_t total_w = (int32_t)SLK_WARP_MAX((uint32_t)total);
+        const int32_t total_w = (int32_t)SLK_WARP_MAX((uint32_t)(len != 0 ? total : 0));
         for (int32_t cb = 0; cb < total_w; cb += 16) {
-          const bool have = cb < total;
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (have) v = __ldg(reinterpret_cast<const uint4*>(abase + cb));
-          const bool interior = cb >= lo0 && cb + 16 <= total;
-#pragma unroll 1
-          for (int wi = 0; wi < 4; wi++) {
-            if (SLK_WARP_ANY(ne > SLK_ECAP - 5)) { any = any || ne != 0; drain(sp, ne); ne = 0; }
-            const uint32_t word = wi == 0 ? v.x : wi == 1 ? v.y : wi == 2 ? v.z : v.w;
-            if (interior) {
+          uint64_t cw = 0;
+          uint32_t mw = 0, i0 = 0, i1 = 0;
+          if (cb < total && len != 0) {
+            i0 = lo0 > cb ? (uint32_t)(lo0 - cb) : 0u;
+            i1 = total - cb > 16 ? 16u : (uint32_t)(total - cb);
+#if defined(__CUDA_ARCH__)
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(abase + cb));
+            const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-              for (int bi = 0; bi < 4; bi++) step(slk_code((word >> (8 * bi)) & 0xffu));
-            } else if (have) {
-#pragma unroll 1
-              for (int bi = 0; bi < 4; bi++) {
-                const int32_t pos = cb + 4 * wi + bi;
-                if (pos >= lo0 && pos < total) step(slk_code((word >> (8 * bi)) & 0xffu));
-              }
+            for (uint32_t i = 0; i < 16; i++) {
+              const uint32_t c = slk_code((wd[i >> 2] >> (8u * (i & 3u))) & 0xffu);
+              cw |= (uint64_t)(c & 3u) << (2u * i);
+              mw |= (c >> 2) << i;
             }
-          }
-        }
 #else
-        for (uint32_t i = 0; i < len; i++) {
-          if ((i & 3) == 0 && ne > SLK_ECAP - 5) { any = true; drain(sp, ne); ne = 0; }
-          step(slk_code(src.ascii[i]));
-        }
+            for (uint32_t i = i0; i < i1; i++) {
+              const uint32_t c = slk_code(reinterpret_cast<const uint8_t*>(abase)[cb + i]);
+              cw |= (uint64_t)(c & 3u) << (2u * i);
+              mw |= (c >> 2) << i;
+            }
 #endif
+          }
+          scan_block(cw, mw, i0, i1);
+        }
       }
       // mate end: at most one pending entry (a run and an ambiguous stretch cannot both be open)
-      if (in_run) { ent.set(ne, run_key, run_cnt); ne++; }
-      if (amb_cnt) { ent.set(ne, 0, amb_cnt | (SLK_E_AMB << 14)); ne++; }
+      if (append(in_run || amb_cnt != 0, in_run ? run_key : 0ull, in_run ? run_cnt : (amb_cnt | (SLK_E_AMB << 14)))) close();
     }
-    if (ne) any = true;
-    drain(sp, ne);
-    if (have_cur) { push_hit(cur_label, cur_count, 2); have_cur = false; }
-    if (nh_spilled) spill(0);   // a fragment that went to the sink keeps all its hits there
-    uint32_t taxon = resolve(confidence);
+#pragma unroll 1
+    for (int e = 0; e < 2; e++) close();   // the first requests the last tile and merges the one before it
+    if (l_have_cur) push_hit(l_label, l_count);
+    nh = l_nh; kmers[0] = l_k0; kmers[1] = l_k1; nd = l_nd; nprobes = l_np;
+    // totalKmers: ambiguous spans count, the border does not (slacken/TaxonCounts.scala:83-87)
+    uint32_t taxon;
+    bool fast_done = false;
+    if (!l_spilled) {   // nearly every fragment: the histogram fits the (now idle) staging area of the fast store
+      Entries hstore = ent;   // device: four shared-space addresses; emulation: see below
+      slk_fast_hist<Entries> fh{hstore, 0u};
+      bool fits = true;
+      for (uint32_t i = 0; i < l_nh && fits; i++) {
+        int32_t l, c;
+        buffered_hit(i, &l, &c);
+        if (l >= 0) fits = fh.add((uint32_t)l, c);
+      }
+      if (fits) { taxon = slk_resolve_tree(fh, tx, confidence, (int32_t)(l_k0 + l_k1)); fast_done = true; }
+    } else {
+      spill(0);   // a fragment that went to the sink keeps all its hits there
+    }
+    if (!fast_done) taxon = resolve_slow(confidence);
     bool classified = taxon != 0 && nd >= (uint32_t)min_hit_groups;  // slacken/Classifier.scala:446
     r.taxon = classified ? tx.raw[taxon] : 0;
     r.flags = (classified ? SLK_F_CLASSIFIED : 0u) | (any ? SLK_F_HAS_SPAN : 0u) | (overflow ? SLK_F_OVERFLOW : 0u);
     r.kmers1 = kmers[0]; r.kmers2 = kmers[1];
     r.num_distinct = nd; r.n_hits = nh + nh_spilled; r.n_probes = nprobes;
+#undef SLK_LANES
 #undef SLK_WARP_ANY
+#undef SLK_WARP_ALL
 #undef SLK_WARP_MAX
+#undef SLK_BALLOT
+#undef SLK_POPC
+#undef SLK_SYNCWARP
   }
 };
 

@@ -12,18 +12,30 @@
       a.confidence, a.min_hit_groups, a.taxon_out, a.flags_out, a.detail_out, hb, hs, hc, a.hits_cursor, a.counts,         \
       a.error_flag, a.stats
 
+// the tiles of a block (71 KB) exceed the static shared-memory limit: opt in once per instantiation and device
+#define SLK_CLS_LAUNCH(HITS, PACKED, hb, hs, hc)                                                                       \
+  do {                                                                                                                 \
+    static bool done[64] = {};                                                                                         \
+    int dev = 0;                                                                                                       \
+    cudaGetDevice(&dev);                                                                                               \
+    if (dev < 0 || dev >= 64 || !done[dev]) {                                                                          \
+      cudaFuncSetAttribute(classify_kernel<SLK_W, HITS, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                           (int)SLK_SMEM_BYTES);                                                                       \
+      cudaFuncSetAttribute(classify_kernel<SLK_W, HITS, PACKED>, cudaFuncAttributePreferredSharedMemoryCarveout,       \
+                           cudaSharedmemCarveoutMaxShared);                                                            \
+      if (dev >= 0 && dev < 64) done[dev] = true;                                                                      \
+    }                                                                                                                  \
+    classify_kernel<SLK_W, HITS, PACKED><<<grid, SLK_CLS_THREADS, SLK_SMEM_BYTES, a.stream>>>(SLK_CLS_ARGS(a, hb, hs, hc)); \
+  } while (0)
+
 void SLK_CAT(slk_launch_classify_w, SLK_W)(const slk_classify_args& a) {
-  unsigned grid = (a.n_reads + 127) / 128;
+  unsigned grid = (a.n_reads + SLK_CLS_THREADS - 1) / SLK_CLS_THREADS;
   if (a.hits) {
-    if (a.packed)
-      classify_kernel<SLK_W, true, true><<<grid, 128, 0, a.stream>>>(SLK_CLS_ARGS(a, a.hits_base, a.hits_shift_ptr, a.hits_cap));
-    else
-      classify_kernel<SLK_W, true, false><<<grid, 128, 0, a.stream>>>(SLK_CLS_ARGS(a, a.hits_base, a.hits_shift_ptr, a.hits_cap));
+    if (a.packed) SLK_CLS_LAUNCH(true, true, a.hits_base, a.hits_shift_ptr, a.hits_cap);
+    else SLK_CLS_LAUNCH(true, false, a.hits_base, a.hits_shift_ptr, a.hits_cap);
   } else {
-    if (a.packed)
-      classify_kernel<SLK_W, false, true><<<grid, 128, 0, a.stream>>>(SLK_CLS_ARGS(a, nullptr, nullptr, 0));
-    else
-      classify_kernel<SLK_W, false, false><<<grid, 128, 0, a.stream>>>(SLK_CLS_ARGS(a, nullptr, nullptr, 0));
+    if (a.packed) SLK_CLS_LAUNCH(false, true, nullptr, nullptr, 0);
+    else SLK_CLS_LAUNCH(false, false, nullptr, nullptr, 0);
   }
 }
 void SLK_CAT(slk_launch_emit_w, SLK_W)(const slk_emit_args& a) {

@@ -87,33 +87,86 @@ __global__ void __launch_bounds__(128) emit_cells_kernel(const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------- classify kernel
-// Per-thread fast store: columns of shared-memory tiles [*][128] (conflict-free for a warp whose lanes use the
-// same row, never evicted, and -- unlike local memory -- one 4-byte access by a lone lane costs 4 bytes, not a sector).
+// Fast store of a warp in shared memory (see slk_store_local for the contract). A tile is
+//   stage A [POOL][16 B] | stage B [POOL][16 B] | keys [POOL][8 B] | metas [POOL][2 B] | nexts [POOL][1 B] | pending [POOL][1 B]
+// so that 32 lanes working on 32 consecutive slots touch consecutive words (no bank conflicts), and the two 16-byte
+// halves of a bucket are the two cp.async (LDGSTS through L1: one sector request per bucket) destinations.
 // It holds 32-bit shared-space addresses and uses ld.shared / st.shared explicitly: with generic pointers the
 // compiler must assume that every store may alias the pointers themselves and reloads them around each access.
+// commit/wait_group give every thread its own FIFO of outstanding copies.
+#define SLK_CLS_THREADS 128
+#define SLK_TILE_BYTES (44u * SLK_POOL)
+#define SLK_WARP_BYTES (2u * SLK_TILE_BYTES)
+#define SLK_SMEM_HITS ((SLK_CLS_THREADS / 32u) * SLK_WARP_BYTES)
+#define SLK_SMEM_BYTES (SLK_SMEM_HITS + SLK_SHITS * 8u * SLK_CLS_THREADS)
+static_assert(SLK_POOL % 32 == 0 && SLK_POOL >= 64 && SLK_POOL <= 256, "SLK_POOL: whole rounds of 32 slots, 8-bit links");
 struct dev_store {
-  uint32_t key, meta, hit;   // shared-space byte addresses of this thread's columns
-  __device__ __forceinline__ void set(uint32_t j, uint64_t k, uint32_t m) const {
-    asm volatile("st.shared.u64 [%0], %1;" ::"r"(key + j * 1024u), "l"(k));
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(meta + j * 256u), "h"((uint16_t)m));
+  uint32_t warp, hits, lane8;   // shared-space byte addresses: the warp's two tiles, this thread's hit column; lane * 8
+  // tile handle = the shared-space address of the tile; all accessors below take the handle
+  __device__ __forceinline__ uint32_t tile(uint32_t t) const { return warp + t * SLK_TILE_BYTES; }
+  __device__ __forceinline__ void put(uint32_t b, uint32_t s, uint64_t k, uint32_t m) const {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(b + 32u * SLK_POOL + s * 8u), "l"(k) : "memory");
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(b + 40u * SLK_POOL + s * 2u), "h"((uint16_t)m) : "memory");
   }
-  __device__ __forceinline__ uint64_t get_key(uint32_t j) const {
+  __device__ __forceinline__ void set_key(uint32_t t, uint32_t s, uint64_t k) const {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(t + 32u * SLK_POOL + s * 8u), "l"(k) : "memory");
+  }
+  __device__ __forceinline__ uint64_t key(uint32_t t, uint32_t s) const {
     uint64_t k;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(k) : "r"(key + j * 1024u));
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(k) : "r"(t + 32u * SLK_POOL + s * 8u) : "memory");
     return k;
   }
-  __device__ __forceinline__ uint32_t get_meta(uint32_t j) const {
+  __device__ __forceinline__ uint32_t meta(uint32_t t, uint32_t s) const {
     uint16_t m;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(m) : "r"(meta + j * 256u));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(m) : "r"(t + 40u * SLK_POOL + s * 2u) : "memory");
     return m;
   }
+  __device__ __forceinline__ void set_next(uint32_t t, uint32_t s, uint32_t n) const {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(t + 42u * SLK_POOL + s), "r"(n) : "memory");
+  }
+  __device__ __forceinline__ uint32_t next(uint32_t t, uint32_t s) const {
+    uint32_t n;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(n) : "r"(t + 42u * SLK_POOL + s) : "memory");
+    return n;
+  }
+  __device__ __forceinline__ void set_pending(uint32_t t, uint32_t q, uint32_t s) const {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(t + 43u * SLK_POOL + q), "r"(s) : "memory");
+  }
+  __device__ __forceinline__ uint32_t pending(uint32_t t, uint32_t q) const {
+    uint32_t s;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(s) : "r"(t + 43u * SLK_POOL + q) : "memory");
+    return s;
+  }
+  __device__ __forceinline__ void fetch(uint32_t t, uint32_t s, const uint64_t* src) const {
+    const uint32_t d = t + s * 16u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + 16u * SLK_POOL), "l"(src + 2) : "memory");
+  }
+  __device__ __forceinline__ void bucket(uint32_t t, uint32_t s, slk_bucket* o) const {
+    const uint32_t d = t + s * 16u;
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(o->c0), "=l"(o->c1) : "r"(d) : "memory");
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(o->c2), "=l"(o->c3) : "r"(d + 16u * SLK_POOL) : "memory");
+  }
+  __device__ __forceinline__ void commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  __device__ __forceinline__ void wait_all() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+  __device__ __forceinline__ void wait_prev() const { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
   __device__ __forceinline__ void set_hit(uint32_t i, int32_t label, int32_t count) const {
-    asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(hit + i * 1024u), "r"(label), "r"(count));
+    asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(hits + i * (8u * SLK_CLS_THREADS)), "r"(label), "r"(count) : "memory");
   }
   __device__ __forceinline__ void get_hit(uint32_t i, int32_t* label, int32_t* count) const {
     int32_t l, c;
-    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(l), "=r"(c) : "r"(hit + i * 1024u));
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(l), "=r"(c) : "r"(hits + i * (8u * SLK_CLS_THREADS)) : "memory");
     *label = l; *count = c;
+  }
+  // histogram pair i of this lane: row i (32 lanes x 8 bytes) of tile 0's staging area
+  __device__ __forceinline__ uint32_t hist_addr(uint32_t i) const { return warp + i * 256u + lane8; }
+  __device__ __forceinline__ void hist_set(uint32_t i, uint32_t t, int32_t v) const {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(hist_addr(i)), "r"(t), "r"((uint32_t)v) : "memory");
+  }
+  __device__ __forceinline__ void hist_get(uint32_t i, uint32_t* t, int32_t* v) const {
+    uint32_t a, b;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(hist_addr(i)) : "memory");
+    *t = a; *v = (int32_t)b;
   }
 };
 
@@ -144,10 +197,10 @@ struct dev_hit_sink {
 };
 
 #ifndef SLK_CLS_MINB
-#define SLK_CLS_MINB 6   // 80 registers: measured best on B200 (96 regs/5 blocks: +4% time, 64 regs: spills, 3.5x slower)
+#define SLK_CLS_MINB 4   // 4 x 51 KB of tiles per SM; up to 128 registers per thread, so nothing spills
 #endif
 template <int W, bool HITS, bool PACKED>
-__global__ void __launch_bounds__(128, SLK_CLS_MINB) classify_kernel(const __grid_constant__ slk_scan_params sp,
+__global__ void __launch_bounds__(SLK_CLS_THREADS, SLK_CLS_MINB) classify_kernel(const __grid_constant__ slk_scan_params sp,
                                                        const __grid_constant__ slk_table_view tb,
                                                        const __grid_constant__ slk_tax_view tx,
                                                        const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ off1,
@@ -166,13 +219,14 @@ __global__ void __launch_bounds__(128, SLK_CLS_MINB) classify_kernel(const __gri
   slk_frag_result res;
   res.taxon = 0; res.flags = 0; res.kmers1 = 0; res.kmers2 = 0; res.num_distinct = 0; res.n_hits = 0; res.n_probes = 0;
   typedef typename std::conditional<HITS, dev_hit_sink, slk_null_sink>::type sink_t;
-  __shared__ uint64_t skey[SLK_ECAP][128];
-  __shared__ uint16_t smeta[SLK_ECAP][128];
-  __shared__ int2 shit[SLK_SHITS][128];
+  extern __shared__ __align__(16) uint8_t slk_smem[];
   dev_store ent;
-  ent.key = (uint32_t)__cvta_generic_to_shared(&skey[0][threadIdx.x]);
-  ent.meta = (uint32_t)__cvta_generic_to_shared(&smeta[0][threadIdx.x]);
-  ent.hit = (uint32_t)__cvta_generic_to_shared(&shit[0][threadIdx.x]);
+  {
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(slk_smem);
+    ent.warp = base + (threadIdx.x >> 5) * SLK_WARP_BYTES;
+    ent.hits = base + SLK_SMEM_HITS + threadIdx.x * 8u;
+    ent.lane8 = (threadIdx.x & 31u) * 8u;
+  }
   sink_t sink;
   if constexpr (HITS) {
     sink.n = 0; sink.spilled = false; sink.goff = 0; sink.gbase = hits_base;
@@ -203,7 +257,8 @@ __global__ void __launch_bounds__(128, SLK_CLS_MINB) classify_kernel(const __gri
         }
       }
     }
-    cl.template run<PACKED>(sp, r1, r2, bases2 != nullptr, confidence, min_hit_groups, res);
+    if (sp.canonical) cl.template run<PACKED, true>(sp, r1, r2, bases2 != nullptr, confidence, min_hit_groups, res);
+    else cl.template run<PACKED, false>(sp, r1, r2, bases2 != nullptr, confidence, min_hit_groups, res);
     if (active) {
       taxon_out[r] = res.taxon;
       flags_out[r] = (uint8_t)(res.flags & 3u);
@@ -216,7 +271,19 @@ __global__ void __launch_bounds__(128, SLK_CLS_MINB) classify_kernel(const __gri
     uint64_t o = warp_agg_alloc(hits_cursor, need);
     if (active) {
       if (!sink.spilled) {
-        for (uint32_t i = 0; i < cl.nh; i++) {
+        // the hits of the fast store first: all dense -> raw lookups are issued before the first store
+        const uint32_t n = cl.nh;
+        int32_t hl[SLK_SHITS], hc[SLK_SHITS];
+#pragma unroll
+        for (uint32_t i = 0; i < SLK_SHITS; i++)
+          if (i < n) ent.get_hit(i, &hl[i], &hc[i]);
+#pragma unroll
+        for (uint32_t i = 0; i < SLK_SHITS; i++)
+          if (i < n && hl[i] >= 0) hl[i] = __ldg(tx.raw + hl[i]);
+#pragma unroll
+        for (uint32_t i = 0; i < SLK_SHITS; i++)
+          if (i < n) sink.put(o + i, hl[i], hc[i]);
+        for (uint32_t i = SLK_SHITS; i < n; i++) {
           int32_t l, c;
           cl.buffered_hit(i, &l, &c);
           sink.put(o + i, l >= 0 ? tx.raw[l] : l, c);

@@ -8,6 +8,8 @@
 #include <algorithm>
 #include <vector>
 
+// a small tile, so that the tests close tiles (and move histograms out of the fast store) all the time
+#define SLK_POOL 8
 #include "../../slacken_b200/csrc/slk_core.h"
 
 #define EMU_API extern "C" __attribute__((visibility("default")))
@@ -20,7 +22,7 @@ EMU_API int emu_sizeof_scan_params() { return (int)sizeof(slk_scan_params); }
 EMU_API uint64_t emu_compress(const slk_scan_params* sp, uint64_t x) { return slk_compress(*sp, x); }
 EMU_API uint64_t emu_expand(const slk_scan_params* sp, uint64_t x) { return slk_expand(*sp, x); }
 EMU_API uint32_t emu_code(uint32_t c) { return slk_code(c); }
-EMU_API uint64_t emu_buckets_for(uint64_t n_keys) { return ((uint64_t)((double)n_keys / 0.70) + 64 + 3) / 4; }
+EMU_API uint64_t emu_buckets_for(uint64_t n_keys) { return (((uint64_t)((double)n_keys / 0.70) + 64 + 15) / 16) * 4; }
 
 // sequential twin of insert_cells_kernel (no atomics needed with one "thread")
 EMU_API void emu_insert_cells(uint64_t* cells, uint64_t n_buckets, const uint16_t* parent, const uint8_t* depth,
@@ -32,13 +34,13 @@ EMU_API void emu_insert_cells(uint64_t* cells, uint64_t n_buckets, const uint16_
     if (!taxon) continue;
     uint64_t b = slk_bucket_of(ckey, n_buckets);
     bool done = false;
-    while (!done) {
+    for (uint64_t tries = 1; !done; tries++) {
       for (int j = 0; j < 4 && !done; j++) {
         uint64_t& c = cells[b * 4 + j];
         if (c == 0) { c = cell; done = true; }
         else if ((c >> 16) == ckey) { c = (ckey << 16) | slk_lca(tx, (uint32_t)(c & 0xffff), taxon); done = true; }
       }
-      b = (b + 1 == n_buckets) ? 0 : b + 1;
+      b = slk_next_bucket(b, tries, n_buckets);
     }
   }
 }
@@ -77,9 +79,11 @@ static int64_t classify_w(const slk_scan_params* sp, uint64_t* cells, uint64_t n
         slk_pack_read(r2.ascii, r2.len, [&](uint32_t, uint64_t cw, uint32_t mw) { c2.push_back(cw); m2.push_back(mw); });
         r2.codes = c2.data(); r2.mask = m2.data();
       }
-      cl.template run<true>(*sp, r1, r2, b2 != nullptr, confidence, min_hit_groups, fr);
+      if (sp->canonical) cl.template run<true, true>(*sp, r1, r2, b2 != nullptr, confidence, min_hit_groups, fr);
+      else cl.template run<true, false>(*sp, r1, r2, b2 != nullptr, confidence, min_hit_groups, fr);
     } else {
-      cl.template run<false>(*sp, r1, r2, b2 != nullptr, confidence, min_hit_groups, fr);
+      if (sp->canonical) cl.template run<false, true>(*sp, r1, r2, b2 != nullptr, confidence, min_hit_groups, fr);
+      else cl.template run<false, false>(*sp, r1, r2, b2 != nullptr, confidence, min_hit_groups, fr);
     }
     res[r] = emu_result{fr.taxon, fr.flags, fr.kmers1, fr.kmers2, fr.num_distinct, fr.n_hits};
     if (cl.nh_spilled == 0)   // the kernel epilogue: buffered hits leave with raw taxon ids
