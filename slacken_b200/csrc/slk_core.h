@@ -27,9 +27,9 @@
 
 #define SLK_MAX_W 8      // k - m + 1 supported by the kernels (35 - 31 + 1 = 5 for the Kraken 2 defaults)
 #ifndef SLK_POOL
-#define SLK_POOL 128     // span entries per tile; a WARP owns two tiles (filling / in flight) in shared memory
+#define SLK_POOL 192     // span entries per tile; a WARP owns two tiles (filling / in flight) in shared memory
 #endif
-#define SLK_SHIST (SLK_POOL / 8)  // (taxon, k-mers) histogram pairs per lane that fit the idle staging area of a tile
+#define SLK_SHIST (SLK_POOL / 8)  // (taxon, k-mers) histogram pairs per lane that fit the idle staging area
 #define SLK_SHITS 8      // merged hits of a fragment kept in the fast store (shared memory on the device)
 #define SLK_XHITS 56     // further merged hits kept in a per-thread overflow array before spilling to global memory
 #define SLK_KMAX 128     // distinct taxa per fragment held in the per-thread histogram
@@ -216,14 +216,13 @@ SLK_HD uint64_t slk_bucket_of(uint64_t ckey, uint64_t n_buckets) {
 // line requests (~36 G/s), not by their bytes. So a collision chain first walks the other three buckets of its own
 // line (cache hits), and only then moves on to the next line. `tries` = buckets already examined (>= 1).
 SLK_HD uint64_t slk_next_bucket(uint64_t b, uint64_t tries, uint64_t n_buckets) {
-  uint64_t nb = (b & ~3ull) | ((b + 1) & 3ull);
-  if ((tries & 3ull) == 0) { nb += 4; if (nb >= n_buckets) nb -= n_buckets; }
+  // bucket number t of a chain is (home line + t / 4, home sub-bucket XOR t % 4): the first step stays inside the
+  // home bucket's 64-byte half line, the next two inside its 128-byte line. `b` is bucket number tries - 1.
+  const uint64_t sub_home = (b ^ (tries - 1)) & 3ull, r = tries & 3ull;
+  uint64_t nb = (b & ~3ull) | (sub_home ^ r);
+  if (r == 0) { nb += 4; if (nb >= n_buckets) nb -= n_buckets; }
   return nb;
 }
-
-// One bucket (= one 32-byte sector) of a probe: both halves are loaded before anything is compared.
-// Returns true when the probe is decided: *dense = the key's taxon, or 0 if an empty cell proves its absence
-// (cells of a bucket fill in order and are never deleted, so nothing can follow an empty cell).
 struct slk_bucket { uint64_t c0, c1, c2, c3; };
 SLK_HD void slk_load_bucket(const slk_table_view& tb, uint64_t b, slk_bucket* o) {
 #if defined(__CUDA_ARCH__)
@@ -362,6 +361,7 @@ struct slk_frag_result {
 // buffer; emulation: a vector). `need` = upper bound of the hits this fragment can still produce.
 struct slk_null_sink {
   SLK_HD void push(int32_t, int32_t, uint32_t) {}
+  SLK_HD void reserve(uint32_t) {}
 };
 
 // LowestCommonAncestor.resolveTree (slacken/LowestCommonAncestor.scala:91-146) over a histogram H of
@@ -434,15 +434,17 @@ struct slk_fast_hist {
 
 // Fast store of a WARP (shared memory on the device, plain arrays in the one-lane emulation):
 //  * two tiles (one being filled, one whose lookups are in flight) of SLK_POOL span entries each. The lanes of a warp
-//    append to the tile in step order; an entry is key (64 bit), meta (count | type << 14), the slot of the same
-//    lane's next entry, and a 32-byte staging area that receives the entry's table bucket through an ASYNCHRONOUS copy;
+//    append to the tile in step order; an entry is key (64 bit), meta (count | type << 14) and the slot of the same
+//    lane's next entry;
+//  * ONE staging area of SLK_POOL x 32 bytes: slot s receives the table bucket of entry s of the tile in flight through
+//    an ASYNCHRONOUS copy (the tile being filled needs none yet, so both tiles can be 1.5x larger for the same memory);
 //  * per lane, the first SLK_SHITS merged hits of its fragment;
-//  * once the scan is over, the staging areas are reused as each lane's first SLK_SHIST (taxon, k-mers) histogram pairs.
+//  * once the scan is over, the staging area is reused as each lane's first SLK_SHIST (taxon, k-mers) histogram pairs.
 struct slk_store_local {
   uint64_t keys[2][SLK_POOL];
   uint16_t metas[2][SLK_POOL];
   uint8_t nexts[2][SLK_POOL], pend[2][SLK_POOL];
-  uint64_t stage[2][SLK_POOL][4];
+  uint64_t stage[SLK_POOL][4];
   int32_t hl[SLK_SHITS], hc[SLK_SHITS];
   SLK_HD uint32_t tile(uint32_t t) const { return t; }   // tile handle (the device's is a shared-space address)
   SLK_HD void put(uint32_t t, uint32_t s, uint64_t k, uint32_t m) { keys[t][s] = k; metas[t][s] = (uint16_t)m; }
@@ -453,17 +455,16 @@ struct slk_store_local {
   SLK_HD uint32_t next(uint32_t t, uint32_t s) const { return nexts[t][s]; }
   SLK_HD void set_pending(uint32_t t, uint32_t q, uint32_t s) { pend[t][q] = (uint8_t)s; }
   SLK_HD uint32_t pending(uint32_t t, uint32_t q) const { return pend[t][q]; }
-  SLK_HD void fetch(uint32_t t, uint32_t s, const uint64_t* src) { for (int i = 0; i < 4; i++) stage[t][s][i] = src[i]; }
-  SLK_HD void bucket(uint32_t t, uint32_t s, slk_bucket* o) const {
-    o->c0 = stage[t][s][0]; o->c1 = stage[t][s][1]; o->c2 = stage[t][s][2]; o->c3 = stage[t][s][3];
+  SLK_HD void fetch(uint32_t s, const uint64_t* src) { for (int i = 0; i < 4; i++) stage[s][i] = src[i]; }
+  SLK_HD void bucket(uint32_t s, slk_bucket* o) const {
+    o->c0 = stage[s][0]; o->c1 = stage[s][1]; o->c2 = stage[s][2]; o->c3 = stage[s][3];
   }
-  SLK_HD void commit() const {}
-  SLK_HD void wait_all() const {}
-  SLK_HD void wait_prev() const {}
+  SLK_HD void commit(uint32_t) const {}      // n: buckets this lane requested since the last commit
+  SLK_HD void wait_all(uint32_t) const {}    // parity: number of commits so far, mod 2
   SLK_HD void set_hit(uint32_t i, int32_t label, int32_t count) { hl[i] = label; hc[i] = count; }
   SLK_HD void get_hit(uint32_t i, int32_t* label, int32_t* count) const { *label = hl[i]; *count = hc[i]; }
-  SLK_HD void hist_set(uint32_t i, uint32_t t, int32_t v) { (&stage[0][0][0])[i] = ((uint64_t)(uint32_t)v << 32) | t; }
-  SLK_HD void hist_get(uint32_t i, uint32_t* t, int32_t* v) const { uint64_t x = (&stage[0][0][0])[i]; *t = (uint32_t)x; *v = (int32_t)(x >> 32); }
+  SLK_HD void hist_set(uint32_t i, uint32_t t, int32_t v) { (&stage[0][0])[i] = ((uint64_t)(uint32_t)v << 32) | t; }
+  SLK_HD void hist_get(uint32_t i, uint32_t* t, int32_t* v) const { uint64_t x = (&stage[0][0])[i]; *t = (uint32_t)x; *v = (int32_t)(x >> 32); }
 };
 
 // One fragment (a read or a read pair) per thread, end to end: scan -> span entries -> table lookups -> merged
@@ -568,6 +569,7 @@ struct slk_frag_classifier {
     uint32_t head_cur = 0, tail_cur = 0, cnt_cur = 0;   // this lane's own entries in the tile being filled
     uint32_t head_prev = 0, cnt_prev = 0;               // ... and in the tile in flight
     bool any = false;                      // did the fragment yield any span at all
+    uint32_t n_commits = 0;                // closes so far (the parity of the store's completion barrier)
 #if defined(__CUDA_ARCH__)
     const Entries ent = this->ent;   // shared-space addresses, in registers
     const slk_table_view tb = this->tb;
@@ -603,30 +605,31 @@ struct slk_frag_classifier {
       l_nh++;
     };
     // Closes the tile being filled. The whole warp comes here together.
-    //  1. the buckets of the PREVIOUS tile, requested one tile ago, have landed in the staging areas;
+    //  1. the buckets of the PREVIOUS tile, requested one tile ago, have landed in the staging area;
     //  2. match pass over the previous tile, 32 entries per round: spanToHit's join (slacken/KeyValueIndex.scala:
     //     176-185). The dense taxon (0 = miss -> Taxonomy.NONE) goes to the top 16 bits of the entry's key slot.
-    //     The few entries whose bucket was full without a match are collected in the tile's pending list; they
-    //     then request the next bucket of their chain (same 128-byte line: a cache hit), 32 per round;
-    //  3. issue pass over the tile just filled, 32 entries per round: compress the key, request its bucket;
-    //  4. the chain buckets of step 2 have landed (the requests of step 3 stay in flight): pending pass;
+    //     The few entries whose bucket was full without a match are collected in the tile's pending list;
+    //  3. issue pass over the tile just filled, 32 entries per round: compress the key, request its bucket (the
+    //     staging area is free again: step 2 has read all of it);
+    //  4. pending pass, 32 entries per round: the chains go on with ordinary loads; their next bucket is in the same
+    //     128-byte line, which the first request already brought into the caches;
     //  5. merge pass: every lane walks ITS entries of the previous tile in span order: numDistinct
     //     (slacken/Classifier.scala:94), k-mer totals, TaxonCounts.fromHits.
-    // A lane only ever waits for copies it issued itself: slot s is requested and matched by lane s % 32, pending
-    // entry q by lane q % 32.
+    // A lane only ever waits for copies it issued itself: slot s is requested and matched by lane s % 32.
     auto close = [&]() {
       any = any || cnt_cur != 0;
       const uint32_t prev = cur ^ ent_tile0 ^ ent_tile1;
       SLK_SYNCWARP();   // the entries other lanes appended are visible
-      ent.wait_all();
+      ent.wait_all(n_commits & 1u);
       uint32_t n_pend = 0;
+#pragma unroll 2
       for (uint32_t s0 = 0; s0 < n_prev; s0 += SLK_LANES) {
         const uint32_t s = s0 + lane;
         bool pend = false;
         if (s < n_prev && (ent.meta(prev, s) >> 14) == SLK_E_SEQ) {
           const uint64_t ck = ent.key(prev, s);
           slk_bucket bk;
-          ent.bucket(prev, s, &bk);
+          ent.bucket(s, &bk);
           uint32_t dense;
           pend = !slk_match_bucket(bk, ck, &dense);
           if (!pend) ent.set_key(prev, s, ck | ((uint64_t)dense << 48));
@@ -635,33 +638,24 @@ struct slk_frag_classifier {
         if (pend) ent.set_pending(prev, n_pend + SLK_POPC(bal & lanes_below), s);
         n_pend += SLK_POPC(bal);
       }
-      SLK_SYNCWARP();   // the pending list is complete, and nobody reads a first bucket any more
-      for (uint32_t q = lane; q < n_pend; q += SLK_LANES) {
-        const uint32_t s = ent.pending(prev, q);
-        const uint64_t nb = slk_next_bucket(slk_bucket_of(ent.key(prev, s), tb.n_buckets), 1, tb.n_buckets);
-        ent.fetch(prev, s, tb.cells + nb * 4);
-      }
-      ent.commit();
+      SLK_SYNCWARP();   // the pending list is complete, and nobody reads the staging area any more
+      uint32_t n_fetched = 0;
+#pragma unroll 2
       for (uint32_t s = lane; s < n_cur; s += SLK_LANES) {
         if ((ent.meta(cur, s) >> 14) == SLK_E_SEQ) {
           const uint64_t key = ent.key(cur, s);
           const uint64_t ck = fast ? slk_compress_fast(key) : slk_compress_generic(sp, key);
           ent.set_key(cur, s, ck);
-          ent.fetch(cur, s, tb.cells + slk_bucket_of(ck, tb.n_buckets) * 4);
+          ent.fetch(s, tb.cells + slk_bucket_of(ck, tb.n_buckets) * 4);
+          n_fetched++;
         }
       }
-      ent.commit();
-      ent.wait_prev();
+      ent.commit(n_fetched);
+      n_commits++;
       for (uint32_t q = lane; q < n_pend; q += SLK_LANES) {
         const uint32_t s = ent.pending(prev, q);
         const uint64_t ck = ent.key(prev, s);
-        slk_bucket bk;
-        ent.bucket(prev, s, &bk);
-        uint32_t dense;
-        if (!slk_match_bucket(bk, ck, &dense)) {
-          const uint64_t b2 = slk_next_bucket(slk_bucket_of(ck, tb.n_buckets), 1, tb.n_buckets);
-          dense = slk_probe_rest(tb, b2, 2, ck);
-        }
+        const uint32_t dense = slk_probe_rest(tb, slk_bucket_of(ck, tb.n_buckets), 1, ck);
         ent.set_key(prev, s, ck | ((uint64_t)dense << 48));
       }
       SLK_SYNCWARP();   // all labels of the previous tile are visible to the lanes that own the entries
@@ -796,19 +790,24 @@ struct slk_frag_classifier {
       if (PACKED) {
         const uint32_t nblk = (len + 31u) >> 5;
         const uint32_t nblk_w = SLK_WARP_MAX(nblk);
-        for (uint32_t b = 0; b < nblk_w; b++) {
-          uint64_t cw = 0;
-          uint32_t mw = 0, nb = 0;
-          if (b < nblk) {
+        uint64_t cw_next = 0;
+        uint32_t mw_next = 0;
 #if defined(__CUDA_ARCH__)
-            cw = __ldg(src.codes + b); mw = __ldg(src.mask + b);
+#define SLK_LOAD_BLOCK(b) do { cw_next = __ldg(src.codes + (b)); mw_next = __ldg(src.mask + (b)); } while (0)
 #else
-            cw = src.codes[b]; mw = src.mask[b];
+#define SLK_LOAD_BLOCK(b) do { cw_next = src.codes[b]; mw_next = src.mask[b]; } while (0)
 #endif
-            nb = len - 32u * b; nb = nb > 32u ? 32u : nb;
-          }
+        if (nblk) SLK_LOAD_BLOCK(0);
+        for (uint32_t b = 0; b < nblk_w; b++) {   // block b+1 is requested before block b is scanned
+          const uint64_t cw = cw_next;
+          const uint32_t mw = mw_next;
+          uint32_t nb = 0;
+          if (b < nblk) { nb = len - 32u * b; nb = nb > 32u ? 32u : nb; }
+          cw_next = 0; mw_next = 0;
+          if (b + 1 < nblk) SLK_LOAD_BLOCK(b + 1);
           scan_block(cw, mw, 0u, nb);
         }
+#undef SLK_LOAD_BLOCK
       } else {
         // 16-byte chunks over [s, s+len), aligned for the device's vector loads. The buffer is readable up to the
         // next 16-byte boundary (library-owned and cudaMalloc'ed buffers are); bytes outside the read are skipped.
@@ -848,6 +847,9 @@ struct slk_frag_classifier {
 #pragma unroll 1
     for (int e = 0; e < 2; e++) close();   // the first requests the last tile and merges the one before it
     if (l_have_cur) push_hit(l_label, l_count);
+    // The number of buffered hits is final: the sink may reserve their place in the output now (on the device one
+    // atomic per warp, whose latency the resolve step below hides). All lanes call it.
+    sink.reserve(l_spilled ? 0u : l_nh);
     nh = l_nh; kmers[0] = l_k0; kmers[1] = l_k1; nd = l_nd; nprobes = l_np;
     // totalKmers: ambiguous spans count, the border does not (slacken/TaxonCounts.scala:83-87)
     uint32_t taxon;

@@ -87,85 +87,85 @@ __global__ void __launch_bounds__(128) emit_cells_kernel(const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------- classify kernel
-// Fast store of a warp in shared memory (see slk_store_local for the contract). A tile is
-//   stage A [POOL][16 B] | stage B [POOL][16 B] | keys [POOL][8 B] | metas [POOL][2 B] | nexts [POOL][1 B] | pending [POOL][1 B]
+// Fast store of a warp in shared memory (see slk_store_local for the contract):
+//   stage A [POOL][16 B] | stage B [POOL][16 B] | tile 0 | tile 1,  tile = keys [POOL][8 B] | metas [POOL][2 B] |
+//   nexts [POOL][1 B] | pending [POOL][1 B]
 // so that 32 lanes working on 32 consecutive slots touch consecutive words (no bank conflicts), and the two 16-byte
 // halves of a bucket are the two cp.async (LDGSTS through L1: one sector request per bucket) destinations.
 // It holds 32-bit shared-space addresses and uses ld.shared / st.shared explicitly: with generic pointers the
 // compiler must assume that every store may alias the pointers themselves and reloads them around each access.
 // commit/wait_group give every thread its own FIFO of outstanding copies.
 #define SLK_CLS_THREADS 128
-#define SLK_TILE_BYTES (44u * SLK_POOL)
-#define SLK_WARP_BYTES (2u * SLK_TILE_BYTES)
+#define SLK_TILE_BYTES (12u * SLK_POOL)
+#define SLK_WARP_BYTES (32u * SLK_POOL + 2u * SLK_TILE_BYTES)
 #define SLK_SMEM_HITS ((SLK_CLS_THREADS / 32u) * SLK_WARP_BYTES)
 #define SLK_SMEM_BYTES (SLK_SMEM_HITS + SLK_SHITS * 8u * SLK_CLS_THREADS)
-static_assert(SLK_POOL % 32 == 0 && SLK_POOL >= 64 && SLK_POOL <= 256, "SLK_POOL: whole rounds of 32 slots, 8-bit links");
+static_assert(SLK_POOL % 32 == 0 && SLK_POOL >= 128 && SLK_POOL <= 256, "SLK_POOL: whole rounds of 32 slots, 8-bit links");
+extern __shared__ __align__(16) uint8_t slk_smem[];
 struct dev_store {
-  uint32_t warp, hits, lane8;   // shared-space byte addresses: the warp's two tiles, this thread's hit column; lane * 8
-  // tile handle = the shared-space address of the tile; all accessors below take the handle
-  __device__ __forceinline__ uint32_t tile(uint32_t t) const { return warp + t * SLK_TILE_BYTES; }
+  uint32_t warp, hits, lane8;
+  __device__ __forceinline__ static uint32_t sa(uint32_t off) { return (uint32_t)__cvta_generic_to_shared(slk_smem) + off; }
+  __device__ __forceinline__ uint32_t tile(uint32_t t) const { return warp + 32u * SLK_POOL + t * SLK_TILE_BYTES; }
   __device__ __forceinline__ void put(uint32_t b, uint32_t s, uint64_t k, uint32_t m) const {
-    asm volatile("st.shared.u64 [%0], %1;" ::"r"(b + 32u * SLK_POOL + s * 8u), "l"(k) : "memory");
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(b + 40u * SLK_POOL + s * 2u), "h"((uint16_t)m) : "memory");
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(sa(b + s * 8u)), "l"(k) : "memory");
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(sa(b + 8u * SLK_POOL + s * 2u)), "h"((uint16_t)m) : "memory");
   }
   __device__ __forceinline__ void set_key(uint32_t t, uint32_t s, uint64_t k) const {
-    asm volatile("st.shared.u64 [%0], %1;" ::"r"(t + 32u * SLK_POOL + s * 8u), "l"(k) : "memory");
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(sa(t + s * 8u)), "l"(k) : "memory");
   }
   __device__ __forceinline__ uint64_t key(uint32_t t, uint32_t s) const {
     uint64_t k;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(k) : "r"(t + 32u * SLK_POOL + s * 8u) : "memory");
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(k) : "r"(sa(t + s * 8u)) : "memory");
     return k;
   }
   __device__ __forceinline__ uint32_t meta(uint32_t t, uint32_t s) const {
     uint16_t m;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(m) : "r"(t + 40u * SLK_POOL + s * 2u) : "memory");
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(m) : "r"(sa(t + 8u * SLK_POOL + s * 2u)) : "memory");
     return m;
   }
   __device__ __forceinline__ void set_next(uint32_t t, uint32_t s, uint32_t n) const {
-    asm volatile("st.shared.u8 [%0], %1;" ::"r"(t + 42u * SLK_POOL + s), "r"(n) : "memory");
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(sa(t + 10u * SLK_POOL + s)), "r"(n) : "memory");
   }
   __device__ __forceinline__ uint32_t next(uint32_t t, uint32_t s) const {
     uint32_t n;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(n) : "r"(t + 42u * SLK_POOL + s) : "memory");
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(n) : "r"(sa(t + 10u * SLK_POOL + s)) : "memory");
     return n;
   }
   __device__ __forceinline__ void set_pending(uint32_t t, uint32_t q, uint32_t s) const {
-    asm volatile("st.shared.u8 [%0], %1;" ::"r"(t + 43u * SLK_POOL + q), "r"(s) : "memory");
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(sa(t + 11u * SLK_POOL + q)), "r"(s) : "memory");
   }
   __device__ __forceinline__ uint32_t pending(uint32_t t, uint32_t q) const {
     uint32_t s;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(s) : "r"(t + 43u * SLK_POOL + q) : "memory");
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(s) : "r"(sa(t + 11u * SLK_POOL + q)) : "memory");
     return s;
   }
-  __device__ __forceinline__ void fetch(uint32_t t, uint32_t s, const uint64_t* src) const {
-    const uint32_t d = t + s * 16u;
+  __device__ __forceinline__ void fetch(uint32_t s, const uint64_t* src) const {
+    const uint32_t d = sa(warp + s * 16u);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + 16u * SLK_POOL), "l"(src + 2) : "memory");
   }
-  __device__ __forceinline__ void bucket(uint32_t t, uint32_t s, slk_bucket* o) const {
-    const uint32_t d = t + s * 16u;
+  __device__ __forceinline__ void bucket(uint32_t s, slk_bucket* o) const {
+    const uint32_t d = sa(warp + s * 16u);
     asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(o->c0), "=l"(o->c1) : "r"(d) : "memory");
     asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(o->c2), "=l"(o->c3) : "r"(d + 16u * SLK_POOL) : "memory");
   }
-  __device__ __forceinline__ void commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
-  __device__ __forceinline__ void wait_all() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-  __device__ __forceinline__ void wait_prev() const { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+  __device__ __forceinline__ void commit(uint32_t) const { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  __device__ __forceinline__ void wait_all(uint32_t) const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
   __device__ __forceinline__ void set_hit(uint32_t i, int32_t label, int32_t count) const {
-    asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(hits + i * (8u * SLK_CLS_THREADS)), "r"(label), "r"(count) : "memory");
+    asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(sa(hits + i * (8u * SLK_CLS_THREADS))), "r"(label), "r"(count) : "memory");
   }
   __device__ __forceinline__ void get_hit(uint32_t i, int32_t* label, int32_t* count) const {
     int32_t l, c;
-    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(l), "=r"(c) : "r"(hits + i * (8u * SLK_CLS_THREADS)) : "memory");
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(l), "=r"(c) : "r"(sa(hits + i * (8u * SLK_CLS_THREADS))) : "memory");
     *label = l; *count = c;
   }
-  // histogram pair i of this lane: row i (32 lanes x 8 bytes) of tile 0's staging area
-  __device__ __forceinline__ uint32_t hist_addr(uint32_t i) const { return warp + i * 256u + lane8; }
   __device__ __forceinline__ void hist_set(uint32_t i, uint32_t t, int32_t v) const {
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(hist_addr(i)), "r"(t), "r"((uint32_t)v) : "memory");
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa(warp + i * 256u + lane8)), "r"(t), "r"((uint32_t)v) : "memory");
   }
   __device__ __forceinline__ void hist_get(uint32_t i, uint32_t* t, int32_t* v) const {
     uint32_t a, b;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(hist_addr(i)) : "memory");
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(sa(warp + i * 256u + lane8)) : "memory");
     *t = a; *v = (int32_t)b;
   }
 };
@@ -175,8 +175,9 @@ struct dev_store {
 // written from the buffers to a compact, warp-allocated block at the end of the kernel.
 struct dev_hit_sink {
   uint32_t n;
-  bool spilled;
+  bool spilled, live;     // live: the lane holds a fragment of the batch (lanes past its end scan an empty one)
   uint64_t goff;
+  uint64_t reserved;      // first slot of this lane's buffered hits in the compact, warp-allocated block
   slk_hit* gbase;         // scratch, indexed by (absolute index - gshift)
   uint64_t gshift, gcap;  // gcap: capacity of gbase in hits
   unsigned long long* cursor;
@@ -186,6 +187,7 @@ struct dev_hit_sink {
     h.taxon = taxon; h.count = count;
     if (rel < gcap) gbase[rel] = h;
   }
+  __device__ __forceinline__ void reserve(uint32_t n_hits);   // all 32 lanes call it
   __device__ __forceinline__ void push(int32_t taxon, int32_t count, uint32_t need) {
     if (!spilled) {
       goff = atomicAdd(cursor, (unsigned long long)need + 2ull);
@@ -195,6 +197,8 @@ struct dev_hit_sink {
     n++;
   }
 };
+
+__device__ __forceinline__ void dev_hit_sink::reserve(uint32_t n_hits) { reserved = warp_agg_alloc(cursor, live ? n_hits : 0u); }
 
 #ifndef SLK_CLS_MINB
 #define SLK_CLS_MINB 4   // 4 x 51 KB of tiles per SM; up to 128 registers per thread, so nothing spills
@@ -219,17 +223,13 @@ __global__ void __launch_bounds__(SLK_CLS_THREADS, SLK_CLS_MINB) classify_kernel
   slk_frag_result res;
   res.taxon = 0; res.flags = 0; res.kmers1 = 0; res.kmers2 = 0; res.num_distinct = 0; res.n_hits = 0; res.n_probes = 0;
   typedef typename std::conditional<HITS, dev_hit_sink, slk_null_sink>::type sink_t;
-  extern __shared__ __align__(16) uint8_t slk_smem[];
   dev_store ent;
-  {
-    const uint32_t base = (uint32_t)__cvta_generic_to_shared(slk_smem);
-    ent.warp = base + (threadIdx.x >> 5) * SLK_WARP_BYTES;
-    ent.hits = base + SLK_SMEM_HITS + threadIdx.x * 8u;
-    ent.lane8 = (threadIdx.x & 31u) * 8u;
-  }
+  ent.warp = (threadIdx.x >> 5) * SLK_WARP_BYTES;
+  ent.hits = SLK_SMEM_HITS + threadIdx.x * 8u;
+  ent.lane8 = (threadIdx.x & 31u) * 8u;
   sink_t sink;
   if constexpr (HITS) {
-    sink.n = 0; sink.spilled = false; sink.goff = 0; sink.gbase = hits_base;
+    sink.n = 0; sink.spilled = false; sink.live = active; sink.goff = 0; sink.reserved = 0; sink.gbase = hits_base;
     sink.gshift = hits_shift_ptr ? *hits_shift_ptr : 0ull;
     sink.gcap = hits_cap; sink.cursor = hits_cursor;
   }
@@ -265,45 +265,20 @@ __global__ void __launch_bounds__(SLK_CLS_THREADS, SLK_CLS_MINB) classify_kernel
       if (res.flags & SLK_F_OVERFLOW) atomicExch(error_flag, 1u);
     }
   }
+  // The merged hits and their (warp-allocated, compact) place in the output. The allocation's atomic was issued inside
+  // run(), before the resolve step; everything that does not need its result is done first.
+  int32_t hl[SLK_SHITS], hc[SLK_SHITS];
+  uint32_t n_buf = 0;
   if constexpr (HITS) {
-    // compact allocation of the buffered merged hits, one atomic per warp; dense labels become raw taxon ids here
-    uint32_t need = (active && !sink.spilled) ? cl.nh : 0u;
-    uint64_t o = warp_agg_alloc(hits_cursor, need);
-    if (active) {
-      if (!sink.spilled) {
-        // the hits of the fast store first: all dense -> raw lookups are issued before the first store
-        const uint32_t n = cl.nh;
-        int32_t hl[SLK_SHITS], hc[SLK_SHITS];
+    if (active && !sink.spilled) {
+      n_buf = cl.nh;
 #pragma unroll
-        for (uint32_t i = 0; i < SLK_SHITS; i++)
-          if (i < n) ent.get_hit(i, &hl[i], &hc[i]);
+      for (uint32_t i = 0; i < SLK_SHITS; i++)
+        if (i < n_buf) ent.get_hit(i, &hl[i], &hc[i]);
 #pragma unroll
-        for (uint32_t i = 0; i < SLK_SHITS; i++)
-          if (i < n && hl[i] >= 0) hl[i] = __ldg(tx.raw + hl[i]);
-#pragma unroll
-        for (uint32_t i = 0; i < SLK_SHITS; i++)
-          if (i < n) sink.put(o + i, hl[i], hc[i]);
-        for (uint32_t i = SLK_SHITS; i < n; i++) {
-          int32_t l, c;
-          cl.buffered_hit(i, &l, &c);
-          sink.put(o + i, l >= 0 ? tx.raw[l] : l, c);
-        }
-      }
-      slk_read_detail d;
-      d.hit_off = sink.spilled ? sink.goff : o;
-      d.hit_cnt = res.n_hits;
-      d.len1 = res.kmers1 + (uint32_t)(sp.k - 1);
-      d.len2 = bases2 ? res.kmers2 + (uint32_t)(sp.k - 1) : 0xFFFFFFFFu;
-      d.num_distinct = res.num_distinct;
-      detail_out[r] = d;
+      for (uint32_t i = 0; i < SLK_SHITS; i++)   // dense labels become raw taxon ids here: all lookups in flight together
+        if (i < n_buf && hl[i] >= 0) hl[i] = __ldg(tx.raw + hl[i]);
     }
-  } else if (detail_out != nullptr && active) {
-    slk_read_detail d;
-    d.hit_off = 0; d.hit_cnt = 0;
-    d.len1 = res.kmers1 + (uint32_t)(sp.k - 1);
-    d.len2 = bases2 ? res.kmers2 + (uint32_t)(sp.k - 1) : 0xFFFFFFFFu;
-    d.num_distinct = res.num_distinct;
-    detail_out[r] = d;
   }
   if (stats != nullptr) {  // probes and merged hits of this launch (the S and H of the roofline arithmetic)
     uint32_t np = __reduce_add_sync(0xffffffffu, active ? res.n_probes : 0u);
@@ -321,6 +296,33 @@ __global__ void __launch_bounds__(SLK_CLS_THREADS, SLK_CLS_MINB) classify_kernel
     uint32_t peers = __match_any_sync(0xffffffffu, key);
     if (cnt && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1))
       atomicAdd(&counts[(uint32_t)res.taxon], (unsigned long long)__popc(peers));
+  }
+  if constexpr (HITS) {
+    if (active) {
+      const uint64_t o = sink.reserved;
+#pragma unroll
+      for (uint32_t i = 0; i < SLK_SHITS; i++)
+        if (i < n_buf) sink.put(o + i, hl[i], hc[i]);
+      for (uint32_t i = SLK_SHITS; i < n_buf; i++) {
+        int32_t l, c;
+        cl.buffered_hit(i, &l, &c);
+        sink.put(o + i, l >= 0 ? tx.raw[l] : l, c);
+      }
+      slk_read_detail d;
+      d.hit_off = sink.spilled ? sink.goff : o;
+      d.hit_cnt = res.n_hits;
+      d.len1 = res.kmers1 + (uint32_t)(sp.k - 1);
+      d.len2 = bases2 ? res.kmers2 + (uint32_t)(sp.k - 1) : 0xFFFFFFFFu;
+      d.num_distinct = res.num_distinct;
+      detail_out[r] = d;
+    }
+  } else if (detail_out != nullptr && active) {
+    slk_read_detail d;
+    d.hit_off = 0; d.hit_cnt = 0;
+    d.len1 = res.kmers1 + (uint32_t)(sp.k - 1);
+    d.len2 = bases2 ? res.kmers2 + (uint32_t)(sp.k - 1) : 0xFFFFFFFFu;
+    d.num_distinct = res.num_distinct;
+    detail_out[r] = d;
   }
 }
 

@@ -48,6 +48,7 @@ EMU_API void emu_insert_cells(uint64_t* cells, uint64_t n_buckets, const uint16_
 struct vec_sink {
   std::vector<slk_hit>* v;
   void push(int32_t taxon, int32_t count, uint32_t) { v->push_back(slk_hit{taxon, count}); }
+  void reserve(uint32_t) {}
 };
 
 struct emu_result { int32_t taxon; uint32_t flags, kmers1, kmers2, num_distinct, n_hits; };
