@@ -214,6 +214,45 @@ SLK_API int slk_memcpy_h2d(slk_ctx* ctx, void* dst_dev, const void* src_host, si
 SLK_API int slk_memcpy_d2h(slk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 SLK_API int slk_memcpy_d2d(slk_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
 SLK_API int slk_ctx_sync(slk_ctx* ctx);
+/* ---- Split path: a library sharded over several GPUs by minimizer hash range ------------------------------------------
+ * Replaces the same join as B1 (slacken/Classifier.scala:84, spansToGroupedHits' left join of spans and records) when
+ * the records do not fit one GPU (Spark does it with a shuffle). Every GPU holds the records
+ * whose key it owns (slk_shard_of_records), classifies its own reads, and exchanges only span keys and taxa:
+ *   slk_scan_spans_dev -> slk_route_spans_dev -> [all-to-all of keys] -> slk_probe_keys_dev on the owner
+ *   -> [all-to-all of taxa] -> slk_resolve_spans_dev.
+ * The two exchanges are the caller's (torch.distributed / NCCL in slacken_b200/sharded.py). All buffers are DEVICE
+ * pointers except where a name ends in _host; every call returns when its work is done.
+ *
+ * A span word is (compressed minimizer << 16 | type << 14 | k-mer count), type 0 = sequence, 1 = ambiguous, 2 = mate
+ * border (slacken/Supermers.scala:49-125). */
+typedef struct slk_resolver slk_resolver;
+/* owner (0 .. world-1) of every record of the Parquet table; host arrays */
+SLK_API int slk_shard_of_records(const slk_params* params, const int64_t* id1, uint64_t n, uint32_t world, uint8_t* shard_out);
+/* the taxa (raw ids, ancestors included) an index can answer with; out == NULL queries the count */
+SLK_API int slk_index_taxa(slk_index* idx, int32_t* out, uint32_t cap, uint32_t* n_out);
+/* the query side's view of the taxonomy: the union of slk_index_taxa over all shards (any order, duplicates allowed) */
+SLK_API int slk_resolver_create(slk_ctx* ctx, slk_tax* tax, const slk_params* params, const int32_t* taxa, uint32_t n,
+                                slk_resolver** out);
+SLK_API void slk_resolver_destroy(slk_resolver* r);
+/* KeyValueIndex.getSpans (slacken/KeyValueIndex.scala:163-173): ASCII fragments -> span words of fragment r at
+ * spans[span_off[r] .. span_off[r+1]). spans == NULL only fills span_off and *n_spans_host (size query). */
+SLK_API int slk_scan_spans_dev(slk_ctx* ctx, const slk_params* params, const uint8_t* bases1, const uint64_t* off1,
+                               const uint8_t* bases2, const uint64_t* off2, uint32_t n_reads, uint64_t* span_off,
+                               uint64_t* spans, uint64_t cap, uint64_t* n_spans_host);
+/* keys of the sequence spans grouped by owner (send_keys, counts_host[world]) and the span each came from (send_idx);
+ * send_keys == NULL only fills counts_host */
+SLK_API int slk_route_spans_dev(slk_ctx* ctx, const uint64_t* spans, uint64_t n_spans, uint32_t world, uint64_t* send_keys,
+                                uint32_t* send_idx, uint64_t cap, uint64_t* counts_host);
+/* the owner's half of the join: compressed keys -> raw taxon of the record, 0 = no record */
+SLK_API int slk_probe_keys_dev(slk_index* idx, const uint64_t* keys, uint64_t n, int32_t* taxa);
+/* spanToHit + classifyHits (slacken/KeyValueIndex.scala:176-185, slacken/Classifier.scala:124-147) from the span words
+ * and the taxa that came back in send order. hits_out (optional) needs room for n_spans hits; the hits of fragment r
+ * start at detail_out[r].hit_off = span_off[r]. */
+SLK_API int slk_resolve_spans_dev(slk_resolver* r, const slk_classify_opts* opts, const uint64_t* spans, const uint64_t* span_off,
+                                  uint64_t n_spans, uint32_t n_reads, int paired, const uint32_t* send_idx, const int32_t* taxa,
+                                  uint64_t n_routed, int32_t* taxon_out, uint8_t* flags_out, slk_read_detail* detail_out,
+                                  slk_hit* hits_out);
+
 /* test hook: the library's radix sort (K3a) on a host array, bits [begin_bit, end_bit), stable */
 SLK_API int slk_debug_sort_u64(slk_ctx* ctx, uint64_t* keys, uint64_t n, int begin_bit, int end_bit);
 

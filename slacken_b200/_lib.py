@@ -86,6 +86,14 @@ SIGNATURES = {
     "slk_memcpy_h2d": (_INT, [_VP, _VP, _VP, C.c_size_t]),
     "slk_memcpy_d2h": (_INT, [_VP, _VP, _VP, C.c_size_t]),
     "slk_debug_sort_u64": (_INT, [_VP, _VP, _U64, _INT, _INT]),
+    "slk_shard_of_records": (_INT, [_VP, _VP, _U64, _U32, _VP]),
+    "slk_index_taxa": (_INT, [_VP, _VP, _U32, _VP]),
+    "slk_resolver_create": (_INT, [_VP, _VP, _VP, _VP, _U32, _PP]),
+    "slk_resolver_destroy": (None, [_VP]),
+    "slk_scan_spans_dev": (_INT, [_VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP, _VP, _U64, _VP]),
+    "slk_route_spans_dev": (_INT, [_VP, _VP, _U64, _U32, _VP, _VP, _U64, _VP]),
+    "slk_probe_keys_dev": (_INT, [_VP, _VP, _U64, _VP]),
+    "slk_resolve_spans_dev": (_INT, [_VP, _VP, _VP, _VP, _U64, _U32, _INT, _VP, _VP, _U64, _VP, _VP, _VP, _VP]),
     "slk_memcpy_d2d": (_INT, [_VP, _VP, _VP, C.c_size_t]),
 }
 

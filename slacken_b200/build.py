@@ -29,10 +29,11 @@ if os.environ.get("SLK_VARIANT"):
 
 
 def _sources():
-    deps = [os.path.join(CSRC, f) for f in ("slk_core.h", "slk_kernels.cuh", "slk_sort.h")]
+    deps = [os.path.join(CSRC, f) for f in ("slk_core.h", "slk_kernels.cuh", "slk_sort.h", "slk_host.h")]
     deps.append(os.path.join(HERE, "..", "include", "slacken_gpu.h"))
     units = [("slacken_gpu", os.path.join(CSRC, "slacken_gpu.cu"), []),
-             ("slk_sort", os.path.join(CSRC, "slk_sort.cu"), [])]
+             ("slk_sort", os.path.join(CSRC, "slk_sort.cu"), []),
+             ("slk_split", os.path.join(CSRC, "slk_split.cu"), [])]
     units += [(f"slk_inst_w{w}", os.path.join(CSRC, "slk_inst.cu"), [f"-DSLK_W={w}"]) for w in WIDTHS]
     return units, deps
 

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/slacken_gpu.h"
+#include "slk_host.h"
 #include "slk_kernels.cuh"
 #include "slk_sort.h"
 
@@ -48,41 +49,17 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 extern "C" const char* slk_last_error(void) { return g_err.c_str(); }
+int slk_fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
 
 // ---------------------------------------------------------------------------------------------- handles
-struct slk_ctx {
-  int device;
-  int sm_count;
-  cudaStream_t stream;
-};
-struct slk_tax {
-  slk_ctx* ctx;
-  std::vector<int32_t> parents;  // raw-indexed
-};
-struct dense_tax {
-  std::vector<int32_t> raw;       // dense -> raw, raw[0] = 0
-  std::vector<uint16_t> parent;   // dense parent
-  std::vector<uint8_t> depth;
-  std::unordered_map<int32_t, uint32_t> to_dense;
-  uint32_t root = 0;
-  uint16_t* d_parent = nullptr;
-  uint8_t* d_depth = nullptr;
-  int32_t* d_raw = nullptr;
-  slk_tax_view view() const {
-    slk_tax_view v;
-    v.parent = d_parent; v.depth = d_depth; v.raw = d_raw; v.n = (uint32_t)raw.size(); v.root = root;
-    return v;
-  }
-};
-struct slk_index {
-  slk_ctx* ctx;
-  slk_tax* tax;
-  slk_params params;
-  slk_scan_params sp;
-  dense_tax dt;
-  slk_table_view table{nullptr, 0, 0, 0};
-  uint64_t n_records = 0;
-};
 struct slk_builder {
   slk_ctx* ctx;
   slk_tax* tax;
@@ -102,6 +79,8 @@ struct slk_counts {
 };
 
 // ---------------------------------------------------------------------------------------------- params
+static int make_scan_params(const slk_params* p, slk_scan_params* sp);
+int slk_make_scan_params_checked(const slk_params* p, slk_scan_params* sp) { return make_scan_params(p, sp); }
 static int make_scan_params(const slk_params* p, slk_scan_params* sp) {
   memset(sp, 0, sizeof(*sp));
   switch (slk_make_scan_params(p->k, p->m, p->spaces, p->toggle_mask, p->canonical, sp)) {
@@ -254,6 +233,10 @@ static void dense_free(dense_tax& dt) {
   cudaFree(dt.d_parent); cudaFree(dt.d_depth); cudaFree(dt.d_raw);
   dt.d_parent = nullptr; dt.d_depth = nullptr; dt.d_raw = nullptr;
 }
+void slk_dense_init(dense_tax& dt) { dense_init(dt); }
+int slk_dense_add(dense_tax& dt, const slk_tax* tax, int32_t raw, uint32_t* out) { return dense_add(dt, tax, raw, out); }
+int slk_dense_upload(dense_tax& dt) { return dense_upload(dt); }
+void slk_dense_free(dense_tax& dt) { dense_free(dt); }
 
 // ---------------------------------------------------------------------------------------------- table kernels
 // K4: insert (compressed key << 16 | dense taxon) cells. Equal keys merge by LCA (TaxonLCA.merge,

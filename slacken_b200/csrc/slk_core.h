@@ -883,6 +883,139 @@ struct slk_frag_classifier {
   }
 };
 
+// ------------------------------------------------------------------------------------------------ split path
+// The same classification as slk_frag_classifier, cut at the table lookup, for libraries that do not fit one GPU:
+// the query side scans its reads into span words, the span keys travel to the GPU that owns their hash range and
+// come back as taxa, and the query side merges and resolves (the join of
+// slacken/Classifier.scala:84 done by an all-to-all instead of a shuffle).
+// A span word is (compressed key << 16 | type << 14 | k-mer count); AMBIGUOUS and BORDER spans carry key 0.
+#define SLK_SPAN_TYPE(w) ((uint32_t)((w) >> 14) & 3u)
+#define SLK_SPAN_CNT(w) ((uint32_t)(w) & SLK_E_CNT_MAX)
+#define SLK_SPAN_KEY(w) ((uint64_t)(w) >> 16)
+
+// Scan of one mate: calls emit(span word) for every span, in order (the per-character logic of
+// slk_frag_classifier::run, without tiles).
+template <int W, class Emit>
+SLK_HD void slk_scan_spans(const slk_scan_params& sp, const uint8_t* s, uint32_t len, Emit&& emit) {
+  const uint32_t k = (uint32_t)sp.k;
+  const int fshift = sp.fshift;
+  const uint64_t mmask = sp.mmask, xor_mask = sp.xor_mask, sig_mask = sp.sig_mask;
+  const bool canonical = sp.canonical != 0;
+  slk_scanner<W> sc;
+  sc.reset();
+  uint64_t run_key = 0;
+  uint32_t run_cnt = 0, ninv = 0, amb_cnt = 0;
+  bool in_run = false;
+  slk_for_each_byte(s, len, [&](uint32_t ch) {
+    const uint32_t c = slk_code(ch);
+    const bool valid = c < 4u;
+    uint64_t mn;
+    const bool window_ok = sc.push(c, k, fshift, mmask, xor_mask, sig_mask, canonical, &mn);
+    ninv = valid ? 0u : ninv + 1u;
+    const bool same = in_run && mn == run_key && run_cnt < SLK_E_CNT_MAX;
+    const bool start_new = window_ok && !same;
+    if (in_run && (start_new || !valid)) emit((slk_compress(sp, run_key) << 16) | (SLK_E_SEQ << 14) | run_cnt);
+    if (amb_cnt != 0 && (valid || amb_cnt == SLK_E_CNT_MAX)) { emit((uint64_t)((SLK_E_AMB << 14) | amb_cnt)); amb_cnt = 0; }
+    amb_cnt = valid ? 0u : amb_cnt;
+    amb_cnt += (!valid && ninv >= k) ? 1u : 0u;
+    run_cnt = start_new ? 1u : run_cnt + ((window_ok && same) ? 1u : 0u);
+    run_key = start_new ? mn : run_key;
+    in_run = valid && (in_run || start_new);
+  });
+  if (in_run) emit((slk_compress(sp, run_key) << 16) | (SLK_E_SEQ << 14) | run_cnt);
+  if (amb_cnt) emit((uint64_t)((SLK_E_AMB << 14) | amb_cnt));
+}
+// ... of a fragment: mate 1, the MATE_PAIR_BORDER pseudo-span, mate 2 (slacken/Supermers.scala:49-97)
+template <int W, class Emit>
+SLK_HD void slk_scan_fragment_spans(const slk_scan_params& sp, const uint8_t* s1, uint32_t len1, const uint8_t* s2,
+                                    uint32_t len2, bool paired, Emit&& emit) {
+  slk_scan_spans<W>(sp, s1, len1, emit);
+  if (paired) {
+    emit((uint64_t)(SLK_E_BORDER << 14));
+    slk_scan_spans<W>(sp, s2, len2, emit);
+  }
+}
+
+// histogram of the split path's resolve step: per-thread arrays
+struct slk_array_hist {
+  uint32_t hk[SLK_KMAX];
+  int32_t hv[SLK_KMAX];
+  uint32_t n;
+  bool overflow;
+  SLK_HD uint32_t size() const { return n; }
+  SLK_HD void at(uint32_t i, uint32_t* t, int32_t* v) const { *t = hk[i]; *v = hv[i]; }
+  SLK_HD int32_t count(uint32_t t) const {
+    for (uint32_t i = 0; i < n; i++)
+      if (hk[i] == t) return hv[i];
+    return 0;
+  }
+  SLK_HD void add(uint32_t t, int32_t c) {
+    for (uint32_t i = 0; i < n; i++)
+      if (hk[i] == t) { hv[i] += c; return; }
+    if (n == SLK_KMAX) { overflow = true; return; }
+    hk[n] = t; hv[n] = c; n++;
+  }
+};
+
+// Merge + resolve of one fragment from its span words and the dense taxon of every span (0 = miss; ignored for
+// AMBIGUOUS / BORDER spans): the merge pass and the final step of slk_frag_classifier::run. hit(label, count) is
+// called for every merged hit in order, label = dense taxon or SLK_AMBIGUOUS_SPAN / SLK_MATE_PAIR_BORDER.
+template <class Hit>
+SLK_HD void slk_resolve_spans(const slk_tax_view& tx, int32_t k, const uint64_t* spans, const uint16_t* dense, uint32_t n_spans,
+                              double confidence, int32_t min_hit_groups, Hit&& hit, slk_frag_result& r) {
+  slk_array_hist h;
+  h.n = 0; h.overflow = false;
+  uint64_t last = 0;
+  bool have_last = false, have_cur = false;
+  int32_t cur_label = 0, cur_count = 0;
+  uint32_t mate = 0, k0 = 0, k1 = 0, nd = 0, np = 0, nh = 0;
+  auto flush = [&]() {
+    hit(cur_label, cur_count);
+    nh++;
+    if (cur_label >= 0) h.add((uint32_t)cur_label, cur_count);   // TaxonCounts.toMap skips AMBIGUOUS / BORDER
+  };
+  for (uint32_t i = 0; i < n_spans; i++) {
+    const uint64_t w = spans[i];
+    const uint32_t type = SLK_SPAN_TYPE(w), cnt = SLK_SPAN_CNT(w);
+    int32_t label, hcnt = (int32_t)cnt;
+    if (type == SLK_E_SEQ) {
+      const uint64_t ck = SLK_SPAN_KEY(w);
+      const uint32_t d = dense[i];
+      np++;
+      nd += ((!have_last || ck != last) && d != 0) ? 1u : 0u;
+      last = ck; have_last = true;
+      label = (int32_t)d;
+    } else if (type == SLK_E_AMB) {
+      label = SLK_AMBIGUOUS_SPAN;
+    } else {
+      label = SLK_MATE_PAIR_BORDER; hcnt = -(k - 1);
+    }
+    if (type != SLK_E_BORDER) { if (mate) k1 += cnt; else k0 += cnt; }
+    if (have_cur && label == cur_label) cur_count += hcnt;
+    else {
+      if (have_cur) flush();
+      cur_label = label; cur_count = hcnt; have_cur = true;
+    }
+    if (type == SLK_E_BORDER) mate = 1;
+  }
+  if (have_cur) flush();
+  const uint32_t taxon = slk_resolve_tree(h, tx, confidence, (int32_t)(k0 + k1));
+  const bool classified = taxon != 0 && nd >= (uint32_t)min_hit_groups;
+  r.taxon = classified ? tx.raw[taxon] : 0;
+  r.flags = (classified ? SLK_F_CLASSIFIED : 0u) | (n_spans != 0 ? SLK_F_HAS_SPAN : 0u) | (h.overflow ? SLK_F_OVERFLOW : 0u);
+  r.kmers1 = k0; r.kmers2 = k1; r.num_distinct = nd; r.n_hits = nh; r.n_probes = np;
+}
+
+// Owner of a compressed key among `world` hash-range shards: a mix independent of the bucket hash, so that every
+// shard's table stays uniformly loaded.
+SLK_HD uint32_t slk_shard_of(uint64_t ckey, uint32_t world) {
+  const uint32_t lo = (uint32_t)ckey, hi = (uint32_t)(ckey >> 32);
+  uint32_t x = (lo ^ 0x7F4A7C15u) * 0x2C1B3C6Du;
+  x ^= x >> 16; x += hi * 0x85EBCA77u;
+  x *= 0x297A2D39u; x ^= x >> 15;
+  return slk_mulhi32(x, world);
+}
+
 // K1 as a stand-alone step: ASCII -> 2-bit codes + ambiguity mask in the packed block layout of slk_read_src.
 // `emit(block index, codes, mask)` is called for every 32-base block of the read.
 template <class Emit>

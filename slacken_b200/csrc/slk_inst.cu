@@ -42,3 +42,8 @@ void SLK_CAT(slk_launch_emit_w, SLK_W)(const slk_emit_args& a) {
   emit_cells_kernel<SLK_W><<<(unsigned)((a.n_items + 127) / 128), 128, 0, a.stream>>>(
       a.sp, a.bases, a.frag_off, a.off_shift, a.frag_dense, a.item_prefix, a.n_frag, a.n_items, a.out, a.cap, a.cursor);
 }
+void SLK_CAT(slk_launch_spans_w, SLK_W)(const slk_spans_args& a) {
+  const unsigned grid = (a.n_reads + 127) / 128;
+  if (a.spans) spans_kernel<SLK_W, true><<<grid, 128, 0, a.stream>>>(a.sp, a.bases1, a.off1, a.bases2, a.off2, a.n_reads, a.span_off, a.spans);
+  else spans_kernel<SLK_W, false><<<grid, 128, 0, a.stream>>>(a.sp, a.bases1, a.off1, a.bases2, a.off2, a.n_reads, a.span_off, a.spans);
+}

@@ -31,7 +31,18 @@ struct slk_emit_args {
   const uint64_t* item_prefix; uint32_t n_frag; uint64_t n_items; uint64_t* out; uint64_t cap; unsigned long long* cursor;
   cudaStream_t stream;
 };
-#define SLK_DECL_W(w) void slk_launch_classify_w##w(const slk_classify_args&); void slk_launch_emit_w##w(const slk_emit_args&);
+// split path, scan step: pass 1 counts the spans of every fragment, pass 2 (after an exclusive scan of the counts)
+// writes the span words to span_off[r] ...
+struct slk_spans_args {
+  slk_scan_params sp;
+  const uint8_t* bases1; const uint64_t* off1; const uint8_t* bases2; const uint64_t* off2;   // ASCII, device
+  uint32_t n_reads;
+  uint64_t* span_off;      // [n_reads + 1]: pass 1 writes counts to [0, n), pass 2 reads offsets
+  uint64_t* spans;         // pass 2 output (nullptr = pass 1)
+  cudaStream_t stream;
+};
+#define SLK_DECL_W(w) void slk_launch_classify_w##w(const slk_classify_args&); void slk_launch_emit_w##w(const slk_emit_args&); \
+  void slk_launch_spans_w##w(const slk_spans_args&);
 SLK_DECL_W(1) SLK_DECL_W(2) SLK_DECL_W(3) SLK_DECL_W(4) SLK_DECL_W(5) SLK_DECL_W(6) SLK_DECL_W(7) SLK_DECL_W(8)
 
 #ifdef __CUDACC__
@@ -84,6 +95,28 @@ __global__ void __launch_bounds__(128) emit_cells_kernel(const __grid_constant__
   uint64_t o = warp_agg_alloc(cursor, nl);
   for (uint32_t j = 0; j < nl; j++)
     if (o + j < cap) out[o + j] = local[j];
+}
+
+// ---------------------------------------------------------------------------------------------- split path: scan
+template <int W, bool EMIT>
+__global__ void __launch_bounds__(128) spans_kernel(const __grid_constant__ slk_scan_params sp, const uint8_t* __restrict__ bases1,
+                                                    const uint64_t* __restrict__ off1, const uint8_t* __restrict__ bases2,
+                                                    const uint64_t* __restrict__ off2, uint32_t n_reads,
+                                                    uint64_t* __restrict__ span_off, uint64_t* __restrict__ spans) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const uint64_t s1 = off1[r], e1 = off1[r + 1];
+  const uint8_t* p2 = nullptr;
+  uint32_t l2 = 0;
+  if (bases2) { const uint64_t s2 = off2[r], e2 = off2[r + 1]; p2 = bases2 + s2; l2 = (uint32_t)(e2 - s2); }
+  if (EMIT) {
+    uint64_t* out = spans + span_off[r];
+    slk_scan_fragment_spans<W>(sp, bases1 + s1, (uint32_t)(e1 - s1), p2, l2, bases2 != nullptr, [&](uint64_t w) { *out++ = w; });
+  } else {
+    uint64_t n = 0;
+    slk_scan_fragment_spans<W>(sp, bases1 + s1, (uint32_t)(e1 - s1), p2, l2, bases2 != nullptr, [&](uint64_t) { n++; });
+    span_off[r] = n;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- classify kernel

@@ -211,3 +211,19 @@ int slk_sort_u64(uint64_t* keys, uint64_t* tmp, uint64_t n, int begin_bit, int e
   *sorted = src;
   return 0;
 }
+
+int slk_exclusive_scan_u64(uint64_t* d, uint64_t n, cudaStream_t stream) {
+  if (n == 0) return 0;
+  uint64_t scratch_len = 0;
+  for (uint64_t x = (n + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK; ; x = (x + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK) {
+    scratch_len += x;
+    if (x <= 1) break;
+  }
+  uint64_t* scratch = nullptr;
+  cudaError_t e = cudaMalloc(&scratch, (scratch_len + 8) * sizeof(uint64_t));
+  if (e != cudaSuccess) return (int)e;
+  e = exclusive_scan_u64(d, n, scratch, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(scratch);
+  return (int)e;
+}

@@ -7,3 +7,7 @@
 // clobbered; *sorted points at whichever of them holds the result. Returns 0 or a non-zero CUDA error code.
 int slk_sort_u64(uint64_t* keys, uint64_t* tmp, uint64_t n, int begin_bit, int end_bit, cudaStream_t stream,
                  uint64_t** sorted);
+
+// In-place exclusive prefix sum of n 64-bit counters on the device (allocates its own scratch; asynchronous on `stream`
+// apart from that allocation). Returns 0 or a non-zero CUDA error code.
+int slk_exclusive_scan_u64(uint64_t* d, uint64_t n, cudaStream_t stream);

@@ -1,0 +1,268 @@
+// slk_split.cu -- the split classification path for libraries sharded over several GPUs by minimizer hash range
+// (SURVEY section 8e): scan -> span words | route by owner | probe on the owner | merge + resolve on the query side.
+// The exchange between the steps (one all-to-all of 8-byte keys, one of 4-byte taxa) is the caller's: the Python
+// host uses torch.distributed (NCCL over NVLink), a JVM host would use its own transport. Every pointer here is a
+// DEVICE pointer unless it says host; every call is synchronous.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "../../include/slacken_gpu.h"
+#include "slk_host.h"
+#include "slk_kernels.cuh"
+#include "slk_sort.h"
+
+// ---------------------------------------------------------------------------------------------- kernels
+// keys (compressed minimizers) -> raw taxon of the record, 0 when the shard has none
+__global__ void __launch_bounds__(256) probe_keys_kernel(slk_table_view tb, slk_tax_view tx, const uint64_t* __restrict__ keys,
+                                                         uint64_t n, int32_t* __restrict__ taxa) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t d = slk_probe(tb, keys[i]);
+  taxa[i] = d ? tx.raw[d] : 0;
+}
+
+// Routing of the SEQ spans of a batch: pass 1 counts per owner, pass 2 writes (key, span index) grouped by owner.
+// One atomic per (warp, owner): the lanes of a warp that share an owner are ranked with match_any.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) route_kernel(const uint64_t* __restrict__ spans, uint64_t n, uint32_t world,
+                                                    unsigned long long* cursors, uint64_t* __restrict__ send_keys,
+                                                    uint32_t* __restrict__ send_idx) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint64_t w = 0;
+  bool seq = false;
+  if (i < n) { w = spans[i]; seq = SLK_SPAN_TYPE(w) == SLK_E_SEQ; }
+  const uint64_t ck = SLK_SPAN_KEY(w);
+  const uint32_t dest = seq ? slk_shard_of(ck, world) : 0xffffffffu;
+  const uint32_t peers = __match_any_sync(0xffffffffu, dest);
+  if (!seq) return;
+  const uint32_t leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(&cursors[dest], (unsigned long long)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  if (SCATTER) { send_keys[base + rank] = ck; send_idx[base + rank] = (uint32_t)i; }
+}
+
+// taxa come back in send order: dense label of span send_idx[j] = raw2dense[taxa[j]]
+__global__ void __launch_bounds__(256) unroute_kernel(const int32_t* __restrict__ taxa, const uint32_t* __restrict__ send_idx,
+                                                      uint64_t n, const uint16_t* __restrict__ raw2dense, int32_t n_tax,
+                                                      uint16_t* __restrict__ dense, uint32_t* bad) {
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int32_t t = taxa[j];
+  uint16_t d = 0;
+  if (t != 0) {
+    if (t < 0 || t >= n_tax || (d = raw2dense[t]) == 0) { atomicExch(bad, 1u); d = 0; }
+  }
+  dense[send_idx[j]] = d;
+}
+
+__global__ void __launch_bounds__(128) resolve_spans_kernel(slk_tax_view tx, int32_t k, const uint64_t* __restrict__ spans,
+                                                            const uint64_t* __restrict__ span_off,
+                                                            const uint16_t* __restrict__ dense, uint32_t n_reads, int paired,
+                                                            double confidence, int32_t min_hit_groups,
+                                                            int32_t* __restrict__ taxon_out, uint8_t* __restrict__ flags_out,
+                                                            slk_read_detail* __restrict__ detail_out,
+                                                            slk_hit* __restrict__ hits_out, uint32_t* error_flag) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const uint64_t s0 = span_off[r], s1 = span_off[r + 1];
+  slk_hit* ho = hits_out ? hits_out + s0 : nullptr;   // a fragment has at most as many merged hits as spans
+  slk_frag_result res;
+  slk_resolve_spans(tx, k, spans + s0, dense + s0, (uint32_t)(s1 - s0), confidence, min_hit_groups,
+                    [&](int32_t l, int32_t c) { if (ho) { slk_hit h; h.taxon = l >= 0 ? tx.raw[l] : l; h.count = c; *ho++ = h; } }, res);
+  taxon_out[r] = res.taxon;
+  flags_out[r] = (uint8_t)(res.flags & 3u);
+  if (res.flags & SLK_F_OVERFLOW) atomicExch(error_flag, 1u);
+  if (detail_out) {
+    slk_read_detail d;
+    d.hit_off = s0; d.hit_cnt = hits_out ? res.n_hits : 0u;
+    d.len1 = res.kmers1 + (uint32_t)(k - 1);
+    d.len2 = paired ? res.kmers2 + (uint32_t)(k - 1) : 0xFFFFFFFFu;
+    d.num_distinct = res.num_distinct;
+    detail_out[r] = d;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+struct slk_resolver {
+  slk_ctx* ctx;
+  slk_tax* tax;
+  slk_scan_params sp;
+  dense_tax dt;
+  uint16_t* d_r2d = nullptr;
+  uint32_t* d_err = nullptr;
+};
+
+extern "C" int slk_index_taxa(slk_index* idx, int32_t* out, uint32_t cap, uint32_t* n_out) {
+  if (!idx || !n_out) return slk_fail(SLK_E_INVALID, "bad arguments");
+  const uint32_t n = (uint32_t)idx->dt.raw.size() - 1;   // without dense 0 = NONE
+  *n_out = n;
+  if (!out) return SLK_OK;
+  if (cap < n) return slk_fail(SLK_E_NOSPACE, "taxa buffer too small: %u < %u", cap, n);
+  for (uint32_t i = 0; i < n; i++) out[i] = idx->dt.raw[i + 1];
+  return SLK_OK;
+}
+
+extern "C" int slk_resolver_create(slk_ctx* ctx, slk_tax* tax, const slk_params* params, const int32_t* taxa, uint32_t n,
+                                   slk_resolver** out) {
+  if (!ctx || !tax || !params || !out || (n && !taxa)) return slk_fail(SLK_E_INVALID, "bad arguments");
+  SLK_CU(cudaSetDevice(ctx->device));
+  slk_resolver* r = new (std::nothrow) slk_resolver;
+  if (!r) return slk_fail(SLK_E_NOMEM, "host allocation failed");
+  r->ctx = ctx; r->tax = tax;
+  int rc = slk_make_scan_params_checked(params, &r->sp);
+  if (rc != SLK_OK) { delete r; return rc; }
+  slk_dense_init(r->dt);
+  const int32_t n_tax = (int32_t)tax->parents.size();
+  // the same numbering on every rank: ROOT first, then the taxa in increasing raw id
+  std::vector<int32_t> sorted(taxa, taxa + n);
+  std::sort(sorted.begin(), sorted.end());
+  rc = slk_dense_add(r->dt, tax, 1, &r->dt.root);
+  for (size_t i = 0; i < sorted.size() && rc == SLK_OK; i++) {
+    if (sorted[i] <= 0 || sorted[i] >= n_tax) rc = slk_fail(SLK_E_INVALID, "taxon %d is outside the taxonomy", sorted[i]);
+    else rc = slk_dense_add(r->dt, tax, sorted[i], nullptr);
+  }
+  if (rc == SLK_OK) rc = slk_dense_upload(r->dt);
+  if (rc != SLK_OK) { slk_dense_free(r->dt); delete r; return rc; }
+  std::vector<uint16_t> r2d((size_t)n_tax, 0);
+  for (auto& kv : r->dt.to_dense) r2d[kv.first] = (uint16_t)kv.second;
+  cudaError_t e = cudaMalloc(&r->d_r2d, (size_t)n_tax * 2);
+  if (e == cudaSuccess) e = cudaMemcpy(r->d_r2d, r2d.data(), (size_t)n_tax * 2, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&r->d_err, 4);
+  if (e == cudaSuccess) e = cudaMemset(r->d_err, 0, 4);
+  if (e != cudaSuccess) {
+    cudaFree(r->d_r2d); cudaFree(r->d_err); slk_dense_free(r->dt); delete r;
+    return slk_fail(SLK_E_CUDA, "resolver allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = r;
+  return SLK_OK;
+}
+extern "C" void slk_resolver_destroy(slk_resolver* r) {
+  if (!r) return;
+  cudaFree(r->d_r2d); cudaFree(r->d_err);
+  slk_dense_free(r->dt);
+  delete r;
+}
+
+#define SLK_DISPATCH_SPANS(w, a)                         \
+  switch (w) {                                           \
+    case 1: slk_launch_spans_w1(a); break; case 2: slk_launch_spans_w2(a); break; \
+    case 3: slk_launch_spans_w3(a); break; case 4: slk_launch_spans_w4(a); break; \
+    case 5: slk_launch_spans_w5(a); break; case 6: slk_launch_spans_w6(a); break; \
+    case 7: slk_launch_spans_w7(a); break; default: slk_launch_spans_w8(a); break; \
+  }
+
+extern "C" int slk_scan_spans_dev(slk_ctx* ctx, const slk_params* params, const uint8_t* bases1, const uint64_t* off1,
+                                  const uint8_t* bases2, const uint64_t* off2, uint32_t n_reads, uint64_t* span_off,
+                                  uint64_t* spans, uint64_t cap, uint64_t* n_spans_host) {
+  if (!ctx || !params || !bases1 || !off1 || !span_off || !n_spans_host || ((bases2 == nullptr) != (off2 == nullptr)))
+    return slk_fail(SLK_E_INVALID, "bad arguments");
+  SLK_CU(cudaSetDevice(ctx->device));
+  slk_spans_args a;
+  int rc = slk_make_scan_params_checked(params, &a.sp);
+  if (rc != SLK_OK) return rc;
+  *n_spans_host = 0;
+  SLK_CU(cudaMemsetAsync(span_off, 0, ((size_t)n_reads + 1) * 8, ctx->stream));
+  if (n_reads == 0) { SLK_CU(cudaStreamSynchronize(ctx->stream)); return SLK_OK; }
+  a.bases1 = bases1; a.off1 = off1; a.bases2 = bases2; a.off2 = off2; a.n_reads = n_reads;
+  a.span_off = span_off; a.spans = nullptr; a.stream = ctx->stream;
+  SLK_DISPATCH_SPANS(a.sp.w, a);
+  SLK_CU(cudaGetLastError());
+  int e = slk_exclusive_scan_u64(span_off, (uint64_t)n_reads + 1, ctx->stream);
+  if (e != 0) return slk_fail(SLK_E_CUDA, "prefix sum of the span counts failed (%d)", e);
+  uint64_t total = 0;
+  SLK_CU(cudaMemcpy(&total, span_off + n_reads, 8, cudaMemcpyDeviceToHost));
+  *n_spans_host = total;
+  if (!spans) return SLK_OK;   // size query
+  if (total > cap) return slk_fail(SLK_E_NOSPACE, "span buffer too small: %llu spans, room for %llu", (unsigned long long)total, (unsigned long long)cap);
+  a.spans = spans;
+  SLK_DISPATCH_SPANS(a.sp.w, a);
+  SLK_CU(cudaGetLastError());
+  SLK_CU(cudaStreamSynchronize(ctx->stream));
+  return SLK_OK;
+}
+
+extern "C" int slk_route_spans_dev(slk_ctx* ctx, const uint64_t* spans, uint64_t n_spans, uint32_t world, uint64_t* send_keys,
+                                   uint32_t* send_idx, uint64_t cap, uint64_t* counts_host) {
+  if (!ctx || !counts_host || world == 0 || world > 1024 || (n_spans && !spans)) return slk_fail(SLK_E_INVALID, "bad arguments");
+  if (n_spans > 0xffffffffull) return slk_fail(SLK_E_UNSUPPORTED, "more than 2^32 spans in one batch");
+  SLK_CU(cudaSetDevice(ctx->device));
+  for (uint32_t i = 0; i < world; i++) counts_host[i] = 0;
+  if (n_spans == 0) return SLK_OK;
+  unsigned long long* d_cur = nullptr;
+  SLK_CU(cudaMalloc(&d_cur, (size_t)world * 8));
+  auto done = [&](int rc) { cudaFree(d_cur); return rc; };
+  const unsigned grid = (unsigned)((n_spans + 255) / 256);
+  if (cudaMemsetAsync(d_cur, 0, (size_t)world * 8, ctx->stream) != cudaSuccess) return done(slk_fail(SLK_E_CUDA, "memset failed"));
+  route_kernel<false><<<grid, 256, 0, ctx->stream>>>(spans, n_spans, world, d_cur, nullptr, nullptr);
+  std::vector<unsigned long long> cnt(world);
+  if (cudaMemcpyAsync(cnt.data(), d_cur, (size_t)world * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+    return done(slk_fail(SLK_E_CUDA, "routing count failed: %s", cudaGetErrorString(cudaGetLastError())));
+  uint64_t total = 0;
+  std::vector<unsigned long long> start(world);
+  for (uint32_t i = 0; i < world; i++) { counts_host[i] = cnt[i]; start[i] = total; total += cnt[i]; }
+  if (!send_keys || !send_idx) return done(SLK_OK);   // size query
+  if (total > cap) return done(slk_fail(SLK_E_NOSPACE, "send buffers too small: %llu keys, room for %llu", (unsigned long long)total, (unsigned long long)cap));
+  if (cudaMemcpyAsync(d_cur, start.data(), (size_t)world * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+    return done(slk_fail(SLK_E_CUDA, "copy failed"));
+  route_kernel<true><<<grid, 256, 0, ctx->stream>>>(spans, n_spans, world, d_cur, send_keys, send_idx);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+    return done(slk_fail(SLK_E_CUDA, "routing failed: %s", cudaGetErrorString(cudaGetLastError())));
+  return done(SLK_OK);
+}
+
+extern "C" int slk_probe_keys_dev(slk_index* idx, const uint64_t* keys, uint64_t n, int32_t* taxa) {
+  if (!idx || (n && (!keys || !taxa))) return slk_fail(SLK_E_INVALID, "bad arguments");
+  SLK_CU(cudaSetDevice(idx->ctx->device));
+  if (n == 0) return SLK_OK;
+  probe_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, idx->ctx->stream>>>(idx->table, idx->dt.view(), keys, n, taxa);
+  SLK_CU(cudaGetLastError());
+  SLK_CU(cudaStreamSynchronize(idx->ctx->stream));
+  return SLK_OK;
+}
+
+extern "C" int slk_resolve_spans_dev(slk_resolver* r, const slk_classify_opts* opts, const uint64_t* spans, const uint64_t* span_off,
+                                     uint64_t n_spans, uint32_t n_reads, int paired, const uint32_t* send_idx, const int32_t* taxa,
+                                     uint64_t n_routed, int32_t* taxon_out, uint8_t* flags_out, slk_read_detail* detail_out,
+                                     slk_hit* hits_out) {
+  if (!r || !opts || !span_off || !taxon_out || !flags_out || (n_spans && !spans) || (n_routed && (!send_idx || !taxa)))
+    return slk_fail(SLK_E_INVALID, "bad arguments");
+  if (hits_out && !detail_out) return slk_fail(SLK_E_INVALID, "hits_out needs detail_out");
+  SLK_CU(cudaSetDevice(r->ctx->device));
+  if (n_reads == 0) return SLK_OK;
+  cudaStream_t st = r->ctx->stream;
+  uint16_t* d_dense = nullptr;
+  SLK_CU(cudaMalloc(&d_dense, std::max<uint64_t>(n_spans, 1) * 2));
+  auto done = [&](int rc) { cudaFree(d_dense); return rc; };
+  cudaMemsetAsync(d_dense, 0, std::max<uint64_t>(n_spans, 1) * 2, st);
+  if (n_routed)
+    unroute_kernel<<<(unsigned)((n_routed + 255) / 256), 256, 0, st>>>(taxa, send_idx, n_routed, r->d_r2d, (int32_t)r->tax->parents.size(),
+                                                                        d_dense, r->d_err);
+  resolve_spans_kernel<<<(n_reads + 127) / 128, 128, 0, st>>>(r->dt.view(), r->sp.k, spans, span_off, d_dense, n_reads, paired,
+                                                            opts->confidence, opts->min_hit_groups, taxon_out, flags_out,
+                                                            detail_out, hits_out, r->d_err + 0);
+  uint32_t err = 0;
+  if (cudaMemcpyAsync(&err, r->d_err, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+    return done(slk_fail(SLK_E_CUDA, "resolve failed: %s", cudaGetErrorString(cudaGetLastError())));
+  if (err) {
+    cudaMemset(r->d_err, 0, 4);
+    return done(slk_fail(SLK_E_UNSUPPORTED, "a returned taxon is unknown to the resolver, or a fragment hit more than %d distinct taxa", SLK_KMAX));
+  }
+  return done(SLK_OK);
+}
+
+// owner of every record (id1 = the uncompressed minimizer of the Parquet column), computed on the host
+extern "C" int slk_shard_of_records(const slk_params* params, const int64_t* id1, uint64_t n, uint32_t world, uint8_t* shard_out) {
+  if (!params || world == 0 || world > 255 || (n && (!id1 || !shard_out))) return slk_fail(SLK_E_INVALID, "bad arguments");
+  slk_scan_params sp;
+  int rc = slk_make_scan_params_checked(params, &sp);
+  if (rc != SLK_OK) return rc;
+  for (uint64_t i = 0; i < n; i++) shard_out[i] = (uint8_t)slk_shard_of(slk_compress(sp, (uint64_t)id1[i]), world);
+  return SLK_OK;
+}

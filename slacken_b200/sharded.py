@@ -1,0 +1,266 @@
+"""A library sharded over several GPUs by minimizer hash range (BASELINE.json configs[4]).
+
+Slacken joins spans and records with a Spark shuffle (slacken/Classifier.scala:77-96); here every rank keeps the
+records whose minimizer it owns in its own HBM table, classifies its own reads, and the join is two all-to-alls over
+NVLink per batch: 8-byte span keys to their owners, 4-byte taxa back. One process per GPU, `torch.distributed` for
+the exchange (NCCL on the GPU box; the CPU tests drive the same code over gloo with a stand-in for the device ops).
+
+    index = ShardedKeyValueIndex.from_records(ctx, tax, params, id1, taxon)      # keeps this rank's shard
+    cls = ShardedClassifier(index)                                               # collective: all ranks
+    batch = cls.classify(bases, off, confidence=0.15)                            # collective: all ranks, own reads each
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import ClassifyOpts, check
+from .host import DETAIL_DTYPE, HIT_DTYPE, ClassifiedBatch, GpuContext, IndexParams, KeyValueIndex, Taxonomy
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def world_of(group=None) -> Tuple[int, int]:
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_of_records(params: IndexParams, id1: np.ndarray, world: int) -> np.ndarray:
+    """Owner rank of every record (id1 = the Parquet column: the left-aligned minimizer priority)."""
+    id1 = np.ascontiguousarray(id1).view(np.int64)
+    out = np.zeros(len(id1), dtype=np.uint8)
+    p = params.c_params()
+    check(_lib.load().slk_shard_of_records(C.byref(p), id1.ctypes.data_as(C.c_void_p), len(id1), world,
+                                           out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ the exchange
+def exchange(send, send_counts: Sequence[int], group=None):
+    """All-to-all of variable-sized slices: rank r receives send[offsets[r] : offsets[r] + send_counts[r]] of every rank,
+    concatenated in rank order. Returns (received tensor, receive counts). NCCL: one all_to_all_single; gloo (CPU tests)
+    has no all-to-all, so the same exchange is written as point-to-point sends."""
+    import torch
+    dist = _dist()
+    rank, world = world_of(group)
+    if world == 1:
+        return send, list(send_counts)
+    cnt = torch.tensor(list(send_counts), dtype=torch.int64, device=send.device)
+    rcnt = torch.empty_like(cnt)
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        dist.all_to_all_single(rcnt, cnt, group=group)
+        recv_counts = [int(x) for x in rcnt.tolist()]
+        recv = torch.empty(sum(recv_counts), dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
+        return recv, recv_counts
+    gathered = [torch.empty_like(cnt) for _ in range(world)]
+    dist.all_gather(gathered, cnt, group=group)
+    recv_counts = [int(g[rank]) for g in gathered]
+    recv = torch.empty(sum(recv_counts), dtype=send.dtype, device=send.device)
+    so = np.concatenate([[0], np.cumsum(send_counts)]).astype(np.int64)
+    ro = np.concatenate([[0], np.cumsum(recv_counts)]).astype(np.int64)
+    recv[ro[rank]:ro[rank + 1]] = send[so[rank]:so[rank + 1]]
+    ops = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        if send_counts[peer]:
+            ops.append(dist.P2POp(dist.isend, send[so[peer]:so[peer + 1]].contiguous(), peer, group=group))
+        if recv_counts[peer]:
+            ops.append(dist.P2POp(dist.irecv, recv[ro[peer]:ro[peer + 1]], peer, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return recv, recv_counts
+
+
+def union_of_taxa(local: np.ndarray, group=None) -> np.ndarray:
+    """Union (sorted, unique) of the taxa all shards can answer with."""
+    import torch
+    dist = _dist()
+    rank, world = world_of(group)
+    local = np.unique(np.asarray(local, dtype=np.int32))
+    if world == 1:
+        return local
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    n = torch.tensor([len(local)], dtype=torch.int64, device=dev)
+    ns = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(ns, n, group=group)
+    cap = max(int(x) for x in ns)
+    buf = torch.zeros(max(cap, 1), dtype=torch.int32, device=dev)
+    buf[:len(local)] = torch.from_numpy(local).to(dev)
+    bufs = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf, group=group)
+    parts = [b[:int(k)].cpu().numpy() for b, k in zip(bufs, ns)]
+    return np.unique(np.concatenate(parts)).astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------------ device ops
+class GpuSplitOps:
+    """The four device steps of the split path through the C ABI, on torch CUDA tensors (torch owns the buffers so that
+    NCCL can send them; the kernels are the library's)."""
+
+    def __init__(self, index: KeyValueIndex, taxa_union: np.ndarray):
+        import torch
+        self.torch = torch
+        self.index, self.ctx, self.params = index, index.ctx, index.params
+        self.device = torch.device("cuda", self.ctx.device)
+        self._L = self.ctx._L
+        self._p = self.params.c_params()
+        taxa_union = np.ascontiguousarray(taxa_union, dtype=np.int32)
+        h = C.c_void_p()
+        check(self._L.slk_resolver_create(self.ctx.h, index.taxonomy.h, C.byref(self._p), taxa_union.ctypes.data_as(C.c_void_p),
+                                          len(taxa_union), C.byref(h)))
+        self.resolver = h
+
+    def close(self):
+        if getattr(self, "resolver", None):
+            self._L.slk_resolver_destroy(self.resolver)
+            self.resolver = None
+
+    @staticmethod
+    def _v(t):
+        return C.c_void_p(t.data_ptr()) if t is not None and t.numel() else (C.c_void_p(t.data_ptr()) if t is not None else None)
+
+    def upload(self, a: np.ndarray):
+        return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+
+    def scan_spans(self, bases1, off1, bases2, off2, n_reads: int):
+        t = self.torch
+        span_off = t.zeros(n_reads + 1, dtype=t.int64, device=self.device)
+        n = C.c_uint64(0)
+        args = (self._v(bases1), self._v(off1), self._v(bases2) if bases2 is not None else None,
+                self._v(off2) if off2 is not None else None, n_reads, self._v(span_off))
+        check(self._L.slk_scan_spans_dev(self.ctx.h, C.byref(self._p), *args, None, 0, C.byref(n)))
+        spans = t.empty(max(int(n.value), 1), dtype=t.int64, device=self.device)
+        check(self._L.slk_scan_spans_dev(self.ctx.h, C.byref(self._p), *args, self._v(spans), int(n.value), C.byref(n)))
+        return span_off, spans, int(n.value)
+
+    def route(self, spans, n_spans: int, world: int):
+        t = self.torch
+        counts = (C.c_uint64 * world)()
+        check(self._L.slk_route_spans_dev(self.ctx.h, self._v(spans), n_spans, world, None, None, 0, counts))
+        total = sum(counts)
+        keys = t.empty(max(total, 1), dtype=t.int64, device=self.device)
+        idx = t.empty(max(total, 1), dtype=t.int32, device=self.device)
+        check(self._L.slk_route_spans_dev(self.ctx.h, self._v(spans), n_spans, world, self._v(keys), self._v(idx), total, counts))
+        return keys[:total], idx[:total], [int(c) for c in counts]
+
+    def probe(self, keys):
+        t = self.torch
+        taxa = t.empty(max(keys.numel(), 1), dtype=t.int32, device=self.device)
+        check(self._L.slk_probe_keys_dev(self.index.h, self._v(keys), keys.numel(), self._v(taxa)))
+        return taxa[:keys.numel()]
+
+    def resolve(self, spans, span_off, n_spans: int, n_reads: int, paired: bool, send_idx, taxa, confidence: float,
+                min_hit_groups: int, want_hits: bool) -> ClassifiedBatch:
+        t = self.torch
+        taxon = t.empty(max(n_reads, 1), dtype=t.int32, device=self.device)
+        flags = t.empty(max(n_reads, 1), dtype=t.uint8, device=self.device)
+        detail = t.empty(max(n_reads, 1) * DETAIL_DTYPE.itemsize, dtype=t.uint8, device=self.device)
+        hits = t.empty(max(n_spans, 1) * HIT_DTYPE.itemsize, dtype=t.uint8, device=self.device) if want_hits else None
+        opts = ClassifyOpts(float(confidence), int(min_hit_groups), 0)
+        check(self._L.slk_resolve_spans_dev(self.resolver, C.byref(opts), self._v(spans), self._v(span_off), n_spans, n_reads,
+                                            1 if paired else 0, self._v(send_idx), self._v(taxa), send_idx.numel(),
+                                            self._v(taxon), self._v(flags), self._v(detail), self._v(hits) if want_hits else None))
+        d = detail.cpu().numpy().view(DETAIL_DTYPE)[:n_reads]
+        h = hits.cpu().numpy().view(HIT_DTYPE)[:n_spans] if want_hits else None
+        return ClassifiedBatch(taxon.cpu().numpy()[:n_reads], flags.cpu().numpy()[:n_reads], d, h, n_spans if want_hits else 0)
+
+
+# ------------------------------------------------------------------------------------------------ index + classifier
+class ShardedKeyValueIndex:
+    """This rank's shard of a KeyValueIndex: the records whose minimizer hashes into the rank's range."""
+
+    def __init__(self, index: KeyValueIndex, rank: int, world: int):
+        self.index, self.rank, self.world = index, rank, world
+        self.ctx, self.taxonomy, self.params = index.ctx, index.taxonomy, index.params
+
+    @classmethod
+    def from_records(cls, ctx: GpuContext, taxonomy: Taxonomy, params: IndexParams, id1: np.ndarray, taxon: np.ndarray,
+                     group=None, rank: Optional[int] = None, world: Optional[int] = None):
+        """Every rank is handed the same (or any superset of its share of the) records and keeps its own shard
+        (KeyValueIndex.loadRecords, slacken/KeyValueIndex.scala:150-159, per shard)."""
+        r, w = world_of(group)
+        rank = r if rank is None else rank
+        world = w if world is None else world
+        mine = shard_of_records(params, id1, world) == rank
+        return cls(KeyValueIndex.from_records(ctx, taxonomy, params, np.ascontiguousarray(id1)[mine],
+                                              np.ascontiguousarray(taxon)[mine]), rank, world)
+
+    @classmethod
+    def build(cls, ctx: GpuContext, taxonomy: Taxonomy, params: IndexParams, local_batches, expected_bases: int = 0,
+              group=None):
+        """Distributed KeyValueIndex.makeRecords (slacken/KeyValueIndex.scala:85-122): every rank scans, sorts and
+        LCA-reduces ITS genomes on its GPU, the reduced records travel to the owner of their key (one all-to-all;
+        LCA is associative and commutative, slacken/LowestCommonAncestor.scala:152-170), and the owner's insert merges
+        records of the same minimizer by LCA again."""
+        import torch
+        rank, world = world_of(group)
+        local = KeyValueIndex.build(ctx, taxonomy, params, local_batches, expected_bases)
+        if world == 1:
+            return cls(local, 0, 1)
+        id1, taxon = local.records(sort=False)
+        local.close()
+        owner = shard_of_records(params, id1, world)
+        order = np.argsort(owner, kind="stable")
+        counts = np.bincount(owner, minlength=world).tolist()
+        dev = "cuda" if _dist().get_backend(group) == "nccl" else "cpu"
+        rid, _ = exchange(torch.from_numpy(id1.view(np.int64)[order]).to(dev), counts, group)
+        rtx, _ = exchange(torch.from_numpy(taxon[order]).to(dev), counts, group)
+        return cls(KeyValueIndex.from_records(ctx, taxonomy, params, rid.cpu().numpy(), rtx.cpu().numpy()), rank, world)
+
+    def taxa(self) -> np.ndarray:
+        n = C.c_uint32(0)
+        check(self.ctx._L.slk_index_taxa(self.index.h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.int32)
+        check(self.ctx._L.slk_index_taxa(self.index.h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+        return out
+
+    def __len__(self) -> int:
+        return len(self.index)
+
+    def close(self):
+        self.index.close()
+
+
+class ShardedClassifier:
+    """Classifier over a sharded library. Construction and classify() are collective: every rank of the group calls them
+    (with its own reads, possibly none)."""
+
+    def __init__(self, shard: Optional[ShardedKeyValueIndex], group=None, ops=None, local_taxa: Optional[np.ndarray] = None):
+        self.group = group
+        self.rank, self.world = world_of(group)
+        taxa = union_of_taxa(shard.taxa() if shard is not None else local_taxa, group)
+        self.ops = ops(taxa) if ops is not None else GpuSplitOps(shard.index, taxa)
+        self.last_exchange_bytes = (0, 0)
+
+    def classify(self, bases1: np.ndarray, off1: np.ndarray, bases2: Optional[np.ndarray] = None,
+                 off2: Optional[np.ndarray] = None, confidence: float = 0.0, min_hit_groups: int = 2,
+                 per_read_output: bool = True) -> ClassifiedBatch:
+        ops = self.ops
+        n = len(off1) - 1
+        paired = bases2 is not None
+        d_b1, d_o1 = ops.upload(bases1 if len(bases1) else np.zeros(16, np.uint8)), ops.upload(off1.astype(np.uint64).view(np.int64))
+        d_b2 = ops.upload(bases2 if len(bases2) else np.zeros(16, np.uint8)) if paired else None
+        d_o2 = ops.upload(off2.astype(np.uint64).view(np.int64)) if paired else None
+        span_off, spans, n_spans = ops.scan_spans(d_b1, d_o1, d_b2, d_o2, n)
+        keys, idx, counts = ops.route(spans, n_spans, self.world)
+        recv_keys, recv_counts = exchange(keys, counts, self.group)          # keys -> owners
+        taxa_here = ops.probe(recv_keys)
+        taxa, _ = exchange(taxa_here, recv_counts, self.group)                 # taxa -> askers, in send order
+        self.last_exchange_bytes = (8 * int(keys.numel()), 4 * int(taxa.numel()))
+        return ops.resolve(spans, span_off, n_spans, n, paired, idx, taxa, confidence, min_hit_groups, per_read_output)
+
+    def close(self):
+        if hasattr(self.ops, "close"):
+            self.ops.close()

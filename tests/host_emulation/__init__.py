@@ -50,6 +50,16 @@ def lib():
         L.emu_classify.argtypes = [C.POINTER(ScanParams), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                    C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+        L.emu_classify_split.restype = C.c_int64
+        L.emu_classify_split.argtypes = L.emu_classify.argtypes[:-1]
+        L.emu_scan_spans.restype = C.c_int64
+        L.emu_scan_spans.argtypes = [C.POINTER(ScanParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                     C.c_void_p, C.c_void_p, C.c_uint64]
+        L.emu_probe_keys.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.emu_resolve_spans.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.emu_shard_of.restype = C.c_uint32
+        L.emu_shard_of.argtypes = [C.c_uint64, C.c_uint32]
         L.emu_emit_cells.restype = C.c_int64
         L.emu_emit_cells.argtypes = [C.POINTER(ScanParams), C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]
         L.emu_synth_genome.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
@@ -116,7 +126,8 @@ class EmuIndex:
         lib().emu_insert_cells(_p(self.cells), self.n_buckets, _p(self.parent), _p(self.depth), self.dt.root,
                                _p(cells_in), len(cells_in))
 
-    def classify(self, bases1, off1, bases2=None, off2=None, confidence=0.0, min_hit_groups=2, packed=False):
+    def classify(self, bases1, off1, bases2=None, off2=None, confidence=0.0, min_hit_groups=2, packed=False, split=False):
+        """split=True: the scan | probe | merge+resolve bodies of the sharded-library path instead of the fused one."""
         n = len(off1) - 1
         off1 = np.ascontiguousarray(off1, dtype=np.uint64)
         if bases2 is not None:
@@ -125,9 +136,14 @@ class EmuIndex:
         cap = int(off1[-1]) + (int(off2[-1]) if bases2 is not None else 0) + 5 * n + 8
         hits = np.zeros(cap, dtype=HIT_DTYPE)
         hit_off = np.zeros(n + 1, dtype=np.uint64)
-        used = lib().emu_classify(C.byref(self.sp), _p(self.cells), self.n_buckets, _p(self.parent), _p(self.depth),
-                                  _p(self.raw), len(self.raw), self.dt.root, _p(bases1), _p(off1), _p(bases2), _p(off2), n,
-                                  float(confidence), int(min_hit_groups), _p(res), _p(hit_off), _p(hits), cap, 1 if packed else 0)
+        if split:
+            used = lib().emu_classify_split(C.byref(self.sp), _p(self.cells), self.n_buckets, _p(self.parent), _p(self.depth),
+                                            _p(self.raw), len(self.raw), self.dt.root, _p(bases1), _p(off1), _p(bases2),
+                                            _p(off2), n, float(confidence), int(min_hit_groups), _p(res), _p(hit_off), _p(hits), cap)
+        else:
+            used = lib().emu_classify(C.byref(self.sp), _p(self.cells), self.n_buckets, _p(self.parent), _p(self.depth),
+                                      _p(self.raw), len(self.raw), self.dt.root, _p(bases1), _p(off1), _p(bases2), _p(off2), n,
+                                      float(confidence), int(min_hit_groups), _p(res), _p(hit_off), _p(hits), cap, 1 if packed else 0)
         assert used >= 0
         hit_off[n] = used
         return res, hit_off, hits[:used]

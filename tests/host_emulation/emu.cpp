@@ -120,6 +120,84 @@ EMU_API int64_t emu_classify(const slk_scan_params* sp, uint64_t* cells, uint64_
   return r;
 }
 
+// The split path (scan -> span words | probe | merge + resolve), one fragment at a time, with the same outputs as
+// emu_classify: what slk_scan_spans_dev / slk_probe_spans_dev / slk_resolve_spans_dev do on the device.
+template <int W>
+static int64_t classify_split_w(const slk_scan_params* sp, uint64_t* cells, uint64_t n_buckets, const uint16_t* parent,
+                                const uint8_t* depth, const int32_t* raw, uint32_t n_dense, uint32_t root, const uint8_t* b1,
+                                const uint64_t* o1, const uint8_t* b2, const uint64_t* o2, uint32_t n, double confidence,
+                                int min_hit_groups, emu_result* res, uint64_t* hit_off, slk_hit* hits_out, uint64_t cap) {
+  slk_table_view tb{cells, n_buckets, 0, 0};
+  slk_tax_view tx{parent, depth, raw, n_dense, root};
+  uint64_t used = 0;
+  std::vector<uint64_t> spans;
+  std::vector<uint16_t> dense;
+  for (uint32_t r = 0; r < n; r++) {
+    spans.clear();
+    slk_scan_fragment_spans<W>(*sp, b1 + o1[r], (uint32_t)(o1[r + 1] - o1[r]), b2 ? b2 + o2[r] : nullptr,
+                               b2 ? (uint32_t)(o2[r + 1] - o2[r]) : 0u, b2 != nullptr, [&](uint64_t w) { spans.push_back(w); });
+    dense.assign(spans.size(), 0);
+    for (size_t i = 0; i < spans.size(); i++)
+      if (SLK_SPAN_TYPE(spans[i]) == SLK_E_SEQ) dense[i] = (uint16_t)slk_probe(tb, SLK_SPAN_KEY(spans[i]));
+    slk_frag_result fr;
+    hit_off[r] = used;
+    bool full = false;
+    slk_resolve_spans(tx, sp->k, spans.data(), dense.data(), (uint32_t)spans.size(), confidence, min_hit_groups,
+                      [&](int32_t l, int32_t c) { if (used < cap) hits_out[used++] = slk_hit{l >= 0 ? raw[l] : l, c}; else full = true; }, fr);
+    if (full) return -1;
+    res[r] = emu_result{fr.taxon, fr.flags, fr.kmers1, fr.kmers2, fr.num_distinct, fr.n_hits};
+  }
+  return (int64_t)used;
+}
+EMU_API int64_t emu_classify_split(const slk_scan_params* sp, uint64_t* cells, uint64_t n_buckets, const uint16_t* parent,
+                                   const uint8_t* depth, const int32_t* raw, uint32_t n_dense, uint32_t root, const uint8_t* b1,
+                                   const uint64_t* o1, const uint8_t* b2, const uint64_t* o2, uint32_t n, double confidence,
+                                   int min_hit_groups, emu_result* res, uint64_t* hit_off, slk_hit* hits_out, uint64_t cap) {
+  int64_t r = -2;
+  DISPATCH_W(sp->w, r = classify_split_w<W_>(sp, cells, n_buckets, parent, depth, raw, n_dense, root, b1, o1, b2, o2, n,
+                                             confidence, min_hit_groups, res, hit_off, hits_out, cap));
+  return r;
+}
+EMU_API uint32_t emu_shard_of(uint64_t ckey, uint32_t world) { return slk_shard_of(ckey, world); }
+
+// the three device steps of the split path one by one (what tests/test_dist_gloo.py plugs into ShardedClassifier)
+template <int W>
+static int64_t scan_spans_w(const slk_scan_params* sp, const uint8_t* b1, const uint64_t* o1, const uint8_t* b2,
+                            const uint64_t* o2, uint32_t n, uint64_t* span_off, uint64_t* spans, uint64_t cap) {
+  uint64_t used = 0;
+  bool full = false;
+  for (uint32_t r = 0; r < n; r++) {
+    span_off[r] = used;
+    slk_scan_fragment_spans<W>(*sp, b1 + o1[r], (uint32_t)(o1[r + 1] - o1[r]), b2 ? b2 + o2[r] : nullptr,
+                               b2 ? (uint32_t)(o2[r + 1] - o2[r]) : 0u, b2 != nullptr,
+                               [&](uint64_t w) { if (spans) { if (used < cap) spans[used] = w; else full = true; } used++; });
+  }
+  span_off[n] = used;
+  return full ? -1 : (int64_t)used;
+}
+EMU_API int64_t emu_scan_spans(const slk_scan_params* sp, const uint8_t* b1, const uint64_t* o1, const uint8_t* b2,
+                               const uint64_t* o2, uint32_t n, uint64_t* span_off, uint64_t* spans, uint64_t cap) {
+  int64_t r = -2;
+  DISPATCH_W(sp->w, r = scan_spans_w<W_>(sp, b1, o1, b2, o2, n, span_off, spans, cap));
+  return r;
+}
+EMU_API void emu_probe_keys(uint64_t* cells, uint64_t n_buckets, const int32_t* raw, const uint64_t* keys, uint64_t n, int32_t* taxa) {
+  slk_table_view tb{cells, n_buckets, 0, 0};
+  for (uint64_t i = 0; i < n; i++) { uint32_t d = slk_probe(tb, keys[i]); taxa[i] = d ? raw[d] : 0; }
+}
+EMU_API void emu_resolve_spans(const uint16_t* parent, const uint8_t* depth, const int32_t* raw, uint32_t n_dense, uint32_t root,
+                               int32_t k, const uint64_t* spans, const uint64_t* span_off, const uint16_t* dense, uint32_t n_reads,
+                               double confidence, int min_hit_groups, emu_result* res, slk_hit* hits_out) {
+  slk_tax_view tx{parent, depth, raw, n_dense, root};
+  for (uint32_t r = 0; r < n_reads; r++) {
+    slk_frag_result fr;
+    slk_hit* ho = hits_out + span_off[r];
+    slk_resolve_spans(tx, k, spans + span_off[r], dense + span_off[r], (uint32_t)(span_off[r + 1] - span_off[r]), confidence,
+                      min_hit_groups, [&](int32_t l, int32_t c) { *ho++ = slk_hit{l >= 0 ? raw[l] : l, c}; }, fr);
+    res[r] = emu_result{fr.taxon, fr.flags, fr.kmers1, fr.kmers2, fr.num_distinct, fr.n_hits};
+  }
+}
+
 // the emit "threads" of one fragment, BUILD_WPT windows each, exactly like emit_cells_kernel partitions the work
 EMU_API int64_t emu_emit_cells(const slk_scan_params* sp, const uint8_t* bases, uint64_t len, uint32_t dense_taxon,
                                uint32_t wpt, uint64_t* out, uint64_t cap) {

@@ -60,3 +60,120 @@ def test_sharded_counts_allreduce_gloo(tmp_path):
     s.close()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert open(tmp_path / "ok").read() == "1"
+
+
+# ---------------------------------------------------------------------------------------------- sharded library
+class EmuSplitOps:
+    """Stand-in for slacken_b200.sharded.GpuSplitOps on CPU tensors: the same per-thread kernel bodies (slk_core.h),
+    run by tests/host_emulation, so that ShardedClassifier's routing and exchanges can be driven over gloo."""
+
+    def __init__(self, sp, parents, shard_id1, shard_taxon, taxa_union, k=35):
+        import ctypes as C
+        import torch
+        from tests import host_emulation as emu
+        self.C, self.torch, self.emu, self.sp, self.k = C, torch, emu, sp, k
+        self.shard = emu.EmuIndex(sp, parents, shard_id1, shard_taxon)          # this rank's table
+        self.dt = emu.DenseTax(parents, taxa_union)                              # the query side's taxonomy
+        self.parent, self.depth, self.raw = self.dt.arrays()
+
+    def upload(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a).copy())
+
+    def scan_spans(self, b1, o1, b2, o2, n):
+        emu, p = self.emu, self.emu._p
+        nb1, no1 = b1.numpy(), o1.numpy().view(np.uint64)
+        nb2 = b2.numpy() if b2 is not None else None
+        no2 = o2.numpy().view(np.uint64) if o2 is not None else None
+        span_off = np.zeros(n + 1, dtype=np.uint64)
+        total = emu.lib().emu_scan_spans(self.C.byref(self.sp), p(nb1), p(no1), p(nb2), p(no2), n, p(span_off), None, 0)
+        spans = np.zeros(max(total, 1), dtype=np.uint64)
+        assert emu.lib().emu_scan_spans(self.C.byref(self.sp), p(nb1), p(no1), p(nb2), p(no2), n, p(span_off), p(spans), total) == total
+        return self.torch.from_numpy(span_off.view(np.int64)), self.torch.from_numpy(spans.view(np.int64)), int(total)
+
+    def route(self, spans, n_spans, world):
+        w = spans.numpy().view(np.uint64)[:n_spans]
+        seq = np.nonzero(((w >> np.uint64(14)) & np.uint64(3)) == 0)[0]
+        dest = np.array([self.emu.lib().emu_shard_of(int(x) >> 16, world) for x in w[seq]], dtype=np.int64)
+        order = np.argsort(dest, kind="stable")
+        keys = (w[seq][order] >> np.uint64(16)).astype(np.uint64).view(np.int64)
+        idx = seq[order].astype(np.int32)
+        return self.torch.from_numpy(keys.copy()), self.torch.from_numpy(idx.copy()), np.bincount(dest, minlength=world).tolist()
+
+    def probe(self, keys):
+        k = np.ascontiguousarray(keys.numpy()).view(np.uint64)
+        taxa = np.zeros(max(len(k), 1), dtype=np.int32)
+        p = self.emu._p
+        self.emu.lib().emu_probe_keys(p(self.shard.cells), self.shard.n_buckets, p(self.shard.raw), p(k), len(k), p(taxa))
+        return self.torch.from_numpy(taxa[:len(k)].copy())
+
+    def resolve(self, spans, span_off, n_spans, n_reads, paired, send_idx, taxa, confidence, min_hit_groups, want_hits):
+        from slacken_b200.host import DETAIL_DTYPE, HIT_DTYPE, ClassifiedBatch
+        emu, p = self.emu, self.emu._p
+        dense = np.zeros(max(n_spans, 1), dtype=np.uint16)
+        dense[send_idx.numpy()] = [self.dt.to_dense[int(t)] for t in taxa.numpy()]
+        res = np.zeros(n_reads, dtype=emu.RESULT_DTYPE)
+        hits = np.zeros(max(n_spans, 1), dtype=HIT_DTYPE)
+        so = np.ascontiguousarray(span_off.numpy()).view(np.uint64)
+        sw = np.ascontiguousarray(spans.numpy()).view(np.uint64)
+        emu.lib().emu_resolve_spans(p(self.parent), p(self.depth), p(self.raw), len(self.raw), self.dt.root, self.k, p(sw), p(so),
+                                    p(dense), n_reads, float(confidence), int(min_hit_groups), p(res), p(hits))
+        detail = np.zeros(n_reads, dtype=DETAIL_DTYPE)
+        detail["hit_off"] = so[:-1]
+        detail["hit_cnt"] = res["n_hits"]
+        detail["num_distinct"] = res["num_distinct"]
+        detail["len1"] = res["kmers1"] + (self.k - 1)
+        detail["len2"] = res["kmers2"] + (self.k - 1) if paired else 0xFFFFFFFF
+        return ClassifiedBatch(res["taxon"].copy(), res["flags"].astype(np.uint8), detail, hits, n_spans)
+
+
+def _sharded_worker(rank, world, port, out_dir):
+    from oracle import oracle
+    from slacken_b200.sharded import ShardedClassifier
+    from tests import host_emulation as emu
+    from tests.util import leaf_taxa, make_taxonomy, random_dna, simulate_reads
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(77)   # same world on every rank
+    parents, _, _ = make_taxonomy(90, 9)
+    leaves = leaf_taxa(parents)
+    genomes = [random_dna(rng, 3000) for _ in range(8)]
+    taxa = np.array([leaves[int(rng.integers(len(leaves)))] for _ in genomes], dtype=np.int32)
+    reads = simulate_reads(rng, genomes, 300, (20, 200), n_rate=0.1)
+    mates = simulate_reads(rng, genomes, 300, (20, 200), n_rate=0.1)
+    lib = oracle.Library(oracle.params(), parents, 1 << 16)
+    b, off = oracle.pack_sequences(genomes)
+    lib.add_fragments(b, off, taxa)
+    id1, tx = lib.records()
+    sp = emu.scan_params(35, 31, 7, oracle.DEFAULT_TOGGLE_MASK, True)
+    # this rank's shard of the records, by the library's own owner function
+    owner = np.array([emu.lib().emu_shard_of(emu.lib().emu_compress(sp, int(k)), world) for k in id1.view(np.uint64)])
+    mine = owner == rank
+    ops = lambda union: EmuSplitOps(sp, parents, id1[mine], tx[mine], union)
+    shard_taxa = np.unique(tx[mine])
+    cls = ShardedClassifier(None, ops=ops, local_taxa=shard_taxa)
+    ok = 0 < mine.sum() < len(id1)
+    for paired in (False, True):
+        lo, hi = shard_bounds(len(reads), rank, world)   # every rank classifies its own reads against ALL shards
+        rb, ro = oracle.pack_sequences(reads[lo:hi])
+        mb, mo = oracle.pack_sequences(mates[lo:hi]) if paired else (None, None)
+        got = cls.classify(rb, ro.astype(np.uint64), mb, mo.astype(np.uint64) if paired else None, confidence=0.1)
+        res, _, _, per = lib.classify(rb, ro, mb, mo, confidence=0.1)   # the oracle with the WHOLE library
+        ok = ok and np.array_equal(res["taxon"], got.taxon) and np.array_equal(res["classified"].astype(bool), got.classified)
+        ok = ok and np.array_equal(res["has_span"].astype(bool), got.has_span)
+        for i in range(hi - lo):
+            h = got.hits_of(i)
+            ok = ok and np.array_equal(h["taxon"], per[i]["taxon"]) and np.array_equal(h["count"], per[i]["count"])
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_sharded_library_classify_gloo(tmp_path):
+    """configs[4] on CPU: the library split over two ranks by minimizer hash, span keys routed to their owner and taxa
+    routed back (point-to-point over gloo), results equal to the oracle that holds the whole library."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert open(tmp_path / "ok0").read() == "1" and open(tmp_path / "ok1").read() == "1"

@@ -1,0 +1,73 @@
+"""The split (sharded-library) path on the GPU through the C ABI: scan -> route -> probe on the owner -> resolve.
+One GPU plays every rank: the library is cut into `world` shards by slk_shard_of_records, the keys routed by the
+device kernel are handed to the shard that owns them, and the results must equal the oracle that holds the whole
+library (and therefore the fused classify kernel). The NCCL exchange itself is exercised by bench_sharded.py."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from slacken_b200 import IndexParams, KeyValueIndex, Taxonomy
+from slacken_b200.host import pack_sequences
+from slacken_b200.sharded import GpuSplitOps, ShardedClassifier, ShardedKeyValueIndex, shard_of_records
+from tests.test_gpu_parity import assert_batch_equal, make_world, oracle_lib
+from tests.util import simulate_reads
+
+pytestmark = pytest.mark.gpu
+
+
+def _world(gpu, seed):
+    rng, parents, ranks, names, genomes, taxa = make_world(seed)
+    p = oracle.params()
+    olib = oracle_lib(p, parents, genomes, taxa)
+    id1, tx = olib.records()
+    tax = Taxonomy(gpu, parents, ranks, names)
+    return rng, genomes, olib, id1, tx, tax
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_split_path_one_shard_equals_oracle(gpu, paired):
+    rng, genomes, olib, id1, tx, tax = _world(gpu, 31)
+    shard = ShardedKeyValueIndex.from_records(gpu, tax, IndexParams(), id1, tx, rank=0, world=1)
+    assert len(shard) == len(id1)
+    cls = ShardedClassifier(shard)
+    reads = simulate_reads(rng, genomes, 1500, (10, 260), n_rate=0.15) + [b"", b"ACGT", b"N" * 80]
+    mates = simulate_reads(rng, genomes, len(reads), (10, 260), n_rate=0.15) if paired else None
+    rb, ro = pack_sequences(reads)
+    mb, mo = pack_sequences(mates) if paired else (None, None)
+    for conf in (0.0, 0.2):
+        got = cls.classify(rb, ro, mb, mo, confidence=conf)
+        res, _, _, per = olib.classify(rb, ro.astype(np.int64), mb, mo.astype(np.int64) if paired else None, confidence=conf)
+        assert_batch_equal(res, per, got, 35)
+    cls.close(); shard.close(); tax.close()
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_split_path_many_shards_on_one_gpu(gpu, world):
+    rng, genomes, olib, id1, tx, tax = _world(gpu, 37)
+    params = IndexParams()
+    owner = shard_of_records(params, id1, world)
+    shards = [KeyValueIndex.from_records(gpu, tax, params, id1[owner == r], tx[owner == r]) for r in range(world)]
+    assert sum(len(s) for s in shards) == len(id1) and all(len(s) > 0 for s in shards)
+    union = np.unique(tx)
+    ops = [GpuSplitOps(s, union) for s in shards]
+    reads = simulate_reads(rng, genomes, 2000, (30, 200), n_rate=0.1)
+    rb, ro = pack_sequences(reads)
+    q = ops[0]   # rank 0 asks, every shard answers
+    d_b, d_o = q.upload(rb), q.upload(ro.view(np.int64))
+    span_off, spans, n_spans = q.scan_spans(d_b, d_o, None, None, len(reads))
+    keys, idx, counts = q.route(spans, n_spans, world)
+    assert sum(counts) == int(keys.numel()) and all(c > 0 for c in counts)
+    import torch
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    taxa = torch.cat([ops[r].probe(keys[starts[r]:starts[r + 1]].contiguous()) for r in range(world)])   # the "all-to-all"
+    got = q.resolve(spans, span_off, n_spans, len(reads), False, idx, taxa, 0.1, 2, True)
+    res, _, _, per = olib.classify(rb, ro.astype(np.int64), confidence=0.1)
+    assert_batch_equal(res, per, got, 35)
+    # a key asked of the wrong shard is a miss there: the owner function of the host and of the device agree
+    wrong = ops[1].probe(keys[starts[0]:starts[1]].contiguous())
+    assert int((wrong != 0).sum()) == 0
+    for o in ops:
+        o.close()
+    for s in shards:
+        s.close()
+    tax.close()

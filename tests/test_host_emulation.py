@@ -30,12 +30,13 @@ def world(seed, k=35, m=31, s=7, canonical=True, n_genomes=16, glen=2500):
 
 def compare(lib, ix, rb, ro, rb2=None, ro2=None, confidence=0.0, k=35):
     for packed in (False, True):   # both input forms of the ABI must give the same answer
-        _compare(lib, ix, rb, ro, rb2, ro2, confidence, k, packed)
+        _compare(lib, ix, rb, ro, rb2, ro2, confidence, k, packed, False)
+    _compare(lib, ix, rb, ro, rb2, ro2, confidence, k, False, True)   # ... and so must the split (sharded-library) path
 
 
-def _compare(lib, ix, rb, ro, rb2, ro2, confidence, k, packed):
+def _compare(lib, ix, rb, ro, rb2, ro2, confidence, k, packed, split):
     res, _, _, per = lib.classify(rb, ro, rb2, ro2, confidence=confidence)
-    eres, ehoff, ehits = ix.classify(rb, ro, rb2, ro2, confidence=confidence, packed=packed)
+    eres, ehoff, ehits = ix.classify(rb, ro, rb2, ro2, confidence=confidence, packed=packed, split=split)
     assert np.array_equal(res["taxon"], eres["taxon"])
     assert np.array_equal(res["classified"], eres["flags"] & 1)
     assert np.array_equal(res["has_span"], (eres["flags"] >> 1) & 1)
