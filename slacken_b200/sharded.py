@@ -61,6 +61,8 @@ def exchange(send, send_counts: Sequence[int], group=None):
         recv_counts = [int(x) for x in rcnt.tolist()]
         recv = torch.empty(sum(recv_counts), dtype=send.dtype, device=send.device)
         dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
+        # the library's kernels run on the library's own stream: the received data must be complete before they start
+        torch.cuda.current_stream(send.device).synchronize()
         return recv, recv_counts
     gathered = [torch.empty_like(cnt) for _ in range(world)]
     dist.all_gather(gathered, cnt, group=group)
@@ -129,14 +131,16 @@ class GpuSplitOps:
 
     @staticmethod
     def _v(t):
-        return C.c_void_p(t.data_ptr()) if t is not None and t.numel() else (C.c_void_p(t.data_ptr()) if t is not None else None)
+        return C.c_void_p(t.data_ptr()) if t is not None else None
 
     def upload(self, a: np.ndarray):
-        return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        t = self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        self.torch.cuda.current_stream(self.device).synchronize()   # torch's stream is not the library's
+        return t
 
     def scan_spans(self, bases1, off1, bases2, off2, n_reads: int):
         t = self.torch
-        span_off = t.zeros(n_reads + 1, dtype=t.int64, device=self.device)
+        span_off = t.empty(n_reads + 1, dtype=t.int64, device=self.device)   # the library zeroes it itself
         n = C.c_uint64(0)
         args = (self._v(bases1), self._v(off1), self._v(bases2) if bases2 is not None else None,
                 self._v(off2) if off2 is not None else None, n_reads, self._v(span_off))
