@@ -88,6 +88,21 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(args, n_reads):
+    """dram__bytes_read + dram__bytes_write of ONE launch of the classify kernel, from the committed ncu --set full capture
+    (profiles/r01_traffic.json); None when the run is not the configuration that was profiled."""
+    if args.traffic is not None:
+        return args.traffic
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        t = json.load(open(p))
+        if int(t["reads_per_launch"]) == int(n_reads):
+            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_library(w, oracle, parents, genome_taxa, threads):
     """The reference's build path on the CPU: synthetic genomes -> removeInvalid -> super-mers -> LCA records."""
@@ -298,11 +313,13 @@ def run_ours(args, w):
     ms_ascii = max_over_ranks(t_a.elapsed_ms())
     cls.attach_counts(None)
     roofline = {"bound": "hbm", "kernel": "classify_kernel<5,true,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": args.traffic,
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": measured_traffic(args, n),
+                "algorithmic_bytes_per_launch": bytes_per_read * n,
                 "bytes_per_read": bytes_per_read, "probes_per_read": S, "merged_hits_per_read": H,
                 "probe_sectors_gbs": 32.0 * S * n * args.steps / (ms / 1e3) / 1e9,
-                "random_gather_ceiling": "35 G 32-byte gathers/s measured on this GPU for a 20 GB table (profiles/r01_probe_microbench.md): "
-                                         "the probe stage cannot exceed 0.17 of the copy-bandwidth roofline"}
+                "random_gather_ceiling": "a random 32-byte sector costs the B200 a whole 128-byte DRAM line and ~36 G such requests/s is "
+                                         "all the chip serves (25 G/s to a kernel that also computes; profiles/r01_probe_microbench.md): "
+                                         "a probe stage of one random sector per lookup cannot exceed ~0.17 of the copy-bandwidth roofline"}
 
     # ---- e2e: the host-buffer entry point, pinned host memory, H2D + D2H inside the timed region
     h_reads = ctx.pinned(n * L, np.uint8)
