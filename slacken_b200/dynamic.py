@@ -1,0 +1,171 @@
+"""Two-step classification with a sample-tailored ("dynamic") library: slacken/Dynamic.scala:250-374, host logic over the
+same kernels. Step 1 finds the taxa present in the sample with one of three heuristics, step 2 rebuilds the library from
+the genomes of those taxa (and all their descendants) and classifies the reads again.
+
+    d = Dynamic(ctx, base_index, genomes, rank="species", criteria=ClassifiedReadCount(100, 0.15))
+    taxon_set, dynamic_index = d.make_index(reads, "<out>_taxonSet.txt")
+    Classifier(dynamic_index).classify(...)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence, Set, Tuple
+
+import numpy as np
+
+from .host import Classifier, GpuContext, IndexParams, KeyValueIndex, ReportCounts, Taxonomy, pack_sequences
+
+RANK_DEPTH = {"root": 0, "superkingdom": 1, "kingdom": 2, "phylum": 3, "class": 4, "order": 5, "family": 6, "genus": 7,
+              "species": 8}   # slacken/Taxonomy.scala:38-47
+
+
+@dataclass
+class ClassifiedReadCount:   # --reads N (with the confidence of the first pass)
+    threshold: int
+    confidence: float = 0.0
+
+
+@dataclass
+class MinimizerTotalCount:   # --min-count N
+    threshold: int
+
+
+@dataclass
+class MinimizerDistinctCount:   # --min-distinct N
+    threshold: int
+
+
+class TaxonomyTree:
+    """The few tree queries of slacken/Taxonomy.scala that the taxon-set step needs."""
+
+    def __init__(self, taxonomy: Taxonomy):
+        self.parents, self.ranks = taxonomy.parents, taxonomy.ranks
+        self._children: Optional[dict] = None
+
+    def depth(self, t: int) -> int:   # slacken/Taxonomy.scala:222-228: rank depth of the nearest ranked node upwards
+        while t != 0:
+            r = self.ranks[t]
+            if r in RANK_DEPTH:
+                return RANK_DEPTH[r]
+            t = int(self.parents[t])
+        return -1
+
+    def children(self, t: int) -> List[int]:
+        if self._children is None:
+            ch: dict = {}
+            p = self.parents
+            for x in np.nonzero(p)[0]:
+                ch.setdefault(int(p[x]), []).append(int(x))
+            self._children = ch
+        return self._children.get(t, [])
+
+    def with_descendants(self, taxa: Iterable[int]) -> Set[int]:   # slacken/Taxonomy.scala:314-320
+        out, stack = set(int(t) for t in taxa), [int(t) for t in taxa]
+        while stack:
+            for c in self.children(stack.pop()):
+                if c not in out:
+                    out.add(c)
+                    stack.append(c)
+        return out
+
+    def clade_totals(self, counts: Sequence[Tuple[int, int]]) -> dict:   # TreeAggregator, slacken/KrakenReport.scala:27-41
+        tot: dict = {}
+        for t, c in counts:
+            x = int(t)
+            while x != 0:
+                tot[x] = tot.get(x, 0) + int(c)
+                x = int(self.parents[x])
+        return tot
+
+
+def count_filter(tree: TaxonomyTree, counts: Sequence[Tuple[int, int]], rank: str, threshold: int) -> Set[int]:
+    """CountFilter.taxa (slacken/Dynamic.scala:191-201): taxa with a count, at `rank` or below, whose clade total reaches
+    the threshold."""
+    tot = tree.clade_totals(counts)
+    d = RANK_DEPTH[rank]
+    return {int(t) for t, _ in counts if t != 0 and tree.depth(int(t)) >= d and tot.get(int(t), 0) >= threshold}
+
+
+class Dynamic:
+    def __init__(self, ctx: GpuContext, base: KeyValueIndex, genomes: Sequence[Tuple[int, bytes]], rank: str = "species",
+                 criteria=ClassifiedReadCount(100, 0.0), min_hit_groups: int = 2):
+        """genomes: (taxon, sequence) pairs of the genome library the dynamic index is rebuilt from."""
+        self.ctx, self.base, self.genomes, self.rank, self.criteria = ctx, base, genomes, rank, criteria
+        self.min_hit_groups = min_hit_groups
+        self.taxonomy = base.taxonomy
+        self.tree = TaxonomyTree(self.taxonomy)
+
+    # ---- the three counting methods (slacken/Dynamic.scala:84-145) -------------------------------------------------
+    def classified_reads_per_taxon(self, bases1, off1, bases2=None, off2=None) -> List[Tuple[int, int]]:
+        cls = Classifier(self.base)
+        counts = ReportCounts(self.ctx, self.taxonomy, 1)
+        cls.attach_counts(counts, 0)
+        cls.classify(bases1, off1, bases2, off2, confidence=self.criteria.confidence, min_hit_groups=self.min_hit_groups,
+                     per_read_output=False)
+        v = counts.fetch(0)
+        cls.attach_counts(None)
+        counts.close(); cls.close()
+        v[0] = 0   # only classified reads count (slacken/Dynamic.scala:137-143)
+        return [(int(t), int(v[t])) for t in np.nonzero(v)[0]]
+
+    def _span_hits(self, bases1, off1, bases2=None, off2=None):
+        """(taxon, minimizer) of every sequence span whose minimizer has a record: findHitsWithMinimizers."""
+        from .sharded import GpuSplitOps
+        ops = GpuSplitOps(self.base, np.zeros(0, dtype=np.int32))
+        try:
+            n = len(off1) - 1
+            d = [ops.upload(bases1 if len(bases1) else np.zeros(16, np.uint8)), ops.upload(off1.astype(np.uint64).view(np.int64))]
+            d2 = [ops.upload(bases2), ops.upload(off2.astype(np.uint64).view(np.int64))] if bases2 is not None else [None, None]
+            span_off, spans, n_spans = ops.scan_spans(d[0], d[1], d2[0], d2[1], n)
+            keys, idx, _ = ops.route(spans, n_spans, 1)
+            taxa = ops.probe(keys)
+            k, t = keys.cpu().numpy().view(np.uint64), taxa.cpu().numpy()
+        finally:
+            ops.close()
+        hit = t > 0
+        keep = np.array([self.tree.depth(int(x)) >= RANK_DEPTH[self.rank] for x in np.unique(t[hit])], dtype=bool)
+        ok_taxa = set(np.unique(t[hit])[keep].tolist())
+        sel = hit & np.isin(t, list(ok_taxa))
+        return t[sel], k[sel]
+
+    def total_minimizers_per_taxon(self, *reads) -> List[Tuple[int, int]]:
+        t, _ = self._span_hits(*reads)
+        u, c = np.unique(t, return_counts=True)
+        return [(int(a), int(b)) for a, b in zip(u, c)]
+
+    def distinct_minimizers_per_taxon(self, *reads) -> List[Tuple[int, int]]:
+        t, k = self._span_hits(*reads)
+        pairs = np.unique(np.stack([t.astype(np.uint64), k]), axis=1)
+        u, c = np.unique(pairs[0], return_counts=True)
+        return [(int(a), int(b)) for a, b in zip(u, c)]
+
+    # ---- findTaxonSet + makeRecords (slacken/Dynamic.scala:250-280,362-374) --------------------------------------------
+    def find_taxon_set(self, bases1, off1, bases2=None, off2=None, write_location: Optional[str] = None) -> Set[int]:
+        c = self.criteria
+        if isinstance(c, ClassifiedReadCount):
+            counts = self.classified_reads_per_taxon(bases1, off1, bases2, off2)
+        elif isinstance(c, MinimizerTotalCount):
+            counts = self.total_minimizers_per_taxon(bases1, off1, bases2, off2)
+        elif isinstance(c, MinimizerDistinctCount):
+            counts = self.distinct_minimizers_per_taxon(bases1, off1, bases2, off2)
+        else:
+            raise ValueError("unknown taxon criteria")
+        keep = count_filter(self.tree, counts, self.rank, c.threshold)
+        if write_location:
+            with open(write_location, "w") as f:   # the detected set BEFORE descendant expansion, one taxid per line
+                for t in sorted(keep):
+                    f.write(f"{t}\n")
+        return self.tree.with_descendants(keep)
+
+    def make_index(self, bases1, off1, bases2=None, off2=None, write_location: Optional[str] = None,
+                   gold_set: Optional[Iterable[int]] = None) -> Tuple[Set[int], KeyValueIndex]:
+        """The dynamic library: records rebuilt from the genomes whose taxon is in the set
+        (KeyValueIndex.makeRecords(library, Some(set)), slacken/KeyValueIndex.scala:102-116)."""
+        taxon_set = (self.tree.with_descendants(gold_set) if gold_set is not None
+                     else self.find_taxon_set(bases1, off1, bases2, off2, write_location))
+        chosen = [(t, s) for t, s in self.genomes if int(t) in taxon_set]
+        gb, goff = pack_sequences([s for _, s in chosen])
+        taxa = np.array([t for t, _ in chosen], dtype=np.int32)
+        index = KeyValueIndex.build(self.ctx, self.taxonomy, self.base.params, [(gb, goff, taxa)] if len(chosen) else [],
+                                    expected_bases=len(gb))
+        return taxon_set, index

@@ -1,0 +1,86 @@
+"""Host logic of SURVEY section 8 rows f2 (output layout) and f3 (taxon-set step of the 2-step mode): no GPU needed."""
+import gzip
+import os
+
+import numpy as np
+
+from slacken_b200.dynamic import RANK_DEPTH, TaxonomyTree, count_filter
+from slacken_b200.host import DETAIL_DTYPE, HIT_DTYPE, ClassifiedBatch
+from slacken_b200.output import ClassificationWriter, sample_ids, threshold_string
+
+
+class _Tax:   # what ClassificationWriter / TaxonomyTree need of a Taxonomy, without a device
+    def __init__(self, parents, ranks, names):
+        self.parents, self.ranks, self.names = np.asarray(parents, dtype=np.int32), ranks, names
+
+
+def _tree():
+    #            1 root
+    #        2 superkingdom
+    #     3 genus          10 species
+    #   4 species  5 species
+    #  6,7,9 strain  8 strain
+    parents = [0, 0, 1, 2, 3, 3, 4, 4, 5, 4, 2]
+    ranks = [None, "root", "superkingdom", "genus", "species", "species", None, None, None, None, "species"]
+    names = [f"t{i}" for i in range(11)]
+    names[0] = "unclassified"
+    return _Tax(parents, ranks, names)
+
+
+def test_threshold_string_uses_the_longest_decimal_part():
+    assert threshold_string(0.0, [0.0]) == "0.0"
+    assert threshold_string(0.0, [0.0, 0.15]) == "0.00"
+    assert threshold_string(0.15, [0.0, 0.15]) == "0.15"
+    assert threshold_string(0.5, [0.05, 0.5, 0.125]) == "0.500"
+
+
+def test_sample_ids():
+    assert sample_ids(["a", "b"], None) == ["all", "all"]
+    assert sample_ids(["S1_read7", "x", "S22_r"], r"(S[0-9]+)_") == ["S1", "other", "S22"]
+
+
+def test_depth_descendants_and_count_filter():
+    tree = TaxonomyTree(_tree())
+    assert [tree.depth(t) for t in (1, 2, 3, 4, 6, 8, 10)] == [0, 1, 7, 8, 8, 8, 8]   # unranked strains inherit 'species'
+    assert tree.depth(0) == -1
+    assert tree.with_descendants([4]) == {4, 6, 7, 9}
+    assert tree.with_descendants([3, 10]) == {3, 4, 5, 6, 7, 8, 9, 10}
+    counts = [(6, 40), (7, 30), (8, 5), (3, 100), (10, 99), (0, 1000)]
+    # species and below with clade total >= 50: 6 and 7 sit below species 4 but are keys with clade totals 40 / 30 only
+    assert count_filter(tree, counts, "species", 50) == {10}
+    assert count_filter(tree, counts, "species", 30) == {6, 7, 10}
+    assert count_filter(tree, counts, "genus", 100) == {3}          # clade(3) = 40 + 30 + 5 + 100
+    assert RANK_DEPTH["species"] == 8
+
+
+def test_writer_layout_and_report(tmp_path):
+    tax = _tree()
+    n = 5
+    taxon = np.array([6, 0, 4, 6, 0], dtype=np.int32)
+    flags = np.array([3, 2, 3, 3, 0], dtype=np.uint8)          # last read has no span: it vanishes
+    detail = np.zeros(n, dtype=DETAIL_DTYPE)
+    detail["len1"] = 150
+    detail["len2"] = 0xFFFFFFFF
+    detail["hit_off"] = [0, 2, 3, 4, 6]
+    detail["hit_cnt"] = [2, 1, 1, 2, 0]
+    hits = np.array([(6, 100), (0, 16), (0, 116), (4, 116), (-1, 3), (6, 113)], dtype=HIT_DTYPE)
+    batch = ClassifiedBatch(taxon, flags, detail, hits, len(hits))
+    titles = ["A_r1", "A_r2", "B_r1", "zzz", "A_r5"]
+    w = ClassificationWriter(tax, str(tmp_path / "out"), 0.15, [0.0, 0.15], sample_regex=r"^([AB])_")
+    w.add(titles, batch)
+    assert w.close() == ["A", "B", "other"]
+    loc = str(tmp_path / "out") + "_c0.15"
+    lines = gzip.open(os.path.join(loc, "sample=A", "part-00000.txt.gz"), "rt").read().splitlines()
+    assert lines == ["C\tA_r1\t6\t150\t6:100 0:16", "U\tA_r2\t0\t150\t0:116"]
+    assert gzip.open(os.path.join(loc, "sample=other", "part-00000.txt.gz"), "rt").read() == "C\tzzz\t6\t150\tA:3 6:113\n"
+    rep = open(os.path.join(loc, "A_kreport.txt")).read().splitlines()
+    assert rep[0] == "#Perc\tAggregate\tIn taxon\tRank\tTaxon\tName"
+    assert rep[1] == " 50.00\t1\t1\tU\t0\tunclassified"
+    assert rep[2] == " 50.00\t1\t0\tR\t1\tt1"
+    assert rep[-1] == " 50.00\t1\t1\tS1\t6\t        t6"
+    # --nounclassified drops the U rows from lines and reports
+    w2 = ClassificationWriter(tax, str(tmp_path / "o2"), 0.0, [0.0], with_unclassified=False)
+    w2.add(titles, batch)
+    assert w2.close() == ["all"]
+    rep2 = open(str(tmp_path / "o2") + "_c0.0/all_kreport.txt").read()
+    assert "unclassified" not in rep2 and rep2.splitlines()[1].startswith("100.00\t3\t0\tR\t1")
