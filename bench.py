@@ -209,6 +209,9 @@ def run_ours(args, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    from slacken_b200.dist import bind_to_gpu_numa
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = bind_to_gpu_numa(local)   # before any pinned buffer exists
     ctx = GpuContext(local)
     parents, ranks, names, genome_taxa = bw.taxonomy(w)
     tax = Taxonomy(ctx, parents, ranks, names)
@@ -361,6 +364,7 @@ def run_ours(args, w):
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": w.name, "reads_per_gpu_per_step": n, "library_records": len(index),
                        "library": "replicated per GPU", "input": "2-bit packed reads + ambiguity mask (72 B/read)", "l2": "inputs (reads 1.5 GB + table) are far larger than L2; no flush needed",
+                       "host_cpus_bound_to_gpu_numa_node": len(numa_cpus),
                        "classified_fraction": float((rep.sum() - rep[0]) / max(1, rep.sum())),
                        "reads_counted_in_report": total_reads_counted},
             "probes_per_s": value * S, "clocks": clocks, "e2e": e2e, "e2e_ascii_input": e2e_ascii,
@@ -373,6 +377,7 @@ def run_ours(args, w):
 
     # ---- cpu_baseline: the oracle on the host cores, bounded sample, rank 0 at N=1 only
     if world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)   # the CPU leg gets every host core again
         from oracle import oracle
         threads = oracle.max_threads()
         t0 = time.perf_counter()

@@ -45,3 +45,26 @@ class DeviceCounterView:
     def tensor(self, device):
         import torch
         return torch.as_tensor(self, device=device)
+
+
+def bind_to_gpu_numa(device: int) -> list:
+    """Pins the calling process to the CPUs that are local to `device` (NVML's CPU affinity of the GPU, intersected with
+    the CPUs the process may use), so that the pinned host buffers it allocates afterwards sit on the GPU's NUMA node and
+    its H2D/D2H copies do not cross the socket interconnect. Matters with one process per GPU on a two-socket box: the
+    copies of 4-8 ranks otherwise share the inter-socket links. Returns the CPU list ([] = left unchanged)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (max(ncpu, 1024) + 63) // 64)
+        local = {i for i in range(64 * len(mask)) if (mask[i // 64] >> (i % 64)) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(local & allowed)
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return []
