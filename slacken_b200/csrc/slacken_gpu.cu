@@ -337,15 +337,62 @@ __global__ void __launch_bounds__(256) reduce_cells_kernel(const uint64_t* __res
 }
 
 // K1: 2-bit encode + ambiguity mask, one read per thread, into the packed block layout (slk_read_src)
-__global__ void __launch_bounds__(128) pack_reads_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ off,
+// K1 as a stand-alone step: ASCII reads -> 2-bit code blocks + ambiguity masks. One 32-base block per lane, so that the
+// lanes of a warp read consecutive 32-byte pieces of the input and write consecutive output words; a warp owns 32
+// consecutive reads and finds the read of a block by a shuffle search over the reads' block offsets.
+__global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ off,
                                                          uint32_t n_reads, const uint64_t* __restrict__ boff,
                                                          uint64_t* __restrict__ codes, uint32_t* __restrict__ mask,
                                                          uint32_t* __restrict__ len_out) {
-  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_reads) return;
-  const uint64_t s = off[r], e = off[r + 1], b0 = boff[r];
-  len_out[r] = (uint32_t)(e - s);
-  slk_pack_read(bases + s, (uint32_t)(e - s), [&](uint32_t b, uint64_t cw, uint32_t mw) { codes[b0 + b] = cw; mask[b0 + b] = mw; });
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t r0 = warp * 32;
+  if (r0 >= n_reads) return;
+  const uint32_t nvalid = (uint32_t)(n_reads - r0 < 32 ? n_reads - r0 : 32);
+  const uint64_t r = r0 + (lane < nvalid ? lane : nvalid - 1);
+  const uint64_t my_off = off[r], my_end = off[r + 1], my_boff = boff[r];
+  if (lane < nvalid) len_out[r] = (uint32_t)(my_end - my_off);
+  const uint64_t b_first = __shfl_sync(0xffffffffu, my_boff, 0);
+  const uint64_t b_last = boff[r0 + nvalid];
+  for (uint64_t b0 = b_first; b0 < b_last; b0 += 32) {
+    const uint64_t b = b0 + lane;
+    uint32_t lo = 0;   // the last read of the warp whose first block is <= b
+#pragma unroll
+    for (uint32_t step = 16; step >= 1; step >>= 1) {
+      const uint32_t cand = lo + step;
+      const uint64_t v = __shfl_sync(0xffffffffu, my_boff, cand & 31u);
+      if (cand < nvalid && v <= b) lo = cand;
+    }
+    const uint64_t roff = __shfl_sync(0xffffffffu, my_off, lo), rend = __shfl_sync(0xffffffffu, my_end, lo);
+    const uint64_t rb = __shfl_sync(0xffffffffu, my_boff, lo);
+    if (b >= b_last) continue;
+    const uint64_t start = roff + 32 * (b - rb);
+    const uint32_t n = (uint32_t)(rend - start < 32 ? rend - start : 32);
+    // 32 bytes from an arbitrary address: nine aligned words, funnel-shifted into place (the buffer is readable up to
+    // the next 16-byte boundary, as everywhere in this library)
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(bases + start);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a0 & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a0 & 3) * 8;
+    const uint32_t nw = (n + (uint32_t)(a0 & 3) + 3) >> 2;   // aligned words that hold the n bytes
+    uint32_t w[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) w[i] = (uint32_t)i < nw ? __ldg(wp + i) : 0u;
+    uint64_t cw = 0;
+    uint32_t mw = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const uint32_t x = __funnelshift_r(w[i], w[i + 1], sh);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t pos = 4 * i + j;
+        const uint32_t c = pos < n ? slk_code((x >> (8 * j)) & 0xffu) : 0u;
+        cw |= (uint64_t)(c & 3u) << (2 * pos);
+        mw |= (c >> 2) << pos;
+      }
+    }
+    codes[b] = cw;
+    mask[b] = mw;
+  }
 }
 
 __global__ void snapshot_kernel(const unsigned long long* src, unsigned long long* dst) { *dst = *src; }
@@ -1001,7 +1048,8 @@ extern "C" int slk_pack_reads_dev(slk_ctx* ctx, const uint8_t* bases_dev, const 
   if (!ctx || !bases_dev || !off_dev || !boff_dev || !codes_dev || !mask_dev || !len_dev) return fail(SLK_E_INVALID, "bad arguments");
   CU(cudaSetDevice(ctx->device));
   if (n_reads == 0) return SLK_OK;
-  pack_reads_kernel<<<(n_reads + 127) / 128, 128, 0, ctx->stream>>>(bases_dev, off_dev, n_reads, boff_dev, codes_dev, mask_dev, len_dev);
+  const uint64_t warps = ((uint64_t)n_reads + 31) / 32;   // one warp per 32 reads, 8 warps per block
+  pack_reads_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, ctx->stream>>>(bases_dev, off_dev, n_reads, boff_dev, codes_dev, mask_dev, len_dev);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
   return SLK_OK;
