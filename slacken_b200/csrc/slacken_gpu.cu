@@ -241,15 +241,11 @@ void slk_dense_free(dense_tax& dt) { dense_free(dt); }
 // ---------------------------------------------------------------------------------------------- table kernels
 // K4: insert (compressed key << 16 | dense taxon) cells. Equal keys merge by LCA (TaxonLCA.merge,
 // slacken/LowestCommonAncestor.scala:152-170), so the kernel also serves incremental builds.
-__global__ void __launch_bounds__(256) insert_cells_kernel(const uint64_t* __restrict__ in, uint64_t n,
-                                                           slk_table_view tb, slk_tax_view tx,
-                                                           unsigned long long* n_new) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint64_t cell = in[i];
+// one thread's insert; returns true when the key was new
+__device__ __forceinline__ bool insert_cell(uint64_t cell, const slk_table_view& tb, const slk_tax_view& tx) {
   uint64_t ckey = cell >> 16;
   uint32_t taxon = (uint32_t)(cell & 0xffffu);
-  if (taxon == 0) return;  // a record whose taxon is NONE behaves exactly like a missing record
+  if (taxon == 0) return false;  // a record whose taxon is NONE behaves exactly like a missing record
   uint64_t b = slk_bucket_of(ckey, tb.n_buckets);
   for (uint64_t tries = 1; tries <= tb.n_buckets; tries++) {
     unsigned long long* slot = reinterpret_cast<unsigned long long*>(tb.cells + b * 4);
@@ -257,23 +253,32 @@ __global__ void __launch_bounds__(256) insert_cells_kernel(const uint64_t* __res
       unsigned long long cur = slot[j];
       if (cur == 0) {
         unsigned long long old = atomicCAS(&slot[j], 0ull, (unsigned long long)cell);
-        if (old == 0) { atomicAdd(n_new, 1ull); return; }
+        if (old == 0) return true;
         cur = old;
       }
       if ((cur >> 16) == ckey) {
         for (;;) {
           uint32_t t_old = (uint32_t)(cur & 0xffffu);
           uint32_t t_new = slk_lca(tx, t_old, taxon);
-          if (t_new == t_old) return;
+          if (t_new == t_old) return false;
           unsigned long long want = (ckey << 16) | t_new;
           unsigned long long old = atomicCAS(&slot[j], cur, want);
-          if (old == cur) return;
+          if (old == cur) return false;
           cur = old;
         }
       }
     }
     b = slk_next_bucket(b, tries, tb.n_buckets);   // the lookup's probe sequence: own 128-byte line first
   }
+  return false;
+}
+__global__ void __launch_bounds__(256) insert_cells_kernel(const uint64_t* __restrict__ in, uint64_t n,
+                                                           slk_table_view tb, slk_tax_view tx,
+                                                           unsigned long long* n_new) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool fresh = i < n && insert_cell(in[i], tb, tx);
+  const uint32_t cnt = (uint32_t)__syncthreads_count(fresh);   // one atomic per block on the record counter
+  if (threadIdx.x == 0 && cnt) atomicAdd(n_new, (unsigned long long)cnt);
 }
 
 // records (id1, raw taxon) -> cells, via the raw->dense lookup table
@@ -332,8 +337,20 @@ __global__ void __launch_bounds__(256) reduce_cells_kernel(const uint64_t* __res
     }
     res = (key << 16) | acc;
   }
-  uint64_t o = warp_agg_alloc(cursor, head ? 1u : 0u);
-  if (head) out[o] = res;
+  // one atomic per BLOCK on the output cursor (41 M same-address atomics, one per warp, were a third of this kernel)
+  __shared__ uint32_t wtot[8];
+  __shared__ unsigned long long bbase;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t bal = __ballot_sync(0xffffffffu, head);
+  if (lane == 0) wtot[warp] = __popc(bal);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 8; w++) { uint32_t c = wtot[w]; wtot[w] = t; t += c; }
+    bbase = t ? atomicAdd(cursor, (unsigned long long)t) : 0ull;
+  }
+  __syncthreads();
+  if (head) out[bbase + wtot[warp] + __popc(bal & ((1u << lane) - 1u))] = res;
 }
 
 // K1: 2-bit encode + ambiguity mask, one read per thread, into the packed block layout (slk_read_src)
