@@ -861,7 +861,10 @@ struct slk_classifier {
   int32_t counts_sample = 0;
   uint64_t launches = 0;
 };
-static const uint32_t CH_READS = 1u << 19;
+#ifndef SLK_CH_READS
+#define SLK_CH_READS (1u << 19)
+#endif
+static const uint32_t CH_READS = SLK_CH_READS;
 static const uint64_t CH_BASES = 96ull << 20;
 
 extern "C" int slk_classifier_create(slk_index* idx, slk_classifier** out) {
