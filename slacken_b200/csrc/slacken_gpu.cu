@@ -742,10 +742,13 @@ extern "C" int slk_build_finish(slk_builder* b, slk_index** out) {
     // K3a: radix sort of the cells
     CUX(cudaMalloc(&d_sorted, n * 8));
     uint64_t* sorted_ptr = nullptr;
-    // bits [16, 16+key_bits): only the minimizer has to be ordered, the reduce folds the taxa of a run in any order
-    rc = slk_sort_u64(b->cells, d_sorted, n, 16, 16 + b->sp.key_bits, ctx->stream, &sorted_ptr);
+    // Ordered by the 32-bit line mix of the minimizer (four passes, whatever the key width): the cells of a key meet,
+    // so the reduce below folds (nearly) all duplicates, and the unique cells come out in the order of the table's
+    // lines, so the insert walks the table front to back instead of hitting random lines. Two different keys with the
+    // same mix may interleave the cells of one of them; what the reduce then leaves double, the insert merges by LCA.
+    rc = slk_sort_cells_by_line(b->cells, d_sorted, n, ctx->stream, &sorted_ptr);
     if (rc != 0) { cleanup(); slk_index_destroy(idx); return fail(SLK_E_CUDA, "radix sort failed (%d)", rc); }
-    b->launches += 3 * ((b->sp.key_bits + 7) / 8);
+    b->launches += 3 * 4;
     // K3b: segmented LCA reduce; the other buffer receives the unique cells
     uint64_t* other = sorted_ptr == d_sorted ? b->cells : d_sorted;
     CUX(cudaMalloc(&d_cur, 8));
@@ -761,6 +764,7 @@ extern "C" int slk_build_finish(slk_builder* b, slk_index** out) {
     CUX(cudaMemsetAsync(d_cur, 0, 8, ctx->stream));
     rc = insert_cells(ctx, idx, other, n_unique, d_cur);
     if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
+    CUX(cudaMemcpyAsync(&n_unique, d_cur, 8, cudaMemcpyDeviceToHost, ctx->stream));   // distinct keys actually stored
     CUX(cudaStreamSynchronize(ctx->stream));
     b->launches++;
   } else {

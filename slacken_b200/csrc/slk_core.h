@@ -202,13 +202,19 @@ SLK_HD uint32_t slk_mulhi32(uint32_t a, uint32_t b) {
 // Home bucket of a compressed key: a 128-byte line (n_buckets / 4 of them, fewer than 2^32 for any table that fits
 // 180 GB) and one of its four 32-byte buckets. 32-bit arithmetic throughout (a 64-bit multiply is four instructions
 // on the device): x, a murmur3-finalizer mix of all 48 key bits, picks the line by multiply-shift; y, a further
-// mix that also separates keys with equal x, picks the bucket.
-SLK_HD uint64_t slk_bucket_of(uint64_t ckey, uint64_t n_buckets) {
+// mix that also separates keys with equal x, picks the bucket. The line is monotone in x: the build sorts its cells
+// by x, so that equal keys meet AND the table is filled line after line instead of at random.
+// x: a 32-bit mix of all 48 key bits (for a fixed high part a bijection of the low word)
+SLK_HD uint32_t slk_key_mix(uint64_t ckey) {
   const uint32_t lo = (uint32_t)ckey, hi = (uint32_t)(ckey >> 32);
   uint32_t x = lo ^ (hi * 0x9E3779B1u);
   x *= 0x85EBCA6Bu; x ^= x >> 15;
   x *= 0xC2B2AE35u; x ^= x >> 13;
-  const uint32_t y = (x ^ hi) * 0x27D4EB2Fu;
+  return x;
+}
+SLK_HD uint64_t slk_bucket_of(uint64_t ckey, uint64_t n_buckets) {
+  const uint32_t x = slk_key_mix(ckey);
+  const uint32_t y = (x ^ (uint32_t)(ckey >> 32)) * 0x27D4EB2Fu;
   return (uint64_t)slk_mulhi32(x, (uint32_t)(n_buckets >> 2)) * 4u + (y >> 30);
 }
 // Probe sequence. B200 answers a random 32-byte sector miss with the whole 128-byte line (measured: 127 B of DRAM

@@ -9,6 +9,7 @@
 // Only the bits that distinguish minimizers have to be sorted for the LCA reduce that follows (equal keys become
 // adjacent; the order of taxa inside a run is irrelevant because LCA is associative and commutative).
 #include "slk_sort.h"
+#include "slk_core.h"
 
 #include <stdint.h>
 
@@ -17,8 +18,12 @@
 #define SORT_TILE (SORT_THREADS * SORT_KPT)        // 4096 keys = 32 KB of shared memory staging
 #define SORT_WARPS (SORT_THREADS / 32)
 
-static __device__ __forceinline__ uint32_t digit_of(uint64_t k, int shift) { return (uint32_t)(k >> shift) & 0xffu; }
+// MIX: the sort key of a build cell is the table-line mix of its minimizer, not the cell itself
+template <bool MIX> static __device__ __forceinline__ uint32_t digit_of(uint64_t k, int shift) {
+  return MIX ? (slk_key_mix(k >> 16) >> shift) & 0xffu : (uint32_t)(k >> shift) & 0xffu;
+}
 
+template <bool MIX>
 __global__ void __launch_bounds__(SORT_THREADS) tile_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n, int shift,
                                                                 uint64_t n_tiles, uint64_t* __restrict__ cnt) {
   __shared__ uint32_t h[256];
@@ -29,7 +34,7 @@ __global__ void __launch_bounds__(SORT_THREADS) tile_hist_kernel(const uint64_t*
 #pragma unroll 4
   for (int i = 0; i < SORT_KPT; i++) {
     uint64_t idx = base + (uint64_t)i * SORT_THREADS + threadIdx.x;   // coalesced; counting needs no order
-    if (idx < n) atomicAdd(&h[digit_of(keys[idx], shift)], 1u);
+    if (idx < n) atomicAdd(&h[digit_of<MIX>(keys[idx], shift)], 1u);
   }
   __syncthreads();
   cnt[(uint64_t)threadIdx.x * n_tiles + tile] = h[threadIdx.x];
@@ -100,6 +105,7 @@ static cudaError_t exclusive_scan_u64(uint64_t* d, uint64_t n, uint64_t* scratch
 }
 
 // ---- stable scatter of one tile
+template <bool MIX>
 __global__ void __launch_bounds__(SORT_THREADS) scatter_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, uint64_t n,
                                                               int shift, uint64_t n_tiles, const uint64_t* __restrict__ pos) {
   __shared__ uint64_t stage[SORT_TILE];
@@ -121,7 +127,7 @@ __global__ void __launch_bounds__(SORT_THREADS) scatter_kernel(const uint64_t* _
     const uint64_t idx = wbase + (uint64_t)r * 32 + lane;
     const bool valid = idx < n;
     key[r] = valid ? in[idx] : ~0ull;
-    const uint32_t d = valid ? digit_of(key[r], shift) : 256u;       // 256: not a digit, groups the tail lanes
+    const uint32_t d = valid ? digit_of<MIX>(key[r], shift) : 256u;       // 256: not a digit, groups the tail lanes
     const uint32_t peers = __match_any_sync(0xffffffffu, d);
     const uint32_t leader = __ffs(peers) - 1;
     uint32_t before = 0;
@@ -162,7 +168,7 @@ __global__ void __launch_bounds__(SORT_THREADS) scatter_kernel(const uint64_t* _
   for (int r = 0; r < SORT_KPT; r++) {
     const uint64_t idx = wbase + (uint64_t)r * 32 + lane;
     if (idx < n) {
-      const uint32_t d = digit_of(key[r], shift);
+      const uint32_t d = digit_of<MIX>(key[r], shift);
       stage[dbase[d] + wcnt[warp][d] + rank[r]] = key[r];
     }
   }
@@ -173,14 +179,15 @@ __global__ void __launch_bounds__(SORT_THREADS) scatter_kernel(const uint64_t* _
     const uint32_t s = i * SORT_THREADS + threadIdx.x;
     if (s < tile_n) {
       const uint64_t k = stage[s];
-      const uint32_t d = digit_of(k, shift);
+      const uint32_t d = digit_of<MIX>(k, shift);
       out[gpos[d] + (s - dbase[d])] = k;
     }
   }
 }
 
-int slk_sort_u64(uint64_t* keys, uint64_t* tmp, uint64_t n, int begin_bit, int end_bit, cudaStream_t stream,
-                 uint64_t** sorted) {
+template <bool MIX>
+static int sort_impl(uint64_t* keys, uint64_t* tmp, uint64_t n, int begin_bit, int end_bit, cudaStream_t stream,
+                     uint64_t** sorted) {
   *sorted = keys;
   if (n <= 1 || end_bit <= begin_bit) return 0;
   const uint64_t n_tiles = (n + SORT_TILE - 1) / SORT_TILE;
@@ -196,11 +203,11 @@ int slk_sort_u64(uint64_t* keys, uint64_t* tmp, uint64_t n, int begin_bit, int e
   uint64_t* src = keys;
   uint64_t* dst = tmp;
   for (int shift = begin_bit; shift < end_bit; shift += 8) {
-    tile_hist_kernel<<<(unsigned)n_tiles, SORT_THREADS, 0, stream>>>(src, n, shift, n_tiles, cnt);
+    tile_hist_kernel<MIX><<<(unsigned)n_tiles, SORT_THREADS, 0, stream>>>(src, n, shift, n_tiles, cnt);
     e = cudaGetLastError();
     if (e == cudaSuccess) e = exclusive_scan_u64(cnt, m, cnt + m, stream);
     if (e != cudaSuccess) break;
-    scatter_kernel<<<(unsigned)n_tiles, SORT_THREADS, 0, stream>>>(src, dst, n, shift, n_tiles, cnt);
+    scatter_kernel<MIX><<<(unsigned)n_tiles, SORT_THREADS, 0, stream>>>(src, dst, n, shift, n_tiles, cnt);
     e = cudaGetLastError();
     if (e != cudaSuccess) break;
     uint64_t* t = src; src = dst; dst = t;
@@ -210,6 +217,13 @@ int slk_sort_u64(uint64_t* keys, uint64_t* tmp, uint64_t n, int begin_bit, int e
   if (e != cudaSuccess) return (int)e;
   *sorted = src;
   return 0;
+}
+int slk_sort_u64(uint64_t* keys, uint64_t* tmp, uint64_t n, int begin_bit, int end_bit, cudaStream_t stream,
+                 uint64_t** sorted) {
+  return sort_impl<false>(keys, tmp, n, begin_bit, end_bit, stream, sorted);
+}
+int slk_sort_cells_by_line(uint64_t* cells, uint64_t* tmp, uint64_t n, cudaStream_t stream, uint64_t** sorted) {
+  return sort_impl<true>(cells, tmp, n, 0, 32, stream, sorted);
 }
 
 int slk_exclusive_scan_u64(uint64_t* d, uint64_t n, cudaStream_t stream) {

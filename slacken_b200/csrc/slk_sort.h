@@ -7,6 +7,9 @@
 // clobbered; *sorted points at whichever of them holds the result. Returns 0 or a non-zero CUDA error code.
 int slk_sort_u64(uint64_t* keys, uint64_t* tmp, uint64_t n, int begin_bit, int end_bit, cudaStream_t stream,
                  uint64_t** sorted);
+// The same for build cells (compressed key << 16 | taxon), ordered by slk_key_mix(key): four 8-bit passes. Cells of
+// the same key end up adjacent, and the order is the order of the table's lines (slk_bucket_of).
+int slk_sort_cells_by_line(uint64_t* cells, uint64_t* tmp, uint64_t n, cudaStream_t stream, uint64_t** sorted);
 
 // In-place exclusive prefix sum of n 64-bit counters on the device (allocates its own scratch; asynchronous on `stream`
 // apart from that allocation). Returns 0 or a non-zero CUDA error code.
