@@ -239,6 +239,10 @@ SLK_API void slk_resolver_destroy(slk_resolver* r);
 SLK_API int slk_scan_spans_dev(slk_ctx* ctx, const slk_params* params, const uint8_t* bases1, const uint64_t* off1,
                                const uint8_t* bases2, const uint64_t* off2, uint32_t n_reads, uint64_t* span_off,
                                uint64_t* spans, uint64_t cap, uint64_t* n_spans_host);
+/* the emit half alone, after a count-only call of slk_scan_spans_dev (span_off as that call left it) */
+SLK_API int slk_emit_spans_dev(slk_ctx* ctx, const slk_params* params, const uint8_t* bases1, const uint64_t* off1,
+                               const uint8_t* bases2, const uint64_t* off2, uint32_t n_reads, const uint64_t* span_off,
+                               uint64_t* spans);
 /* keys of the sequence spans grouped by owner (send_keys, counts_host[world]) and the span each came from (send_idx);
  * send_keys == NULL only fills counts_host */
 SLK_API int slk_route_spans_dev(slk_ctx* ctx, const uint64_t* spans, uint64_t n_spans, uint32_t world, uint64_t* send_keys,

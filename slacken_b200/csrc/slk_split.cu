@@ -26,25 +26,32 @@ __global__ void __launch_bounds__(256) probe_keys_kernel(slk_table_view tb, slk_
 }
 
 // Routing of the SEQ spans of a batch: pass 1 counts per owner, pass 2 writes (key, span index) grouped by owner.
-// One atomic per (warp, owner): the lanes of a warp that share an owner are ranked with match_any.
+// Counters per owner live in shared memory; a block touches the global counters once per owner.
+#define ROUTE_MAX_WORLD 1024
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) route_kernel(const uint64_t* __restrict__ spans, uint64_t n, uint32_t world,
                                                     unsigned long long* cursors, uint64_t* __restrict__ send_keys,
                                                     uint32_t* __restrict__ send_idx) {
+  __shared__ uint32_t s_cnt[ROUTE_MAX_WORLD];
+  __shared__ unsigned long long s_base[ROUTE_MAX_WORLD];
+  for (uint32_t d = threadIdx.x; d < world; d += blockDim.x) s_cnt[d] = 0;
+  __syncthreads();
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t lane = threadIdx.x & 31u;
-  uint64_t w = 0;
+  uint64_t ck = 0;
+  uint32_t dest = 0, pos = 0;
   bool seq = false;
-  if (i < n) { w = spans[i]; seq = SLK_SPAN_TYPE(w) == SLK_E_SEQ; }
-  const uint64_t ck = SLK_SPAN_KEY(w);
-  const uint32_t dest = seq ? slk_shard_of(ck, world) : 0xffffffffu;
-  const uint32_t peers = __match_any_sync(0xffffffffu, dest);
-  if (!seq) return;
-  const uint32_t leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
-  unsigned long long base = 0;
-  if (lane == leader) base = atomicAdd(&cursors[dest], (unsigned long long)__popc(peers));
-  base = __shfl_sync(peers, base, leader);
-  if (SCATTER) { send_keys[base + rank] = ck; send_idx[base + rank] = (uint32_t)i; }
+  if (i < n) {
+    const uint64_t w = spans[i];
+    seq = SLK_SPAN_TYPE(w) == SLK_E_SEQ;
+    ck = SLK_SPAN_KEY(w);
+  }
+  if (seq) { dest = slk_shard_of(ck, world); pos = atomicAdd(&s_cnt[dest], 1u); }
+  __syncthreads();
+  for (uint32_t d = threadIdx.x; d < world; d += blockDim.x)
+    if (s_cnt[d]) s_base[d] = atomicAdd(&cursors[d], (unsigned long long)s_cnt[d]);
+  if (!SCATTER) return;
+  __syncthreads();
+  if (seq) { send_keys[s_base[dest] + pos] = ck; send_idx[s_base[dest] + pos] = (uint32_t)i; }
 }
 
 // taxa come back in send order: dense label of span send_idx[j] = raw2dense[taxa[j]]
@@ -96,6 +103,8 @@ struct slk_resolver {
   dense_tax dt;
   uint16_t* d_r2d = nullptr;
   uint32_t* d_err = nullptr;
+  uint16_t* d_dense = nullptr;   // scratch: dense taxon of every span of the batch being resolved (grow-only)
+  uint64_t dense_cap = 0;
 };
 
 extern "C" int slk_index_taxa(slk_index* idx, int32_t* out, uint32_t cap, uint32_t* n_out) {
@@ -144,7 +153,7 @@ extern "C" int slk_resolver_create(slk_ctx* ctx, slk_tax* tax, const slk_params*
 }
 extern "C" void slk_resolver_destroy(slk_resolver* r) {
   if (!r) return;
-  cudaFree(r->d_r2d); cudaFree(r->d_err);
+  cudaFree(r->d_r2d); cudaFree(r->d_err); cudaFree(r->d_dense);
   slk_dense_free(r->dt);
   delete r;
 }
@@ -178,9 +187,27 @@ extern "C" int slk_scan_spans_dev(slk_ctx* ctx, const slk_params* params, const 
   uint64_t total = 0;
   SLK_CU(cudaMemcpy(&total, span_off + n_reads, 8, cudaMemcpyDeviceToHost));
   *n_spans_host = total;
-  if (!spans) return SLK_OK;   // size query
+  if (!spans) return SLK_OK;   // count only: the caller sizes its buffer and calls slk_emit_spans_dev
   if (total > cap) return slk_fail(SLK_E_NOSPACE, "span buffer too small: %llu spans, room for %llu", (unsigned long long)total, (unsigned long long)cap);
   a.spans = spans;
+  SLK_DISPATCH_SPANS(a.sp.w, a);
+  SLK_CU(cudaGetLastError());
+  SLK_CU(cudaStreamSynchronize(ctx->stream));
+  return SLK_OK;
+}
+// second half of slk_scan_spans_dev for a caller that asked for the count first: span_off is what that call left
+extern "C" int slk_emit_spans_dev(slk_ctx* ctx, const slk_params* params, const uint8_t* bases1, const uint64_t* off1,
+                                  const uint8_t* bases2, const uint64_t* off2, uint32_t n_reads, const uint64_t* span_off,
+                                  uint64_t* spans) {
+  if (!ctx || !params || !bases1 || !off1 || !span_off || !spans || ((bases2 == nullptr) != (off2 == nullptr)))
+    return slk_fail(SLK_E_INVALID, "bad arguments");
+  SLK_CU(cudaSetDevice(ctx->device));
+  if (n_reads == 0) return SLK_OK;
+  slk_spans_args a;
+  int rc = slk_make_scan_params_checked(params, &a.sp);
+  if (rc != SLK_OK) return rc;
+  a.bases1 = bases1; a.off1 = off1; a.bases2 = bases2; a.off2 = off2; a.n_reads = n_reads;
+  a.span_off = const_cast<uint64_t*>(span_off); a.spans = spans; a.stream = ctx->stream;
   SLK_DISPATCH_SPANS(a.sp.w, a);
   SLK_CU(cudaGetLastError());
   SLK_CU(cudaStreamSynchronize(ctx->stream));
@@ -237,9 +264,14 @@ extern "C" int slk_resolve_spans_dev(slk_resolver* r, const slk_classify_opts* o
   SLK_CU(cudaSetDevice(r->ctx->device));
   if (n_reads == 0) return SLK_OK;
   cudaStream_t st = r->ctx->stream;
-  uint16_t* d_dense = nullptr;
-  SLK_CU(cudaMalloc(&d_dense, std::max<uint64_t>(n_spans, 1) * 2));
-  auto done = [&](int rc) { cudaFree(d_dense); return rc; };
+  if (r->dense_cap < std::max<uint64_t>(n_spans, 1)) {
+    cudaFree(r->d_dense); r->d_dense = nullptr; r->dense_cap = 0;
+    const uint64_t cap = std::max<uint64_t>(n_spans + n_spans / 8, 1024);
+    SLK_CU(cudaMalloc(&r->d_dense, cap * 2));
+    r->dense_cap = cap;
+  }
+  uint16_t* d_dense = r->d_dense;
+  auto done = [&](int rc) { return rc; };
   cudaMemsetAsync(d_dense, 0, std::max<uint64_t>(n_spans, 1) * 2, st);
   if (n_routed)
     unroute_kernel<<<(unsigned)((n_routed + 255) / 256), 256, 0, st>>>(taxa, send_idx, n_routed, r->d_r2d, (int32_t)r->tax->parents.size(),

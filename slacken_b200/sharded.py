@@ -146,7 +146,7 @@ class GpuSplitOps:
                 self._v(off2) if off2 is not None else None, n_reads, self._v(span_off))
         check(self._L.slk_scan_spans_dev(self.ctx.h, C.byref(self._p), *args, None, 0, C.byref(n)))
         spans = t.empty(max(int(n.value), 1), dtype=t.int64, device=self.device)
-        check(self._L.slk_scan_spans_dev(self.ctx.h, C.byref(self._p), *args, self._v(spans), int(n.value), C.byref(n)))
+        check(self._L.slk_emit_spans_dev(self.ctx.h, C.byref(self._p), *args, self._v(spans)))
         return span_off, spans, int(n.value)
 
     def route(self, spans, n_spans: int, world: int):
@@ -170,13 +170,14 @@ class GpuSplitOps:
         t = self.torch
         taxon = t.empty(max(n_reads, 1), dtype=t.int32, device=self.device)
         flags = t.empty(max(n_reads, 1), dtype=t.uint8, device=self.device)
-        detail = t.empty(max(n_reads, 1) * DETAIL_DTYPE.itemsize, dtype=t.uint8, device=self.device)
+        # detail and hits only when the per-read output is wanted (they are 24 B per read + 8 B per hit to bring back)
+        detail = t.empty(max(n_reads, 1) * DETAIL_DTYPE.itemsize, dtype=t.uint8, device=self.device) if want_hits else None
         hits = t.empty(max(n_spans, 1) * HIT_DTYPE.itemsize, dtype=t.uint8, device=self.device) if want_hits else None
         opts = ClassifyOpts(float(confidence), int(min_hit_groups), 0)
         check(self._L.slk_resolve_spans_dev(self.resolver, C.byref(opts), self._v(spans), self._v(span_off), n_spans, n_reads,
                                             1 if paired else 0, self._v(send_idx), self._v(taxa), send_idx.numel(),
-                                            self._v(taxon), self._v(flags), self._v(detail), self._v(hits) if want_hits else None))
-        d = detail.cpu().numpy().view(DETAIL_DTYPE)[:n_reads]
+                                            self._v(taxon), self._v(flags), self._v(detail), self._v(hits)))
+        d = detail.cpu().numpy().view(DETAIL_DTYPE)[:n_reads] if want_hits else None
         h = hits.cpu().numpy().view(HIT_DTYPE)[:n_spans] if want_hits else None
         return ClassifiedBatch(taxon.cpu().numpy()[:n_reads], flags.cpu().numpy()[:n_reads], d, h, n_spans if want_hits else 0)
 
@@ -247,23 +248,55 @@ class ShardedClassifier:
         taxa = union_of_taxa(shard.taxa() if shard is not None else local_taxa, group)
         self.ops = ops(taxa) if ops is not None else GpuSplitOps(shard.index, taxa)
         self.last_exchange_bytes = (0, 0)
+        self.last_times: dict = {}
 
     def classify(self, bases1: np.ndarray, off1: np.ndarray, bases2: Optional[np.ndarray] = None,
                  off2: Optional[np.ndarray] = None, confidence: float = 0.0, min_hit_groups: int = 2,
                  per_read_output: bool = True) -> ClassifiedBatch:
+        """Host arrays in, host arrays out (the reads are uploaded first)."""
+        import time
         ops = self.ops
-        n = len(off1) - 1
         paired = bases2 is not None
+        t0 = time.perf_counter()
         d_b1, d_o1 = ops.upload(bases1 if len(bases1) else np.zeros(16, np.uint8)), ops.upload(off1.astype(np.uint64).view(np.int64))
         d_b2 = ops.upload(bases2 if len(bases2) else np.zeros(16, np.uint8)) if paired else None
         d_o2 = ops.upload(off2.astype(np.uint64).view(np.int64)) if paired else None
+        t_up = time.perf_counter() - t0
+        out = self.classify_uploaded(d_b1, d_o1, d_b2, d_o2, len(off1) - 1, confidence, min_hit_groups, per_read_output)
+        self.last_times["upload"] = t_up
+        return out
+
+    def classify_uploaded(self, d_b1, d_o1, d_b2, d_o2, n: int, confidence: float = 0.0, min_hit_groups: int = 2,
+                          per_read_output: bool = True) -> ClassifiedBatch:
+        """The same for reads already on the device (tensors made by ops.upload): scan, route, exchange, probe, exchange,
+        resolve. `last_times` holds the wall time of every step of the last call, `last_exchange_bytes` what went over
+        the wire from this rank."""
+        import time
+        ops = self.ops
+        paired = d_b2 is not None
+        tm = {}
+        t = time.perf_counter()
+
+        def lap(name):
+            nonlocal t
+            now = time.perf_counter()
+            tm[name] = now - t
+            t = now
         span_off, spans, n_spans = ops.scan_spans(d_b1, d_o1, d_b2, d_o2, n)
+        lap("scan")
         keys, idx, counts = ops.route(spans, n_spans, self.world)
+        lap("route")
         recv_keys, recv_counts = exchange(keys, counts, self.group)          # keys -> owners
+        lap("keys_all_to_all")
         taxa_here = ops.probe(recv_keys)
+        lap("probe")
         taxa, _ = exchange(taxa_here, recv_counts, self.group)                 # taxa -> askers, in send order
+        lap("taxa_all_to_all")
         self.last_exchange_bytes = (8 * int(keys.numel()), 4 * int(taxa.numel()))
-        return ops.resolve(spans, span_off, n_spans, n, paired, idx, taxa, confidence, min_hit_groups, per_read_output)
+        out = ops.resolve(spans, span_off, n_spans, n, paired, idx, taxa, confidence, min_hit_groups, per_read_output)
+        lap("resolve_and_download")
+        self.last_times = tm
+        return out
 
     def close(self):
         if hasattr(self.ops, "close"):
