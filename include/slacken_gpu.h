@@ -257,6 +257,18 @@ SLK_API int slk_resolve_spans_dev(slk_resolver* r, const slk_classify_opts* opts
                                   uint64_t n_routed, int32_t* taxon_out, uint8_t* flags_out, slk_read_detail* detail_out,
                                   slk_hit* hits_out);
 
+/* ---- Bracken weights (slacken/BrackenWeights.scala:312-354) ------------------------------------------------------------------
+ * All reads of length read_len of every genome fragment, self-classified against the library with the sliding window of
+ * FragmentWindow (confidence 0, minHitGroups 2). The caller cuts the genomes like TaxonFragment.splitToMaxLength
+ * (slacken/BrackenWeights.scala:152-164) and adds up the triples; host arrays in and out. */
+typedef struct {
+  int32_t dest;     /* taxon the reads classify to (0 = unclassified) */
+  int32_t source;   /* taxon of the genome the reads come from */
+  uint64_t reads;
+} slk_bracken_triple;
+SLK_API int slk_bracken_weights(slk_index* idx, const uint8_t* bases, const uint64_t* frag_off, const int32_t* frag_taxon,
+                                uint32_t n_frag, uint32_t read_len, slk_bracken_triple* out, uint64_t cap, uint64_t* n_out);
+
 /* test hook: the library's radix sort (K3a) on a host array, bits [begin_bit, end_bit), stable */
 SLK_API int slk_debug_sort_u64(slk_ctx* ctx, uint64_t* keys, uint64_t n, int begin_bit, int end_bit);
 

@@ -398,3 +398,111 @@ def synth_reads(gseed: int, rseed: int, n_genomes: int, genome_len: int, first: 
     out = np.zeros(n * L, dtype=np.uint8)
     lib().slko_synth_reads(gseed, rseed, n_genomes, genome_len, first, n, L, _ptr(out))
     return out
+
+
+# ----------------------------------------------------------------------------- Bracken weights
+# Restatement of slacken/BrackenWeights.scala:46-284,312-354. TEST INFRASTRUCTURE like the rest of this file; parity
+# unpinned (the reference's known-answer test needs testData/slacken/slacken_tinydata.fna, which is not in the repo).
+def split_to_max_length(seq: bytes, max_len: int, k: int):
+    """TaxonFragment.splitToMaxLength (slacken/BrackenWeights.scala:152-164): (start, subsequence); consecutive pieces
+    overlap by k-1 letters (k = the READ length here, as BrackenWeights.buildWeights calls it)."""
+    if len(seq) <= max_len:
+        return [(0, seq)]
+    return [(s, seq[s:min(len(seq), s + max_len)]) for s in range(0, len(seq) - k + 1, max_len - (k - 1))]
+
+
+def bracken_taxon_hits(p: Params, lookup, seq: bytes):
+    """TaxonFragment.taxonHits (slacken/BrackenWeights.scala:199-236): [distinct, ordinal, taxon, count] per super-mer,
+    plus the NONE quasi-hits that keep the k-mer positions of the fragment complete. `lookup(minimizer)` -> taxon or
+    None. The filler after a sequence segment carries ordinal = seq.length - (k-1) WITHOUT the segment's position,
+    exactly as the reference writes it."""
+    k = p.k
+    hits = []
+    first, last = True, None
+    for piece, flag, pos in split_by_ambiguity(seq, k):
+        if flag == 1:   # SEQUENCE_FLAG
+            for loc, rank, length in superkmers(p, piece):
+                distinct = first or rank != last
+                first, last = False, rank
+                hits.append([distinct, loc + pos, lookup(rank) or 0, length - (k - 1)])
+            hits.append([False, len(piece) - (k - 1), 0, k - 1])
+        else:
+            hits.append([False, pos, 0, len(piece)])
+    return hits
+
+
+def bracken_read_classifications(p: Params, parents: np.ndarray, lookup, seq: bytes, read_len: int):
+    """TaxonFragment.readClassifications + FragmentWindow (slacken/BrackenWeights.scala:46-137,251-284): the destination
+    taxon of every read of length read_len of the fragment, in order of its start position."""
+    k = p.k
+    K = read_len - (k - 1)
+    hits = bracken_taxon_hits(p, lookup, seq)
+    n_reads = len(seq) - read_len + 1
+    if n_reads <= 0 or not hits:
+        return []
+    w_start, w_end = 0, K
+    nxt = 0
+    while nxt < len(hits) and hits[nxt][1] < w_end:     # hits.span(inWindow)
+        nxt += 1
+    window = list(range(nxt))                            # indices of the hits in the window
+    groups = sum(1 for i in window if hits[i][0] and hits[i][2] != 0)
+    last_in = window[-1]
+    summary = {}
+    for i in window:
+        _, o, t, c = hits[i]
+        for pos in range(o, o + c):
+            if w_start <= pos < w_end:
+                summary[t] = summary.get(t, 0) + 1
+    out = []
+    for start in range(n_reads):
+        if start > 0:   # advance()
+            rm = hits[window[0]]
+            u = summary.get(rm[2], 0) - 1
+            if u > 0:
+                summary[rm[2]] = u
+            else:
+                summary.pop(rm[2], None)
+            w_start += 1
+            w_end += 1
+            h0 = hits[window[0]]
+            if h0[1] + (h0[3] - 1) < w_start:
+                window.pop(0)
+                if rm[0] and rm[2] != 0:
+                    groups -= 1
+            li = hits[last_in]
+            if li[1] + li[3] < w_end and nxt < len(hits):
+                window.append(nxt)
+                last_in = nxt
+                if hits[nxt][0] and hits[nxt][2] != 0:
+                    groups += 1
+                nxt += 1
+            t = hits[last_in][2]
+            summary[t] = summary.get(t, 0) + 1
+        dest = resolve_tree(parents, list(summary.items()), 0.0) if groups >= 2 else 0
+        out.append(dest)
+    return out
+
+
+def bracken_weights(p: Params, parents: np.ndarray, lookup, genomes, read_len: int, fragment_max: int = 1 << 20):
+    """BrackenWeights.buildWeights (slacken/BrackenWeights.scala:312-354) for genomes = [(taxon, sequence)]: every genome
+    sequence is one TaxonFragment, cut by splitToMaxLength(fragment_max, read_len). Returns {(dest, source): reads}."""
+    out = {}
+    for taxon, seq in genomes:
+        seq = _bytes(seq)
+        for _, piece in split_to_max_length(seq, fragment_max, read_len):
+            for dest in bracken_read_classifications(p, parents, lookup, piece, read_len):
+                out[(dest, int(taxon))] = out.get((dest, int(taxon)), 0) + 1
+    return out
+
+
+def kmer_distrib_lines(weights) -> list:
+    """writeKmerDistrib (slacken/BrackenWeights.scala:418-430): one line per destination taxon,
+    `dest \\t source:reads:total_reads_of_source ...` (the order of lines and of triples is Spark's, i.e. unspecified:
+    here sorted)."""
+    total = {}
+    for (dest, src), c in weights.items():
+        total[src] = total.get(src, 0) + c
+    by_dest = {}
+    for (dest, src), c in sorted(weights.items()):
+        by_dest.setdefault(dest, []).append(f"{src}:{c}:{total[src]}")
+    return ["mapped_taxid\tgenome_taxids:kmers_mapped:total_genome_kmers"] + [f"{d}\t{' '.join(v)}" for d, v in sorted(by_dest.items())]

@@ -91,6 +91,7 @@ SIGNATURES = {
     "slk_resolver_create": (_INT, [_VP, _VP, _VP, _VP, _U32, _PP]),
     "slk_resolver_destroy": (None, [_VP]),
     "slk_scan_spans_dev": (_INT, [_VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP, _VP, _U64, _VP]),
+    "slk_bracken_weights": (_INT, [_VP, _VP, _VP, _VP, _U32, _U32, _VP, _U64, _VP]),
     "slk_emit_spans_dev": (_INT, [_VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP, _VP]),
     "slk_route_spans_dev": (_INT, [_VP, _VP, _U64, _U32, _VP, _VP, _U64, _VP]),
     "slk_probe_keys_dev": (_INT, [_VP, _VP, _U64, _VP]),

@@ -1022,6 +1022,149 @@ SLK_HD uint32_t slk_shard_of(uint64_t ckey, uint32_t world) {
   return slk_mulhi32(x, world);
 }
 
+// ------------------------------------------------------------------------------------------------ Bracken weights
+// slacken/BrackenWeights.scala: every read of length readLen of every genome is "classified" against the library with
+// a window that slides over the genome's taxon hits.
+struct slk_bhit {      // TaxonHit (slacken/package.scala) of a genome fragment
+  uint64_t key;        // compressed minimizer of a sequence super-mer (0 for the NONE quasi-hits)
+  uint32_t ordinal;    // k-mer start position in the fragment (for the filler after a sequence segment: the reference's
+                       // seq.length - (k-1), which lacks the segment's own position)
+  uint32_t count;      // k-mer positions covered
+  uint32_t flags;      // bit 0: distinct, bit 1: sequence super-mer (has a key to look up)
+  uint32_t taxon;      // dense taxon, filled by the lookup step (0 = NONE)
+};
+#define SLK_BHIT_DISTINCT 1u
+#define SLK_BHIT_SEQ 2u
+
+// TaxonFragment.taxonHits (slacken/BrackenWeights.scala:199-236) without the taxa: calls emit(hit) for every hit of the
+// fragment in order. Pieces as Supermers.splitByAmbiguity cuts them (slacken/Supermers.scala:150-177): a valid run with at
+// least k characters gives its super-mers plus one NONE filler of k-1 positions, a shorter valid run and every gap give
+// one NONE hit of their length.
+template <int W, class Emit>
+SLK_HD void slk_bracken_scan(const slk_scan_params& sp, const uint8_t* s, uint32_t len, Emit&& emit) {
+  const uint32_t k = (uint32_t)sp.k;
+  const int fshift = sp.fshift;
+  const uint64_t mmask = sp.mmask, xor_mask = sp.xor_mask, sig_mask = sp.sig_mask;
+  const bool canonical = sp.canonical != 0;
+  slk_scanner<W> sc;
+  sc.reset();
+  uint64_t run_key = 0, last_key = 0;
+  uint32_t run_cnt = 0, run_ord = 0, i = 0, piece_start = 0;
+  bool in_run = false, first = true, piece_valid = false, have_piece = false;
+  auto none_hit = [&](uint32_t ordinal, uint32_t count) {
+    slk_bhit h; h.key = 0; h.ordinal = ordinal; h.count = count; h.flags = 0; h.taxon = 0;
+    emit(h);
+  };
+  auto seq_hit = [&]() {
+    slk_bhit h;
+    h.key = slk_compress(sp, run_key); h.ordinal = run_ord; h.count = run_cnt; h.taxon = 0;
+    h.flags = SLK_BHIT_SEQ | ((first || run_key != last_key) ? SLK_BHIT_DISTINCT : 0u);
+    first = false; last_key = run_key;
+    emit(h);
+  };
+  auto close_piece = [&](uint32_t end) {   // the piece [piece_start, end) is over
+    const uint32_t plen = end - piece_start;
+    if (piece_valid && plen >= k) {
+      if (in_run) seq_hit();
+      none_hit(plen - (k - 1), k - 1);
+    } else {
+      none_hit(piece_start, plen);
+    }
+    in_run = false;
+  };
+  slk_for_each_byte(s, len, [&](uint32_t ch) {
+    const uint32_t c = slk_code(ch);
+    const bool valid = c < 4u;
+    if (!have_piece) { have_piece = true; piece_valid = valid; piece_start = i; }
+    else if (valid != piece_valid) { close_piece(i); piece_valid = valid; piece_start = i; }
+    uint64_t mn;
+    const bool window_ok = sc.push(c, k, fshift, mmask, xor_mask, sig_mask, canonical, &mn);
+    if (window_ok) {
+      if (!(in_run && mn == run_key)) {
+        if (in_run) seq_hit();
+        run_key = mn; run_cnt = 1; run_ord = i - (k - 1); in_run = true;
+      } else {
+        run_cnt++;
+      }
+    }
+    i++;
+  });
+  if (have_piece) close_piece(len);
+}
+
+// a small (taxon -> k-mers) map with removal: FragmentWindow.countSummary
+struct slk_window_hist {
+  uint32_t hk[SLK_KMAX];
+  int32_t hv[SLK_KMAX];
+  uint32_t n;
+  bool overflow;
+  SLK_HD uint32_t size() const { return n; }
+  SLK_HD void at(uint32_t i, uint32_t* t, int32_t* v) const { *t = hk[i]; *v = hv[i]; }
+  SLK_HD int32_t count(uint32_t t) const {
+    for (uint32_t i = 0; i < n; i++)
+      if (hk[i] == t) return hv[i];
+    return 0;
+  }
+  SLK_HD void inc(uint32_t t) {
+    for (uint32_t i = 0; i < n; i++)
+      if (hk[i] == t) { hv[i]++; return; }
+    if (n == SLK_KMAX) { overflow = true; return; }
+    hk[n] = t; hv[n] = 1; n++;
+  }
+  SLK_HD void dec(uint32_t t) {   // put(updated) if updated > 0, else remove(key); an absent key stays absent
+    for (uint32_t i = 0; i < n; i++)
+      if (hk[i] == t) {
+        if (--hv[i] <= 0) { n--; hk[i] = hk[n]; hv[i] = hv[n]; }
+        return;
+      }
+  }
+};
+
+// FragmentWindow + TaxonFragment.readClassifications (slacken/BrackenWeights.scala:46-137,251-284): slides a window of
+// read_len - (k-1) k-mer positions over the hits and calls dest(dense taxon) for every read start 0 .. len - read_len.
+template <class Dest>
+SLK_HD bool slk_bracken_window(const slk_tax_view& tx, const slk_bhit* hits, uint32_t n_hits, uint32_t len, uint32_t read_len,
+                               uint32_t k, Dest&& dest) {
+  if (len < read_len || n_hits == 0) return true;
+  const uint32_t n_reads = len - read_len + 1;
+  uint32_t w_start = 0, w_end = read_len - (k - 1);
+  uint32_t head = 0, next = 0;
+  while (next < n_hits && hits[next].ordinal < w_end) next++;   // hits.span(inWindow)
+  slk_window_hist h;
+  h.n = 0; h.overflow = false;
+  uint32_t groups = 0;
+  for (uint32_t i = head; i < next; i++) {
+    const slk_bhit& x = hits[i];
+    if ((x.flags & SLK_BHIT_DISTINCT) && x.taxon != 0) groups++;
+    // k-mer positions of the hit that lie in [w_start, w_end)
+    const uint64_t lo = x.ordinal > w_start ? x.ordinal : w_start;
+    const uint64_t hi = (uint64_t)x.ordinal + x.count < w_end ? (uint64_t)x.ordinal + x.count : w_end;
+    for (uint64_t q = lo; q < hi; q++) h.inc(x.taxon);
+  }
+  uint32_t last_in = next - 1;
+  for (uint32_t start = 0; start < n_reads; start++) {
+    if (start > 0) {   // advance()
+      const slk_bhit rm = hits[head];
+      h.dec(rm.taxon);
+      w_start++; w_end++;
+      if ((uint64_t)hits[head].ordinal + (hits[head].count - 1) < w_start) {
+        head++;
+        if ((rm.flags & SLK_BHIT_DISTINCT) && rm.taxon != 0) groups--;
+      }
+      if ((uint64_t)hits[last_in].ordinal + hits[last_in].count < w_end && next < n_hits) {
+        last_in = next;
+        if ((hits[next].flags & SLK_BHIT_DISTINCT) && hits[next].taxon != 0) groups++;
+        next++;
+      }
+      h.inc(hits[last_in].taxon);
+    }
+    // TaxonFragment.classify: confidence 0, minHitGroups 2
+    int32_t total = 0;
+    dest(groups >= 2 ? slk_resolve_tree(h, tx, 0.0, total) : 0u);
+  }
+  return !h.overflow;
+}
+
 // K1 as a stand-alone step: ASCII -> 2-bit codes + ambiguity mask in the packed block layout of slk_read_src.
 // `emit(block index, codes, mask)` is called for every 32-base block of the read.
 template <class Emit>

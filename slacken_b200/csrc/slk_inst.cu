@@ -47,3 +47,8 @@ void SLK_CAT(slk_launch_spans_w, SLK_W)(const slk_spans_args& a) {
   if (a.spans) spans_kernel<SLK_W, true><<<grid, 128, 0, a.stream>>>(a.sp, a.bases1, a.off1, a.bases2, a.off2, a.n_reads, a.span_off, a.spans);
   else spans_kernel<SLK_W, false><<<grid, 128, 0, a.stream>>>(a.sp, a.bases1, a.off1, a.bases2, a.off2, a.n_reads, a.span_off, a.spans);
 }
+void SLK_CAT(slk_launch_bracken_scan_w, SLK_W)(const slk_bracken_scan_args& a) {
+  const unsigned grid = (a.n_frag + 31) / 32;
+  if (a.hits) bracken_scan_kernel<SLK_W, true><<<grid, 32, 0, a.stream>>>(a.sp, a.bases, a.frag_off, a.n_frag, a.hit_off, a.hits);
+  else bracken_scan_kernel<SLK_W, false><<<grid, 32, 0, a.stream>>>(a.sp, a.bases, a.frag_off, a.n_frag, a.hit_off, a.hits);
+}

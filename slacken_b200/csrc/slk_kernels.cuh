@@ -41,8 +41,16 @@ struct slk_spans_args {
   uint64_t* spans;         // pass 2 output (nullptr = pass 1)
   cudaStream_t stream;
 };
+// Bracken weights, scan step: pass 1 counts the hits of every genome fragment, pass 2 writes them at hit_off[f] ...
+struct slk_bracken_scan_args {
+  slk_scan_params sp;
+  const uint8_t* bases; const uint64_t* frag_off; uint32_t n_frag;
+  uint64_t* hit_off;       // [n_frag + 1]
+  slk_bhit* hits;          // nullptr = pass 1
+  cudaStream_t stream;
+};
 #define SLK_DECL_W(w) void slk_launch_classify_w##w(const slk_classify_args&); void slk_launch_emit_w##w(const slk_emit_args&); \
-  void slk_launch_spans_w##w(const slk_spans_args&);
+  void slk_launch_spans_w##w(const slk_spans_args&); void slk_launch_bracken_scan_w##w(const slk_bracken_scan_args&);
 SLK_DECL_W(1) SLK_DECL_W(2) SLK_DECL_W(3) SLK_DECL_W(4) SLK_DECL_W(5) SLK_DECL_W(6) SLK_DECL_W(7) SLK_DECL_W(8)
 
 #ifdef __CUDACC__
@@ -116,6 +124,24 @@ __global__ void __launch_bounds__(128) spans_kernel(const __grid_constant__ slk_
     uint64_t n = 0;
     slk_scan_fragment_spans<W>(sp, bases1 + s1, (uint32_t)(e1 - s1), p2, l2, bases2 != nullptr, [&](uint64_t) { n++; });
     span_off[r] = n;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- Bracken weights: scan
+template <int W, bool EMIT>
+__global__ void __launch_bounds__(32) bracken_scan_kernel(const __grid_constant__ slk_scan_params sp, const uint8_t* __restrict__ bases,
+                                                          const uint64_t* __restrict__ frag_off, uint32_t n_frag,
+                                                          uint64_t* __restrict__ hit_off, slk_bhit* __restrict__ hits) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frag) return;
+  const uint64_t s = frag_off[f], e = frag_off[f + 1];
+  if (EMIT) {
+    slk_bhit* out = hits + hit_off[f];
+    slk_bracken_scan<W>(sp, bases + s, (uint32_t)(e - s), [&](const slk_bhit& h) { *out++ = h; });
+  } else {
+    uint64_t n = 0;
+    slk_bracken_scan<W>(sp, bases + s, (uint32_t)(e - s), [&](const slk_bhit&) { n++; });
+    hit_off[f] = n;
   }
 }
 

@@ -298,3 +298,109 @@ extern "C" int slk_shard_of_records(const slk_params* params, const int64_t* id1
   for (uint64_t i = 0; i < n; i++) shard_out[i] = (uint8_t)slk_shard_of(slk_compress(sp, (uint64_t)id1[i]), world);
   return SLK_OK;
 }
+
+// ---------------------------------------------------------------------------------------------- Bracken weights
+// slacken/BrackenWeights.scala:312-354 on the device: scan every genome fragment into its taxon hits (two passes: count,
+// emit), look the super-mers up (one thread per hit), then one thread per fragment slides the read window over the hits
+// (the window is inherently sequential, and the reference's quasi-hit ordinals make it non-local) and counts the
+// destination taxon of every read. Output: (destination, source, reads) triples per fragment; the caller adds them up.
+__global__ void __launch_bounds__(256) bracken_probe_kernel(slk_table_view tb, slk_bhit* __restrict__ hits, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (hits[i].flags & SLK_BHIT_SEQ) hits[i].taxon = slk_probe(tb, hits[i].key);
+}
+#define BRACKEN_DESTS 64
+__global__ void __launch_bounds__(32) bracken_window_kernel(slk_tax_view tx, const slk_bhit* __restrict__ hits,
+                                                            const uint64_t* __restrict__ hit_off, const uint64_t* __restrict__ frag_off,
+                                                            const int32_t* __restrict__ frag_taxon, uint32_t n_frag, uint32_t read_len,
+                                                            uint32_t k, slk_bracken_triple* __restrict__ out, uint64_t cap,
+                                                            unsigned long long* cursor, uint32_t* error_flag) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frag) return;
+  uint32_t dk[BRACKEN_DESTS];
+  unsigned long long dv[BRACKEN_DESTS];
+  uint32_t nd = 0;
+  bool lost = false;
+  const bool ok = slk_bracken_window(tx, hits + hit_off[f], (uint32_t)(hit_off[f + 1] - hit_off[f]), (uint32_t)(frag_off[f + 1] - frag_off[f]),
+                                     read_len, k, [&](uint32_t d) {
+    for (uint32_t i = 0; i < nd; i++)
+      if (dk[i] == d) { dv[i]++; return; }
+    if (nd == BRACKEN_DESTS) { lost = true; return; }
+    dk[nd] = d; dv[nd] = 1; nd++;
+  });
+  if (!ok || lost) atomicExch(error_flag, 1u);
+  if (nd == 0) return;
+  const unsigned long long o = atomicAdd(cursor, (unsigned long long)nd);
+  for (uint32_t i = 0; i < nd; i++)
+    if (o + i < cap) {
+      slk_bracken_triple t;
+      t.dest = tx.raw[dk[i]]; t.source = frag_taxon[f]; t.reads = dv[i];
+      out[o + i] = t;
+    }
+}
+#define SLK_DISPATCH_BRACKEN(w, a)                       \
+  switch (w) {                                           \
+    case 1: slk_launch_bracken_scan_w1(a); break; case 2: slk_launch_bracken_scan_w2(a); break; \
+    case 3: slk_launch_bracken_scan_w3(a); break; case 4: slk_launch_bracken_scan_w4(a); break; \
+    case 5: slk_launch_bracken_scan_w5(a); break; case 6: slk_launch_bracken_scan_w6(a); break; \
+    case 7: slk_launch_bracken_scan_w7(a); break; default: slk_launch_bracken_scan_w8(a); break; \
+  }
+
+extern "C" int slk_bracken_weights(slk_index* idx, const uint8_t* bases, const uint64_t* frag_off, const int32_t* frag_taxon,
+                                   uint32_t n_frag, uint32_t read_len, slk_bracken_triple* out, uint64_t cap, uint64_t* n_out) {
+  if (!idx || !n_out || (n_frag && (!bases || !frag_off || !frag_taxon)) || (cap && !out)) return slk_fail(SLK_E_INVALID, "bad arguments");
+  if (read_len < (uint32_t)idx->sp.k) return slk_fail(SLK_E_INVALID, "read length %u is shorter than k = %d", read_len, idx->sp.k);
+  *n_out = 0;
+  if (n_frag == 0) return SLK_OK;
+  slk_ctx* ctx = idx->ctx;
+  SLK_CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const uint64_t total = frag_off[n_frag] - frag_off[0];
+  for (uint32_t f = 0; f < n_frag; f++)
+    if (frag_off[f + 1] - frag_off[f] > 0xfffffff0ull) return slk_fail(SLK_E_UNSUPPORTED, "fragment %u is longer than 2^32 bases", f);
+  uint8_t* d_bases = nullptr; uint64_t *d_foff = nullptr, *d_hoff = nullptr; int32_t* d_ftax = nullptr; slk_bhit* d_hits = nullptr;
+  slk_bracken_triple* d_out = nullptr; unsigned long long* d_cur = nullptr; uint32_t* d_err = nullptr;
+  auto done = [&](int rc) {
+    cudaFree(d_bases); cudaFree(d_foff); cudaFree(d_hoff); cudaFree(d_ftax); cudaFree(d_hits); cudaFree(d_out); cudaFree(d_cur); cudaFree(d_err);
+    return rc;
+  };
+#define BCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(slk_fail(e_ == cudaErrorMemoryAllocation ? SLK_E_NOMEM : SLK_E_CUDA, \
+    "%s failed: %s", #call, cudaGetErrorString(e_))); } while (0)
+  std::vector<uint64_t> rel(n_frag + 1);
+  for (uint32_t f = 0; f <= n_frag; f++) rel[f] = frag_off[f] - frag_off[0];
+  BCU(cudaMalloc(&d_bases, total + 64)); BCU(cudaMalloc(&d_foff, ((size_t)n_frag + 1) * 8)); BCU(cudaMalloc(&d_hoff, ((size_t)n_frag + 1) * 8));
+  BCU(cudaMalloc(&d_ftax, (size_t)n_frag * 4)); BCU(cudaMalloc(&d_cur, 8)); BCU(cudaMalloc(&d_err, 4));
+  BCU(cudaMemcpyAsync(d_bases, bases + frag_off[0], total, cudaMemcpyHostToDevice, st));
+  BCU(cudaMemcpyAsync(d_foff, rel.data(), ((size_t)n_frag + 1) * 8, cudaMemcpyHostToDevice, st));
+  BCU(cudaMemcpyAsync(d_ftax, frag_taxon, (size_t)n_frag * 4, cudaMemcpyHostToDevice, st));
+  BCU(cudaMemsetAsync(d_hoff, 0, ((size_t)n_frag + 1) * 8, st)); BCU(cudaMemsetAsync(d_cur, 0, 8, st)); BCU(cudaMemsetAsync(d_err, 0, 4, st));
+  slk_bracken_scan_args a;
+  a.sp = idx->sp; a.bases = d_bases; a.frag_off = d_foff; a.n_frag = n_frag; a.hit_off = d_hoff; a.hits = nullptr; a.stream = st;
+  SLK_DISPATCH_BRACKEN(a.sp.w, a);
+  BCU(cudaGetLastError());
+  if (slk_exclusive_scan_u64(d_hoff, (uint64_t)n_frag + 1, st) != 0) return done(slk_fail(SLK_E_CUDA, "prefix sum of the hit counts failed"));
+  uint64_t n_hits = 0;
+  BCU(cudaMemcpy(&n_hits, d_hoff + n_frag, 8, cudaMemcpyDeviceToHost));
+  BCU(cudaMalloc(&d_hits, std::max<uint64_t>(n_hits, 1) * sizeof(slk_bhit)));
+  a.hits = d_hits;
+  SLK_DISPATCH_BRACKEN(a.sp.w, a);
+  BCU(cudaGetLastError());
+  if (n_hits) bracken_probe_kernel<<<(unsigned)((n_hits + 255) / 256), 256, 0, st>>>(idx->table, d_hits, n_hits);
+  BCU(cudaGetLastError());
+  const uint64_t dcap = std::max<uint64_t>(cap, 1);
+  BCU(cudaMalloc(&d_out, dcap * sizeof(slk_bracken_triple)));
+  bracken_window_kernel<<<(n_frag + 31) / 32, 32, 0, st>>>(idx->dt.view(), d_hits, d_hoff, d_foff, d_ftax, n_frag, read_len, (uint32_t)idx->sp.k,
+                                                         d_out, cap, d_cur, d_err);
+  BCU(cudaGetLastError());
+  unsigned long long used = 0;
+  uint32_t err = 0;
+  BCU(cudaMemcpyAsync(&used, d_cur, 8, cudaMemcpyDeviceToHost, st));
+  BCU(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
+  BCU(cudaStreamSynchronize(st));
+  *n_out = used;
+  if (err) return done(slk_fail(SLK_E_UNSUPPORTED, "a read window held more than %d taxa, or a fragment more than %d destination taxa", SLK_KMAX, BRACKEN_DESTS));
+  if (used > cap) return done(slk_fail(SLK_E_NOSPACE, "out needs room for %llu triples", used));
+  if (used) BCU(cudaMemcpy(out, d_out, used * sizeof(slk_bracken_triple), cudaMemcpyDeviceToHost));
+#undef BCU
+  return done(SLK_OK);
+}

@@ -58,6 +58,9 @@ def lib():
         L.emu_probe_keys.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.emu_resolve_spans.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.emu_bracken.restype = C.c_int64
+        L.emu_bracken.argtypes = [C.POINTER(ScanParams), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                  C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.emu_shard_of.restype = C.c_uint32
         L.emu_shard_of.argtypes = [C.c_uint64, C.c_uint32]
         L.emu_emit_cells.restype = C.c_int64
@@ -147,6 +150,16 @@ class EmuIndex:
         assert used >= 0
         hit_off[n] = used
         return res, hit_off, hits[:used]
+
+
+def bracken_dests(ix: "EmuIndex", seq: bytes, read_len: int) -> np.ndarray:
+    """Destination taxon (raw id) of every read of length read_len of one genome fragment."""
+    b = np.frombuffer(seq, dtype=np.uint8).copy() if len(seq) else np.zeros(1, dtype=np.uint8)
+    out = np.zeros(max(len(seq), 1), dtype=np.int32)
+    n = lib().emu_bracken(C.byref(ix.sp), _p(ix.cells), ix.n_buckets, _p(ix.parent), _p(ix.depth), _p(ix.raw), len(ix.raw),
+                          ix.dt.root, _p(b), len(seq), read_len, _p(out))
+    assert n >= 0
+    return out[:n]
 
 
 def emit_cells(sp: ScanParams, seq: bytes, dense_taxon: int, wpt: int = BUILD_WPT) -> np.ndarray:

@@ -198,6 +198,31 @@ EMU_API void emu_resolve_spans(const uint16_t* parent, const uint8_t* depth, con
   }
 }
 
+// Bracken weights of one genome fragment: scan -> hits, lookup, sliding window; dest_out[i] = raw destination taxon of the
+// read that starts at i (what bracken_count/emit/probe/window kernels do on the device)
+template <int W>
+static int64_t bracken_w(const slk_scan_params* sp, uint64_t* cells, uint64_t n_buckets, const uint16_t* parent, const uint8_t* depth,
+                         const int32_t* raw, uint32_t n_dense, uint32_t root, const uint8_t* bases, uint32_t len, uint32_t read_len,
+                         int32_t* dest_out) {
+  slk_table_view tb{cells, n_buckets, 0, 0};
+  slk_tax_view tx{parent, depth, raw, n_dense, root};
+  std::vector<slk_bhit> hits;
+  slk_bracken_scan<W>(*sp, bases, len, [&](const slk_bhit& h) { hits.push_back(h); });
+  for (auto& h : hits)
+    if (h.flags & SLK_BHIT_SEQ) h.taxon = slk_probe(tb, h.key);
+  int64_t n = 0;
+  bool ok = slk_bracken_window(tx, hits.data(), (uint32_t)hits.size(), len, read_len, (uint32_t)sp->k,
+                               [&](uint32_t d) { dest_out[n++] = raw[d]; });
+  return ok ? n : -1;
+}
+EMU_API int64_t emu_bracken(const slk_scan_params* sp, uint64_t* cells, uint64_t n_buckets, const uint16_t* parent,
+                            const uint8_t* depth, const int32_t* raw, uint32_t n_dense, uint32_t root, const uint8_t* bases,
+                            uint32_t len, uint32_t read_len, int32_t* dest_out) {
+  int64_t r = -2;
+  DISPATCH_W(sp->w, r = bracken_w<W_>(sp, cells, n_buckets, parent, depth, raw, n_dense, root, bases, len, read_len, dest_out));
+  return r;
+}
+
 // the emit "threads" of one fragment, BUILD_WPT windows each, exactly like emit_cells_kernel partitions the work
 EMU_API int64_t emu_emit_cells(const slk_scan_params* sp, const uint8_t* bases, uint64_t len, uint32_t dense_taxon,
                                uint32_t wpt, uint64_t* out, uint64_t cap) {

@@ -146,3 +146,21 @@ def test_synthetic_generators_agree_with_the_oracle_copy():
     r = np.zeros(3000 * 150, dtype=np.uint8)
     emu.lib().emu_synth_reads(7, 8, 4, 70_000, 11, 3000, 150, emu._p(r))
     assert np.array_equal(r, oracle.synth_reads(7, 8, 4, 70_000, 11, 3000, 150))
+
+
+@pytest.mark.parametrize("read_len", [50, 100])
+def test_bracken_window_body_matches_the_oracle(read_len):
+    """hits of a genome fragment (incl. the NONE quasi-hits around ambiguous stretches) and the
+    sliding window of FragmentWindow, read by read, against the oracle's restatement of slacken/BrackenWeights.scala."""
+    rng, parents, genomes, taxa, p, lib, sp = world(11, n_genomes=6, glen=1800)
+    id1, tx = lib.records()
+    ix = emu.EmuIndex(sp, parents, id1, tx)
+    cases = list(genomes[:3])
+    g = bytearray(genomes[3]); g[300:350] = b"N" * 50; g[700] = ord("N"); g[720:740] = b"n" * 20; g[1790:] = b"N" * 10
+    cases.append(bytes(g))
+    cases.append(b"N" * 30 + genomes[4][:400] + b"NN" + genomes[4][400:430] + b"N" + genomes[4][430:900])
+    cases += [genomes[5][:read_len], genomes[5][:read_len - 1], b"N" * 200, random_dna(rng, 600)]
+    for seq in cases:
+        want = oracle.bracken_read_classifications(p, parents, lib.lookup, seq, read_len)
+        got = emu.bracken_dests(ix, seq, read_len)
+        assert list(got) == want, (len(seq), read_len)
