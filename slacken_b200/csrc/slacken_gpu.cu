@@ -1161,7 +1161,13 @@ static int classify_host_common(slk_classifier* c, const slk_classify_opts* opts
   uint32_t r0 = 0;
   while (r0 < n_reads) {
     // chunk [r0, r1): bounded by reads and by the data volume of either mate
-    uint32_t r1 = (uint32_t)std::min<uint64_t>(n_reads, (uint64_t)r0 + CH_READS);
+    // chunk sizes ramp up at the start and down at the end of a batch, so that the first kernel does not wait for a
+    // full-size copy and the last copy back is short
+    uint32_t want = CH_READS;
+    if (ci < 3) want = std::max<uint32_t>(CH_READS >> (3 - ci), 32768u);
+    const uint32_t left = n_reads - r0;
+    if (left < 2 * (uint64_t)want) want = std::max<uint32_t>(left / 2, 32768u);
+    uint32_t r1 = (uint32_t)std::min<uint64_t>(n_reads, (uint64_t)r0 + want);
     auto fits = [&](uint32_t e) {
       if (h1.off[e] - h1.off[r0] > unit_cap) return false;
       if (paired && h2.off[e] - h2.off[r0] > unit_cap) return false;
