@@ -1,8 +1,9 @@
 // slk_core.h -- per-thread bodies of the sm_100a kernels of the Slacken classify/build hot path.
 //
-// Everything here is written as plain per-thread functions (no warp collectives), so that the very same
-// source can also be compiled by g++ into tests/host_emulation (a TEST-ONLY harness that runs the kernel
-// bodies thread by thread on the CPU; it is never loaded by the product path, which fails loudly without a GPU).
+// Everything here is written as per-thread functions whose few warp collectives (votes, ballots, warp barriers of
+// the fused classifier) go through macros with a one-lane meaning, so that the very same source can also be compiled
+// by g++ into tests/host_emulation (a TEST-ONLY harness that runs the kernel bodies one "lane" at a time on the CPU;
+// it is never loaded by the product path, which fails loudly without a GPU).
 //
 // Reference semantics reproduced (paths relative to /root/reference/src/main/scala/com/jnpersson/):
 //   2-bit codes / validity ........ kmers/util/BitRepresentation.scala:35-39,127-143
@@ -13,6 +14,7 @@
 //   hit labels, numDistinct ....... slacken/KeyValueIndex.scala:176-185, slacken/Classifier.scala:92-95
 //   merged hits, totals ........... slacken/TaxonCounts.scala:31-48,70-87,114-121
 //   resolveTree, LCA .............. slacken/LowestCommonAncestor.scala:49-146
+//   Bracken weights ............... slacken/BrackenWeights.scala:46-284
 #pragma once
 #include <math.h>
 #include <stdint.h>
