@@ -320,6 +320,8 @@ def run_ours(args, w):
                 "algorithmic_bytes_per_launch": bytes_per_read * n,
                 "bytes_per_read": bytes_per_read, "probes_per_read": S, "merged_hits_per_read": H,
                 "probe_sectors_gbs": 32.0 * S * n * args.steps / (ms / 1e3) / 1e9,
+                "lookups_per_s": S * n * args.steps / (ms / 1e3),
+                "frac_of_measured_request_ceiling": S * n * args.steps / (ms / 1e3) / 42.8e9,
                 "random_gather_ceiling": "a random 32-byte sector costs the B200 a whole 128-byte DRAM line, and the chip serves at most ~43 G "
                                          "random line requests/s to a plain lookup kernel (profiles/r01_probe_microbench.md, DESIGN.md section 3): "
                                          "one random sector per lookup cannot exceed ~0.21 of the copy-bandwidth roofline"}
