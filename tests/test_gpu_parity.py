@@ -291,3 +291,34 @@ def test_radix_sort_matches_numpy(gpu, n):
     check(gpu._L.slk_debug_sort_u64(gpu.h, c.ctypes.data_as(C.c_void_p), n, 16, 56))
     want = keys[np.argsort((keys >> np.uint64(16)) & np.uint64((1 << 40) - 1), kind="stable")]
     assert np.array_equal(c, want)
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 33, 129])
+def test_tiny_batches(gpu, n):
+    """Batches that do not fill a warp / a block, and the empty batch, single and paired, both input forms."""
+    rng, parents, ranks, names, genomes, taxa = make_world(71, n_genomes=6, glen=3000)
+    p = oracle.params()
+    olib = oracle_lib(p, parents, genomes, taxa)
+    id1, tx = olib.records()
+    tax = Taxonomy(gpu, parents, ranks, names)
+    index = KeyValueIndex.from_records(gpu, tax, IndexParams(), id1, tx)
+    cls = Classifier(index)
+    r1 = simulate_reads(rng, genomes, n, (34, 160), n_rate=0.2)
+    r2 = simulate_reads(rng, genomes, n, (1, 160), n_rate=0.2)
+    if n >= 31:
+        r1[0], r2[0] = b"", b""          # a pair of empty mates still has its border span
+        r1[5], r2[7] = genomes[0][:35], genomes[1][:34]   # exactly k, exactly k-1
+    b1, o1 = pack_sequences(r1)
+    b2, o2 = pack_sequences(r2)
+    for paired in (False, True):
+        args = (b1, o1, b2, o2) if paired else (b1, o1)
+        got = cls.classify(*args, confidence=0.1)
+        oargs = (b1, o1.astype(np.int64), b2, o2.astype(np.int64)) if paired else (b1, o1.astype(np.int64))
+        res, _, _, per = olib.classify(*oargs, confidence=0.1)
+        assert len(got.taxon) == n
+        if n:
+            assert_batch_equal(res, per, got, 35)
+            pk = (pack_reads(b1, o1), pack_reads(b2, o2)) if paired else (pack_reads(b1, o1),)
+            got = cls.classify_packed(*pk, confidence=0.1)
+            assert_batch_equal(res, per, got, 35)
+    cls.close(); index.close(); tax.close()
