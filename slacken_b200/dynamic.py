@@ -35,6 +35,21 @@ class MinimizerDistinctCount:   # --min-distinct N
     threshold: int
 
 
+@dataclass
+class GoldSetOptions:   # slacken/Dynamic.scala:55-62
+    """taxon_file: one taxid per line (first CSV column) or an iterable of taxids; promote_rank: keep taxa that had to be
+    promoted to an ancestor present in the library when they sit at this rank or below; classify_with: build the dynamic
+    library from the gold set itself instead of only comparing the detected set with it."""
+    taxon_file: object
+    promote_rank: Optional[str] = None
+    classify_with: bool = False
+
+
+def format_perc(d: float) -> str:   # kmers/package.scala:60
+    from .report import java_fixed
+    return "NaN%" if d != d else java_fixed(d * 100, 2) + "%"
+
+
 class TaxonomyTree:
     """The few tree queries of slacken/Taxonomy.scala that the taxon-set step needs."""
 
@@ -68,6 +83,21 @@ class TaxonomyTree:
                     stack.append(c)
         return out
 
+    def path_to_root(self, t: int):   # slacken/Taxonomy.scala:204-215
+        t = int(t)
+        while t != 0:
+            yield t
+            t = int(self.parents[t])
+
+    def with_ancestors(self, taxa: Iterable[int]) -> Set[int]:   # slacken/Taxonomy.scala:307-311
+        out: Set[int] = set()
+        for a in taxa:
+            for e in self.path_to_root(a):
+                if e in out:
+                    break
+                out.add(e)
+        return out
+
     def clade_totals(self, counts: Sequence[Tuple[int, int]]) -> dict:   # TreeAggregator, slacken/KrakenReport.scala:27-41
         tot: dict = {}
         for t, c in counts:
@@ -88,12 +118,69 @@ def count_filter(tree: TaxonomyTree, counts: Sequence[Tuple[int, int]], rank: st
 
 class Dynamic:
     def __init__(self, ctx: GpuContext, base: KeyValueIndex, genomes: Sequence[Tuple[int, bytes]], rank: str = "species",
-                 criteria=ClassifiedReadCount(100, 0.0), min_hit_groups: int = 2):
-        """genomes: (taxon, sequence) pairs of the genome library the dynamic index is rebuilt from."""
+                 criteria=ClassifiedReadCount(100, 0.0), min_hit_groups: int = 2,
+                 gold_set_opts: Optional[GoldSetOptions] = None, primary: Optional[Sequence[int]] = None):
+        """genomes: (taxon, sequence) pairs of the genome library the dynamic index is rebuilt from.
+        primary: the merged.dmp mapping (secondary id -> primary id, slacken/Taxonomy.scala:100-103), identity if None."""
         self.ctx, self.base, self.genomes, self.rank, self.criteria = ctx, base, genomes, rank, criteria
         self.min_hit_groups = min_hit_groups
+        self.gold_set_opts, self.primary = gold_set_opts, primary
         self.taxonomy = base.taxonomy
         self.tree = TaxonomyTree(self.taxonomy)
+        self.log: List[str] = []   # what the reference prints to stdout, line by line
+        self._in_library: Optional[Set[int]] = None
+
+    def _say(self, msg: str):
+        self.log.append(msg)
+
+    # ---- the gold set (slacken/Dynamic.scala:282-318) ----------------------------------------------------------------
+    def taxon_set_in_library(self) -> Set[int]:   # GenomeLibrary.taxonSet, slacken/GenomeLibrary.scala:35-44
+        if self._in_library is None:
+            self._in_library = self.tree.with_ancestors({int(t) for t, _ in self.genomes})
+        return self._in_library
+
+    def read_gold_set(self, opts: Optional[GoldSetOptions] = None) -> Set[int]:
+        """readGoldSet: the taxa of the gold-set file (mapped through merged.dmp), those that have no sequence in the library
+        promoted to their nearest ancestor that has, everything filtered at the reclassify rank; promoted taxa at
+        promote_rank or below are kept whatever their depth."""
+        opts = opts or self.gold_set_opts
+        src = opts.taxon_file
+        if isinstance(src, (str, bytes)):
+            with open(src) as f:
+                ids = [int(line.split(",")[0]) for line in f if line.strip()]
+        else:
+            ids = [int(x) for x in src]
+        prim = (lambda x: x) if self.primary is None else (lambda x: int(self.primary[x]))
+        gold = {prim(x) for x in ids}
+        self._say(f"Gold set contained {len(gold)} taxa")
+        lib = self.taxon_set_in_library()
+        not_found = gold - lib
+        promoted: Set[int] = set()
+        for t in not_found:
+            for a in self.tree.path_to_root(t):
+                if a in lib:
+                    promoted.add(a)
+                    break
+        self._say(f"{len(not_found)} taxa from gold set not found in library, promoted to {len(promoted)} taxa.")
+        kept: Set[int] = set()
+        if opts.promote_rank is not None:
+            kept = {t for t in promoted if self.tree.depth(t) >= RANK_DEPTH[opts.promote_rank]}
+            self._say(f"Keeping {len(kept)} taxa at rank {opts.promote_rank} and below from promoted set")
+        total = gold | promoted
+        filtered = {t for t in total if self.tree.depth(t) >= RANK_DEPTH[self.rank]} | kept
+        self._say(f"Initial adjusted gold set size {len(total)}, filtered at {self.rank} to {len(filtered)}")
+        return filtered
+
+    def compare_with_gold_set(self, keep: Set[int]) -> dict:
+        """The comparison findTaxonSet prints when a gold set is given (slacken/Dynamic.scala:265-275)."""
+        gold = self.read_gold_set()
+        tp = len(keep & gold)
+        fp, fn = len(keep) - tp, len(gold) - tp
+        precision = tp / (tp + fp) if tp + fp else float("nan")
+        recall = tp / len(gold) if gold else float("nan")
+        self._say(f"Comparing detected set with supplied gold set. True Positives: {tp}, False Positives: {fp}, "
+                  f"False Negatives: {fn}, Precision: {format_perc(precision)}, Recall: {format_perc(recall)}")
+        return {"tp": tp, "fp": fp, "fn": fn, "precision": precision, "recall": recall}
 
     # ---- the three counting methods (slacken/Dynamic.scala:84-145) -------------------------------------------------
     def classified_reads_per_taxon(self, bases1, off1, bases2=None, off2=None) -> List[Tuple[int, int]]:
@@ -120,21 +207,23 @@ class Dynamic:
             keys, idx, _ = ops.route(spans, n_spans, 1)
             taxa = ops.probe(keys)
             k, t = keys.cpu().numpy().view(np.uint64), taxa.cpu().numpy()
+            # k-mers of each span: the low 14 bits of its span word (slk_core.h: SLK_SPAN_CNT)
+            c = (spans.cpu().numpy().view(np.uint64)[idx.cpu().numpy().astype(np.int64)] & np.uint64(0x3fff)).astype(np.int64)
         finally:
             ops.close()
         hit = t > 0
         keep = np.array([self.tree.depth(int(x)) >= RANK_DEPTH[self.rank] for x in np.unique(t[hit])], dtype=bool)
         ok_taxa = set(np.unique(t[hit])[keep].tolist())
         sel = hit & np.isin(t, list(ok_taxa))
-        return t[sel], k[sel]
+        return t[sel], k[sel], c[sel]
 
     def total_minimizers_per_taxon(self, *reads) -> List[Tuple[int, int]]:
-        t, _ = self._span_hits(*reads)
+        t, _, _ = self._span_hits(*reads)
         u, c = np.unique(t, return_counts=True)
         return [(int(a), int(b)) for a, b in zip(u, c)]
 
     def distinct_minimizers_per_taxon(self, *reads) -> List[Tuple[int, int]]:
-        t, k = self._span_hits(*reads)
+        t, k, _ = self._span_hits(*reads)
         pairs = np.unique(np.stack([t.astype(np.uint64), k]), axis=1)
         u, c = np.unique(pairs[0], return_counts=True)
         return [(int(a), int(b)) for a, b in zip(u, c)]
@@ -155,12 +244,47 @@ class Dynamic:
             with open(write_location, "w") as f:   # the detected set BEFORE descendant expansion, one taxid per line
                 for t in sorted(keep):
                     f.write(f"{t}\n")
-        return self.tree.with_descendants(keep)
+        if self.gold_set_opts is not None:
+            self.compare_with_gold_set(keep)
+        expanded = self.tree.with_descendants(keep)
+        self._say(f"Detected set: Initial scan (criterion {c}) produced {len(keep)} taxa at rank {self.rank}, "
+                  f"expanded with descendants to {len(expanded)}")
+        return expanded
+
+    # ---- reportDynamicIndexSupport (slacken/Dynamic.scala:146-180,210-230): the four Kraken-style support reports ------
+    def report_dynamic_index_support(self, output_location: str, bases1, off1, bases2=None, off2=None) -> List[str]:
+        """<out>_support_report_{totalKmerCount,distinctMinimizerCount,totalMinimizerCount,classifiedReadCount}.txt:
+        per taxon at the reclassify rank or below, the k-mers and (distinct) minimizers of the sample's sequence spans that
+        hit it, and the reads classified to it at confidence 0. (The two minimizerCoverage directories of the reference
+        describe the genome library, not the sample, and are not written.)"""
+        from .report import KrakenReport
+        t, k, c = self._span_hits(bases1, off1, bases2, off2)
+        taxa = np.unique(t)
+        tot_kmers = [(int(a), int(c[t == a].sum())) for a in taxa]
+        tot_mins = [(int(a), int((t == a).sum())) for a in taxa]
+        dist_mins = [(int(a), int(len(np.unique(k[t == a])))) for a in taxa]
+        saved = self.criteria
+        self.criteria = ClassifiedReadCount(0, 0.0)   # initThreshold = 0.0 (slacken/Dynamic.scala:154)
+        try:
+            cls_reads = self.classified_reads_per_taxon(bases1, off1, bases2, off2)
+        finally:
+            self.criteria = saved
+        tx = self.taxonomy
+        written = []
+        for name, counts in (("totalKmerCount", tot_kmers), ("distinctMinimizerCount", dist_mins),
+                             ("totalMinimizerCount", tot_mins), ("classifiedReadCount", cls_reads)):
+            path = f"{output_location}_support_report_{name}.txt"
+            with open(path, "w") as f:
+                f.write(KrakenReport(tx.parents, tx.ranks, tx.names, counts).text())
+            written.append(path)
+        return written
 
     def make_index(self, bases1, off1, bases2=None, off2=None, write_location: Optional[str] = None,
                    gold_set: Optional[Iterable[int]] = None) -> Tuple[Set[int], KeyValueIndex]:
         """The dynamic library: records rebuilt from the genomes whose taxon is in the set
         (KeyValueIndex.makeRecords(library, Some(set)), slacken/KeyValueIndex.scala:102-116)."""
+        if gold_set is None and self.gold_set_opts is not None and self.gold_set_opts.classify_with:
+            gold_set = self.read_gold_set()   # makeRecords, slacken/Dynamic.scala:362-370
         taxon_set = (self.tree.with_descendants(gold_set) if gold_set is not None
                      else self.find_taxon_set(bases1, off1, bases2, off2, write_location))
         chosen = [(t, s) for t, s in self.genomes if int(t) in taxon_set]

@@ -76,3 +76,51 @@ def test_two_step_dynamic_library(gpu, tmp_path, criteria):
     res, _, _, per = dlib.classify(rb, ro.astype(np.int64), confidence=0.1)
     assert_batch_equal(res, per, got, 35)
     index.close(); base.close(); tax.close()
+
+
+def test_gold_set_library_and_support_reports(gpu, tmp_path):
+    """The gold-set variant of makeRecords (slacken/Dynamic.scala:362-370) and the four Kraken-style support reports of
+    reportDynamicIndexSupport (slacken/Dynamic.scala:146-180,210-230), against the oracle."""
+    from slacken_b200.dynamic import GoldSetOptions
+    from slacken_b200.report import KrakenReport
+    rng, parents, genomes, taxa, p, olib, tax, base, rb, ro = _setup(gpu)
+    tree = TaxonomyTree(tax)
+    gold = [int(taxa[0]), int(taxa[3]), int(parents[int(taxa[7])])]
+    dyn = Dynamic(gpu, base, list(zip(taxa.tolist(), genomes)), rank="species", criteria=ClassifiedReadCount(20, 0.05),
+                  gold_set_opts=GoldSetOptions(gold, classify_with=True))
+    want_set = tree.with_descendants(dyn.read_gold_set())
+    taxon_set, index = dyn.make_index(rb, ro)
+    assert taxon_set == want_set
+    chosen = [i for i in range(len(genomes)) if int(taxa[i]) in taxon_set]
+    assert len(chosen) >= 2
+    dlib = oracle_lib(p, parents, [genomes[i] for i in chosen], taxa[chosen])
+    oid, otx = dlib.records()
+    gid, gtx = index.records()
+    assert np.array_equal(oid, gid) and np.array_equal(otx, gtx)
+    index.close()
+    # compare-only gold set: the detected set is unchanged, the statistics are logged
+    dyn2 = Dynamic(gpu, base, list(zip(taxa.tolist(), genomes)), rank="species", criteria=ClassifiedReadCount(20, 0.05),
+                   gold_set_opts=GoldSetOptions(gold))
+    dyn2.find_taxon_set(rb, ro)
+    assert any(m.startswith("Comparing detected set with supplied gold set.") for m in dyn2.log)
+    # support reports
+    out = str(tmp_path / "dyn")
+    files = dyn2.report_dynamic_index_support(out, rb, ro)
+    assert [f[len(out):] for f in files] == ["_support_report_totalKmerCount.txt", "_support_report_distinctMinimizerCount.txt",
+                                             "_support_report_totalMinimizerCount.txt", "_support_report_classifiedReadCount.txt"]
+    kmers, mins, dist = {}, {}, {}
+    for i in range(len(ro) - 1):
+        for minimizer, _distinct, n_kmers, flag in oracle.spans(p, bytes(rb[int(ro[i]):int(ro[i + 1])])):
+            if flag == 1:
+                t = olib.lookup(minimizer)
+                if t and tree.depth(t) >= 8:
+                    kmers[t] = kmers.get(t, 0) + n_kmers
+                    mins[t] = mins.get(t, 0) + 1
+                    dist.setdefault(t, set()).add(minimizer)
+    res, _, _, _ = olib.classify(rb, ro.astype(np.int64), confidence=0.0, with_hits=False)
+    u, c = np.unique(res["taxon"][res["classified"].astype(bool)], return_counts=True)
+    for f, counts in zip(files, [sorted(kmers.items()), sorted((t, len(s)) for t, s in dist.items()), sorted(mins.items()),
+                                 list(zip(u.tolist(), c.tolist()))]):
+        assert open(f).read() == KrakenReport(tax.parents, tax.ranks, tax.names, counts).text(), f
+        assert len(counts) > 0
+    base.close(); tax.close()

@@ -84,3 +84,40 @@ def test_writer_layout_and_report(tmp_path):
     assert w2.close() == ["all"]
     rep2 = open(str(tmp_path / "o2") + "_c0.0/all_kreport.txt").read()
     assert "unclassified" not in rep2 and rep2.splitlines()[1].startswith("100.00\t3\t0\tR\t1")
+
+
+def test_gold_set_promotion_filter_and_comparison():
+    """readGoldSet + the comparison of findTaxonSet (slacken/Dynamic.scala:265-275,282-318), host logic only."""
+    from slacken_b200.dynamic import Dynamic, GoldSetOptions, format_perc
+
+    class _Base:
+        taxonomy = _tree()
+        params = None
+
+    # the library has sequence for strains 6 and 8 and species 10 (plus, implicitly, all their ancestors)
+    genomes = [(6, b""), (8, b""), (10, b"")]
+    gold = [6, 7, 9, 10, 3]   # 7 and 9 have no sequence: both are promoted to species 4; 3 (genus) is filtered at species
+    d = Dynamic(None, _Base(), genomes, rank="species", gold_set_opts=GoldSetOptions(gold))
+    assert d.taxon_set_in_library() == {1, 2, 3, 4, 5, 6, 8, 10}
+    assert d.read_gold_set() == {4, 6, 7, 9, 10}
+    assert d.log[:3] == ["Gold set contained 5 taxa", "2 taxa from gold set not found in library, promoted to 1 taxa.",
+                         "Initial adjusted gold set size 6, filtered at species to 5"]
+    # at rank genus nothing is filtered; promote_rank keeps promoted taxa at that rank or below even if the filter drops them
+    assert Dynamic(None, _Base(), genomes, rank="genus", gold_set_opts=GoldSetOptions(gold)).read_gold_set() == {3, 4, 6, 7, 9, 10}
+    d2 = Dynamic(None, _Base(), [(3, b"")], rank="species", gold_set_opts=GoldSetOptions([6, 10], promote_rank="genus"))
+    assert d2.read_gold_set() == {6, 10, 3}        # 6 -> promoted to genus 3 (kept by promote_rank), 10 -> superkingdom 2 (dropped)
+    d3 = Dynamic(None, _Base(), [(3, b"")], rank="species", gold_set_opts=GoldSetOptions([6, 10]))
+    assert d3.read_gold_set() == {6, 10}
+    # merged.dmp mapping and a gold-set file
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False) as f:
+        f.write("9\n10,extra\n")
+    primary = list(range(11))
+    primary[9] = 6
+    d4 = Dynamic(None, _Base(), genomes, rank="species", gold_set_opts=GoldSetOptions(f.name), primary=primary)
+    assert d4.read_gold_set() == {6, 10}
+    # comparison: detected {6, 5} against gold {4, 6, 7, 9, 10}
+    st = d.compare_with_gold_set({6, 5})
+    assert (st["tp"], st["fp"], st["fn"]) == (1, 1, 4)
+    assert d.log[-1].endswith("True Positives: 1, False Positives: 1, False Negatives: 4, Precision: 50.00%, Recall: 20.00%")
+    assert format_perc(1 / 3) == "33.33%"
