@@ -257,6 +257,30 @@ SLK_API int slk_resolve_spans_dev(slk_resolver* r, const slk_classify_opts* opts
                                   uint64_t n_routed, int32_t* taxon_out, uint8_t* flags_out, slk_read_detail* detail_out,
                                   slk_hit* hits_out);
 
+/* ---- NVLink mailbox: the two exchanges of the split path as stores into peer memory ----------------------------------------
+ * The same join (slacken/Classifier.scala:84) with the all-to-alls fused into the kernels on either side of them: the
+ * routing kernel stores every key straight into its owner's inbox over NVLink, the owner's lookup kernel stores every
+ * taxon straight into the asker's reply area, and completion travels as one flag per (source, owner) pair that the
+ * consuming kernels wait for on the device. No NCCL and no host synchronisation between the steps.
+ *   every rank, per batch:  slk_scan_spans_dev -> slk_mailbox_route -> slk_mailbox_probe -> slk_mailbox_resolve
+ * All three are collective (every rank calls them once per batch, with its own spans, possibly none); route and probe
+ * only enqueue work. cap = room for the keys one rank sends to one owner in one batch (exceeding it fails loudly with
+ * SLK_E_NOSPACE); a mailbox takes world * cap * 16 bytes of HBM. Index, resolver and mailbox must share one slk_ctx. */
+typedef struct slk_mailbox slk_mailbox;
+#define SLK_IPC_HANDLE_BYTES 64
+/* handle_out (SLK_IPC_HANDLE_BYTES, may be NULL): what the other ranks' processes need to reach this mailbox */
+SLK_API int slk_mailbox_create(slk_ctx* ctx, uint32_t rank, uint32_t world, uint64_t cap, slk_mailbox** out, uint8_t* handle_out);
+/* one process per GPU: handles = the handle_out of every rank, in rank order (world * SLK_IPC_HANDLE_BYTES) */
+SLK_API int slk_mailbox_connect(slk_mailbox* m, const uint8_t* handles);
+/* one process driving every rank (ranks may even share a device): connects the mailboxes by pointer */
+SLK_API int slk_mailbox_connect_local(slk_mailbox* const* boxes, uint32_t world);
+SLK_API void slk_mailbox_destroy(slk_mailbox* m);
+SLK_API int slk_mailbox_route(slk_mailbox* m, const uint64_t* spans, uint64_t n_spans);
+SLK_API int slk_mailbox_probe(slk_mailbox* m, slk_index* idx);
+SLK_API int slk_mailbox_resolve(slk_mailbox* m, slk_resolver* r, const slk_classify_opts* opts, const uint64_t* spans,
+                                const uint64_t* span_off, uint64_t n_spans, uint32_t n_reads, int paired, int32_t* taxon_out,
+                                uint8_t* flags_out, slk_read_detail* detail_out, slk_hit* hits_out);
+
 /* ---- Bracken weights (slacken/BrackenWeights.scala:312-354) ------------------------------------------------------------------
  * All reads of length read_len of every genome fragment, self-classified against the library with the sliding window of
  * FragmentWindow (confidence 0, minHitGroups 2). The caller cuts the genomes like TaxonFragment.splitToMaxLength

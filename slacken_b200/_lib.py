@@ -97,7 +97,15 @@ SIGNATURES = {
     "slk_probe_keys_dev": (_INT, [_VP, _VP, _U64, _VP]),
     "slk_resolve_spans_dev": (_INT, [_VP, _VP, _VP, _VP, _U64, _U32, _INT, _VP, _VP, _U64, _VP, _VP, _VP, _VP]),
     "slk_memcpy_d2d": (_INT, [_VP, _VP, _VP, C.c_size_t]),
+    "slk_mailbox_create": (_INT, [_VP, _U32, _U32, _U64, _PP, _VP]),
+    "slk_mailbox_connect": (_INT, [_VP, _VP]),
+    "slk_mailbox_connect_local": (_INT, [_PP, _U32]),
+    "slk_mailbox_destroy": (None, [_VP]),
+    "slk_mailbox_route": (_INT, [_VP, _VP, _U64]),
+    "slk_mailbox_probe": (_INT, [_VP, _VP]),
+    "slk_mailbox_resolve": (_INT, [_VP, _VP, _VP, _VP, _VP, _U64, _U32, _INT, _VP, _VP, _VP, _VP]),
 }
+IPC_HANDLE_BYTES = 64
 
 _lib = None
 

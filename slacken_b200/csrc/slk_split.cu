@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string.h>
+
 #include <algorithm>
 #include <new>
 #include <vector>
@@ -287,6 +289,336 @@ extern "C" int slk_resolve_spans_dev(slk_resolver* r, const slk_classify_opts* o
     return done(slk_fail(SLK_E_UNSUPPORTED, "a returned taxon is unknown to the resolver, or a fragment hit more than %d distinct taxa", SLK_KMAX));
   }
   return done(SLK_OK);
+}
+
+// ---------------------------------------------------------------------------------------------- NVLink mailbox
+// The two exchanges of the split path as stores into PEER memory, fused into the kernels on either side of them
+// (no NCCL, no host in the loop): the route kernel groups the keys of a block by owner in shared memory and stores every
+// run straight into the owner's inbox over NVLink; the owner's lookup kernel stores every taxon straight into the
+// asker's reply area. Completion travels as one 8-byte flag per (source, owner) pair, written after the data by a
+// one-block kernel on the same stream (epoch << 32 | key count); the consuming kernel's blocks spin on the flag of the
+// peer whose data they read. Every rank's mailbox is ONE allocation with the same layout:
+//   flag1[world] | flag2[world] | keys_in[world][cap] (u64) | taxa_back[world][cap] (i32)
+// keys_in[s] = keys rank s wants looked up here; taxa_back[d] = answers of owner d, in the order the keys were sent.
+#define MBX_MAX_WORLD 64
+#define MBX_ROUTE_ITEMS 4          // spans per thread of the route kernel (1024 per block: runs of ~1 KB per owner at 8 ranks)
+#define MBX_SPIN_NS 10000000000ull // a peer that does not show up within 10 s is reported as an error instead of a hang
+struct mbx_layout {
+  uint32_t world; uint64_t cap;
+  SLK_HD size_t flag1_off() const { return 0; }
+  SLK_HD size_t flag2_off() const { return (size_t)world * 8; }
+  SLK_HD size_t keys_off() const { return (((size_t)world * 16) + 255) & ~(size_t)255; }
+  SLK_HD size_t taxa_off() const { return keys_off() + (size_t)world * cap * 8; }
+  SLK_HD size_t bytes() const { return taxa_off() + (size_t)world * cap * 4; }
+};
+struct slk_mailbox {
+  slk_ctx* ctx;
+  uint32_t rank, world;
+  uint64_t cap;
+  mbx_layout lay;
+  uint8_t* base = nullptr;                 // this rank's mailbox (peers store into it)
+  std::vector<uint8_t*> peer;              // every rank's mailbox as seen from here (peer[rank] == base)
+  std::vector<bool> opened;                // peer[i] came from cudaIpcOpenMemHandle
+  uint8_t** d_peer = nullptr;
+  uint32_t* d_send_idx = nullptr;          // [world][cap]: span index of every key sent, per owner
+  unsigned long long* d_cursors = nullptr; // [world]: keys sent to every owner in the current batch
+  uint32_t* d_err = nullptr;               // bit 0: inbox overflow, bit 1: a peer timed out, bit 2: bad taxon / overflow of taxa
+  uint16_t* d_dense = nullptr; uint64_t dense_cap = 0;
+  uint32_t epoch = 0;
+  bool connected = false;
+};
+
+__device__ __forceinline__ unsigned long long mbx_ld_flag(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mbx_st_flag(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long mbx_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// waits until the flag carries `epoch`; returns its low word (the count), 0 on time-out
+__device__ __forceinline__ uint32_t mbx_wait(const unsigned long long* flag, uint32_t epoch, uint32_t* err) {
+  const unsigned long long t0 = mbx_now();
+  for (;;) {
+    const unsigned long long v = mbx_ld_flag(flag);
+    if ((uint32_t)(v >> 32) == epoch) return (uint32_t)v;
+    if (mbx_now() - t0 > MBX_SPIN_NS) { atomicOr(err, 2u); return 0; }
+    __nanosleep(256);
+  }
+}
+
+// Route + send. A block takes 1024 consecutive span words, counts its sequence spans per owner in shared memory,
+// reserves a range of every owner's inbox slice with one atomic per owner, orders its keys by owner in shared memory and
+// stores the runs: consecutive threads store consecutive 8-byte words of one peer's memory.
+__global__ void __launch_bounds__(256) mbx_route_kernel(const uint64_t* __restrict__ spans, uint64_t n, mbx_layout lay, uint32_t rank,
+                                                        unsigned long long* cursors, uint8_t* const* __restrict__ peers,
+                                                        uint32_t* __restrict__ send_idx, uint32_t* err) {
+  constexpr uint32_t PER_BLOCK = 256 * MBX_ROUTE_ITEMS;
+  __shared__ uint32_t s_cnt[MBX_MAX_WORLD], s_off[MBX_MAX_WORLD + 1];
+  __shared__ unsigned long long s_base[MBX_MAX_WORLD];
+  __shared__ uint64_t s_key[PER_BLOCK];
+  __shared__ uint32_t s_idx[PER_BLOCK];
+  __shared__ uint8_t s_dest[PER_BLOCK];
+  const uint32_t world = lay.world;
+  if (threadIdx.x < world) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t i0 = (uint64_t)blockIdx.x * PER_BLOCK;
+  uint64_t ck[MBX_ROUTE_ITEMS];
+  uint32_t dest[MBX_ROUTE_ITEMS], pos[MBX_ROUTE_ITEMS];
+#pragma unroll
+  for (int j = 0; j < MBX_ROUTE_ITEMS; j++) {
+    const uint64_t i = i0 + (uint64_t)j * 256 + threadIdx.x;
+    dest[j] = 0xffffffffu;
+    if (i < n) {
+      const uint64_t w = spans[i];
+      if (SLK_SPAN_TYPE(w) == SLK_E_SEQ) {
+        ck[j] = SLK_SPAN_KEY(w);
+        dest[j] = slk_shard_of(ck[j], world);
+        pos[j] = atomicAdd(&s_cnt[dest[j]], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < world && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&cursors[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+  if (threadIdx.x == 0) {
+    uint32_t o = 0;
+    for (uint32_t d = 0; d < world; d++) { s_off[d] = o; o += s_cnt[d]; }
+    s_off[world] = o;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < MBX_ROUTE_ITEMS; j++)
+    if (dest[j] != 0xffffffffu) {
+      const uint32_t q = s_off[dest[j]] + pos[j];
+      s_key[q] = ck[j]; s_idx[q] = (uint32_t)(i0 + (uint64_t)j * 256 + threadIdx.x); s_dest[q] = (uint8_t)dest[j];
+    }
+  __syncthreads();
+  const uint32_t total = s_off[world];
+  for (uint32_t q = threadIdx.x; q < total; q += 256) {
+    const uint32_t d = s_dest[q];
+    const unsigned long long p = s_base[d] + (q - s_off[d]);
+    if (p < lay.cap) {
+      reinterpret_cast<uint64_t*>(peers[d] + lay.keys_off())[(uint64_t)rank * lay.cap + p] = s_key[q];
+      send_idx[(uint64_t)d * lay.cap + p] = s_idx[q];
+    } else {
+      atomicOr(err, 1u);
+    }
+  }
+}
+// after the route kernel: tells every owner how many keys are waiting for it
+__global__ void mbx_signal_keys_kernel(mbx_layout lay, uint32_t rank, uint32_t epoch, const unsigned long long* cursors,
+                                       uint8_t* const* __restrict__ peers) {
+  const uint32_t d = threadIdx.x;
+  if (d >= lay.world) return;
+  unsigned long long c = cursors[d];
+  if (c > lay.cap) c = lay.cap;
+  __threadfence_system();
+  mbx_st_flag(reinterpret_cast<unsigned long long*>(peers[d] + lay.flag1_off()) + rank, ((unsigned long long)epoch << 32) | c);
+}
+// Owner side: `per` blocks per source; a block waits for the keys of its source s, then strides over them 256 at a time:
+// look up, store the raw taxon into s's reply area.
+__global__ void __launch_bounds__(256) mbx_probe_kernel(slk_table_view tb, slk_tax_view tx, mbx_layout lay, uint32_t rank, uint32_t epoch,
+                                                        uint32_t per, const uint8_t* __restrict__ base,
+                                                        uint8_t* const* __restrict__ peers, uint32_t* err) {
+  __shared__ uint32_t s_n;
+  const uint32_t s = blockIdx.x / per, c0 = blockIdx.x % per;
+  if (threadIdx.x == 0) s_n = mbx_wait(reinterpret_cast<const unsigned long long*>(base + lay.flag1_off()) + s, epoch, err);
+  __syncthreads();
+  const uint64_t n = s_n;
+  const uint64_t* keys = reinterpret_cast<const uint64_t*>(base + lay.keys_off()) + (uint64_t)s * lay.cap;
+  int32_t* back = reinterpret_cast<int32_t*>(peers[s] + lay.taxa_off()) + (uint64_t)rank * lay.cap;
+  for (uint64_t j = (uint64_t)c0 * 256 + threadIdx.x; j < n; j += (uint64_t)per * 256) {
+    const uint32_t d = slk_probe(tb, __ldcg(keys + j));
+    back[j] = d ? tx.raw[d] : 0;
+  }
+}
+__global__ void mbx_signal_taxa_kernel(mbx_layout lay, uint32_t rank, uint32_t epoch, uint8_t* const* __restrict__ peers) {
+  const uint32_t s = threadIdx.x;
+  if (s >= lay.world) return;
+  __threadfence_system();
+  mbx_st_flag(reinterpret_cast<unsigned long long*>(peers[s] + lay.flag2_off()) + rank, ((unsigned long long)epoch << 32) | 1ull);
+}
+// Asker side: `per` blocks per owner; a block waits for the answers of its owner d and scatters them to their spans as
+// dense labels.
+__global__ void __launch_bounds__(256) mbx_unroute_kernel(mbx_layout lay, uint32_t epoch, uint32_t per, const uint8_t* __restrict__ base,
+                                                          const unsigned long long* __restrict__ cursors,
+                                                          const uint32_t* __restrict__ send_idx, const uint16_t* __restrict__ raw2dense,
+                                                          int32_t n_tax, uint16_t* __restrict__ dense, uint32_t* err) {
+  const uint32_t d = blockIdx.x / per, c0 = blockIdx.x % per;
+  unsigned long long n = cursors[d];
+  if (n > lay.cap) n = lay.cap;
+  if ((uint64_t)c0 * 256 >= n) return;   // nothing of this block's share was sent to d: no need to wait for it
+  if (threadIdx.x == 0) mbx_wait(reinterpret_cast<const unsigned long long*>(base + lay.flag2_off()) + d, epoch, err);
+  __syncthreads();
+  const int32_t* back = reinterpret_cast<const int32_t*>(base + lay.taxa_off()) + (uint64_t)d * lay.cap;
+  const uint32_t* idx = send_idx + (uint64_t)d * lay.cap;
+  for (uint64_t j = (uint64_t)c0 * 256 + threadIdx.x; j < n; j += (uint64_t)per * 256) {
+    const int32_t t = __ldcg(back + j);
+    uint16_t dn = 0;
+    if (t != 0) {
+      if (t < 0 || t >= n_tax || (dn = raw2dense[t]) == 0) { atomicOr(err, 4u); dn = 0; }
+    }
+    dense[idx[j]] = dn;
+  }
+}
+
+extern "C" int slk_mailbox_create(slk_ctx* ctx, uint32_t rank, uint32_t world, uint64_t cap, slk_mailbox** out, uint8_t* handle_out) {
+  if (!ctx || !out || world == 0 || world > MBX_MAX_WORLD || rank >= world || cap == 0 || cap > 0xffffffffull)
+    return slk_fail(SLK_E_INVALID, "bad arguments (1 <= world <= %d, rank < world, 0 < cap < 2^32)", MBX_MAX_WORLD);
+  SLK_CU(cudaSetDevice(ctx->device));
+  slk_mailbox* m = new (std::nothrow) slk_mailbox;
+  if (!m) return slk_fail(SLK_E_NOMEM, "host allocation failed");
+  m->ctx = ctx; m->rank = rank; m->world = world; m->cap = cap;
+  m->lay.world = world; m->lay.cap = cap;
+  m->peer.assign(world, nullptr); m->opened.assign(world, false);
+  cudaError_t e = cudaMalloc(&m->base, m->lay.bytes());
+  if (e == cudaSuccess) e = cudaMemset(m->base, 0, m->lay.keys_off());
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_peer, (size_t)world * sizeof(uint8_t*));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_send_idx, (size_t)world * cap * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_cursors, (size_t)world * 8);
+  if (e == cudaSuccess) e = cudaMemset(m->d_cursors, 0, (size_t)world * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_err, 4);
+  if (e == cudaSuccess) e = cudaMemset(m->d_err, 0, 4);
+  if (e == cudaSuccess && handle_out) {
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == SLK_IPC_HANDLE_BYTES, "IPC handle size");
+    e = cudaIpcGetMemHandle(&h, m->base);
+    if (e == cudaSuccess) memcpy(handle_out, &h, sizeof(h));
+  }
+  if (e != cudaSuccess) {
+    const int rc = slk_fail(e == cudaErrorMemoryAllocation ? SLK_E_NOMEM : SLK_E_CUDA, "mailbox allocation failed: %s", cudaGetErrorString(e));
+    slk_mailbox_destroy(m);
+    return rc;
+  }
+  m->peer[rank] = m->base;
+  *out = m;
+  return SLK_OK;
+}
+// one wave of 256-thread blocks over the whole chip (8 per SM), shared out evenly among the peers
+static uint32_t mbx_blocks_per_peer(const slk_mailbox* m) {
+  const uint32_t per = (uint32_t)(m->ctx->sm_count * 8) / m->world;
+  const uint32_t most = (uint32_t)((m->cap + 255) / 256);
+  return std::max(1u, std::min(per, most));
+}
+static int mbx_upload_peers(slk_mailbox* m) {
+  SLK_CU(cudaMemcpy(m->d_peer, m->peer.data(), (size_t)m->world * sizeof(uint8_t*), cudaMemcpyHostToDevice));
+  m->connected = true;
+  return SLK_OK;
+}
+// one process per GPU: handles = world x SLK_IPC_HANDLE_BYTES, gathered from slk_mailbox_create on every rank
+extern "C" int slk_mailbox_connect(slk_mailbox* m, const uint8_t* handles) {
+  if (!m || !handles) return slk_fail(SLK_E_INVALID, "bad arguments");
+  SLK_CU(cudaSetDevice(m->ctx->device));
+  for (uint32_t r = 0; r < m->world; r++) {
+    if (r == m->rank || m->peer[r]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * SLK_IPC_HANDLE_BYTES, sizeof(h));
+    void* p = nullptr;
+    SLK_CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    m->peer[r] = (uint8_t*)p; m->opened[r] = true;
+  }
+  return mbx_upload_peers(m);
+}
+// one process driving all ranks (tests; several ranks may share a device): peers by pointer
+extern "C" int slk_mailbox_connect_local(slk_mailbox* const* boxes, uint32_t world) {
+  if (!boxes || world == 0) return slk_fail(SLK_E_INVALID, "bad arguments");
+  for (uint32_t r = 0; r < world; r++)
+    if (!boxes[r] || boxes[r]->world != world || boxes[r]->rank != r || boxes[r]->cap != boxes[0]->cap)
+      return slk_fail(SLK_E_INVALID, "mailbox %u does not belong to this group", r);
+  for (uint32_t r = 0; r < world; r++) {
+    SLK_CU(cudaSetDevice(boxes[r]->ctx->device));
+    for (uint32_t q = 0; q < world; q++) {
+      if (boxes[q]->ctx->device != boxes[r]->ctx->device) {
+        int can = 0;
+        SLK_CU(cudaDeviceCanAccessPeer(&can, boxes[r]->ctx->device, boxes[q]->ctx->device));
+        if (!can) return slk_fail(SLK_E_UNSUPPORTED, "device %d cannot access device %d", boxes[r]->ctx->device, boxes[q]->ctx->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(boxes[q]->ctx->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) SLK_CU(e);
+        cudaGetLastError();
+      }
+      boxes[r]->peer[q] = boxes[q]->base;
+    }
+    int rc = mbx_upload_peers(boxes[r]);
+    if (rc != SLK_OK) return rc;
+  }
+  return SLK_OK;
+}
+extern "C" void slk_mailbox_destroy(slk_mailbox* m) {
+  if (!m) return;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  for (uint32_t r = 0; r < m->world; r++)
+    if (m->opened[r] && m->peer[r]) cudaIpcCloseMemHandle(m->peer[r]);
+  cudaFree(m->base); cudaFree(m->d_peer); cudaFree(m->d_send_idx); cudaFree(m->d_cursors); cudaFree(m->d_err); cudaFree(m->d_dense);
+  delete m;
+}
+// step 1 (asynchronous): this rank's sequence-span keys go to their owners' inboxes
+extern "C" int slk_mailbox_route(slk_mailbox* m, const uint64_t* spans, uint64_t n_spans) {
+  if (!m || !m->connected || (n_spans && !spans)) return slk_fail(SLK_E_INVALID, "bad arguments (is the mailbox connected?)");
+  if (n_spans > 0xffffffffull) return slk_fail(SLK_E_UNSUPPORTED, "more than 2^32 spans in one batch");
+  SLK_CU(cudaSetDevice(m->ctx->device));
+  cudaStream_t st = m->ctx->stream;
+  m->epoch++;
+  SLK_CU(cudaMemsetAsync(m->d_cursors, 0, (size_t)m->world * 8, st));
+  if (n_spans) {
+    const uint64_t per = 256ull * MBX_ROUTE_ITEMS;
+    mbx_route_kernel<<<(unsigned)((n_spans + per - 1) / per), 256, 0, st>>>(spans, n_spans, m->lay, m->rank, m->d_cursors, m->d_peer,
+                                                                            m->d_send_idx, m->d_err);
+  }
+  mbx_signal_keys_kernel<<<1, MBX_MAX_WORLD, 0, st>>>(m->lay, m->rank, m->epoch, m->d_cursors, m->d_peer);
+  SLK_CU(cudaGetLastError());
+  return SLK_OK;
+}
+// step 2 (asynchronous): the owner's half of the join for the keys of every rank, answers stored into the askers
+extern "C" int slk_mailbox_probe(slk_mailbox* m, slk_index* idx) {
+  if (!m || !m->connected || !idx || idx->ctx != m->ctx) return slk_fail(SLK_E_INVALID, "bad arguments (index and mailbox must share a context)");
+  SLK_CU(cudaSetDevice(m->ctx->device));
+  cudaStream_t st = m->ctx->stream;
+  const uint32_t per = mbx_blocks_per_peer(m);
+  mbx_probe_kernel<<<m->world * per, 256, 0, st>>>(idx->table, idx->dt.view(), m->lay, m->rank, m->epoch, per, m->base, m->d_peer, m->d_err);
+  mbx_signal_taxa_kernel<<<1, MBX_MAX_WORLD, 0, st>>>(m->lay, m->rank, m->epoch, m->d_peer);
+  SLK_CU(cudaGetLastError());
+  return SLK_OK;
+}
+// step 3 (returns when the results are complete): slk_resolve_spans_dev on the answers in the reply area
+extern "C" int slk_mailbox_resolve(slk_mailbox* m, slk_resolver* r, const slk_classify_opts* opts, const uint64_t* spans,
+                                   const uint64_t* span_off, uint64_t n_spans, uint32_t n_reads, int paired, int32_t* taxon_out,
+                                   uint8_t* flags_out, slk_read_detail* detail_out, slk_hit* hits_out) {
+  if (!m || !m->connected || !r || r->ctx != m->ctx || !opts || !span_off || !taxon_out || !flags_out || (n_spans && !spans))
+    return slk_fail(SLK_E_INVALID, "bad arguments (resolver and mailbox must share a context)");
+  if (hits_out && !detail_out) return slk_fail(SLK_E_INVALID, "hits_out needs detail_out");
+  SLK_CU(cudaSetDevice(m->ctx->device));
+  cudaStream_t st = m->ctx->stream;
+  if (m->dense_cap < std::max<uint64_t>(n_spans, 1)) {
+    cudaFree(m->d_dense); m->d_dense = nullptr; m->dense_cap = 0;
+    const uint64_t cap = std::max<uint64_t>(n_spans + n_spans / 8, 1024);
+    SLK_CU(cudaMalloc(&m->d_dense, cap * 2));
+    m->dense_cap = cap;
+  }
+  SLK_CU(cudaMemsetAsync(m->d_dense, 0, std::max<uint64_t>(n_spans, 1) * 2, st));
+  const uint32_t per = mbx_blocks_per_peer(m);
+  mbx_unroute_kernel<<<m->world * per, 256, 0, st>>>(m->lay, m->epoch, per, m->base, m->d_cursors, m->d_send_idx, r->d_r2d,
+                                                        (int32_t)r->tax->parents.size(), m->d_dense, m->d_err);
+  if (n_reads)
+    resolve_spans_kernel<<<(n_reads + 127) / 128, 128, 0, st>>>(r->dt.view(), r->sp.k, spans, span_off, m->d_dense, n_reads, paired,
+                                                                opts->confidence, opts->min_hit_groups, taxon_out, flags_out,
+                                                                detail_out, hits_out, r->d_err);
+  uint32_t err = 0, rerr = 0;
+  if (cudaMemcpyAsync(&err, m->d_err, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaMemcpyAsync(&rerr, r->d_err, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+    return slk_fail(SLK_E_CUDA, "mailbox resolve failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (err || rerr) {
+    cudaMemset(m->d_err, 0, 4); cudaMemset(r->d_err, 0, 4);
+    if (err & 2u) return slk_fail(SLK_E_CUDA, "a peer did not deliver its part of the exchange within 10 s");
+    if (err & 1u) return slk_fail(SLK_E_NOSPACE, "more than %llu keys for one owner in a batch: create the mailbox with a larger cap", (unsigned long long)m->cap);
+    return slk_fail(SLK_E_UNSUPPORTED, "a returned taxon is unknown to the resolver, or a fragment hit more than %d distinct taxa", SLK_KMAX);
+  }
+  return SLK_OK;
 }
 
 // owner of every record (id1 = the uncompressed minimizer of the Parquet column), computed on the host

@@ -182,6 +182,51 @@ class GpuSplitOps:
         return ClassifiedBatch(taxon.cpu().numpy()[:n_reads], flags.cpu().numpy()[:n_reads], d, h, n_spans if want_hits else 0)
 
 
+# ------------------------------------------------------------------------------------------------ NVLink mailbox
+class Mailbox:
+    """The two exchanges of the split path as stores into peer memory (include/slacken_gpu.h, "NVLink mailbox"): keys go
+    straight from the routing kernel into their owner's inbox, taxa straight from the owner's lookup kernel into the
+    asker's reply area, completion flags are awaited on the device. torch.distributed is only used once, to hand the
+    CUDA IPC handles around. cap = room for the keys one rank sends to one owner per batch."""
+
+    def __init__(self, ctx: GpuContext, rank: int, world: int, cap: int, group=None, connect: bool = True):
+        self.ctx, self.rank, self.world, self.cap = ctx, rank, world, int(cap)
+        self._L = ctx._L
+        h = C.c_void_p()
+        handle = (C.c_uint8 * _lib.IPC_HANDLE_BYTES)()
+        check(self._L.slk_mailbox_create(ctx.h, rank, world, self.cap, C.byref(h), handle))
+        self.h = h
+        self.handle = bytes(handle)
+        if connect:
+            self.connect(group)
+
+    def connect(self, group=None):
+        """Collective: every rank's process learns every other rank's mailbox."""
+        import torch
+        dist = _dist()
+        if self.world == 1:
+            check(self._L.slk_mailbox_connect(self.h, self.handle))
+            return
+        dev = torch.device("cuda", self.ctx.device)
+        mine = torch.frombuffer(bytearray(self.handle), dtype=torch.uint8).to(dev)
+        every = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(every, mine, group=group)
+        blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in every)
+        check(self._L.slk_mailbox_connect(self.h, blob))
+        dist.barrier(group=group)
+
+    @staticmethod
+    def connect_local(boxes: Sequence["Mailbox"]):
+        """One process driving all ranks (tests): connects by pointer."""
+        arr = (C.c_void_p * len(boxes))(*[b.h for b in boxes])
+        check(boxes[0]._L.slk_mailbox_connect_local(arr, len(boxes)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.slk_mailbox_destroy(self.h)
+            self.h = None
+
+
 # ------------------------------------------------------------------------------------------------ index + classifier
 class ShardedKeyValueIndex:
     """This rank's shard of a KeyValueIndex: the records whose minimizer hashes into the rank's range."""
@@ -242,11 +287,17 @@ class ShardedClassifier:
     """Classifier over a sharded library. Construction and classify() are collective: every rank of the group calls them
     (with its own reads, possibly none)."""
 
-    def __init__(self, shard: Optional[ShardedKeyValueIndex], group=None, ops=None, local_taxa: Optional[np.ndarray] = None):
+    def __init__(self, shard: Optional[ShardedKeyValueIndex], group=None, ops=None, local_taxa: Optional[np.ndarray] = None,
+                 mailbox_cap: int = 0, mailbox: Optional[Mailbox] = None, taxa_union: Optional[np.ndarray] = None):
+        """mailbox_cap > 0 (or a ready-made mailbox): the exchanges go through the NVLink mailbox instead of NCCL;
+        mailbox_cap = room for the keys this rank sends to ONE owner per batch (about spans per batch / world, plus slack)."""
         self.group = group
-        self.rank, self.world = world_of(group)
-        taxa = union_of_taxa(shard.taxa() if shard is not None else local_taxa, group)
+        self.rank, self.world = world_of(group) if shard is None or mailbox is None else (shard.rank, shard.world)
+        taxa = taxa_union if taxa_union is not None else union_of_taxa(shard.taxa() if shard is not None else local_taxa, group)
         self.ops = ops(taxa) if ops is not None else GpuSplitOps(shard.index, taxa)
+        self.mailbox = mailbox
+        if mailbox is None and mailbox_cap > 0:
+            self.mailbox = Mailbox(shard.ctx, self.rank, self.world, mailbox_cap, group)
         self.last_exchange_bytes = (0, 0)
         self.last_times: dict = {}
 
@@ -284,6 +335,13 @@ class ShardedClassifier:
             t = now
         span_off, spans, n_spans = ops.scan_spans(d_b1, d_o1, d_b2, d_o2, n)
         lap("scan")
+        if self.mailbox is not None:
+            self.mailbox_route(spans, n_spans)
+            self.mailbox_probe()
+            out = self.mailbox_resolve(spans, span_off, n_spans, n, paired, confidence, min_hit_groups, per_read_output)
+            lap("route_probe_resolve_and_download")
+            self.last_times = tm
+            return out
         keys, idx, counts = ops.route(spans, n_spans, self.world)
         lap("route")
         recv_keys, recv_counts = exchange(keys, counts, self.group)          # keys -> owners
@@ -298,6 +356,30 @@ class ShardedClassifier:
         self.last_times = tm
         return out
 
+    # the three mailbox steps, separately (a single process driving several ranks interleaves them: tests)
+    def mailbox_route(self, spans, n_spans: int):
+        check(self.ops._L.slk_mailbox_route(self.mailbox.h, self.ops._v(spans), n_spans))
+
+    def mailbox_probe(self):
+        check(self.ops._L.slk_mailbox_probe(self.mailbox.h, self.ops.index.h))
+
+    def mailbox_resolve(self, spans, span_off, n_spans: int, n_reads: int, paired: bool, confidence: float, min_hit_groups: int,
+                        want_hits: bool) -> ClassifiedBatch:
+        ops, t = self.ops, self.ops.torch
+        taxon = t.empty(max(n_reads, 1), dtype=t.int32, device=ops.device)
+        flags = t.empty(max(n_reads, 1), dtype=t.uint8, device=ops.device)
+        detail = t.empty(max(n_reads, 1) * DETAIL_DTYPE.itemsize, dtype=t.uint8, device=ops.device) if want_hits else None
+        hits = t.empty(max(n_spans, 1) * HIT_DTYPE.itemsize, dtype=t.uint8, device=ops.device) if want_hits else None
+        opts = ClassifyOpts(float(confidence), int(min_hit_groups), 0)
+        check(ops._L.slk_mailbox_resolve(self.mailbox.h, ops.resolver, C.byref(opts), ops._v(spans), ops._v(span_off), n_spans,
+                                         n_reads, 1 if paired else 0, ops._v(taxon), ops._v(flags), ops._v(detail), ops._v(hits)))
+        d = detail.cpu().numpy().view(DETAIL_DTYPE)[:n_reads] if want_hits else None
+        h = hits.cpu().numpy().view(HIT_DTYPE)[:n_spans] if want_hits else None
+        return ClassifiedBatch(taxon.cpu().numpy()[:n_reads], flags.cpu().numpy()[:n_reads], d, h, n_spans if want_hits else 0)
+
     def close(self):
+        if self.mailbox is not None:
+            self.mailbox.close()
+            self.mailbox = None
         if hasattr(self.ops, "close"):
             self.ops.close()

@@ -71,3 +71,95 @@ def test_split_path_many_shards_on_one_gpu(gpu, world):
     for s in shards:
         s.close()
     tax.close()
+
+
+def _mailbox_world(devices, seed=41, n_reads=1800, cap=40000):
+    """One process plays every rank of the NVLink-mailbox exchange: rank r lives on devices[r] (several ranks may share a
+    device), holds shard r and classifies its own share of the reads."""
+    from slacken_b200.host import GpuContext
+    from slacken_b200.sharded import Mailbox
+    world = len(devices)
+    rng, parents, ranks, names, genomes, taxa = make_world(seed)
+    p = oracle.params()
+    olib = oracle_lib(p, parents, genomes, taxa)
+    id1, tx = olib.records()
+    params = IndexParams()
+    owner = shard_of_records(params, id1, world)
+    ctxs = {d: GpuContext(d) for d in sorted(set(devices))}
+    taxs = {d: Taxonomy(c, parents, ranks, names) for d, c in ctxs.items()}
+    union = np.unique(tx)
+    cls = []
+    for r, d in enumerate(devices):
+        shard = ShardedKeyValueIndex(KeyValueIndex.from_records(ctxs[d], taxs[d], params, id1[owner == r], tx[owner == r]), r, world)
+        cls.append(ShardedClassifier(shard, mailbox=Mailbox(ctxs[d], r, world, cap, connect=False), taxa_union=union))
+    Mailbox.connect_local([c.mailbox for c in cls])
+    return rng, genomes, olib, cls, (ctxs, taxs)
+
+
+def _mailbox_round(cls, olib, per_rank_reads, conf, paired_mates=None):
+    """scan on every rank, then route, probe, resolve: the order one-process emulation needs so that no kernel waits for a
+    signal that is queued behind it on the same stream."""
+    world = len(cls)
+    st = []
+    for r in range(world):
+        rb, ro = pack_sequences(per_rank_reads[r])
+        ops = cls[r].ops
+        d_b, d_o = ops.upload(rb if len(rb) else np.zeros(16, np.uint8)), ops.upload(ro.view(np.int64))
+        d_b2 = d_o2 = mb = mo = None
+        if paired_mates is not None:
+            mb, mo = pack_sequences(paired_mates[r])
+            d_b2, d_o2 = ops.upload(mb if len(mb) else np.zeros(16, np.uint8)), ops.upload(mo.view(np.int64))
+        span_off, spans, n_spans = ops.scan_spans(d_b, d_o, d_b2, d_o2, len(per_rank_reads[r]))
+        st.append((rb, ro, mb, mo, span_off, spans, n_spans))
+    for r in range(world):
+        cls[r].mailbox_route(st[r][5], st[r][6])
+    for r in range(world):
+        cls[r].mailbox_probe()
+    for r in range(world):
+        rb, ro, mb, mo, span_off, spans, n_spans = st[r]
+        n = len(per_rank_reads[r])
+        got = cls[r].mailbox_resolve(spans, span_off, n_spans, n, paired_mates is not None, conf, 2, True)
+        if n:
+            res, _, _, per = olib.classify(rb, ro.astype(np.int64), mb, mo.astype(np.int64) if mo is not None else None, confidence=conf)
+            assert_batch_equal(res, per, got, 35)
+
+
+@pytest.mark.parametrize("world", [1, 2, 5])
+def test_mailbox_exchange_ranks_on_one_gpu(gpu, world):
+    rng, genomes, olib, cls, keep = _mailbox_world([gpu.device] * world)
+    reads = simulate_reads(rng, genomes, 1800, (30, 220), n_rate=0.1) + [b"", b"ACGT", b"N" * 80]
+    share = [reads[r::world] for r in range(world)]
+    _mailbox_round(cls, olib, share, 0.0)
+    # a second batch through the same mailboxes (next epoch), one rank without reads, paired, other confidence
+    reads2 = simulate_reads(rng, genomes, 900, (30, 220), n_rate=0.1)
+    mates2 = simulate_reads(rng, genomes, 900, (30, 220), n_rate=0.1)
+    share2 = [reads2[r::world] for r in range(world)]
+    mshare2 = [mates2[r::world] for r in range(world)]
+    if world > 1:
+        share2[world - 1], mshare2[world - 1] = [], []
+    _mailbox_round(cls, olib, share2, 0.15, mshare2)
+    for c in cls:
+        c.close()
+
+
+def test_mailbox_overflow_fails_loudly(gpu):
+    from slacken_b200._lib import SLK_E_NOSPACE, SlackenGpuError
+    rng, genomes, olib, cls, keep = _mailbox_world([gpu.device] * 2, cap=64)
+    reads = simulate_reads(rng, genomes, 400, (100, 200))
+    with pytest.raises(SlackenGpuError) as e:
+        _mailbox_round(cls, olib, [reads[0::2], reads[1::2]], 0.0)
+    assert e.value.code == SLK_E_NOSPACE
+    for c in cls:
+        c.close()
+
+
+def test_mailbox_exchange_over_nvlink_two_gpus(gpu):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng, genomes, olib, cls, keep = _mailbox_world([0, 1, 0, 1], n_reads=3000)
+    reads = simulate_reads(rng, genomes, 3000, (30, 220), n_rate=0.1)
+    for conf in (0.0, 0.1):
+        _mailbox_round(cls, olib, [reads[r::4] for r in range(4)], conf)
+    for c in cls:
+        c.close()
