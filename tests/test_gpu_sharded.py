@@ -73,7 +73,7 @@ def test_split_path_many_shards_on_one_gpu(gpu, world):
     tax.close()
 
 
-def _mailbox_world(devices, seed=41, n_reads=1800, cap=40000):
+def _mailbox_world(devices, seed=41, n_reads=1800, cap=120000):
     """One process plays every rank of the NVLink-mailbox exchange: rank r lives on devices[r] (several ranks may share a
     device), holds shard r and classifies its own share of the reads."""
     from slacken_b200.host import GpuContext
