@@ -128,10 +128,38 @@ class GpuSplitOps:
         if getattr(self, "resolver", None):
             self._L.slk_resolver_destroy(self.resolver)
             self.resolver = None
+        for buf in getattr(self, "_pinned", {}).values():
+            self.ctx.free_pinned(buf)
+        self._pinned = {}
 
     @staticmethod
     def _v(t):
         return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    def download(self, name: str, t, dtype, n: int) -> np.ndarray:
+        """Device tensor -> pinned host array (grow-only, one per result kind; pageable copies run at a few GB/s). The
+        returned view is valid until the next download of the same kind."""
+        dtype = np.dtype(dtype)
+        nbytes = n * dtype.itemsize
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        buf = self._pinned.get(name)
+        if buf is None or buf.nbytes < nbytes:
+            if buf is not None:
+                self.ctx.free_pinned(buf)
+            buf = self.ctx.pinned((max(nbytes + nbytes // 4, 4096),), np.uint8)
+            self._pinned[name] = buf
+        out = buf[:nbytes]
+        if nbytes:
+            self.ctx.d2h(out, t.data_ptr())
+        return out.view(dtype)
+
+    def _results(self, taxon, flags, detail, hits, n_reads: int, n_spans: int, want_hits: bool) -> ClassifiedBatch:
+        """The arrays of the batch live in pinned buffers that the next batch overwrites: copy what must outlive it."""
+        d = self.download("detail", detail, DETAIL_DTYPE, n_reads) if want_hits else None
+        h = self.download("hits", hits, HIT_DTYPE, n_spans) if want_hits else None
+        return ClassifiedBatch(self.download("taxon", taxon, np.int32, n_reads), self.download("flags", flags, np.uint8, n_reads),
+                               d, h, n_spans if want_hits else 0)
 
     def upload(self, a: np.ndarray):
         t = self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
@@ -177,9 +205,7 @@ class GpuSplitOps:
         check(self._L.slk_resolve_spans_dev(self.resolver, C.byref(opts), self._v(spans), self._v(span_off), n_spans, n_reads,
                                             1 if paired else 0, self._v(send_idx), self._v(taxa), send_idx.numel(),
                                             self._v(taxon), self._v(flags), self._v(detail), self._v(hits)))
-        d = detail.cpu().numpy().view(DETAIL_DTYPE)[:n_reads] if want_hits else None
-        h = hits.cpu().numpy().view(HIT_DTYPE)[:n_spans] if want_hits else None
-        return ClassifiedBatch(taxon.cpu().numpy()[:n_reads], flags.cpu().numpy()[:n_reads], d, h, n_spans if want_hits else 0)
+        return self._results(taxon, flags, detail, hits, n_reads, n_spans, want_hits)
 
 
 # ------------------------------------------------------------------------------------------------ NVLink mailbox
@@ -373,9 +399,7 @@ class ShardedClassifier:
         opts = ClassifyOpts(float(confidence), int(min_hit_groups), 0)
         check(ops._L.slk_mailbox_resolve(self.mailbox.h, ops.resolver, C.byref(opts), ops._v(spans), ops._v(span_off), n_spans,
                                          n_reads, 1 if paired else 0, ops._v(taxon), ops._v(flags), ops._v(detail), ops._v(hits)))
-        d = detail.cpu().numpy().view(DETAIL_DTYPE)[:n_reads] if want_hits else None
-        h = hits.cpu().numpy().view(HIT_DTYPE)[:n_spans] if want_hits else None
-        return ClassifiedBatch(taxon.cpu().numpy()[:n_reads], flags.cpu().numpy()[:n_reads], d, h, n_spans if want_hits else 0)
+        return ops._results(taxon, flags, detail, hits, n_reads, n_spans, want_hits)
 
     def close(self):
         if self.mailbox is not None:
