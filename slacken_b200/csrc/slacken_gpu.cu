@@ -131,6 +131,7 @@ extern "C" void slk_ctx_destroy(slk_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamDestroy(c->stream);
+  cudaFree(c->span_scratch); cudaFree(c->d_maxlen);
   delete c;
 }
 extern "C" int slk_ctx_device(const slk_ctx* c) { return c ? c->device : -1; }

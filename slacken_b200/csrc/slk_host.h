@@ -13,6 +13,15 @@ struct slk_ctx {
   int device;
   int sm_count;
   cudaStream_t stream;
+  // split path, one-pass scan: the span words of the last count-only slk_scan_spans_dev call, `stride` slots per
+  // fragment, waiting for slk_emit_spans_dev to compact them (grow-only scratch owned by the context)
+  uint64_t* span_scratch = nullptr;
+  size_t span_scratch_words = 0;
+  uint32_t* d_maxlen = nullptr;      // [3]: longest mate 1, longest mate 2, overflow flag
+  struct {
+    const void* bases1 = nullptr; const void* off1 = nullptr; const void* bases2 = nullptr; const void* off2 = nullptr;
+    const void* span_off = nullptr; uint32_t n_reads = 0; uint32_t stride = 0; bool valid = false;
+  } pending_spans;
 };
 struct slk_tax {
   slk_ctx* ctx;

@@ -44,7 +44,9 @@ void SLK_CAT(slk_launch_emit_w, SLK_W)(const slk_emit_args& a) {
 }
 void SLK_CAT(slk_launch_spans_w, SLK_W)(const slk_spans_args& a) {
   const unsigned grid = (a.n_reads + 127) / 128;
-  if (a.spans) spans_kernel<SLK_W, true><<<grid, 128, 0, a.stream>>>(a.sp, a.bases1, a.off1, a.bases2, a.off2, a.n_reads, a.span_off, a.spans);
+  if (a.scratch) spans_strided_kernel<SLK_W><<<grid, 128, 0, a.stream>>>(a.sp, a.bases1, a.off1, a.bases2, a.off2, a.n_reads, a.stride,
+                                                                          a.span_off, a.scratch, a.overflow);
+  else if (a.spans) spans_kernel<SLK_W, true><<<grid, 128, 0, a.stream>>>(a.sp, a.bases1, a.off1, a.bases2, a.off2, a.n_reads, a.span_off, a.spans);
   else spans_kernel<SLK_W, false><<<grid, 128, 0, a.stream>>>(a.sp, a.bases1, a.off1, a.bases2, a.off2, a.n_reads, a.span_off, a.spans);
 }
 void SLK_CAT(slk_launch_bracken_scan_w, SLK_W)(const slk_bracken_scan_args& a) {

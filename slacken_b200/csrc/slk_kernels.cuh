@@ -40,6 +40,8 @@ struct slk_spans_args {
   uint64_t* span_off;      // [n_reads + 1]: pass 1 writes counts to [0, n), pass 2 reads offsets
   uint64_t* spans;         // pass 2 output (nullptr = pass 1)
   cudaStream_t stream;
+  // one-pass variant: counts to span_off AND span words to scratch[r * stride ...] (stride > 0); overflow = flag word
+  uint64_t* scratch = nullptr; uint32_t stride = 0; uint32_t* overflow = nullptr;
 };
 // Bracken weights, scan step: pass 1 counts the hits of every genome fragment, pass 2 writes them at hit_off[f] ...
 struct slk_bracken_scan_args {
@@ -125,6 +127,31 @@ __global__ void __launch_bounds__(128) spans_kernel(const __grid_constant__ slk_
     slk_scan_fragment_spans<W>(sp, bases1 + s1, (uint32_t)(e1 - s1), p2, l2, bases2 != nullptr, [&](uint64_t) { n++; });
     span_off[r] = n;
   }
+}
+
+// One pass instead of two: fragment r writes its span words to its own row of `stride` slots (stride = the most spans
+// a fragment of the batch's longest reads can have: one per k-mer window, plus the mate border) and its count to
+// span_off[r]; after the prefix sum compact_spans_kernel moves the rows together, one warp per fragment.
+template <int W>
+__global__ void __launch_bounds__(128) spans_strided_kernel(const __grid_constant__ slk_scan_params sp, const uint8_t* __restrict__ bases1,
+                                                            const uint64_t* __restrict__ off1, const uint8_t* __restrict__ bases2,
+                                                            const uint64_t* __restrict__ off2, uint32_t n_reads, uint32_t stride,
+                                                            uint64_t* __restrict__ span_off, uint64_t* __restrict__ scratch,
+                                                            uint32_t* overflow) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const uint64_t s1 = off1[r], e1 = off1[r + 1];
+  const uint8_t* p2 = nullptr;
+  uint32_t l2 = 0;
+  if (bases2) { const uint64_t s2 = off2[r], e2 = off2[r + 1]; p2 = bases2 + s2; l2 = (uint32_t)(e2 - s2); }
+  uint64_t* out = scratch + (uint64_t)r * stride;
+  uint32_t n = 0;
+  slk_scan_fragment_spans<W>(sp, bases1 + s1, (uint32_t)(e1 - s1), p2, l2, bases2 != nullptr, [&](uint64_t w) {
+    if (n < stride) out[n] = w;
+    n++;
+  });
+  if (n > stride) atomicExch(overflow, 1u);
+  span_off[r] = n;
 }
 
 // ---------------------------------------------------------------------------------------------- Bracken weights: scan

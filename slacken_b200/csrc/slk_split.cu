@@ -27,6 +27,31 @@ __global__ void __launch_bounds__(256) probe_keys_kernel(slk_table_view tb, slk_
   taxa[i] = d ? tx.raw[d] : 0;
 }
 
+// longest mate 1 / mate 2 of a batch (out[0], out[1])
+__global__ void __launch_bounds__(256) max_len_kernel(const uint64_t* __restrict__ off1, const uint64_t* __restrict__ off2, uint32_t n,
+                                                      uint32_t* out) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t l1 = 0, l2 = 0;
+  if (r < n) {
+    const uint64_t a = off1[r + 1] - off1[r];
+    l1 = a > 0xffffffffull ? 0xffffffffu : (uint32_t)a;
+    if (off2) { const uint64_t b = off2[r + 1] - off2[r]; l2 = b > 0xffffffffull ? 0xffffffffu : (uint32_t)b; }
+  }
+  l1 = __reduce_max_sync(0xffffffffu, l1); l2 = __reduce_max_sync(0xffffffffu, l2);
+  if ((threadIdx.x & 31) == 0) { if (l1) atomicMax(out, l1); if (l2) atomicMax(out + 1, l2); }
+}
+// rows of `stride` slots -> the packed span array, one warp per fragment
+__global__ void __launch_bounds__(256) compact_spans_kernel(const uint64_t* __restrict__ scratch, uint32_t stride,
+                                                            const uint64_t* __restrict__ span_off, uint32_t n_reads,
+                                                            uint64_t* __restrict__ spans) {
+  const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= n_reads) return;
+  const uint64_t s0 = span_off[r];
+  const uint32_t n = (uint32_t)(span_off[r + 1] - s0);
+  const uint64_t* row = scratch + (uint64_t)r * stride;
+  for (uint32_t j = lane; j < n; j += 32) spans[s0 + j] = row[j];
+}
+
 // Routing of the SEQ spans of a batch: pass 1 counts per owner, pass 2 writes (key, span index) grouped by owner.
 // Counters per owner live in shared memory; a block touches the global counters once per owner.
 #define ROUTE_MAX_WORLD 1024
@@ -98,6 +123,7 @@ __global__ void __launch_bounds__(128) resolve_spans_kernel(slk_tax_view tx, int
 }
 
 // ---------------------------------------------------------------------------------------------- host
+#define SLK_SPAN_SCRATCH_MAX (16ull << 30)   // most scratch the one-pass scan may take (it falls back to two passes beyond)
 struct slk_resolver {
   slk_ctx* ctx;
   slk_tax* tax;
@@ -182,6 +208,35 @@ extern "C" int slk_scan_spans_dev(slk_ctx* ctx, const slk_params* params, const 
   if (n_reads == 0) { SLK_CU(cudaStreamSynchronize(ctx->stream)); return SLK_OK; }
   a.bases1 = bases1; a.off1 = off1; a.bases2 = bases2; a.off2 = off2; a.n_reads = n_reads;
   a.span_off = span_off; a.spans = nullptr; a.stream = ctx->stream;
+  ctx->pending_spans.valid = false;
+  // A count-only call that slk_emit_spans_dev will follow: scan ONCE, into rows of the context's scratch, when the rows
+  // of this batch (one slot per k-mer window of its longest reads) fit a bounded scratch; otherwise count now, scan again later.
+  bool strided = false;
+  if (!spans && !getenv("SLK_SPANS_TWO_PASS")) {
+    if (!ctx->d_maxlen) SLK_CU(cudaMalloc(&ctx->d_maxlen, 12));
+    SLK_CU(cudaMemsetAsync(ctx->d_maxlen, 0, 12, ctx->stream));
+    max_len_kernel<<<(n_reads + 255) / 256, 256, 0, ctx->stream>>>(off1, off2, n_reads, ctx->d_maxlen);
+    uint32_t ml[2] = {0, 0};
+    SLK_CU(cudaMemcpyAsync(ml, ctx->d_maxlen, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SLK_CU(cudaStreamSynchronize(ctx->stream));
+    const uint64_t k = (uint64_t)a.sp.k;
+    const uint64_t stride = (ml[0] >= k ? ml[0] - k + 1 : 0) + (bases2 ? 1 + (ml[1] >= k ? ml[1] - k + 1 : 0) : 0) + 1;
+    const uint64_t words = stride * (uint64_t)n_reads;
+    if (stride <= 4096 && words * 8 <= SLK_SPAN_SCRATCH_MAX) {
+      if (ctx->span_scratch_words < words) {
+        cudaFree(ctx->span_scratch); ctx->span_scratch = nullptr; ctx->span_scratch_words = 0;
+        size_t free_b = 0, total_b = 0;
+        SLK_CU(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t want = words + words / 8;
+        if (want * 8 <= free_b / 4 && cudaMalloc(&ctx->span_scratch, want * 8) == cudaSuccess) ctx->span_scratch_words = want;
+        else cudaGetLastError();
+      }
+      if (ctx->span_scratch_words >= words) {
+        a.scratch = ctx->span_scratch; a.stride = (uint32_t)stride; a.overflow = ctx->d_maxlen + 2;
+        strided = true;
+      }
+    }
+  }
   SLK_DISPATCH_SPANS(a.sp.w, a);
   SLK_CU(cudaGetLastError());
   int e = slk_exclusive_scan_u64(span_off, (uint64_t)n_reads + 1, ctx->stream);
@@ -189,6 +244,15 @@ extern "C" int slk_scan_spans_dev(slk_ctx* ctx, const slk_params* params, const 
   uint64_t total = 0;
   SLK_CU(cudaMemcpy(&total, span_off + n_reads, 8, cudaMemcpyDeviceToHost));
   *n_spans_host = total;
+  if (strided) {
+    uint32_t over = 0;
+    SLK_CU(cudaMemcpy(&over, ctx->d_maxlen + 2, 4, cudaMemcpyDeviceToHost));
+    if (!over) {   // (never expected: the stride is an upper bound; if it were exceeded the emit call simply scans again)
+      ctx->pending_spans.bases1 = bases1; ctx->pending_spans.off1 = off1; ctx->pending_spans.bases2 = bases2; ctx->pending_spans.off2 = off2;
+      ctx->pending_spans.span_off = span_off; ctx->pending_spans.n_reads = n_reads; ctx->pending_spans.stride = a.stride;
+      ctx->pending_spans.valid = true;
+    }
+  }
   if (!spans) return SLK_OK;   // count only: the caller sizes its buffer and calls slk_emit_spans_dev
   if (total > cap) return slk_fail(SLK_E_NOSPACE, "span buffer too small: %llu spans, room for %llu", (unsigned long long)total, (unsigned long long)cap);
   a.spans = spans;
@@ -205,6 +269,17 @@ extern "C" int slk_emit_spans_dev(slk_ctx* ctx, const slk_params* params, const 
     return slk_fail(SLK_E_INVALID, "bad arguments");
   SLK_CU(cudaSetDevice(ctx->device));
   if (n_reads == 0) return SLK_OK;
+  auto& pd = ctx->pending_spans;
+  if (pd.valid && pd.bases1 == bases1 && pd.off1 == off1 && pd.bases2 == bases2 && pd.off2 == off2 && pd.span_off == span_off &&
+      pd.n_reads == n_reads) {   // the count-only call already scanned: only move the rows together
+    pd.valid = false;
+    compact_spans_kernel<<<(unsigned)(((uint64_t)n_reads * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->span_scratch, pd.stride, span_off,
+                                                                                                    n_reads, spans);
+    SLK_CU(cudaGetLastError());
+    SLK_CU(cudaStreamSynchronize(ctx->stream));
+    return SLK_OK;
+  }
+  pd.valid = false;
   slk_spans_args a;
   int rc = slk_make_scan_params_checked(params, &a.sp);
   if (rc != SLK_OK) return rc;
