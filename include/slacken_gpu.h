@@ -107,11 +107,13 @@ SLK_API void slk_taxonomy_destroy(slk_tax* tax);
 
 /* ---- B3: library load, replaces KeyValueIndex.loadRecords + the join side (slacken/KeyValueIndex.scala:150-159,
  *          slacken/Classifier.scala:84). Columns of the Parquet table: id1:int64, taxon:int32. ------------------ */
+/* id1 / taxon: host OR device pointers (the copies infer the direction; the distributed build hands over device memory) */
 SLK_API int slk_index_from_records(slk_ctx* ctx, slk_tax* tax, const slk_params* params, const int64_t* id1,
                            const int32_t* taxon, uint64_t n, slk_index** out);
 SLK_API void slk_index_destroy(slk_index* idx);
 SLK_API uint64_t slk_index_size(const slk_index* idx);   /* number of records (distinct minimizers) */
-/* copy the records back (for the Parquet writer, KeyValueIndex.writeRecords :125-139); order unspecified */
+/* copy the records back (for the Parquet writer, KeyValueIndex.writeRecords :125-139); order unspecified; the output
+ * arrays may be host or device memory */
 SLK_API int slk_index_records(slk_index* idx, int64_t* id1_out, int32_t* taxon_out, uint64_t cap, uint64_t* n_out);
 
 /* ---- B2: library build, replaces SplitterMinimizers.find + groupBy(id1).agg(TaxonLCA)
@@ -228,6 +230,9 @@ SLK_API int slk_ctx_sync(slk_ctx* ctx);
 typedef struct slk_resolver slk_resolver;
 /* owner (0 .. world-1) of every record of the Parquet table; host arrays */
 SLK_API int slk_shard_of_records(const slk_params* params, const int64_t* id1, uint64_t n, uint32_t world, uint8_t* shard_out);
+/* the same for records that live in device memory (id1 and shard_out are device pointers) */
+SLK_API int slk_shard_of_records_dev(slk_ctx* ctx, const slk_params* params, const int64_t* id1, uint64_t n, uint32_t world,
+                                     uint8_t* shard_out);
 /* the taxa (raw ids, ancestors included) an index can answer with; out == NULL queries the count */
 SLK_API int slk_index_taxa(slk_index* idx, int32_t* out, uint32_t cap, uint32_t* n_out);
 /* the query side's view of the taxonomy: the union of slk_index_taxa over all shards (any order, duplicates allowed) */

@@ -524,7 +524,7 @@ extern "C" int slk_index_from_records(slk_ctx* ctx, slk_tax* tax, const slk_para
   CUX(cudaMemset(d_bitmap, 0, words * 4)); CUX(cudaMemset(d_bad, 0, 4)); CUX(cudaMemset(d_new, 0, 8));
   for (uint64_t s = 0; s < n; s += chunk) {
     uint64_t c = std::min(chunk, n - s);
-    CUX(cudaMemcpyAsync(d_tx, taxon + s, c * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUX(cudaMemcpyAsync(d_tx, taxon + s, c * 4, cudaMemcpyDefault, ctx->stream));
     mark_taxa_kernel<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(d_tx, c, n_tax, d_bitmap, d_bad);
     CUX(cudaGetLastError());
     CUX(cudaStreamSynchronize(ctx->stream));
@@ -549,8 +549,8 @@ extern "C" int slk_index_from_records(slk_ctx* ctx, slk_tax* tax, const slk_para
   if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
   for (uint64_t s = 0; s < n; s += chunk) {
     uint64_t c = std::min(chunk, n - s);
-    CUX(cudaMemcpyAsync(d_id, id1 + s, c * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CUX(cudaMemcpyAsync(d_tx, taxon + s, c * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUX(cudaMemcpyAsync(d_id, id1 + s, c * 8, cudaMemcpyDefault, ctx->stream));
+    CUX(cudaMemcpyAsync(d_tx, taxon + s, c * 4, cudaMemcpyDefault, ctx->stream));
     records_to_cells_kernel<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(d_id, d_tx, c, d_r2d, idx->sp, d_cells);
     CUX(cudaGetLastError());
     rc = insert_cells(ctx, idx, d_cells, c, d_new);
@@ -590,8 +590,8 @@ extern "C" int slk_index_records(slk_index* idx, int64_t* id1_out, int32_t* taxo
   dump_table_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, ctx->stream>>>(idx->table, idx->sp, idx->dt.d_raw, d_id, d_tx,
                                                                               idx->n_records, d_cur);
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(id1_out, d_id, idx->n_records * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(taxon_out, d_tx, idx->n_records * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(id1_out, d_id, idx->n_records * 8, cudaMemcpyDefault, ctx->stream));
+  CU(cudaMemcpyAsync(taxon_out, d_tx, idx->n_records * 4, cudaMemcpyDefault, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   cudaFree(d_id); cudaFree(d_tx); cudaFree(d_cur);
   return SLK_OK;

@@ -366,6 +366,26 @@ extern "C" int slk_resolve_spans_dev(slk_resolver* r, const slk_classify_opts* o
   return done(SLK_OK);
 }
 
+// ... and on the device (the distributed build keeps its records in HBM)
+__global__ void __launch_bounds__(256) shard_of_records_kernel(slk_scan_params sp, const int64_t* __restrict__ id1, uint64_t n,
+                                                               uint32_t world, uint8_t* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint8_t)slk_shard_of(slk_compress(sp, (uint64_t)id1[i]), world);
+}
+extern "C" int slk_shard_of_records_dev(slk_ctx* ctx, const slk_params* params, const int64_t* id1, uint64_t n, uint32_t world,
+                                        uint8_t* shard_out) {
+  if (!ctx || !params || world == 0 || world > 255 || (n && (!id1 || !shard_out))) return slk_fail(SLK_E_INVALID, "bad arguments");
+  slk_scan_params sp;
+  int rc = slk_make_scan_params_checked(params, &sp);
+  if (rc != SLK_OK) return rc;
+  SLK_CU(cudaSetDevice(ctx->device));
+  if (n == 0) return SLK_OK;
+  shard_of_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(sp, id1, n, world, shard_out);
+  SLK_CU(cudaGetLastError());
+  SLK_CU(cudaStreamSynchronize(ctx->stream));
+  return SLK_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- NVLink mailbox
 // The two exchanges of the split path as stores into PEER memory, fused into the kernels on either side of them
 // (no NCCL, no host in the loop): the route kernel groups the keys of a block by owner in shared memory and stores every

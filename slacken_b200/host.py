@@ -178,6 +178,30 @@ class KeyValueIndex:
         o = np.argsort(id1.view(np.uint64), kind="stable")
         return id1.view(np.uint64)[o], taxon[o]
 
+    def records_dev(self):
+        """The same rows as torch tensors in device memory (id1 int64, taxon int32), unsorted."""
+        import torch
+        n = len(self)
+        dev = torch.device("cuda", self.ctx.device)
+        id1 = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        taxon = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        got = C.c_uint64()
+        check(self.ctx._L.slk_index_records(self.h, C.c_void_p(id1.data_ptr()), C.c_void_p(taxon.data_ptr()), n, C.byref(got)))
+        return id1[:n], taxon[:n]
+
+    @classmethod
+    def from_records_dev(cls, ctx: GpuContext, taxonomy: Taxonomy, params: IndexParams, id1, taxon):
+        """from_records for torch tensors that already live on the context's device."""
+        import torch
+        id1, taxon = id1.contiguous(), taxon.contiguous()
+        assert id1.dtype == torch.int64 and taxon.dtype == torch.int32 and id1.numel() == taxon.numel()
+        torch.cuda.current_stream(id1.device).synchronize()   # torch's stream is not the library's
+        p = params.c_params()
+        h = C.c_void_p()
+        check(ctx._L.slk_index_from_records(ctx.h, taxonomy.h, C.byref(p), C.c_void_p(id1.data_ptr()),
+                                            C.c_void_p(taxon.data_ptr()), id1.numel(), C.byref(h)))
+        return cls(ctx, taxonomy, params, h)
+
     def close(self):
         if getattr(self, "h", None):
             self.ctx._L.slk_index_destroy(self.h)

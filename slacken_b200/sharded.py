@@ -285,15 +285,35 @@ class ShardedKeyValueIndex:
         local = KeyValueIndex.build(ctx, taxonomy, params, local_batches, expected_bases)
         if world == 1:
             return cls(local, 0, 1)
-        id1, taxon = local.records(sort=False)
+        if _dist().get_backend(group) != "nccl":   # CPU tests (gloo): the records travel through host memory
+            id1, taxon = local.records(sort=False)
+            local.close()
+            owner = shard_of_records(params, id1, world)
+            order = np.argsort(owner, kind="stable")
+            counts = np.bincount(owner, minlength=world).tolist()
+            rid, _ = exchange(torch.from_numpy(id1.view(np.int64)[order]), counts, group)
+            rtx, _ = exchange(torch.from_numpy(taxon[order]), counts, group)
+            return cls(KeyValueIndex.from_records(ctx, taxonomy, params, rid.numpy(), rtx.numpy()), rank, world)
+        # the records never leave HBM: dump the local table, group the rows by owner, all-to-all, insert on the owner
+        id1, taxon = local.records_dev()
         local.close()
-        owner = shard_of_records(params, id1, world)
-        order = np.argsort(owner, kind="stable")
-        counts = np.bincount(owner, minlength=world).tolist()
-        dev = "cuda" if _dist().get_backend(group) == "nccl" else "cpu"
-        rid, _ = exchange(torch.from_numpy(id1.view(np.int64)[order]).to(dev), counts, group)
-        rtx, _ = exchange(torch.from_numpy(taxon[order]).to(dev), counts, group)
-        return cls(KeyValueIndex.from_records(ctx, taxonomy, params, rid.cpu().numpy(), rtx.cpu().numpy()), rank, world)
+        owner = torch.empty(max(id1.numel(), 1), dtype=torch.uint8, device=id1.device)
+        p = params.c_params()
+        check(ctx._L.slk_shard_of_records_dev(ctx.h, C.byref(p), C.c_void_p(id1.data_ptr()), id1.numel(), world,
+                                              C.c_void_p(owner.data_ptr())))
+        owner = owner[:id1.numel()]
+        masks = [owner == r for r in range(world)]
+        counts = [int(m.sum()) for m in masks]
+        sid = torch.cat([id1[m] for m in masks])
+        stx = torch.cat([taxon[m] for m in masks])
+        del id1, taxon, owner, masks
+        rid, _ = exchange(sid, counts, group)
+        rtx, _ = exchange(stx, counts, group)
+        del sid, stx
+        out = cls(KeyValueIndex.from_records_dev(ctx, taxonomy, params, rid, rtx), rank, world)
+        del rid, rtx
+        torch.cuda.empty_cache()   # the staging tensors must not keep HBM that the classifier's buffers will want
+        return out
 
     def taxa(self) -> np.ndarray:
         n = C.c_uint32(0)

@@ -163,3 +163,29 @@ def test_mailbox_exchange_over_nvlink_two_gpus(gpu):
         _mailbox_round(cls, olib, [reads[r::4] for r in range(4)], conf)
     for c in cls:
         c.close()
+
+
+def test_records_stay_on_the_device(gpu):
+    """The pieces of the distributed build that keep the records in HBM: table -> device rows, owner of every row on the
+    device (equal to the host's), device rows -> table."""
+    import ctypes as C
+
+    import torch
+    from slacken_b200._lib import check
+    rng, genomes, olib, id1, tx, tax = _world(gpu, 43)
+    params = IndexParams()
+    full = KeyValueIndex.from_records(gpu, tax, params, id1, tx)
+    d_id, d_tx = full.records_dev()
+    assert d_id.is_cuda and d_id.numel() == len(id1)
+    o = np.argsort(d_id.cpu().numpy().view(np.uint64), kind="stable")
+    assert np.array_equal(d_id.cpu().numpy().view(np.uint64)[o], id1) and np.array_equal(d_tx.cpu().numpy()[o], tx)
+    owner = torch.empty(d_id.numel(), dtype=torch.uint8, device=d_id.device)
+    p = params.c_params()
+    check(gpu._L.slk_shard_of_records_dev(gpu.h, C.byref(p), C.c_void_p(d_id.data_ptr()), d_id.numel(), 3, C.c_void_p(owner.data_ptr())))
+    assert np.array_equal(owner.cpu().numpy(), shard_of_records(params, d_id.cpu().numpy(), 3))
+    mine = owner == 1
+    part = KeyValueIndex.from_records_dev(gpu, tax, params, d_id[mine], d_tx[mine])
+    pid, ptx = part.records()
+    sel = shard_of_records(params, id1, 3) == 1
+    assert np.array_equal(pid, id1[sel]) and np.array_equal(ptx, tx[sel])
+    part.close(); full.close(); tax.close()
