@@ -280,9 +280,16 @@ class ShardedKeyValueIndex:
         LCA-reduces ITS genomes on its GPU, the reduced records travel to the owner of their key (one all-to-all;
         LCA is associative and commutative, slacken/LowestCommonAncestor.scala:152-170), and the owner's insert merges
         records of the same minimizer by LCA again."""
-        import torch
-        rank, world = world_of(group)
         local = KeyValueIndex.build(ctx, taxonomy, params, local_batches, expected_bases)
+        return cls.from_local(local, group)
+
+    @classmethod
+    def from_local(cls, local: KeyValueIndex, group=None):
+        """The exchange half of the distributed build: `local` holds the LCA-reduced records of this rank's genomes (it is
+        consumed); the result holds the records this rank owns, merged over all ranks."""
+        import torch
+        ctx, taxonomy, params = local.ctx, local.taxonomy, local.params
+        rank, world = world_of(group)
         if world == 1:
             return cls(local, 0, 1)
         if _dist().get_backend(group) != "nccl":   # CPU tests (gloo): the records travel through host memory
@@ -297,6 +304,7 @@ class ShardedKeyValueIndex:
         # the records never leave HBM: dump the local table, group the rows by owner, all-to-all, insert on the owner
         id1, taxon = local.records_dev()
         local.close()
+        torch.cuda.empty_cache()
         owner = torch.empty(max(id1.numel(), 1), dtype=torch.uint8, device=id1.device)
         p = params.c_params()
         check(ctx._L.slk_shard_of_records_dev(ctx.h, C.byref(p), C.c_void_p(id1.data_ptr()), id1.numel(), world,
@@ -307,9 +315,11 @@ class ShardedKeyValueIndex:
         sid = torch.cat([id1[m] for m in masks])
         stx = torch.cat([taxon[m] for m in masks])
         del id1, taxon, owner, masks
+        torch.cuda.empty_cache()
         rid, _ = exchange(sid, counts, group)
         rtx, _ = exchange(stx, counts, group)
         del sid, stx
+        torch.cuda.empty_cache()   # the library allocates its table with cudaMalloc: torch must not sit on freed blocks
         out = cls(KeyValueIndex.from_records_dev(ctx, taxonomy, params, rid, rtx), rank, world)
         del rid, rtx
         torch.cuda.empty_cache()   # the staging tensors must not keep HBM that the classifier's buffers will want
