@@ -59,7 +59,9 @@ def main():
     d_bases = ctx.dev_alloc(per * w.genome_len)
     d_off = ctx.dev_alloc((per + 1) * 8)
     d_tax = ctx.dev_alloc(per * 4)
-    if world > 1:
+    if world > 1:   # NCCL sets its communicators up lazily: not part of the build
+        warm = torch.zeros(world * 4, dtype=torch.int64, device="cuda")
+        dist.all_to_all_single(torch.empty_like(warm), warm)
         dist.barrier()
     ctx.sync()
     t0 = time.perf_counter()
@@ -95,7 +97,8 @@ def main():
             "timing": "host wall clock from the first genome batch to the finished sharded table, genome generation on the "
                       "device included, max over ranks",
             "phases_s": {"local scan + sort + LCA reduce + local table": t_local,
-                         "records to their owners (all-to-all) + insert on the owner": t_all - t_local},
+                         "records to their owners (all-to-all) + insert on the owner": t_all - t_local,
+                         "exchange_breakdown_rank0": ShardedKeyValueIndex.last_build_times},
             "config": {"workload": f"{w.n_genomes} synthetic genomes x {w.genome_len} bp = {w.total_bases / 1e9:.2f} Gbp, "
                                    f"{len(parents)}-node taxonomy, k{w.k}/m{w.m}/s{w.spaces}",
                        "records_before_exchange": int(cnt[0]), "library_records": int(cnt[1]), "records_on_rank0": len(shard)}}),

@@ -233,6 +233,9 @@ SLK_API int slk_shard_of_records(const slk_params* params, const int64_t* id1, u
 /* the same for records that live in device memory (id1 and shard_out are device pointers) */
 SLK_API int slk_shard_of_records_dev(slk_ctx* ctx, const slk_params* params, const int64_t* id1, uint64_t n, uint32_t world,
                                      uint8_t* shard_out);
+/* the records of an index grouped by owner, in DEVICE memory: rows of owner d at [sum(counts_host[0..d)), +counts_host[d]) */
+SLK_API int slk_index_records_by_owner_dev(slk_index* idx, uint32_t world, int64_t* id1_out, int32_t* taxon_out, uint64_t cap,
+                                           uint64_t* counts_host);
 /* the taxa (raw ids, ancestors included) an index can answer with; out == NULL queries the count */
 SLK_API int slk_index_taxa(slk_index* idx, int32_t* out, uint32_t cap, uint32_t* n_out);
 /* the query side's view of the taxonomy: the union of slk_index_taxa over all shards (any order, duplicates allowed) */

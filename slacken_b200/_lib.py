@@ -88,6 +88,7 @@ SIGNATURES = {
     "slk_debug_sort_u64": (_INT, [_VP, _VP, _U64, _INT, _INT]),
     "slk_shard_of_records": (_INT, [_VP, _VP, _U64, _U32, _VP]),
     "slk_shard_of_records_dev": (_INT, [_VP, _VP, _VP, _U64, _U32, _VP]),
+    "slk_index_records_by_owner_dev": (_INT, [_VP, _U32, _VP, _VP, _U64, _VP]),
     "slk_index_taxa": (_INT, [_VP, _VP, _U32, _VP]),
     "slk_resolver_create": (_INT, [_VP, _VP, _VP, _VP, _U32, _PP]),
     "slk_resolver_destroy": (None, [_VP]),

@@ -386,6 +386,68 @@ extern "C" int slk_shard_of_records_dev(slk_ctx* ctx, const slk_params* params, 
   return SLK_OK;
 }
 
+// The export half of the distributed build: the records of a table grouped by the rank that owns their minimizer, in
+// device memory. Pass 1 counts per owner, pass 2 writes (id1, raw taxon) to owner_start[d] + position; a block takes
+// 1024 cells, counts in shared memory and touches the global cursors once per owner.
+#define DUMP_MAX_WORLD 256
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) dump_by_owner_kernel(slk_table_view tb, slk_scan_params sp, const int32_t* __restrict__ raw,
+                                                            uint32_t world, unsigned long long* cursors, int64_t* __restrict__ id1,
+                                                            int32_t* __restrict__ taxon, uint64_t cap) {
+  __shared__ uint32_t s_cnt[DUMP_MAX_WORLD];
+  __shared__ unsigned long long s_base[DUMP_MAX_WORLD];
+  for (uint32_t d = threadIdx.x; d < world; d += 256) s_cnt[d] = 0;
+  __syncthreads();
+  const uint64_t ncell = tb.n_buckets * 4, i0 = (uint64_t)blockIdx.x * 1024;
+  uint64_t cell[4];
+  uint32_t dest[4], pos[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const uint64_t i = i0 + (uint64_t)j * 256 + threadIdx.x;
+    cell[j] = i < ncell ? tb.cells[i] : 0;
+    if (cell[j]) { dest[j] = slk_shard_of(cell[j] >> 16, world); pos[j] = atomicAdd(&s_cnt[dest[j]], 1u); }
+  }
+  __syncthreads();
+  for (uint32_t d = threadIdx.x; d < world; d += 256)
+    if (s_cnt[d]) s_base[d] = atomicAdd(&cursors[d], (unsigned long long)s_cnt[d]);
+  if (!SCATTER) return;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+    if (cell[j]) {
+      const unsigned long long o = s_base[dest[j]] + pos[j];
+      if (o < cap) { id1[o] = (int64_t)slk_expand(sp, cell[j] >> 16); taxon[o] = raw[cell[j] & 0xffffu]; }
+    }
+}
+extern "C" int slk_index_records_by_owner_dev(slk_index* idx, uint32_t world, int64_t* id1_out, int32_t* taxon_out, uint64_t cap,
+                                              uint64_t* counts_host) {
+  if (!idx || !counts_host || world == 0 || world > DUMP_MAX_WORLD) return slk_fail(SLK_E_INVALID, "bad arguments");
+  slk_ctx* ctx = idx->ctx;
+  SLK_CU(cudaSetDevice(ctx->device));
+  for (uint32_t d = 0; d < world; d++) counts_host[d] = 0;
+  if (idx->n_records == 0) return SLK_OK;
+  if (!id1_out || !taxon_out || cap < idx->n_records) return slk_fail(SLK_E_NOSPACE, "records need room for %llu rows", (unsigned long long)idx->n_records);
+  unsigned long long* d_cur = nullptr;
+  SLK_CU(cudaMalloc(&d_cur, (size_t)world * 8));
+  auto done = [&](int rc) { cudaFree(d_cur); return rc; };
+  const uint64_t ncell = idx->table.n_buckets * 4;
+  const unsigned grid = (unsigned)((ncell + 1023) / 1024);
+  std::vector<unsigned long long> cnt(world), start(world);
+  if (cudaMemsetAsync(d_cur, 0, (size_t)world * 8, ctx->stream) != cudaSuccess) return done(slk_fail(SLK_E_CUDA, "memset failed"));
+  dump_by_owner_kernel<false><<<grid, 256, 0, ctx->stream>>>(idx->table, idx->sp, idx->dt.d_raw, world, d_cur, nullptr, nullptr, 0);
+  if (cudaMemcpyAsync(cnt.data(), d_cur, (size_t)world * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+    return done(slk_fail(SLK_E_CUDA, "owner count failed: %s", cudaGetErrorString(cudaGetLastError())));
+  unsigned long long total = 0;
+  for (uint32_t d = 0; d < world; d++) { counts_host[d] = cnt[d]; start[d] = total; total += cnt[d]; }
+  if (total != idx->n_records) return done(slk_fail(SLK_E_CUDA, "table holds %llu records, expected %llu", total, (unsigned long long)idx->n_records));
+  if (cudaMemcpyAsync(d_cur, start.data(), (size_t)world * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+    return done(slk_fail(SLK_E_CUDA, "copy failed"));
+  dump_by_owner_kernel<true><<<grid, 256, 0, ctx->stream>>>(idx->table, idx->sp, idx->dt.d_raw, world, d_cur, id1_out, taxon_out, cap);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return done(slk_fail(SLK_E_CUDA, "record export failed: %s", cudaGetErrorString(cudaGetLastError())));
+  return done(SLK_OK);
+}
+
 // ---------------------------------------------------------------------------------------------- NVLink mailbox
 // The two exchanges of the split path as stores into PEER memory, fused into the kernels on either side of them
 // (no NCCL, no host in the loop): the route kernel groups the keys of a block by owner in shared memory and stores every

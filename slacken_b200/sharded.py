@@ -302,28 +302,37 @@ class ShardedKeyValueIndex:
             rtx, _ = exchange(torch.from_numpy(taxon[order]), counts, group)
             return cls(KeyValueIndex.from_records(ctx, taxonomy, params, rid.numpy(), rtx.numpy()), rank, world)
         # the records never leave HBM: dump the local table, group the rows by owner, all-to-all, insert on the owner
-        id1, taxon = local.records_dev()
+        import time
+        tm, t0 = {}, time.perf_counter()
+
+        def lap(name):
+            nonlocal t0
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            tm[name] = now - t0
+            t0 = now
+        n = len(local)
+        dev = torch.device("cuda", ctx.device)
+        sid = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        stx = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        cnt = (C.c_uint64 * world)()
+        check(ctx._L.slk_index_records_by_owner_dev(local.h, world, C.c_void_p(sid.data_ptr()), C.c_void_p(stx.data_ptr()), n, cnt))
+        counts = [int(c) for c in cnt]
+        sid, stx = sid[:n], stx[:n]
         local.close()
-        torch.cuda.empty_cache()
-        owner = torch.empty(max(id1.numel(), 1), dtype=torch.uint8, device=id1.device)
-        p = params.c_params()
-        check(ctx._L.slk_shard_of_records_dev(ctx.h, C.byref(p), C.c_void_p(id1.data_ptr()), id1.numel(), world,
-                                              C.c_void_p(owner.data_ptr())))
-        owner = owner[:id1.numel()]
-        masks = [owner == r for r in range(world)]
-        counts = [int(m.sum()) for m in masks]
-        sid = torch.cat([id1[m] for m in masks])
-        stx = torch.cat([taxon[m] for m in masks])
-        del id1, taxon, owner, masks
-        torch.cuda.empty_cache()
+        lap("dump_local_table_by_owner")
         rid, _ = exchange(sid, counts, group)
         rtx, _ = exchange(stx, counts, group)
         del sid, stx
-        torch.cuda.empty_cache()   # the library allocates its table with cudaMalloc: torch must not sit on freed blocks
+        lap("all_to_all")
         out = cls(KeyValueIndex.from_records_dev(ctx, taxonomy, params, rid, rtx), rank, world)
         del rid, rtx
         torch.cuda.empty_cache()   # the staging tensors must not keep HBM that the classifier's buffers will want
+        lap("insert_on_owner")
+        cls.last_build_times = tm
         return out
+
+    last_build_times: dict = {}
 
     def taxa(self) -> np.ndarray:
         n = C.c_uint32(0)

@@ -188,4 +188,18 @@ def test_records_stay_on_the_device(gpu):
     pid, ptx = part.records()
     sel = shard_of_records(params, id1, 3) == 1
     assert np.array_equal(pid, id1[sel]) and np.array_equal(ptx, tx[sel])
+    # the export grouped by owner: the rows of owner d are a contiguous range, and each range holds exactly d's records
+    g_id = torch.empty(len(id1), dtype=torch.int64, device=d_id.device)
+    g_tx = torch.empty(len(id1), dtype=torch.int32, device=d_id.device)
+    cnt = (C.c_uint64 * 3)()
+    check(gpu._L.slk_index_records_by_owner_dev(full.h, 3, C.c_void_p(g_id.data_ptr()), C.c_void_p(g_tx.data_ptr()), len(id1), cnt))
+    host_owner = shard_of_records(params, id1, 3)
+    assert [int(c) for c in cnt] == np.bincount(host_owner, minlength=3).tolist()
+    at = 0
+    for d in range(3):
+        rows_id = g_id[at:at + int(cnt[d])].cpu().numpy().view(np.uint64)
+        rows_tx = g_tx[at:at + int(cnt[d])].cpu().numpy()
+        o2 = np.argsort(rows_id, kind="stable")
+        assert np.array_equal(rows_id[o2], id1[host_owner == d]) and np.array_equal(rows_tx[o2], tx[host_owner == d])
+        at += int(cnt[d])
     part.close(); full.close(); tax.close()
