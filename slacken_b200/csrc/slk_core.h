@@ -297,14 +297,35 @@ SLK_HD bool slk_has_ancestor(const slk_tax_view& tx, uint32_t t, uint32_t anc) {
 
 // ------------------------------------------------------------------------------------------------ scanner
 SLK_HD uint64_t slk_min64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+// Minimum of two values below 2^62. The scan is bound by the SM's integer pipe (ncu: ALU pipe 96 % busy, FMA pipe 11 %,
+// profiles/r01_scan_pipes.md), and a 64-bit integer minimum is two compares and two selects there. Bit patterns below
+// 2^62 are non-negative finite doubles whose order is the order of the integers, so ONE compare on the otherwise idle
+// FP64 pipe replaces the two integer compares; the selects stay.
+SLK_HD uint64_t slk_min62(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__) && !defined(SLK_INT_MIN)
+  return __longlong_as_double((long long)a) < __longlong_as_double((long long)b) ? a : b;
+#else
+  return a < b ? a : b;
+#endif
+}
 
-// Rolling m-mer (forward and reverse complement, both left-aligned), its priority, and the minimum over the
-// last W priorities = the minimizer of the k-mer window that ends at the base just pushed (the monotone deque of
-// PosRankWindow.scala:47-74 collapses to this for a fixed, small W; ties do not matter because super-mers merge
-// on equal VALUE, MinSplitter.scala:200-201). The window minimum is kept as suffix minima: sfx[j] = min of the
-// last j+1 priorities, updated in place, so no ring buffer has to be shifted.
+// Rolling m-mer (forward and reverse complement), its priority, and the minimum over the last W priorities = the
+// minimizer of the k-mer window that ends at the base just pushed (the monotone deque of PosRankWindow.scala:47-74
+// collapses to this for a fixed, small W; ties do not matter because super-mers merge on equal VALUE,
+// MinSplitter.scala:200-201). The window minimum is kept as suffix minima: sfx[j] = min of the last j+1 priorities,
+// updated in place, so no ring buffer has to be shifted.
+// Everything here is RIGHT-aligned (the m-mer in bits 2m-1..0, at most 62 bits): the reference's left-aligned priority is
+// this value << (64 - 2m), an order-preserving shift, applied where a minimizer leaves the scan (slk_scan_masks::fshift).
 // Branch-free by design: an invalid character only resets `nvalid`; stale bits in fwd/rc/sfx are flushed by the
 // k valid bases that must follow before the next window is reported.
+struct slk_scan_masks {
+  int fshift;        // left-aligned = right-aligned << fshift
+  int rshift;        // 2m - 2: position of the first base of a right-aligned m-mer
+  uint64_t mmask, xor_mask, sig_mask;   // the masks of slk_scan_params, right-aligned
+  SLK_HD explicit slk_scan_masks(const slk_scan_params& sp)
+      : fshift(sp.fshift), rshift(62 - sp.fshift), mmask(sp.mmask >> sp.fshift), xor_mask(sp.xor_mask >> sp.fshift),
+        sig_mask(sp.sig_mask >> sp.fshift) {}
+};
 template <int W>
 struct slk_scanner {
   uint64_t fwd, rc;
@@ -316,20 +337,21 @@ struct slk_scanner {
 #pragma unroll
     for (int i = 0; i < (W > 1 ? W - 1 : 1); i++) sfx[i] = 0;
   }
-  // c: 0..3 for a base, 4 for anything else. Returns true when a full k-mer window of valid bases ends here.
-  SLK_HD bool push(uint32_t c, uint32_t k, int fshift, uint64_t mmask, uint64_t xor_mask, uint64_t sig_mask,
+  // c: 0..3 for a base, 4 for anything else. Returns true when a full k-mer window of valid bases ends here;
+  // *minv = the window's minimizer, right-aligned.
+  SLK_HD bool push(uint32_t c, uint32_t k, int rshift, uint64_t mmask, uint64_t xor_mask, uint64_t sig_mask,
                    bool canonical, uint64_t* minv) {
     uint32_t b = c & 3u;
-    fwd = (fwd << 2) | ((uint64_t)b << fshift);
-    rc = ((rc >> 2) | ((uint64_t)(b ^ 3u) << 62)) & mmask;
+    fwd = ((fwd << 2) | (uint64_t)b) & mmask;
+    rc = (rc >> 2) | ((uint64_t)(b ^ 3u) << rshift);
     nvalid = c < 4u ? nvalid + 1 : 0;
-    uint64_t x = canonical ? slk_min64(fwd, rc) : fwd;
+    uint64_t x = canonical ? slk_min62(fwd, rc) : fwd;
     x = (x ^ xor_mask) & sig_mask;
     uint64_t mn = x;
     if (W > 1) {
-      mn = slk_min64(x, sfx[W > 1 ? W - 2 : 0]);
+      mn = slk_min62(x, sfx[W > 1 ? W - 2 : 0]);
 #pragma unroll
-      for (int j = W - 2; j >= 1; j--) sfx[j] = slk_min64(x, sfx[j - 1]);
+      for (int j = W - 2; j >= 1; j--) sfx[j] = slk_min62(x, sfx[j - 1]);
       sfx[0] = x;
     }
     *minv = mn;
@@ -567,8 +589,9 @@ struct slk_frag_classifier {
     nh = 0; nh_spilled = 0; nk = 0; overflow = false;
     bool l_spilled = false;
     const uint32_t k = (uint32_t)sp.k, km1 = k - 1;
-    const int fshift = sp.fshift;
-    const uint64_t mmask = sp.mmask, xor_mask = sp.xor_mask, sig_mask = sp.sig_mask;
+    const slk_scan_masks sm(sp);   // right-aligned masks: run keys are right-aligned until the issue pass compresses them
+    const int fshift = sm.fshift, rshift = sm.rshift;
+    const uint64_t mmask = sm.mmask, xor_mask = sm.xor_mask, sig_mask = sm.sig_mask;
     const bool fast = sp.fast_compress != 0;
     const int32_t border_cnt = -(sp.k - 1);
     // upper bound of the merged hits of the fragment (for the sink's spill allocation)
@@ -651,7 +674,7 @@ struct slk_frag_classifier {
 #pragma unroll 2
       for (uint32_t s = lane; s < n_cur; s += SLK_LANES) {
         if ((ent.meta(cur, s) >> 14) == SLK_E_SEQ) {
-          const uint64_t key = ent.key(cur, s);
+          const uint64_t key = ent.key(cur, s) << fshift;
           const uint64_t ck = fast ? slk_compress_fast(key) : slk_compress_generic(sp, key);
           ent.set_key(cur, s, ck);
           ent.fetch(s, tb.cells + slk_bucket_of(ck, tb.n_buckets) * 4);
@@ -729,7 +752,7 @@ struct slk_frag_classifier {
         uint64_t mn = 0;
         if (act) {
           valid = c < 4u;
-          window_ok = sc.push(c, k, fshift, mmask, xor_mask, sig_mask, CANON, &mn);
+          window_ok = sc.push(c, k, rshift, mmask, xor_mask, sig_mask, CANON, &mn);
           ninv = valid ? 0u : ninv + 1u;
         }
         const bool same = in_run && mn == run_key && run_cnt < SLK_E_CNT_MAX;
@@ -753,7 +776,7 @@ struct slk_frag_classifier {
       auto fstep = [&](uint32_t b, bool act) -> bool {
         bool window_ok = false;
         uint64_t mn = 0;
-        if (act) window_ok = sc.push(b, k, fshift, mmask, xor_mask, sig_mask, CANON, &mn);
+        if (act) window_ok = sc.push(b, k, rshift, mmask, xor_mask, sig_mask, CANON, &mn);
         const bool same = in_run && mn == run_key && run_cnt < SLK_E_CNT_MAX;
         const bool start_new = window_ok && !same;
         const bool emit = in_run && start_new;
@@ -906,8 +929,9 @@ struct slk_frag_classifier {
 template <int W, class Emit>
 SLK_HD void slk_scan_spans(const slk_scan_params& sp, const uint8_t* s, uint32_t len, Emit&& emit) {
   const uint32_t k = (uint32_t)sp.k;
-  const int fshift = sp.fshift;
-  const uint64_t mmask = sp.mmask, xor_mask = sp.xor_mask, sig_mask = sp.sig_mask;
+  const slk_scan_masks sm(sp);
+  const int fshift = sm.fshift, rshift = sm.rshift;
+  const uint64_t mmask = sm.mmask, xor_mask = sm.xor_mask, sig_mask = sm.sig_mask;
   const bool canonical = sp.canonical != 0;
   slk_scanner<W> sc;
   sc.reset();
@@ -918,11 +942,11 @@ SLK_HD void slk_scan_spans(const slk_scan_params& sp, const uint8_t* s, uint32_t
     const uint32_t c = slk_code(ch);
     const bool valid = c < 4u;
     uint64_t mn;
-    const bool window_ok = sc.push(c, k, fshift, mmask, xor_mask, sig_mask, canonical, &mn);
+    const bool window_ok = sc.push(c, k, rshift, mmask, xor_mask, sig_mask, canonical, &mn);
     ninv = valid ? 0u : ninv + 1u;
     const bool same = in_run && mn == run_key && run_cnt < SLK_E_CNT_MAX;
     const bool start_new = window_ok && !same;
-    if (in_run && (start_new || !valid)) emit((slk_compress(sp, run_key) << 16) | (SLK_E_SEQ << 14) | run_cnt);
+    if (in_run && (start_new || !valid)) emit((slk_compress(sp, run_key << fshift) << 16) | (SLK_E_SEQ << 14) | run_cnt);
     if (amb_cnt != 0 && (valid || amb_cnt == SLK_E_CNT_MAX)) { emit((uint64_t)((SLK_E_AMB << 14) | amb_cnt)); amb_cnt = 0; }
     amb_cnt = valid ? 0u : amb_cnt;
     amb_cnt += (!valid && ninv >= k) ? 1u : 0u;
@@ -930,7 +954,7 @@ SLK_HD void slk_scan_spans(const slk_scan_params& sp, const uint8_t* s, uint32_t
     run_key = start_new ? mn : run_key;
     in_run = valid && (in_run || start_new);
   });
-  if (in_run) emit((slk_compress(sp, run_key) << 16) | (SLK_E_SEQ << 14) | run_cnt);
+  if (in_run) emit((slk_compress(sp, run_key << fshift) << 16) | (SLK_E_SEQ << 14) | run_cnt);
   if (amb_cnt) emit((uint64_t)((SLK_E_AMB << 14) | amb_cnt));
 }
 // ... of a fragment: mate 1, the MATE_PAIR_BORDER pseudo-span, mate 2 (slacken/Supermers.scala:49-97)
@@ -1045,8 +1069,9 @@ struct slk_bhit {      // TaxonHit (slacken/package.scala) of a genome fragment
 template <int W, class Emit>
 SLK_HD void slk_bracken_scan(const slk_scan_params& sp, const uint8_t* s, uint32_t len, Emit&& emit) {
   const uint32_t k = (uint32_t)sp.k;
-  const int fshift = sp.fshift;
-  const uint64_t mmask = sp.mmask, xor_mask = sp.xor_mask, sig_mask = sp.sig_mask;
+  const slk_scan_masks sm(sp);
+  const int fshift = sm.fshift, rshift = sm.rshift;
+  const uint64_t mmask = sm.mmask, xor_mask = sm.xor_mask, sig_mask = sm.sig_mask;
   const bool canonical = sp.canonical != 0;
   slk_scanner<W> sc;
   sc.reset();
@@ -1059,7 +1084,7 @@ SLK_HD void slk_bracken_scan(const slk_scan_params& sp, const uint8_t* s, uint32
   };
   auto seq_hit = [&]() {
     slk_bhit h;
-    h.key = slk_compress(sp, run_key); h.ordinal = run_ord; h.count = run_cnt; h.taxon = 0;
+    h.key = slk_compress(sp, run_key << fshift); h.ordinal = run_ord; h.count = run_cnt; h.taxon = 0;
     h.flags = SLK_BHIT_SEQ | ((first || run_key != last_key) ? SLK_BHIT_DISTINCT : 0u);
     first = false; last_key = run_key;
     emit(h);
@@ -1080,7 +1105,7 @@ SLK_HD void slk_bracken_scan(const slk_scan_params& sp, const uint8_t* s, uint32
     if (!have_piece) { have_piece = true; piece_valid = valid; piece_start = i; }
     else if (valid != piece_valid) { close_piece(i); piece_valid = valid; piece_start = i; }
     uint64_t mn;
-    const bool window_ok = sc.push(c, k, fshift, mmask, xor_mask, sig_mask, canonical, &mn);
+    const bool window_ok = sc.push(c, k, rshift, mmask, xor_mask, sig_mask, canonical, &mn);
     if (window_ok) {
       if (!(in_run && mn == run_key)) {
         if (in_run) seq_hit();
@@ -1194,17 +1219,18 @@ SLK_HD void slk_emit_cells(const slk_scan_params& sp, const uint8_t* s, uint64_t
   slk_scanner<W> sc;
   sc.reset();
   const uint32_t k = (uint32_t)sp.k;
-  const int fshift = sp.fshift;
-  const uint64_t mmask = sp.mmask, xor_mask = sp.xor_mask, sig_mask = sp.sig_mask;
+  const slk_scan_masks sm(sp);
+  const int fshift = sm.fshift, rshift = sm.rshift;
+  const uint64_t mmask = sm.mmask, xor_mask = sm.xor_mask, sig_mask = sm.sig_mask;
   const bool canonical = sp.canonical != 0;
   uint64_t run_key = 0;
   bool in_run = false;
   slk_for_each_byte(s, nbases, [&](uint32_t ch) {
     const uint32_t c = slk_code(ch);
     uint64_t mn;
-    const bool window_ok = sc.push(c, k, fshift, mmask, xor_mask, sig_mask, canonical, &mn);
+    const bool window_ok = sc.push(c, k, rshift, mmask, xor_mask, sig_mask, canonical, &mn);
     if (window_ok && (!in_run || mn != run_key)) {
-      out((slk_compress(sp, mn) << 16) | dense_taxon);
+      out((slk_compress(sp, mn << fshift) << 16) | dense_taxon);
       run_key = mn;
     }
     in_run = window_ok;
