@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--mailbox", action="store_true",
                     help="exchange keys and taxa through the NVLink mailbox (peer-memory stores from the kernels) instead of NCCL")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="with --mailbox: scan batch e+1 while the exchange of batch e is in flight (classify_pipelined)")
     args = ap.parse_args()
 
     import torch
@@ -107,17 +109,23 @@ def main():
         return cls.classify_uploaded(d_reads, d_off, None, None, n, confidence=0.15, min_hit_groups=w.min_hit_groups,
                                      per_read_output=False)
 
-    for _ in range(args.warmup):
-        got = step()
+    def run(k):
+        if not (args.pipeline and args.mailbox):
+            for _ in range(k):
+                out = step()
+            return out
+        out = None
+        for out in cls.classify_pipelined([(d_reads, d_off, None, None, n)] * k, confidence=0.15, min_hit_groups=w.min_hit_groups,
+                                          per_read_output=False):
+            pass
+        return out
+
+    got = run(args.warmup)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        got = step()
-    e1.record()
+    got = run(args.steps)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     if world > 1:
@@ -145,6 +153,7 @@ def main():
             "metric": "reads/sec classified (150bp), library sharded by minimizer hash range", "value": world * n * args.steps / wall,
             "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
             "exchange": "NVLink mailbox (peer-memory stores fused into the route and lookup kernels)" if args.mailbox else "NCCL all-to-all",
+            "pipelined": bool(args.pipeline and args.mailbox),
             "timing": "host wall clock around the collective classify_uploaded() calls (reads resident in HBM: scan, route, two "
                       "exchanges, probe, resolve, D2H of taxon and flags), max over ranks",
             "step_breakdown_rank0_s": cls.last_times,

@@ -283,6 +283,9 @@ SLK_API int slk_mailbox_connect(slk_mailbox* m, const uint8_t* handles);
 /* one process driving every rank (ranks may even share a device): connects the mailboxes by pointer */
 SLK_API int slk_mailbox_connect_local(slk_mailbox* const* boxes, uint32_t world);
 SLK_API void slk_mailbox_destroy(slk_mailbox* m);
+/* occupancy of the lookup kernels (256-thread blocks per SM, 1..8, default 8); a caller that overlaps the span scan of
+ * the next batch (slk_scan_spans_dev has its own stream) sets 4 */
+SLK_API int slk_mailbox_set_blocks_per_sm(slk_mailbox* m, uint32_t blocks_per_sm);
 SLK_API int slk_mailbox_route(slk_mailbox* m, const uint64_t* spans, uint64_t n_spans);
 SLK_API int slk_mailbox_probe(slk_mailbox* m, slk_index* idx);
 SLK_API int slk_mailbox_resolve(slk_mailbox* m, slk_resolver* r, const slk_classify_opts* opts, const uint64_t* spans,

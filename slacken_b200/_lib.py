@@ -103,6 +103,7 @@ SIGNATURES = {
     "slk_mailbox_connect": (_INT, [_VP, _VP]),
     "slk_mailbox_connect_local": (_INT, [_PP, _U32]),
     "slk_mailbox_destroy": (None, [_VP]),
+    "slk_mailbox_set_blocks_per_sm": (_INT, [_VP, _U32]),
     "slk_mailbox_route": (_INT, [_VP, _VP, _U64]),
     "slk_mailbox_probe": (_INT, [_VP, _VP]),
     "slk_mailbox_resolve": (_INT, [_VP, _VP, _VP, _VP, _VP, _U64, _U32, _INT, _VP, _VP, _VP, _VP]),

@@ -121,6 +121,7 @@ extern "C" int slk_ctx_create(int device, slk_ctx** out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->scan_stream, cudaStreamNonBlocking));
   // The probes are random 32-byte sectors: ask L2 to fetch single sectors from HBM instead of the default 64 bytes.
   if (!getenv("SLK_L2_FETCH_DEFAULT")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
   cudaGetLastError();
@@ -131,6 +132,7 @@ extern "C" void slk_ctx_destroy(slk_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->scan_stream);
   cudaFree(c->span_scratch); cudaFree(c->d_maxlen);
   delete c;
 }

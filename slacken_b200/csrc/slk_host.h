@@ -13,6 +13,8 @@ struct slk_ctx {
   int device;
   int sm_count;
   cudaStream_t stream;
+  cudaStream_t scan_stream;   // slk_scan_spans_dev / slk_emit_spans_dev (synchronous calls) run here, so that a caller may
+                              // scan the next batch while the mailbox kernels of the current one are still in flight
   // split path, one-pass scan: the span words of the last count-only slk_scan_spans_dev call, `stride` slots per
   // fragment, waiting for slk_emit_spans_dev to compact them (grow-only scratch owned by the context)
   uint64_t* span_scratch = nullptr;

@@ -204,21 +204,21 @@ extern "C" int slk_scan_spans_dev(slk_ctx* ctx, const slk_params* params, const 
   int rc = slk_make_scan_params_checked(params, &a.sp);
   if (rc != SLK_OK) return rc;
   *n_spans_host = 0;
-  SLK_CU(cudaMemsetAsync(span_off, 0, ((size_t)n_reads + 1) * 8, ctx->stream));
-  if (n_reads == 0) { SLK_CU(cudaStreamSynchronize(ctx->stream)); return SLK_OK; }
+  SLK_CU(cudaMemsetAsync(span_off, 0, ((size_t)n_reads + 1) * 8, ctx->scan_stream));
+  if (n_reads == 0) { SLK_CU(cudaStreamSynchronize(ctx->scan_stream)); return SLK_OK; }
   a.bases1 = bases1; a.off1 = off1; a.bases2 = bases2; a.off2 = off2; a.n_reads = n_reads;
-  a.span_off = span_off; a.spans = nullptr; a.stream = ctx->stream;
+  a.span_off = span_off; a.spans = nullptr; a.stream = ctx->scan_stream;
   ctx->pending_spans.valid = false;
   // A count-only call that slk_emit_spans_dev will follow: scan ONCE, into rows of the context's scratch, when the rows
   // of this batch (one slot per k-mer window of its longest reads) fit a bounded scratch; otherwise count now, scan again later.
   bool strided = false;
   if (!spans && !getenv("SLK_SPANS_TWO_PASS")) {
     if (!ctx->d_maxlen) SLK_CU(cudaMalloc(&ctx->d_maxlen, 12));
-    SLK_CU(cudaMemsetAsync(ctx->d_maxlen, 0, 12, ctx->stream));
-    max_len_kernel<<<(n_reads + 255) / 256, 256, 0, ctx->stream>>>(off1, off2, n_reads, ctx->d_maxlen);
+    SLK_CU(cudaMemsetAsync(ctx->d_maxlen, 0, 12, ctx->scan_stream));
+    max_len_kernel<<<(n_reads + 255) / 256, 256, 0, ctx->scan_stream>>>(off1, off2, n_reads, ctx->d_maxlen);
     uint32_t ml[2] = {0, 0};
-    SLK_CU(cudaMemcpyAsync(ml, ctx->d_maxlen, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    SLK_CU(cudaStreamSynchronize(ctx->stream));
+    SLK_CU(cudaMemcpyAsync(ml, ctx->d_maxlen, 8, cudaMemcpyDeviceToHost, ctx->scan_stream));
+    SLK_CU(cudaStreamSynchronize(ctx->scan_stream));
     const uint64_t k = (uint64_t)a.sp.k;
     const uint64_t stride = (ml[0] >= k ? ml[0] - k + 1 : 0) + (bases2 ? 1 + (ml[1] >= k ? ml[1] - k + 1 : 0) : 0) + 1;
     const uint64_t words = stride * (uint64_t)n_reads;
@@ -239,14 +239,16 @@ extern "C" int slk_scan_spans_dev(slk_ctx* ctx, const slk_params* params, const 
   }
   SLK_DISPATCH_SPANS(a.sp.w, a);
   SLK_CU(cudaGetLastError());
-  int e = slk_exclusive_scan_u64(span_off, (uint64_t)n_reads + 1, ctx->stream);
+  int e = slk_exclusive_scan_u64(span_off, (uint64_t)n_reads + 1, ctx->scan_stream);
   if (e != 0) return slk_fail(SLK_E_CUDA, "prefix sum of the span counts failed (%d)", e);
   uint64_t total = 0;
-  SLK_CU(cudaMemcpy(&total, span_off + n_reads, 8, cudaMemcpyDeviceToHost));
+  SLK_CU(cudaMemcpyAsync(&total, span_off + n_reads, 8, cudaMemcpyDeviceToHost, ctx->scan_stream));
+  SLK_CU(cudaStreamSynchronize(ctx->scan_stream));
   *n_spans_host = total;
   if (strided) {
     uint32_t over = 0;
-    SLK_CU(cudaMemcpy(&over, ctx->d_maxlen + 2, 4, cudaMemcpyDeviceToHost));
+    SLK_CU(cudaMemcpyAsync(&over, ctx->d_maxlen + 2, 4, cudaMemcpyDeviceToHost, ctx->scan_stream));
+    SLK_CU(cudaStreamSynchronize(ctx->scan_stream));
     if (!over) {   // (never expected: the stride is an upper bound; if it were exceeded the emit call simply scans again)
       ctx->pending_spans.bases1 = bases1; ctx->pending_spans.off1 = off1; ctx->pending_spans.bases2 = bases2; ctx->pending_spans.off2 = off2;
       ctx->pending_spans.span_off = span_off; ctx->pending_spans.n_reads = n_reads; ctx->pending_spans.stride = a.stride;
@@ -258,7 +260,7 @@ extern "C" int slk_scan_spans_dev(slk_ctx* ctx, const slk_params* params, const 
   a.spans = spans;
   SLK_DISPATCH_SPANS(a.sp.w, a);
   SLK_CU(cudaGetLastError());
-  SLK_CU(cudaStreamSynchronize(ctx->stream));
+  SLK_CU(cudaStreamSynchronize(ctx->scan_stream));
   return SLK_OK;
 }
 // second half of slk_scan_spans_dev for a caller that asked for the count first: span_off is what that call left
@@ -273,10 +275,10 @@ extern "C" int slk_emit_spans_dev(slk_ctx* ctx, const slk_params* params, const 
   if (pd.valid && pd.bases1 == bases1 && pd.off1 == off1 && pd.bases2 == bases2 && pd.off2 == off2 && pd.span_off == span_off &&
       pd.n_reads == n_reads) {   // the count-only call already scanned: only move the rows together
     pd.valid = false;
-    compact_spans_kernel<<<(unsigned)(((uint64_t)n_reads * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->span_scratch, pd.stride, span_off,
+    compact_spans_kernel<<<(unsigned)(((uint64_t)n_reads * 32 + 255) / 256), 256, 0, ctx->scan_stream>>>(ctx->span_scratch, pd.stride, span_off,
                                                                                                     n_reads, spans);
     SLK_CU(cudaGetLastError());
-    SLK_CU(cudaStreamSynchronize(ctx->stream));
+    SLK_CU(cudaStreamSynchronize(ctx->scan_stream));
     return SLK_OK;
   }
   pd.valid = false;
@@ -284,10 +286,10 @@ extern "C" int slk_emit_spans_dev(slk_ctx* ctx, const slk_params* params, const 
   int rc = slk_make_scan_params_checked(params, &a.sp);
   if (rc != SLK_OK) return rc;
   a.bases1 = bases1; a.off1 = off1; a.bases2 = bases2; a.off2 = off2; a.n_reads = n_reads;
-  a.span_off = const_cast<uint64_t*>(span_off); a.spans = spans; a.stream = ctx->stream;
+  a.span_off = const_cast<uint64_t*>(span_off); a.spans = spans; a.stream = ctx->scan_stream;
   SLK_DISPATCH_SPANS(a.sp.w, a);
   SLK_CU(cudaGetLastError());
-  SLK_CU(cudaStreamSynchronize(ctx->stream));
+  SLK_CU(cudaStreamSynchronize(ctx->scan_stream));
   return SLK_OK;
 }
 
@@ -482,6 +484,7 @@ struct slk_mailbox {
   uint32_t* d_err = nullptr;               // bit 0: inbox overflow, bit 1: a peer timed out, bit 2: bad taxon / overflow of taxa
   uint16_t* d_dense = nullptr; uint64_t dense_cap = 0;
   uint32_t epoch = 0;
+  uint32_t blocks_per_sm = 8;              // size of the lookup / unroute grids (slk_mailbox_set_blocks_per_sm)
   bool connected = false;
 };
 
@@ -658,7 +661,10 @@ extern "C" int slk_mailbox_create(slk_ctx* ctx, uint32_t rank, uint32_t world, u
 }
 // one wave of 256-thread blocks over the whole chip (8 per SM), shared out evenly among the peers
 static uint32_t mbx_blocks_per_peer(const slk_mailbox* m) {
-  const uint32_t per = (uint32_t)(m->ctx->sm_count * 8) / m->world;
+  // SLK_MBX_BLOCKS_PER_SM (1..8) overrides the mailbox's own setting (tuning runs)
+  static const int env_per_sm = [] { const char* e = getenv("SLK_MBX_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v < 0 ? 0 : v > 8 ? 8 : v; }();
+  const uint32_t per_sm = env_per_sm ? (uint32_t)env_per_sm : m->blocks_per_sm;
+  const uint32_t per = (uint32_t)m->ctx->sm_count * per_sm / m->world;
   const uint32_t most = (uint32_t)((m->cap + 255) / 256);
   return std::max(1u, std::min(per, most));
 }
@@ -713,6 +719,13 @@ extern "C" void slk_mailbox_destroy(slk_mailbox* m) {
     if (m->opened[r] && m->peer[r]) cudaIpcCloseMemHandle(m->peer[r]);
   cudaFree(m->base); cudaFree(m->d_peer); cudaFree(m->d_send_idx); cudaFree(m->d_cursors); cudaFree(m->d_err); cudaFree(m->d_dense);
   delete m;
+}
+// 256-thread blocks per SM of the lookup and unroute kernels (1..8, default 8 = every thread slot). A caller that scans
+// the next batch meanwhile (slk_scan_spans_dev runs on its own stream) leaves room for it: measured best at 4.
+extern "C" int slk_mailbox_set_blocks_per_sm(slk_mailbox* m, uint32_t blocks_per_sm) {
+  if (!m || blocks_per_sm < 1 || blocks_per_sm > 8) return slk_fail(SLK_E_INVALID, "blocks per SM must be 1..8");
+  m->blocks_per_sm = blocks_per_sm;
+  return SLK_OK;
 }
 // step 1 (asynchronous): this rank's sequence-span keys go to their owners' inboxes
 extern "C" int slk_mailbox_route(slk_mailbox* m, const uint64_t* spans, uint64_t n_spans) {

@@ -401,6 +401,7 @@ class ShardedClassifier:
         span_off, spans, n_spans = ops.scan_spans(d_b1, d_o1, d_b2, d_o2, n)
         lap("scan")
         if self.mailbox is not None:
+            check(ops._L.slk_mailbox_set_blocks_per_sm(self.mailbox.h, 8))
             self.mailbox_route(spans, n_spans)
             self.mailbox_probe()
             out = self.mailbox_resolve(spans, span_off, n_spans, n, paired, confidence, min_hit_groups, per_read_output)
@@ -420,6 +421,27 @@ class ShardedClassifier:
         lap("resolve_and_download")
         self.last_times = tm
         return out
+
+    def classify_pipelined(self, batches, confidence: float = 0.0, min_hit_groups: int = 2, per_read_output: bool = True):
+        """Generator over the results of a sequence of uploaded batches (tuples d_b1, d_o1, d_b2, d_o2, n), mailbox only.
+        The span scan of batch e+1 runs (on the library's scan stream) while the mailbox kernels of batch e are in flight:
+        the scan is bound by the integer pipe, the exchange by HBM and NVLink. Collective: every rank passes the same
+        number of batches. A result is valid until the next one is produced (pinned buffers)."""
+        assert self.mailbox is not None, "the pipelined path needs the NVLink mailbox"
+        ops = self.ops
+        check(ops._L.slk_mailbox_set_blocks_per_sm(self.mailbox.h, 4))   # leave half of every SM to the overlapping scan
+        it = iter(batches)
+        cur = next(it, None)
+        scanned = ops.scan_spans(*cur) if cur is not None else None
+        while cur is not None:
+            span_off, spans, n_spans = scanned
+            self.mailbox_route(spans, n_spans)
+            self.mailbox_probe()
+            nxt = next(it, None)
+            scanned_next = ops.scan_spans(*nxt) if nxt is not None else None   # overlaps with the exchange of `cur`
+            yield self.mailbox_resolve(spans, span_off, n_spans, cur[4], cur[2] is not None, confidence, min_hit_groups,
+                                       per_read_output)
+            cur, scanned = nxt, scanned_next
 
     # the three mailbox steps, separately (a single process driving several ranks interleaves them: tests)
     def mailbox_route(self, spans, n_spans: int):

@@ -203,3 +203,31 @@ def test_records_stay_on_the_device(gpu):
         assert np.array_equal(rows_id[o2], id1[host_owner == d]) and np.array_equal(rows_tx[o2], tx[host_owner == d])
         at += int(cnt[d])
     part.close(); full.close(); tax.close()
+
+
+def test_pipelined_batches_through_the_mailbox(gpu):
+    """classify_pipelined: the scan of the next batch overlaps the exchange of the current one; results per batch must
+    still equal the oracle's (one rank, three batches of different sizes, one of them paired, one empty)."""
+    from slacken_b200.sharded import Mailbox
+    rng, genomes, olib, id1, tx, tax = _world(gpu, 47)
+    shard = ShardedKeyValueIndex.from_records(gpu, tax, IndexParams(), id1, tx, rank=0, world=1)
+    cls = ShardedClassifier(shard, mailbox=Mailbox(gpu, 0, 1, 200000), taxa_union=np.unique(tx))
+    sets = [simulate_reads(rng, genomes, 1200, (30, 220), n_rate=0.1), simulate_reads(rng, genomes, 700, (30, 220)), [],
+            simulate_reads(rng, genomes, 900, (30, 220), n_rate=0.05)]
+    mates = [None, simulate_reads(rng, genomes, 700, (30, 220)), None, None]
+    host, dev = [], []
+    for reads, m in zip(sets, mates):
+        rb, ro = pack_sequences(reads)
+        mb, mo = pack_sequences(m) if m is not None else (None, None)
+        host.append((rb, ro, mb, mo))
+        up = cls.ops.upload
+        dev.append((up(rb if len(rb) else np.zeros(16, np.uint8)), up(ro.view(np.int64)),
+                    up(mb) if m is not None else None, up(mo.view(np.int64)) if m is not None else None, len(reads)))
+    n_out = 0
+    for (rb, ro, mb, mo), got in zip(host, cls.classify_pipelined(dev, confidence=0.1)):
+        if len(ro) > 1:
+            res, _, _, per = olib.classify(rb, ro.astype(np.int64), mb, mo.astype(np.int64) if mo is not None else None, confidence=0.1)
+            assert_batch_equal(res, per, got, 35)
+        n_out += 1
+    assert n_out == len(sets)
+    cls.close(); shard.close(); tax.close()
