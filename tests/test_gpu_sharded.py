@@ -231,3 +231,36 @@ def test_pipelined_batches_through_the_mailbox(gpu):
         n_out += 1
     assert n_out == len(sets)
     cls.close(); shard.close(); tax.close()
+
+
+def test_span_scan_one_pass_and_two_pass_agree(gpu, monkeypatch):
+    """slk_scan_spans_dev + slk_emit_spans_dev: the one-pass scan (rows of a scratch, then compaction), the two-pass scan
+    forced by the environment, and the two-pass scan a very long read falls back to give the same span words."""
+    from tests.util import chimeric_reads
+    rng, genomes, olib, id1, tx, tax = _world(gpu, 59)
+    shard = ShardedKeyValueIndex.from_records(gpu, tax, IndexParams(), id1, tx, rank=0, world=1)
+    ops = GpuSplitOps(shard.index, np.unique(tx))
+    reads = simulate_reads(rng, genomes, 1500, (10, 300), n_rate=0.15) + [b"", b"ACGT", b"N" * 90]
+    mates = simulate_reads(rng, genomes, len(reads), (10, 300), n_rate=0.15)
+    rb, ro = pack_sequences(reads)
+    mb, mo = pack_sequences(mates)
+    d = [ops.upload(rb), ops.upload(ro.view(np.int64)), ops.upload(mb), ops.upload(mo.view(np.int64))]
+    for paired in (False, True):
+        args = (d[0], d[1], d[2] if paired else None, d[3] if paired else None, len(reads))
+        monkeypatch.delenv("SLK_SPANS_TWO_PASS", raising=False)
+        off1, spans1, n1 = ops.scan_spans(*args)
+        monkeypatch.setenv("SLK_SPANS_TWO_PASS", "1")
+        off2, spans2, n2 = ops.scan_spans(*args)
+        assert n1 == n2 and n1 > 10000
+        assert np.array_equal(off1.cpu().numpy(), off2.cpu().numpy())
+        assert np.array_equal(spans1.cpu().numpy()[:n1], spans2.cpu().numpy()[:n2])
+    monkeypatch.delenv("SLK_SPANS_TWO_PASS", raising=False)
+    # one read of 6000 bases makes the rows too long for the scratch: the call falls back to two passes by itself
+    long_reads = reads[:200] + chimeric_reads(rng, genomes, 1, 80, (70, 80))
+    assert max(len(r) for r in long_reads) > 4200
+    lb, lo = pack_sequences(long_reads)
+    cls = ShardedClassifier(shard)
+    got = cls.classify(lb, lo, confidence=0.05)
+    res, _, _, per = olib.classify(lb, lo.astype(np.int64), confidence=0.05)
+    assert_batch_equal(res, per, got, 35)
+    ops.close(); cls.close(); shard.close(); tax.close()
