@@ -306,6 +306,8 @@ SLK_API int slk_bracken_weights(slk_index* idx, const uint8_t* bases, const uint
 
 /* test hook: the library's radix sort (K3a) on a host array, bits [begin_bit, end_bit), stable */
 SLK_API int slk_debug_sort_u64(slk_ctx* ctx, uint64_t* keys, uint64_t n, int begin_bit, int end_bit);
+/* test hook: out[i] = the scan's minimum of a[i] and b[i] (values below 2^62, compared on the FP64 pipe); host arrays */
+SLK_API int slk_debug_min62(slk_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t* out);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,7 @@ SIGNATURES = {
     "slk_memcpy_h2d": (_INT, [_VP, _VP, _VP, C.c_size_t]),
     "slk_memcpy_d2h": (_INT, [_VP, _VP, _VP, C.c_size_t]),
     "slk_debug_sort_u64": (_INT, [_VP, _VP, _U64, _INT, _INT]),
+    "slk_debug_min62": (_INT, [_VP, _VP, _VP, _U64, _VP]),
     "slk_shard_of_records": (_INT, [_VP, _VP, _U64, _U32, _VP]),
     "slk_shard_of_records_dev": (_INT, [_VP, _VP, _VP, _U64, _U32, _VP]),
     "slk_index_records_by_owner_dev": (_INT, [_VP, _U32, _VP, _VP, _U64, _VP]),

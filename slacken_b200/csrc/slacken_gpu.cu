@@ -981,6 +981,29 @@ extern "C" int slk_debug_sort_u64(slk_ctx* ctx, uint64_t* keys, uint64_t n, int 
   if (rc != 0) return fail(SLK_E_CUDA, "radix sort failed (%d)", rc);
   return SLK_OK;
 }
+// test hook: the scan's 64-bit minimum (one FP64-pipe compare on the device, slk_min62) on host arrays of values < 2^62
+__global__ void __launch_bounds__(256) debug_min62_kernel(const uint64_t* __restrict__ a, const uint64_t* __restrict__ b, uint64_t n,
+                                                          uint64_t* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = slk_min62(a[i], b[i]);
+}
+extern "C" int slk_debug_min62(slk_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t* out) {
+  if (!ctx || (n && (!a || !b || !out))) return fail(SLK_E_INVALID, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  if (n == 0) return SLK_OK;
+  uint64_t *da = nullptr, *db = nullptr, *dout = nullptr;
+  CU(cudaMalloc(&da, n * 8)); CU(cudaMalloc(&db, n * 8)); CU(cudaMalloc(&dout, n * 8));
+  cudaError_t e = cudaMemcpy(da, a, n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(db, b, n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    debug_min62_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(da, db, n, dout);
+    e = cudaStreamSynchronize(ctx->stream);
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost);
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  if (e != cudaSuccess) return fail(SLK_E_CUDA, "slk_debug_min62 failed: %s", cudaGetErrorString(e));
+  return SLK_OK;
+}
 extern "C" int slk_memcpy_d2d(slk_ctx* c, void* dst, const void* src, size_t bytes) {
   CU(cudaSetDevice(c->device));
   CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));

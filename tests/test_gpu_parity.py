@@ -322,3 +322,27 @@ def test_tiny_batches(gpu, n):
             got = cls.classify_packed(*pk, confidence=0.1)
             assert_batch_equal(res, per, got, 35)
     cls.close(); index.close(); tax.close()
+
+
+def test_fp64_pipe_minimum_is_the_integer_minimum(gpu):
+    """slk_min62 (slk_core.h): the scanner compares right-aligned priorities (< 2^62) as doubles on the device. Every
+    bit pattern below 2^62 is a non-negative finite double (zero, subnormal or normal), so the result must equal the
+    unsigned integer minimum, bit for bit: edge values, neighbours, and random pairs over every magnitude."""
+    import ctypes as C
+    from slacken_b200._lib import check
+    rng = np.random.default_rng(5)
+    edge = [0, 1, 2, 3, (1 << 52) - 1, 1 << 52, (1 << 52) + 1, (1 << 53) - 1, 1 << 53, (1 << 61) - 1, 1 << 61, (1 << 62) - 1,
+            0x000fffffffffffff, 0x0010000000000000, 0x3fefffffffffffff, 0x3ff0000000000000, 0x3fffffffffffffff]
+    a = [x for x in edge for _ in edge]
+    b = [y for _ in edge for y in edge]
+    for bits in range(1, 63):   # random pairs of every magnitude, and pairs that differ only in low / only in high bits
+        x = rng.integers(0, 1 << bits, size=400, dtype=np.uint64)
+        y = rng.integers(0, 1 << bits, size=400, dtype=np.uint64)
+        a += x.tolist(); b += y.tolist()
+        a += x.tolist(); b += (x ^ np.uint64(1)).tolist()
+        a += x.tolist(); b += (x ^ (np.uint64(1) << np.uint64(bits - 1))).tolist()
+    a, b = np.array(a, dtype=np.uint64), np.array(b, dtype=np.uint64)
+    out = np.zeros(len(a), dtype=np.uint64)
+    v = lambda z: z.ctypes.data_as(C.c_void_p)
+    check(gpu._L.slk_debug_min62(gpu.h, v(a), v(b), len(a), v(out)))
+    assert np.array_equal(out, np.minimum(a, b))
