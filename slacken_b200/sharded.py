@@ -357,7 +357,9 @@ class ShardedClassifier:
         """mailbox_cap > 0 (or a ready-made mailbox): the exchanges go through the NVLink mailbox instead of NCCL;
         mailbox_cap = room for the keys this rank sends to ONE owner per batch (about spans per batch / world, plus slack)."""
         self.group = group
-        self.rank, self.world = world_of(group) if shard is None or mailbox is None else (shard.rank, shard.world)
+        # a ready-made mailbox means the caller drives the ranks itself (one process, several ranks: the tests): the
+        # shard knows its place; otherwise the process group does
+        self.rank, self.world = (mailbox.rank, mailbox.world) if mailbox is not None else world_of(group)
         taxa = taxa_union if taxa_union is not None else union_of_taxa(shard.taxa() if shard is not None else local_taxa, group)
         self.ops = ops(taxa) if ops is not None else GpuSplitOps(shard.index, taxa)
         self.mailbox = mailbox
