@@ -651,8 +651,40 @@ struct slk_frag_classifier {
       any = any || cnt_cur != 0;
       const uint32_t prev = cur ^ ent_tile0 ^ ent_tile1;
       SLK_SYNCWARP();   // the entries other lanes appended are visible
-      ent.wait_all(n_commits & 1u);
       uint32_t n_pend = 0;
+#if defined(__CUDA_ARCH__) && defined(SLK_SYNC_FETCH)
+      // Plain loads instead of asynchronous copies: a stream of cp.async gathers that miss to DRAM blocks the SM's
+      // shared-memory path for every other warp (tools/probe_microbench5.cu: shared-memory work next to 33 G/s of
+      // cp.async gathers runs 6-10x slower, next to the same rate of ld.global.nc gathers not at all). Each lane loads
+      // the buckets of SLK_SYNC_FETCH of its entries into registers, then matches them; the warp waits for DRAM once
+      // per batch while the other warps of the SM scan.
+      for (uint32_t s0 = 0; s0 < n_prev; s0 += SLK_SYNC_FETCH * SLK_LANES) {
+        slk_bucket bks[SLK_SYNC_FETCH];
+        uint64_t cks[SLK_SYNC_FETCH];
+        bool sq[SLK_SYNC_FETCH];
+#pragma unroll
+        for (int j = 0; j < SLK_SYNC_FETCH; j++) {
+          const uint32_t s = s0 + (uint32_t)j * SLK_LANES + lane;
+          sq[j] = s < n_prev && (ent.meta(prev, s) >> 14) == SLK_E_SEQ;
+          cks[j] = 0; bks[j].c0 = 0; bks[j].c1 = 0; bks[j].c2 = 0; bks[j].c3 = 0;
+          if (sq[j]) { cks[j] = ent.key(prev, s); slk_load_bucket(tb, slk_bucket_of(cks[j], tb.n_buckets), &bks[j]); }
+        }
+#pragma unroll
+        for (int j = 0; j < SLK_SYNC_FETCH; j++) {
+          const uint32_t s = s0 + (uint32_t)j * SLK_LANES + lane;
+          bool pend = false;
+          if (sq[j]) {
+            uint32_t dense;
+            pend = !slk_match_bucket(bks[j], cks[j], &dense);
+            if (!pend) ent.set_key(prev, s, cks[j] | ((uint64_t)dense << 48));
+          }
+          const uint32_t bal = SLK_BALLOT(pend);
+          if (pend) ent.set_pending(prev, n_pend + SLK_POPC(bal & lanes_below), s);
+          n_pend += SLK_POPC(bal);
+        }
+      }
+#else
+      ent.wait_all(n_commits & 1u);
 #pragma unroll 2
       for (uint32_t s0 = 0; s0 < n_prev; s0 += SLK_LANES) {
         const uint32_t s = s0 + lane;
@@ -669,6 +701,7 @@ struct slk_frag_classifier {
         if (pend) ent.set_pending(prev, n_pend + SLK_POPC(bal & lanes_below), s);
         n_pend += SLK_POPC(bal);
       }
+#endif
       SLK_SYNCWARP();   // the pending list is complete, and nobody reads the staging area any more
       uint32_t n_fetched = 0;
 #pragma unroll 2
@@ -677,11 +710,15 @@ struct slk_frag_classifier {
           const uint64_t key = ent.key(cur, s) << fshift;
           const uint64_t ck = fast ? slk_compress_fast(key) : slk_compress_generic(sp, key);
           ent.set_key(cur, s, ck);
+#if !(defined(__CUDA_ARCH__) && defined(SLK_SYNC_FETCH))
           ent.fetch(s, tb.cells + slk_bucket_of(ck, tb.n_buckets) * 4);
+#endif
           n_fetched++;
         }
       }
+#if !(defined(__CUDA_ARCH__) && defined(SLK_SYNC_FETCH))
       ent.commit(n_fetched);
+#endif
       n_commits++;
       for (uint32_t q = lane; q < n_pend; q += SLK_LANES) {
         const uint32_t s = ent.pending(prev, q);
