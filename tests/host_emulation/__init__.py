@@ -9,7 +9,9 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libslk_emu.so")
+# SLK_EMU_DEFS="-DSLK_DRIP" builds (and loads) the emulation of a kernel variant next to the default one
+_DEFS = os.environ.get("SLK_EMU_DEFS", "").split()
+_SO = os.path.join(_HERE, "libslk_emu" + "".join(d.replace("-D", "_").replace("=", "") for d in _DEFS) + ".so")
 _CORE = os.path.join(_HERE, "..", "..", "slacken_b200", "csrc", "slk_core.h")
 BUILD_WPT = 96
 
@@ -32,8 +34,8 @@ def lib():
         src = os.path.join(_HERE, "emu.cpp")
         newest = max(os.path.getmtime(src), os.path.getmtime(_CORE))
         if not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
-            subprocess.check_call(["/usr/bin/g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
-                                   "-o", _SO, src])
+            subprocess.check_call(["/usr/bin/g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden"] + _DEFS +
+                                  ["-o", _SO, src])
         L = C.CDLL(_SO)
         assert L.emu_sizeof_scan_params() == C.sizeof(ScanParams), "ScanParams mirror out of date"
         L.emu_scan_params.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(ScanParams)]
