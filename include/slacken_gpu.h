@@ -247,7 +247,10 @@ SLK_API void slk_resolver_destroy(slk_resolver* r);
 SLK_API int slk_scan_spans_dev(slk_ctx* ctx, const slk_params* params, const uint8_t* bases1, const uint64_t* off1,
                                const uint8_t* bases2, const uint64_t* off2, uint32_t n_reads, uint64_t* span_off,
                                uint64_t* spans, uint64_t cap, uint64_t* n_spans_host);
-/* the emit half alone, after a count-only call of slk_scan_spans_dev (span_off as that call left it) */
+/* the emit half alone, after a count-only call of slk_scan_spans_dev (span_off as that call left it). When the reads of
+ * the batch are short enough the count-only call has already scanned them into a scratch owned by the context and this
+ * call only compacts the rows (one scan instead of two); a (count, emit) pair on one slk_ctx must therefore not be
+ * interleaved with another pair on the same slk_ctx from a second thread: give every scanning thread its own context. */
 SLK_API int slk_emit_spans_dev(slk_ctx* ctx, const slk_params* params, const uint8_t* bases1, const uint64_t* off1,
                                const uint8_t* bases2, const uint64_t* off2, uint32_t n_reads, const uint64_t* span_off,
                                uint64_t* spans);
