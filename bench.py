@@ -78,6 +78,9 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+KERNEL_NAME = "classify_kernel<5,true,true>"
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -122,7 +125,7 @@ def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
-    threads = oracle.max_threads()
+    threads = oracle.set_threads(oracle.host_threads())   # torchrun exports OMP_NUM_THREADS=1: not what this arm runs on
     parents, ranks, names, genome_taxa = bw.taxonomy(w)
     log(f"[reference] building the {w.total_bases/1e9:.2f} Gbp library on {threads} host threads ...")
     lib, tb = cpu_library(w, oracle, parents, genome_taxa, threads)
@@ -179,6 +182,42 @@ def build_gpu_library(ctx, tax, params, w, genome_taxa):
     return index, dt
 
 
+def compare_with_oracle(res, o_off, o_hits, out, sample, n_taxa):
+    """Everything the reference's output line and report are made of, read by read, on the first `sample` reads of a batch:
+    taxon, classified / has-span flags, hit groups, both length fields, the merged hit list, and the per-taxon report counts
+    of the sample (slacken/Classifier.scala:39-45,214-217)."""
+    hs = res["has_span"].astype(bool)
+    d = out.detail[:sample]
+    l2 = d["len2"].astype(np.int64)
+    l2[l2 == 0xFFFFFFFF] = -1
+    chk = {
+        "taxon": bool(np.array_equal(res["taxon"], out.taxon[:sample])),
+        "classified": bool(np.array_equal(res["classified"].astype(bool), (out.flags[:sample] & 1) != 0)),
+        "has_span": bool(np.array_equal(hs, (out.flags[:sample] & 2) != 0)),
+        "num_distinct": bool(np.array_equal(res["num_distinct"][hs], d["num_distinct"][hs].astype(np.int32))),
+        "len1": bool(np.array_equal(res["len1"][hs], d["len1"][hs].astype(np.int32))),
+        "len2": bool(np.array_equal(res["len2"][hs], l2[hs])),
+    }
+    cnt = res["n_hits"].astype(np.int64)
+    chk["hit_counts"] = bool(np.array_equal(cnt, d["hit_cnt"].astype(np.int64)))
+    if chk["hit_counts"]:
+        tot = int(cnt.sum())
+        within = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        gi = np.repeat(d["hit_off"].astype(np.int64), cnt) + within
+        oi = np.repeat(o_off[:sample].astype(np.int64), cnt) + within
+        chk["merged_hits"] = bool(np.array_equal(out.hits["taxon"][gi], o_hits["taxon"][oi]) and
+                                  np.array_equal(out.hits["count"][gi], o_hits["count"][oi]))
+        chk["merged_hits_compared"] = tot
+    else:
+        chk["merged_hits"] = False
+    rep_o = np.bincount(res["taxon"][hs], minlength=n_taxa)
+    ghs = (out.flags[:sample] & 2) != 0
+    rep_g = np.bincount(out.taxon[:sample][ghs], minlength=n_taxa)
+    chk["report_counts"] = bool(np.array_equal(rep_o, rep_g))
+    chk["all"] = all(v for k, v in chk.items() if isinstance(v, bool))
+    return chk
+
+
 def run_ours(args, w):
     import ctypes as C
     from slacken_b200 import Classifier, DeviceTimer, GpuContext, IndexParams, ReportCounts, Taxonomy
@@ -224,24 +263,50 @@ def run_ours(args, w):
     # this rank's shard of reads (weak scaling: every GPU classifies n_reads reads of its own)
     n, L = w.n_reads, w.read_len
     first = rank * n
-    d_reads = ctx.dev_alloc(n * L)
-    check(ctx._L.slk_synth_reads_dev(ctx.h, w.gseed, w.rseed, w.n_genomes, w.genome_len, first, n, L, C.c_void_p(d_reads)))
     off = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
-    d_off = ctx.dev_alloc(off.nbytes)
-    ctx.h2d(d_off, off)
-    # stage 1 on the device: the same reads as 2-bit packed blocks + ambiguity masks (the input form the north star names)
     boff = block_offsets(off)
     n_blocks = int(boff[-1])
-    d_boff, d_codes, d_mask, d_len = ctx.dev_alloc(boff.nbytes), ctx.dev_alloc(n_blocks * 8), ctx.dev_alloc(n_blocks * 4), ctx.dev_alloc(n * 4)
+    d_off, d_boff = ctx.dev_alloc(off.nbytes), ctx.dev_alloc(boff.nbytes)
+    ctx.h2d(d_off, off)
     ctx.h2d(d_boff, boff)
-    ctx.pack_reads_dev(d_reads, d_off, n, d_boff, d_codes, d_mask, d_len)
-    t0 = time.perf_counter()
-    ctx.pack_reads_dev(d_reads, d_off, n, d_boff, d_codes, d_mask, d_len)
-    t_pack = time.perf_counter() - t0
+
+    class Mate:   # one mate of the batch resident in HBM, ASCII and packed (stage 1 on the device)
+        def __init__(self, mate):
+            self.reads = ctx.dev_alloc(n * L)
+            check(ctx._L.slk_synth_mates_dev(ctx.h, w.gseed, w.rseed, w.n_genomes, w.genome_len, first, n, L, mate, C.c_void_p(self.reads)))
+            self.codes, self.mask, self.len = ctx.dev_alloc(n_blocks * 8), ctx.dev_alloc(n_blocks * 4), ctx.dev_alloc(n * 4)
+            ctx.pack_reads_dev(self.reads, d_off, n, d_boff, self.codes, self.mask, self.len)
+
+        def host_packed(self):
+            hp = PackedReads(ctx.pinned(n_blocks, np.uint64), ctx.pinned(n_blocks, np.uint32), ctx.pinned(n + 1, np.uint64), ctx.pinned(n, np.uint32))
+            ctx.d2h(hp.codes, self.codes); ctx.d2h(hp.mask, self.mask); ctx.d2h(hp.len, self.len)
+            hp.boff[:] = boff
+            return hp
+
+        def free(self):
+            for p in (self.reads, self.codes, self.mask, self.len):
+                ctx.dev_free(p)
+
+    m1 = Mate(0)
+    # stage 1 alone, timed with CUDA events on the stream it runs on
+    ev = [C.c_void_p(), C.c_void_p()]
+    for e in ev:
+        check(ctx._L.slk_event_create(ctx.h, C.byref(e)))
+    pack_reps = 5
+    check(ctx._L.slk_event_record_ctx(ev[0], ctx.h))
+    for _ in range(pack_reps):
+        ctx.pack_reads_dev(m1.reads, d_off, n, d_boff, m1.codes, m1.mask, m1.len)
+    check(ctx._L.slk_event_record_ctx(ev[1], ctx.h))
+    ms_pack = C.c_float()
+    check(ctx._L.slk_event_elapsed_ms(ev[0], ev[1], C.byref(ms_pack)))
+    t_pack = ms_pack.value / 1e3 / pack_reps
+    for e in ev:
+        ctx._L.slk_event_destroy(e)
+
     cls = Classifier(index)
     counts = ReportCounts(ctx, tax, 1)
     cls.attach_counts(counts, 0)
-    hits_cap = cls.hits_bound(n, n * L, False)
+    hits_cap = cls.hits_bound(n, 2 * n * L, True)
     d_taxon, d_flags = ctx.dev_alloc(n * 4), ctx.dev_alloc(n)
     d_detail, d_hits, d_used = ctx.dev_alloc(n * DETAIL_DTYPE.itemsize), ctx.dev_alloc(hits_cap * 8), ctx.dev_alloc(8)
 
@@ -253,89 +318,37 @@ def run_ours(args, w):
             __cuda_array_interface__ = {"shape": (tax.size,), "typestr": "<i8", "data": (counts.device_ptr(), False), "version": 2}
         counts_t = torch.as_tensor(_Wrap(), device=f"cuda:{local}")
 
-    def device_step_ascii():
-        cls.classify_dev(d_reads, d_off, 0, 0, n, d_taxon, d_flags, d_detail, d_hits, hits_cap, d_used,
-                         confidence=w.confidence, min_hit_groups=w.min_hit_groups)
-
-    def device_step():
-        cls.classify_packed_dev(d_codes, d_mask, d_boff, d_len, 0, 0, 0, 0, n, d_taxon, d_flags, d_detail, d_hits, hits_cap,
-                                d_used, confidence=w.confidence, min_hit_groups=w.min_hit_groups)
-
     sampler = ClockSampler(local)
     sampler.start()
-    # ---- value: inputs resident in HBM, CUDA events on the launch stream
-    for _ in range(args.warmup):
-        device_step()
-    cls.sync()
-    p0, h0 = cls.stats()
-    l0 = cls.launches
-    counts.reset()
-    timer = DeviceTimer(cls)
-    barrier()
-    tw0 = time.perf_counter()
-    timer.start()
-    for _ in range(args.steps):
-        device_step()
-    timer.stop()
-    ms = timer.elapsed_ms()
-    if counts_t is not None:   # report aggregation across ranks: one all-reduce of the counter vector
-        import torch
-        t_ar = time.perf_counter()
-        dist.all_reduce(counts_t)
-        torch.cuda.synchronize()
-        ms += 1e3 * (time.perf_counter() - t_ar)
-    barrier()
-    tw1 = time.perf_counter()
-    ms = max_over_ranks(ms)
-    p1, h1 = cls.stats()
-    launches = cls.launches - l0
-    probes_per_read = (p1 - p0) / (args.steps * n)
-    hits_per_read = (h1 - h0) / (args.steps * n)
-    clocks = ClockSampler.summarize(sampler.window(tw0, tw1))
-    value = world * n * args.steps / (ms / 1e3)
-    used = np.zeros(1, dtype=np.uint64)
-    ctx.d2h(used, d_used)
-    assert int(used[0]) <= hits_cap
-    rep = counts.fetch(0)
-    total_reads_counted = int(rep.sum())
 
-    # roofline of the dominant (only) kernel of the step: the fused classify kernel
-    S, H = probes_per_read, hits_per_read
-    bytes_per_read = 12.0 * n_blocks / n + 8 + 4 + 32.0 * S + (4 + 1 + 24) + 8.0 * H   # packed input
-    achieved = bytes_per_read * n * args.steps / (ms / 1e3) / 1e9 / 1.0  # per GPU: every rank runs the same launch
-    peak, peak_src = measured_peak()
-    # the same launch on ASCII-resident input (stage 1 fused into the kernel), for comparison
-    for _ in range(2):
-        device_step_ascii()
-    cls.sync()
-    t_a = DeviceTimer(cls)
-    t_a.start()
-    for _ in range(args.steps):
-        device_step_ascii()
-    t_a.stop()
-    ms_ascii = max_over_ranks(t_a.elapsed_ms())
-    cls.attach_counts(None)
-    roofline = {"bound": "hbm", "kernel": "classify_kernel<5,true,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": measured_traffic(args, n),
-                "algorithmic_bytes_per_launch": bytes_per_read * n,
-                "bytes_per_read": bytes_per_read, "probes_per_read": S, "merged_hits_per_read": H,
-                "probe_sectors_gbs": 32.0 * S * n * args.steps / (ms / 1e3) / 1e9,
-                "lookups_per_s": S * n * args.steps / (ms / 1e3),
-                "frac_of_measured_request_ceiling": S * n * args.steps / (ms / 1e3) / 42.8e9,
-                "random_gather_ceiling": "a random 32-byte sector costs the B200 a whole 128-byte DRAM line, and the chip serves at most ~43 G "
-                                         "random line requests/s to a plain lookup kernel (profiles/r01_probe_microbench.md, DESIGN.md section 3): "
-                                         "one random sector per lookup cannot exceed ~0.21 of the copy-bandwidth roofline"}
-
-    # ---- e2e: the host-buffer entry point, pinned host memory, H2D + D2H inside the timed region
-    h_reads = ctx.pinned(n * L, np.uint8)
-    ctx.d2h(h_reads, d_reads)
-    h_off = ctx.pinned(n + 1, np.uint64)
-    h_off[:] = off
-    e2e_cap = 16 * n
-    out = ClassifiedBatch(ctx.pinned(n, np.int32), ctx.pinned(n, np.uint8), ctx.pinned(n, DETAIL_DTYPE), ctx.pinned(e2e_cap, HIT_DTYPE))
-    hp = PackedReads(ctx.pinned(n_blocks, np.uint64), ctx.pinned(n_blocks, np.uint32), ctx.pinned(n + 1, np.uint64), ctx.pinned(n, np.uint32))
-    ctx.d2h(hp.codes, d_codes); ctx.d2h(hp.mask, d_mask); ctx.d2h(hp.len, d_len)
-    hp.boff[:] = boff
+    def timed_device(step_fn, steps, warmup):
+        """`steps` launches timed with CUDA events on the launch stream, plus the report all-reduce; max over ranks."""
+        for _ in range(warmup):
+            step_fn()
+        cls.sync()
+        p0, h0 = cls.stats()
+        l0 = cls.launches
+        counts.reset()
+        timer = DeviceTimer(cls)
+        barrier()
+        tw0 = time.perf_counter()
+        timer.start()
+        for _ in range(steps):
+            step_fn()
+        timer.stop()
+        ms = timer.elapsed_ms()
+        if counts_t is not None:   # report aggregation across ranks: one all-reduce of the counter vector
+            import torch
+            t_ar = time.perf_counter()
+            dist.all_reduce(counts_t)
+            torch.cuda.synchronize()
+            ms += 1e3 * (time.perf_counter() - t_ar)
+        barrier()
+        tw1 = time.perf_counter()
+        ms = max_over_ranks(ms)
+        p1, h1 = cls.stats()
+        return {"ms": ms, "launches": cls.launches - l0, "S": (p1 - p0) / (steps * n), "H": (h1 - h0) / (steps * n),
+                "clocks": ClockSampler.summarize(sampler.window(tw0, tw1))}
 
     def timed_e2e(fn):
         for _ in range(max(1, min(args.warmup, 2))):
@@ -348,23 +361,101 @@ def run_ours(args, w):
         barrier()
         return max_over_ranks(dt), t0, time.perf_counter()
 
-    e2e_s, te0, te1 = timed_e2e(lambda: cls.classify_packed(hp, confidence=w.confidence, min_hit_groups=w.min_hit_groups, out=out))
-    clocks_e2e = ClockSampler.summarize(sampler.window(te0, te1))
-    e2e = {"value": world * n * args.steps / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": int(hp.nbytes),
-           "d2h_bytes_per_step": int(out.taxon.nbytes + out.flags.nbytes + out.detail.nbytes + out.hits_used * 8),
-           "ms_per_step": 1e3 * e2e_s / args.steps,
-           "api": "slk_classify_batch_packed: pinned HOST buffers holding 2-bit packed reads + ambiguity masks (the host-side "
-                  "packing is the Scala driver's batching work and is outside the timed region), per-read hit lists on",
-           "clocks": clocks_e2e}
-    r_s, _, _ = timed_e2e(lambda: cls.classify_packed(hp, confidence=w.confidence, min_hit_groups=w.min_hit_groups,
-                                                      per_read_output=False, out=out))
-    e2e_report = {"value": world * n * args.steps / r_s, "unit": "reads/s", "h2d_bytes_per_step": int(hp.nbytes),
-                  "d2h_bytes_per_step": int(out.taxon.nbytes + out.flags.nbytes + out.detail.nbytes), "ms_per_step": 1e3 * r_s / args.steps,
-                  "api": "slk_classify_batch_packed without per-read hit lists (the reference's --nodetailed mode, "
-                         "slacken/Classifier.scala:259-410): taxon, flags and lengths per read come back, no hits"}
-    a_s, _, _ = timed_e2e(lambda: cls.classify(h_reads, h_off, confidence=w.confidence, min_hit_groups=w.min_hit_groups, out=out))
-    e2e_ascii = {"value": world * n * args.steps / a_s, "unit": "reads/s", "h2d_bytes_per_step": int(h_reads.nbytes + h_off.nbytes),
-                 "ms_per_step": 1e3 * a_s / args.steps, "api": "slk_classify_batch: pinned HOST buffers holding ASCII reads"}
+    # ================================================================== leg 1: configs[1], single-end, confidence 0.0
+    def device_step():
+        cls.classify_packed_dev(m1.codes, m1.mask, d_boff, m1.len, 0, 0, 0, 0, n, d_taxon, d_flags, d_detail, d_hits, hits_cap,
+                                d_used, confidence=w.confidence, min_hit_groups=w.min_hit_groups)
+
+    def device_step_ascii():
+        cls.classify_dev(m1.reads, d_off, 0, 0, n, d_taxon, d_flags, d_detail, d_hits, hits_cap, d_used,
+                         confidence=w.confidence, min_hit_groups=w.min_hit_groups)
+
+    r = timed_device(device_step, args.steps, args.warmup)
+    ms, S, H, launches, clocks = r["ms"], r["S"], r["H"], r["launches"], r["clocks"]
+    value = world * n * args.steps / (ms / 1e3)
+    used = np.zeros(1, dtype=np.uint64)
+    ctx.d2h(used, d_used)
+    assert int(used[0]) <= hits_cap
+    rep = counts.fetch(0)
+    total_reads_counted = int(rep.sum())
+    # the device counters against the per-read results of the last launch, at full size
+    h_taxon_full, h_flags_full = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.uint8)
+    ctx.d2h(h_taxon_full, d_taxon); ctx.d2h(h_flags_full, d_flags)
+    rep_one = np.bincount(h_taxon_full[(h_flags_full & 2) != 0], minlength=tax.size)
+    report_consistent = bool(world > 1 or np.array_equal(rep_one * args.steps, rep))
+
+    # roofline of the dominant (only) kernel of the step: the fused classify kernel
+    bytes_per_read = 12.0 * n_blocks / n + 8 + 4 + 32.0 * S + (4 + 1 + 24) + 8.0 * H   # packed input
+    achieved = bytes_per_read * n * args.steps / (ms / 1e3) / 1e9   # per GPU: every rank runs the same launch
+    peak, peak_src = measured_peak()
+    ms_ascii = timed_device(device_step_ascii, args.steps, 2)["ms"]
+    roofline = {"bound": "hbm", "kernel": KERNEL_NAME, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": measured_traffic(args, n),
+                "algorithmic_bytes_per_launch": bytes_per_read * n,
+                "bytes_per_read": bytes_per_read, "probes_per_read": S, "merged_hits_per_read": H,
+                "probe_sectors_gbs": 32.0 * S * n * args.steps / (ms / 1e3) / 1e9,
+                "lookups_per_s": S * n * args.steps / (ms / 1e3),
+                "frac_of_measured_request_ceiling": S * n * args.steps / (ms / 1e3) / 42.8e9,
+                "random_gather_ceiling": "a random 32-byte sector costs the B200 a whole 128-byte DRAM line, and the chip serves at most ~43 G "
+                                         "random line requests/s to a plain lookup kernel (profiles/r01_probe_microbench.md, DESIGN.md section 3): "
+                                         "one random sector per lookup cannot exceed ~0.21 of the copy-bandwidth roofline"}
+
+    # ---- e2e: the host-buffer entry point, pinned host memory, H2D + D2H inside the timed region
+    h_reads = ctx.pinned(n * L, np.uint8)
+    ctx.d2h(h_reads, m1.reads)
+    h_off = ctx.pinned(n + 1, np.uint64)
+    h_off[:] = off
+    e2e_cap = 24 * n
+    out = ClassifiedBatch(ctx.pinned(n, np.int32), ctx.pinned(n, np.uint8), ctx.pinned(n, DETAIL_DTYPE), ctx.pinned(e2e_cap, HIT_DTYPE))
+    hp1 = m1.host_packed()
+
+    def e2e_line(fn, h2d_bytes, hits, api):
+        s, t0, t1 = timed_e2e(fn)
+        d2h = int(out.taxon.nbytes + out.flags.nbytes + out.detail.nbytes + (out.hits_used * 8 if hits else 0))
+        return {"value": world * n * args.steps / s, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * s / args.steps, "api": api, "clocks": ClockSampler.summarize(sampler.window(t0, t1))}
+
+    e2e_report = e2e_line(lambda: cls.classify_packed(hp1, confidence=w.confidence, min_hit_groups=w.min_hit_groups, per_read_output=False, out=out),
+                          hp1.nbytes, False,
+                          "slk_classify_batch_packed without per-read hit lists (the reference's --nodetailed mode, "
+                          "slacken/Classifier.scala:259-410): taxon, flags and lengths per read come back, no hits")
+    e2e_ascii = e2e_line(lambda: cls.classify(h_reads, h_off, confidence=w.confidence, min_hit_groups=w.min_hit_groups, out=out),
+                         h_reads.nbytes + h_off.nbytes, True, "slk_classify_batch: pinned HOST buffers holding ASCII reads")
+    e2e = e2e_line(lambda: cls.classify_packed(hp1, confidence=w.confidence, min_hit_groups=w.min_hit_groups, out=out), hp1.nbytes, True,
+                   "slk_classify_batch_packed: pinned HOST buffers holding 2-bit packed reads + ambiguity masks (the host-side "
+                   "packing is the Scala driver's batching work and is outside the timed region), per-read hit lists on")
+    # `out` now holds the single-end results of the whole batch (the CPU leg below checks a sample of them)
+    single_out = ClassifiedBatch(out.taxon.copy(), out.flags.copy(), out.detail.copy(), out.hits[:out.hits_used].copy(), out.hits_used)
+
+    # ================================================================== leg 2: configs[3] shape, paired-end 2 x 150 bp, confidence 0.15
+    m2 = Mate(1)
+    pc = args.paired_confidence
+
+    def paired_step():
+        cls.classify_packed_dev(m1.codes, m1.mask, d_boff, m1.len, m2.codes, m2.mask, d_boff, m2.len, n, d_taxon, d_flags, d_detail,
+                                d_hits, hits_cap, d_used, confidence=pc, min_hit_groups=w.min_hit_groups)
+
+    psteps = max(1, args.steps // 2)
+    rp = timed_device(paired_step, psteps, min(args.warmup, 2))
+    ctx.d2h(used, d_used)
+    assert int(used[0]) <= hits_cap
+    hp2 = m2.host_packed()
+    steps_keep = args.steps
+    args.steps = psteps
+    paired_e2e = e2e_line(lambda: cls.classify_packed(hp1, hp2, confidence=pc, min_hit_groups=w.min_hit_groups, out=out),
+                          hp1.nbytes + hp2.nbytes, True, "slk_classify_batch_packed, both mates, per-read hit lists on")
+    args.steps = steps_keep
+    p_bytes = 2 * 12.0 * n_blocks / n + 2 * (8 + 4) + 32.0 * rp["S"] + (4 + 1 + 24) + 8.0 * rp["H"]
+    paired = {"metric": "read pairs/sec classified (2 x 150bp)", "value": world * n * psteps / (rp["ms"] / 1e3), "unit": "pairs/s",
+              "steps": psteps, "ms_per_step": rp["ms"] / psteps, "confidence": pc, "pairs_per_gpu_per_step": n,
+              "workload": f"synthetic {n} read pairs (2 x {L} bp: mate 2 from the same genome 250 bases on, opposite strand) vs the same "
+                          f"{w.total_bases/1e9:.2f} Gbp library, confidence {pc} -- the per-GPU shape of BASELINE.json configs[3]; its "
+                          "70 Gbp library does not fit one GPU replicated (22.9 G records), see the sharded leg",
+              "probes_per_pair": rp["S"], "merged_hits_per_pair": rp["H"], "lookups_per_s": rp["S"] * n * psteps / (rp["ms"] / 1e3),
+              "roofline_frac": p_bytes * n * psteps / (rp["ms"] / 1e3) / 1e9 / peak,
+              "frac_of_measured_request_ceiling": rp["S"] * n * psteps / (rp["ms"] / 1e3) / 42.8e9,
+              "gpu_launches": int(rp["launches"]), "clocks": rp["clocks"], "e2e": paired_e2e}
+    cls.attach_counts(None)
     sampler.stop()
 
     line = {"metric": "reads/sec classified (150bp)", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
@@ -374,20 +465,22 @@ def run_ours(args, w):
                        "library": "replicated per GPU", "input": "2-bit packed reads + ambiguity mask (72 B/read)", "l2": "inputs (reads 1.5 GB + table) are far larger than L2; no flush needed",
                        "host_cpus_bound_to_gpu_numa_node": len(numa_cpus),
                        "classified_fraction": float((rep.sum() - rep[0]) / max(1, rep.sum())),
-                       "reads_counted_in_report": total_reads_counted},
+                       "reads_counted_in_report": total_reads_counted,
+                       "device_report_counters_equal_per_read_results": report_consistent},
             "probes_per_s": value * S, "clocks": clocks, "e2e": e2e, "e2e_report_only": e2e_report, "e2e_ascii_input": e2e_ascii,
             "value_ascii_input": {"value": world * n * args.steps / (ms_ascii / 1e3), "unit": "reads/s", "ms_per_step": ms_ascii / args.steps,
-                                  "note": "same launch with ASCII reads resident in HBM (stage 1 fused into the kernel)"},
+                                  "note": "same launch with ASCII reads resident in HBM (stage 1 runs first as its own kernel)"},
             "encode_kernel": {"ms": 1e3 * t_pack, "reads_per_s": n / t_pack, "gbs": (L + 8 + 12.0 * n_blocks / n + 4) * n / t_pack / 1e9,
-                              "note": "stage 1 alone (pack_reads_kernel: ASCII -> 2-bit blocks + mask), wall clock around a synchronous call"},
-            "gpu_launches": int(launches), "roofline": roofline,
+                              "frac_of_hbm_peak": (L + 8 + 12.0 * n_blocks / n + 4) * n / t_pack / 1e9 / peak,
+                              "note": f"stage 1 alone (pack_reads_kernel: ASCII -> 2-bit blocks + mask), CUDA events on its stream, mean of {pack_reps} launches"},
+            "gpu_launches": int(launches), "roofline": roofline, "paired": paired,
             "build": {"seconds": t_build, "gbases_per_s": w.total_bases / t_build / 1e9, "records": len(index)}}
 
-    # ---- cpu_baseline: the oracle on the host cores, bounded sample, rank 0 at N=1 only
+    # ---- cpu_baseline: the oracle on the host cores, bounded sample, rank 0 at N=1 only; checks BOTH legs read by read
     if world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)   # the CPU leg gets every host core again
         from oracle import oracle
-        threads = oracle.max_threads()
+        threads = oracle.set_threads(len(all_cpus))
         t0 = time.perf_counter()
         id1, tx = index.records(sort=False)
         olib = oracle.Library(oracle.params(k=w.k, m=w.m, spaces=w.spaces), parents, len(id1))
@@ -397,18 +490,184 @@ def run_ours(args, w):
         sample = min(n, args.cpu_sample)
         o64 = off[:sample + 1].astype(np.int64)
         t0 = time.perf_counter()
-        res, _, _, _ = olib.classify(h_reads[:sample * L], o64, confidence=w.confidence, min_hit_groups=w.min_hit_groups,
-                                     threads=threads, with_hits=True)
+        res, o_off, o_hits, _ = olib.classify(h_reads[:sample * L], o64, confidence=w.confidence, min_hit_groups=w.min_hit_groups,
+                                              threads=threads, with_hits=True, lists=False)
         dt = time.perf_counter() - t0
-        same = bool(np.array_equal(res["taxon"], out.taxon[:sample]))
+        chk = compare_with_oracle(res, o_off, o_hits, single_out, sample, tax.size)
         line["cpu_baseline"] = {"value": sample / dt, "unit": "reads/s", "cores": threads, "kind": "port",
                                 "sample": f"first {sample} reads of the same batch, {dt:.1f} s; library = the {len(olib)} records "
                                           f"of the GPU build loaded into the oracle's CPU table in {t_lib:.0f} s",
-                                "taxa_equal_to_gpu_on_sample": same}
+                                "taxa_equal_to_gpu_on_sample": chk["taxon"], "equal_to_gpu_on_sample": chk}
+        psample = min(n, args.cpu_sample // 2)
+        h_reads2 = np.zeros(psample * L, dtype=np.uint8)
+        ctx.d2h(h_reads2, m2.reads)   # copies the first psample * L bytes
+        po = off[:psample + 1].astype(np.int64)
+        t0 = time.perf_counter()
+        res, o_off, o_hits, _ = olib.classify(h_reads[:psample * L], po, h_reads2, po, confidence=pc, min_hit_groups=w.min_hit_groups,
+                                              threads=threads, with_hits=True, lists=False)
+        dtp = time.perf_counter() - t0
+        chk2 = compare_with_oracle(res, o_off, o_hits, out, psample, tax.size)   # `out` holds the paired e2e results
+        line["paired"]["cpu_baseline"] = {"value": psample / dtp, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                          "sample": f"first {psample} pairs of the same batch, {dtp:.1f} s", "equal_to_gpu_on_sample": chk2}
+        del olib
+    # ---- N > 1: the sharded-library path and the distributed build, on the same JSON line
+    if world > 1 and not args.no_sharded:
+        line["sharded"] = sharded_leg(args, w, ctx, tax, params, index, cls, m1, d_off, n, L, genome_taxa, rank, world, dist)
+    m1.free(); m2.free()
+    for p in (d_taxon, d_flags, d_detail, d_hits, d_used, d_off, d_boff):
+        ctx.dev_free(p)
+    cls.close()
+    counts.close()
+    index.close()
+    if world > 1 and not args.no_sharded:
+        line["dist_build"] = dist_build_leg(args, w, ctx, tax, params, genome_taxa, rank, world, dist)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+class _DevView:
+    """Zero-copy torch view of raw device memory owned by the library."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def sharded_leg(args, w, ctx, tax, params, index, cls, m1, d_off, n, L, genome_taxa, rank, world, dist):
+    """BASELINE.json configs[4] shape inside the driver's run: the SAME library sharded over the N GPUs by minimizer hash
+    range (every rank keeps the records it owns), every rank classifies its own reads, span keys and taxa travel through the
+    NVLink mailbox (peer-memory stores fused into the route / lookup kernels), scan of batch e+1 overlapped with the exchange
+    of batch e. Checked on every rank against the fused kernel on the replicated library."""
+    import ctypes as C
+    import torch
+    from slacken_b200 import KeyValueIndex
+    from slacken_b200._lib import check
+    from slacken_b200.sharded import ShardedClassifier, ShardedKeyValueIndex
+    dev = torch.device("cuda", ctx.device)
+    sr = min(n, args.sharded_reads)
+    conf = args.paired_confidence
+    # this rank's shard of the replicated index
+    nrec = len(index)
+    sid = torch.empty(nrec, dtype=torch.int64, device=dev)
+    stx = torch.empty(nrec, dtype=torch.int32, device=dev)
+    cnt = (C.c_uint64 * world)()
+    torch.cuda.synchronize()
+    check(ctx._L.slk_index_records_by_owner_dev(index.h, world, C.c_void_p(sid.data_ptr()), C.c_void_p(stx.data_ptr()), nrec, cnt))
+    lo = sum(int(c) for c in cnt[:rank])
+    mine = int(cnt[rank])
+    shard = ShardedKeyValueIndex(KeyValueIndex.from_records_dev(ctx, tax, params, sid[lo:lo + mine].clone(), stx[lo:lo + mine].clone()), rank, world)
+    del sid, stx
+    torch.cuda.empty_cache()
+    cap = int(sr * 44 / world * 1.25) + 65536
+    scl = ShardedClassifier(shard, mailbox_cap=cap)
+    d_b = torch.as_tensor(_DevView(m1.reads, sr * L, "|u1"), device=dev)
+    d_o = torch.as_tensor(_DevView(d_off, sr + 1, "<i8"), device=dev)
+
+    def run(k):
+        out = None
+        for out in scl.classify_pipelined([(d_b, d_o, None, None, sr)] * k, confidence=conf, min_hit_groups=w.min_hit_groups,
+                                          per_read_output=False):
+            pass
+        return out
+
+    steps = max(2, args.steps // 2)
+    got = run(2)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    got = run(steps)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    dist.barrier()
+    t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall = float(t.item())
+    s_taxon, s_flags = got.taxon.copy(), got.flags.copy()
+    # the same reads through the fused kernel on the replicated library
+    d_t, d_f = ctx.dev_alloc(sr * 4), ctx.dev_alloc(sr)
+    cls.classify_dev(m1.reads, d_off, 0, 0, sr, d_t, d_f, 0, 0, 0, 0, confidence=conf, min_hit_groups=w.min_hit_groups)
+    cls.sync()
+    r_taxon, r_flags = np.zeros(sr, dtype=np.int32), np.zeros(sr, dtype=np.uint8)
+    ctx.d2h(r_taxon, d_t); ctx.d2h(r_flags, d_f)
+    ctx.dev_free(d_t); ctx.dev_free(d_f)
+    same = torch.tensor([1 if (np.array_equal(r_taxon, s_taxon) and np.array_equal(r_flags, s_flags)) else 0], dtype=torch.int64, device="cuda")
+    tot = torch.tensor([mine], dtype=torch.int64, device="cuda")
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    dist.all_reduce(tot)
+    res = {"metric": "reads/sec classified (150bp), library sharded by minimizer hash range", "value": world * sr * steps / wall,
+           "unit": "reads/s", "steps": steps, "ms_per_step": 1e3 * wall / steps, "reads_per_gpu_per_step": sr, "confidence": conf,
+           "exchange": "NVLink mailbox (peer-memory stores fused into the route and lookup kernels), scan of the next batch overlapped",
+           "timing": "host wall clock around the collective pipelined classify calls (reads resident in HBM; scan, route, exchange, "
+                     "lookups, exchange, resolve, D2H of taxon and flags), max over ranks",
+           "library_records": int(tot.item()), "records_on_rank0": mine, "sum_of_shards_equals_replicated": int(tot.item()) == nrec,
+           "equal_to_replicated_fused_kernel": bool(int(same.item()) == 1),
+           "checked": f"taxon and flags of all {sr} reads of every rank against classify_kernel on the replicated library"}
+    scl.close()
+    shard.close()
+    torch.cuda.empty_cache()
+    return res
+
+
+def dist_build_leg(args, w0, ctx, tax, params, genome_taxa0, rank, world, dist):
+    """BASELINE.json configs[2]: every rank scans, sorts and LCA-reduces its own genomes (weak scaling: --build-gbp-per-gpu each,
+    8.75 x 8 = 70 Gbp = the standard library's size), the reduced records travel to the owner of their minimizer, the owner's
+    insert merges equal minimizers by LCA. Result: the library sharded by minimizer hash range."""
+    import ctypes as C
+    import torch
+    from slacken_b200 import LibraryBuilder
+    from slacken_b200._lib import check
+    from slacken_b200.dist import shard_bounds
+    from slacken_b200.sharded import ShardedKeyValueIndex
+    w = bw.Workload()
+    w.genome_len = w0.genome_len
+    w.n_genomes = max(world, int(round(args.build_gbp_per_gpu * 1e9 * world / w.genome_len)))
+    parents, ranks, names, genome_taxa = bw.taxonomy(w)
+    g_lo, g_hi = shard_bounds(w.n_genomes, rank, world)
+    per = max(1, min(g_hi - g_lo, (256 << 20) // w.genome_len))
+    d_bases, d_off, d_tax = ctx.dev_alloc(per * w.genome_len), ctx.dev_alloc((per + 1) * 8), ctx.dev_alloc(per * 4)
+    warm = torch.zeros(world * 4, dtype=torch.int64, device="cuda")   # NCCL sets its communicators up lazily: not part of the build
+    dist.all_to_all_single(torch.empty_like(warm), warm)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ctx.sync()
+    t0 = time.perf_counter()
+    b = LibraryBuilder(ctx, tax, params, expected_bases=(g_hi - g_lo) * w.genome_len)
+    for g0 in range(g_lo, g_hi, per):
+        g1 = min(g_hi, g0 + per)
+        nb = (g1 - g0) * w.genome_len
+        check(ctx._L.slk_synth_genome_dev(ctx.h, w.gseed, g0 * w.genome_len, nb, C.c_void_p(d_bases)))
+        ctx.h2d(d_off, np.arange(g1 - g0 + 1, dtype=np.uint64) * np.uint64(w.genome_len))
+        ctx.h2d(d_tax, genome_taxa[g0:g1])
+        b.add_dev(d_bases, d_off, d_tax, g1 - g0, nb)
+    local_index = b.finish()
+    b.close()
+    for p in (d_bases, d_off, d_tax):
+        ctx.dev_free(p)
+    ctx.sync()
+    t_local = time.perf_counter() - t0
+    n_local = len(local_index)
+    shard = ShardedKeyValueIndex.from_local(local_index)
+    ctx.sync()
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t0
+    t = torch.tensor([t_local, t_all], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([n_local, len(shard)], dtype=torch.int64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(cnt)
+    t_local, t_all = float(t[0]), float(t[1])
+    res = {"metric": "library build throughput (scan + sort + LCA reduce + hash-table construction)",
+           "value": w.total_bases / t_all / 1e9, "unit": "Gbases/s", "seconds": t_all, "scaling": "weak",
+           "timing": "host wall clock from the first genome batch to the finished sharded table, genome generation on the device "
+                     "included, max over ranks",
+           "phases_s": {"local scan + sort + LCA reduce + local table": t_local,
+                        "records to their owners + insert on the owner": t_all - t_local,
+                        "exchange_breakdown_rank0": ShardedKeyValueIndex.last_build_times},
+           "workload": f"{w.n_genomes} synthetic genomes x {w.genome_len} bp = {w.total_bases / 1e9:.2f} Gbp, {len(parents)}-node "
+                       f"taxonomy, k{w.k}/m{w.m}/s{w.spaces}",
+           "records_before_exchange": int(cnt[0]), "library_records": int(cnt[1]), "records_on_rank0": len(shard)}
+    shard.close()
+    return res
 
 
 def main():
@@ -422,6 +681,10 @@ def main():
     ap.add_argument("--genome-len", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="reads in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded-library and distributed-build legs")
+    ap.add_argument("--paired-confidence", type=float, default=0.15)
+    ap.add_argument("--sharded-reads", type=int, default=4_000_000, help="N > 1: reads per GPU per step of the sharded-library leg")
+    ap.add_argument("--build-gbp-per-gpu", type=float, default=8.75, help="N > 1: genome bases per GPU of the distributed-build leg")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")
     args = ap.parse_args()
     w = bw.Workload()

@@ -184,6 +184,8 @@ typedef struct slk_event slk_event;
 SLK_API int slk_event_create(slk_ctx* ctx, slk_event** out);
 SLK_API void slk_event_destroy(slk_event* e);
 SLK_API int slk_event_record(slk_event* e, slk_classifier* c);
+/* the same on the context's own stream (slk_pack_reads_dev, the build and the split-path kernels launch there) */
+SLK_API int slk_event_record_ctx(slk_event* e, slk_ctx* ctx);
 SLK_API int slk_event_elapsed_ms(slk_event* start, slk_event* end, float* ms);
 
 /* ---- B4: report counts, replaces groupBy(sampleId, taxon).count (slacken/Classifier.scala:214-217). The host
@@ -206,6 +208,10 @@ SLK_API int slk_counts_reset(slk_counts* cn);
 SLK_API int slk_synth_genome_dev(slk_ctx* ctx, uint64_t seed, uint64_t start, uint64_t n, uint8_t* out_dev);
 SLK_API int slk_synth_reads_dev(slk_ctx* ctx, uint64_t gseed, uint64_t rseed, uint64_t n_genomes, uint64_t genome_len,
                         uint64_t first_read, uint64_t n_reads, uint32_t read_len, uint8_t* out_dev);
+/* mate = 0: the same reads as slk_synth_reads_dev; mate = 1: their mates of a read pair (same genome, 250 bases further
+ * along, opposite strand, errors of their own) -- the paired-end shape of BASELINE.json configs[3] */
+SLK_API int slk_synth_mates_dev(slk_ctx* ctx, uint64_t gseed, uint64_t rseed, uint64_t n_genomes, uint64_t genome_len,
+                        uint64_t first_read, uint64_t n_reads, uint32_t read_len, uint32_t mate, uint8_t* out_dev);
 /* device-resident variant of slk_build_add (bases/frag_off/frag_taxon in device memory) */
 SLK_API int slk_build_add_dev(slk_builder* b, const uint8_t* bases, const uint64_t* frag_off, const int32_t* frag_taxon,
                       uint32_t n_frag, uint64_t total_bases);

@@ -104,6 +104,8 @@ def lib():
         L.slko_max_threads.restype = C.c_int
         L.slko_synth_genome.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         L.slko_synth_reads.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+        L.slko_synth_mates.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+        L.slko_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -273,7 +275,7 @@ class Library:
         return int(t.value) if lib().slko_lib_lookup(self.h, key, C.byref(t)) else None
 
     def classify(self, bases1, off1, bases2=None, off2=None, confidence=0.0, min_hit_groups=2, threads=0,
-                 with_hits=True):
+                 with_hits=True, lists=True):
         n = len(off1) - 1
         off1 = np.ascontiguousarray(off1, dtype=np.int64)
         res = np.zeros(n, dtype=RESULT_DTYPE)
@@ -296,13 +298,28 @@ class Library:
         if rc < 0:
             raise ValueError(f"classify failed ({rc})")
         if with_hits:
-            per_read = [hits[hit_off[i]:hit_off[i] + res["n_hits"][i]] for i in range(n)] if n <= 2_000_000 else None
+            per_read = [hits[hit_off[i]:hit_off[i] + res["n_hits"][i]] for i in range(n)] if (lists and n <= 2_000_000) else None
             return res, hit_off, hits, per_read
         return res, None, None, None
 
 
 def max_threads() -> int:
     return lib().slko_max_threads()
+
+
+def host_threads() -> int:
+    """The host cores this process may run on. torchrun exports OMP_NUM_THREADS=1, so the OpenMP default is not it."""
+    import os
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def set_threads(n: int) -> int:
+    """Fixes the OpenMP team size of every later oracle call (ignores OMP_NUM_THREADS)."""
+    lib().slko_set_threads(int(n))
+    return max_threads()
 
 
 # ----------------------------------------------------------------------------- text level
@@ -394,9 +411,12 @@ def synth_genome(seed: int, start: int, n: int) -> np.ndarray:
     return out
 
 
-def synth_reads(gseed: int, rseed: int, n_genomes: int, genome_len: int, first: int, n: int, L: int) -> np.ndarray:
+def synth_reads(gseed: int, rseed: int, n_genomes: int, genome_len: int, first: int, n: int, L: int, mate: int = 0) -> np.ndarray:
     out = np.zeros(n * L, dtype=np.uint8)
-    lib().slko_synth_reads(gseed, rseed, n_genomes, genome_len, first, n, L, _ptr(out))
+    if mate:
+        lib().slko_synth_mates(gseed, rseed, n_genomes, genome_len, first, n, L, mate, _ptr(out))
+    else:
+        lib().slko_synth_reads(gseed, rseed, n_genomes, genome_len, first, n, L, _ptr(out))
     return out
 
 

@@ -760,9 +760,12 @@ SLKO_API void slko_synth_genome(uint64_t seed, uint64_t start, uint64_t n, char*
 static inline char comp_char(char c) { switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; default: return c; } }
 
 /* read r of length L: 80% from the genome set (total G bases in n_genomes genomes of genome_len; half reverse
- * complemented; each base substituted with p = 1/100), 20% i.i.d. random; 1 read in 200 carries one N. */
-SLKO_API void slko_synth_reads(uint64_t gseed, uint64_t rseed, uint64_t n_genomes, uint64_t genome_len,
-                               uint64_t first_read, uint64_t n_reads, int L, char* out) {
+ * complemented; each base substituted with p = 1/100), 20% i.i.d. random; 1 read in 200 carries one N.
+ * mate = 1 gives the read's mate of a read pair: same genome, 250 bases further along where the genome allows it,
+ * the opposite strand, errors / N / random bases from streams of its own. */
+static void synth_reads_mate(uint64_t gseed, uint64_t rseed, uint64_t n_genomes, uint64_t genome_len,
+                             uint64_t first_read, uint64_t n_reads, int L, int mate, char* out) {
+  const uint64_t ms = mate ? 10u : 0u;
   #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < (int64_t)n_reads; i++) {
     uint64_t r = first_read + (uint64_t)i;
@@ -772,21 +775,39 @@ SLKO_API void slko_synth_reads(uint64_t gseed, uint64_t rseed, uint64_t n_genome
     if (from_genome) {
       uint64_t g = (h >> 8) % n_genomes;
       uint64_t pos = rnd(rseed, 11, r) % (genome_len - (uint64_t)L + 1);
-      int rc = (h >> 40) & 1;
+      if (mate && pos + 250 <= genome_len - (uint64_t)L) pos += 250;
+      int rc = (int)((h >> 40) & 1) ^ (mate ? 1 : 0);
       uint64_t base = g * genome_len + pos;
       for (int j = 0; j < L; j++) {
         char c = rc ? comp_char(synth_genome_base(gseed, base + (uint64_t)(L - 1 - j))) : synth_genome_base(gseed, base + (uint64_t)j);
-        uint64_t e = rnd(rseed, 12, r * 1024 + (uint64_t)j);
+        uint64_t e = rnd(rseed, 12 + ms, r * 1024 + (uint64_t)j);
         if ((e % 100) == 0 && c != 'N') c = ACGT[((e >> 8) & 3)];
         o[j] = c;
       }
     } else {
       for (int j = 0; j < L; j++) {
-        uint64_t w = rnd(rseed, 13, r * 32 + (uint64_t)(j >> 5));
+        uint64_t w = rnd(rseed, 13 + ms, r * 32 + (uint64_t)(j >> 5));
         o[j] = ACGT[(w >> (2 * (j & 31))) & 3];
       }
     }
-    uint64_t nn = rnd(rseed, 14, r);
+    uint64_t nn = rnd(rseed, 14 + ms, r);
     if ((nn % 200) == 0) o[(nn >> 8) % (uint64_t)L] = 'N';
   }
+}
+SLKO_API void slko_synth_reads(uint64_t gseed, uint64_t rseed, uint64_t n_genomes, uint64_t genome_len,
+                               uint64_t first_read, uint64_t n_reads, int L, char* out) {
+  synth_reads_mate(gseed, rseed, n_genomes, genome_len, first_read, n_reads, L, 0, out);
+}
+SLKO_API void slko_synth_mates(uint64_t gseed, uint64_t rseed, uint64_t n_genomes, uint64_t genome_len,
+                               uint64_t first_read, uint64_t n_reads, int L, int mate, char* out) {
+  synth_reads_mate(gseed, rseed, n_genomes, genome_len, first_read, n_reads, L, mate, out);
+}
+/* the OpenMP team size of every later call (torchrun exports OMP_NUM_THREADS=1, which the CPU arm of the bench must
+ * not inherit) */
+SLKO_API void slko_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
 }

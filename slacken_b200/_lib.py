@@ -71,6 +71,7 @@ SIGNATURES = {
     "slk_event_create": (_INT, [_VP, _PP]),
     "slk_event_destroy": (None, [_VP]),
     "slk_event_record": (_INT, [_VP, _VP]),
+    "slk_event_record_ctx": (_INT, [_VP, _VP]),
     "slk_event_elapsed_ms": (_INT, [_VP, _VP, C.POINTER(C.c_float)]),
     "slk_counts_create": (_INT, [_VP, _VP, _I32, _PP]),
     "slk_counts_destroy": (None, [_VP]),
@@ -81,6 +82,7 @@ SIGNATURES = {
     "slk_counts_reset": (_INT, [_VP]),
     "slk_synth_genome_dev": (_INT, [_VP, _U64, _U64, _U64, _VP]),
     "slk_synth_reads_dev": (_INT, [_VP, _U64, _U64, _U64, _U64, _U64, _U64, _U32, _VP]),
+    "slk_synth_mates_dev": (_INT, [_VP, _U64, _U64, _U64, _U64, _U64, _U64, _U32, _U32, _VP]),
     "slk_dev_alloc": (_INT, [_VP, C.c_size_t, _PP]),
     "slk_dev_free": (None, [_VP, _VP]),
     "slk_memcpy_h2d": (_INT, [_VP, _VP, _VP, C.c_size_t]),

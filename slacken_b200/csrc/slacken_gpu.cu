@@ -435,12 +435,12 @@ __global__ void __launch_bounds__(256) synth_genome_kernel(uint64_t seed, uint64
 }
 __global__ void __launch_bounds__(256) synth_reads_kernel(uint64_t gseed, uint64_t rseed, uint64_t n_genomes,
                                                           uint64_t genome_len, uint64_t first, uint64_t n_reads,
-                                                          uint32_t L, uint8_t* out) {
+                                                          uint32_t L, uint32_t mate, uint8_t* out) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_reads * L) return;
   uint64_t r = i / L;
   uint32_t j = (uint32_t)(i - r * L);
-  out[i] = slk_synth_read_base(gseed, rseed, n_genomes, genome_len, first + r, L, j);
+  out[i] = slk_synth_read_base(gseed, rseed, n_genomes, genome_len, first + r, L, j, mate);
 }
 
 extern "C" int slk_synth_genome_dev(slk_ctx* ctx, uint64_t seed, uint64_t start, uint64_t n, uint8_t* out) {
@@ -451,17 +451,22 @@ extern "C" int slk_synth_genome_dev(slk_ctx* ctx, uint64_t seed, uint64_t start,
   CU(cudaStreamSynchronize(ctx->stream));
   return SLK_OK;
 }
-extern "C" int slk_synth_reads_dev(slk_ctx* ctx, uint64_t gseed, uint64_t rseed, uint64_t n_genomes, uint64_t genome_len,
-                                   uint64_t first_read, uint64_t n_reads, uint32_t read_len, uint8_t* out) {
+extern "C" int slk_synth_mates_dev(slk_ctx* ctx, uint64_t gseed, uint64_t rseed, uint64_t n_genomes, uint64_t genome_len,
+                                   uint64_t first_read, uint64_t n_reads, uint32_t read_len, uint32_t mate, uint8_t* out) {
+  if (!ctx || !out) return fail(SLK_E_INVALID, "bad arguments");
   CU(cudaSetDevice(ctx->device));
   if (n_reads == 0) return SLK_OK;
-  if (read_len == 0 || genome_len < read_len) return fail(SLK_E_INVALID, "bad read/genome length");
+  if (read_len == 0 || genome_len < read_len || mate > 1) return fail(SLK_E_INVALID, "bad read/genome length or mate");
   uint64_t n = n_reads * read_len;
   synth_reads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(gseed, rseed, n_genomes, genome_len, first_read,
-                                                                            n_reads, read_len, out);
+                                                                            n_reads, read_len, mate, out);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
   return SLK_OK;
+}
+extern "C" int slk_synth_reads_dev(slk_ctx* ctx, uint64_t gseed, uint64_t rseed, uint64_t n_genomes, uint64_t genome_len,
+                                   uint64_t first_read, uint64_t n_reads, uint32_t read_len, uint8_t* out) {
+  return slk_synth_mates_dev(ctx, gseed, rseed, n_genomes, genome_len, first_read, n_reads, read_len, 0, out);
 }
 
 // ---------------------------------------------------------------------------------------------- index construction
@@ -957,6 +962,12 @@ extern "C" int slk_event_record(slk_event* e, slk_classifier* c) {
   if (!e || !c) return fail(SLK_E_INVALID, "bad arguments");
   CU(cudaSetDevice(e->device));
   CU(cudaEventRecord(e->ev, c->s_k));
+  return SLK_OK;
+}
+extern "C" int slk_event_record_ctx(slk_event* e, slk_ctx* ctx) {
+  if (!e || !ctx) return fail(SLK_E_INVALID, "bad arguments");
+  CU(cudaSetDevice(e->device));
+  CU(cudaEventRecord(e->ev, ctx->stream));
   return SLK_OK;
 }
 extern "C" int slk_event_elapsed_ms(slk_event* start, slk_event* end, float* ms) {

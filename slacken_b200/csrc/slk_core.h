@@ -1384,21 +1384,25 @@ SLK_HD uint8_t slk_synth_genome_base(uint64_t seed, uint64_t g) {
   return slk_acgt((uint32_t)((w >> (2 * (g & 31))) & 3));
 }
 SLK_HD uint8_t slk_comp_char(uint8_t c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c; }
+// mate = 0: the read itself; mate = 1: its mate of a read pair -- the same genome (or the same "random" decision), 250 bases
+// further along where the genome allows it, the opposite strand, and independent errors.
 SLK_HD uint8_t slk_synth_read_base(uint64_t gseed, uint64_t rseed, uint64_t n_genomes, uint64_t genome_len,
-                                   uint64_t r, uint32_t L, uint32_t j) {
-  uint64_t nn = slk_rnd(rseed, 14, r);
+                                   uint64_t r, uint32_t L, uint32_t j, uint32_t mate = 0) {
+  const uint64_t ms = mate ? 10u : 0u;   // mate 2 draws its N, its errors and its random bases from streams of its own
+  uint64_t nn = slk_rnd(rseed, 14 + ms, r);
   if ((nn % 200) == 0 && (nn >> 8) % L == j) return 'N';
   uint64_t h = slk_rnd(rseed, 10, r);
   if ((h % 10) < 8) {
     uint64_t g = (h >> 8) % n_genomes;
     uint64_t pos = slk_rnd(rseed, 11, r) % (genome_len - L + 1);
+    if (mate && pos + 250 <= genome_len - L) pos += 250;
     uint64_t base = g * genome_len + pos;
-    uint8_t c = ((h >> 40) & 1) ? slk_comp_char(slk_synth_genome_base(gseed, base + (L - 1 - j)))
-                                : slk_synth_genome_base(gseed, base + j);
-    uint64_t e = slk_rnd(rseed, 12, r * 1024 + j);
+    uint8_t c = ((((h >> 40) & 1) != 0) != (mate != 0)) ? slk_comp_char(slk_synth_genome_base(gseed, base + (L - 1 - j)))
+                                                        : slk_synth_genome_base(gseed, base + j);
+    uint64_t e = slk_rnd(rseed, 12 + ms, r * 1024 + j);
     if ((e % 100) == 0 && c != 'N') c = slk_acgt((uint32_t)((e >> 8) & 3));
     return c;
   }
-  uint64_t w = slk_rnd(rseed, 13, r * 32 + (j >> 5));
+  uint64_t w = slk_rnd(rseed, 13 + ms, r * 32 + (j >> 5));
   return slk_acgt((uint32_t)((w >> (2 * (j & 31))) & 3));
 }

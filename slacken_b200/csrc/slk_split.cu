@@ -506,8 +506,11 @@ __device__ __forceinline__ uint32_t mbx_wait(const unsigned long long* flag, uin
   const unsigned long long t0 = mbx_now();
   for (;;) {
     const unsigned long long v = mbx_ld_flag(flag);
-    if ((uint32_t)(v >> 32) == epoch) return (uint32_t)v;
-    if (mbx_now() - t0 > MBX_SPIN_NS) { atomicOr(err, 2u); return 0; }
+    const uint32_t ep = (uint32_t)(v >> 32);
+    if (ep == epoch) return (uint32_t)v;
+    // a NEWER epoch means the peer overwrote the flag before it was read here: a protocol violation (every rank consumes
+    // every owner's flag2 before it routes again, so this cannot happen), reported at once instead of after the time-out
+    if ((int32_t)(ep - epoch) > 0 || mbx_now() - t0 > MBX_SPIN_NS) { atomicOr(err, 2u); return 0; }
     __nanosleep(256);
   }
 }
@@ -612,7 +615,10 @@ __global__ void __launch_bounds__(256) mbx_unroute_kernel(mbx_layout lay, uint32
   const uint32_t d = blockIdx.x / per, c0 = blockIdx.x % per;
   unsigned long long n = cursors[d];
   if (n > lay.cap) n = lay.cap;
-  if ((uint64_t)c0 * 256 >= n) return;   // nothing of this block's share was sent to d: no need to wait for it
+  // Block 0 of every owner ALWAYS consumes the owner's flag2, even when nothing was sent to it: the owner raises flag2 only
+  // after its lookup kernel has read this rank's flag1 (and count) of the batch, so once this kernel is through, the next
+  // route may overwrite flag1 and the keys, and the mailbox may be freed, without racing with any peer.
+  if ((uint64_t)c0 * 256 >= n && c0 != 0) return;   // nothing of this block's share was sent to d
   if (threadIdx.x == 0) mbx_wait(reinterpret_cast<const unsigned long long*>(base + lay.flag2_off()) + d, epoch, err);
   __syncthreads();
   const int32_t* back = reinterpret_cast<const int32_t*>(base + lay.taxa_off()) + (uint64_t)d * lay.cap;

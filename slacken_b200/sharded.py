@@ -223,6 +223,7 @@ class Mailbox:
         check(self._L.slk_mailbox_create(ctx.h, rank, world, self.cap, C.byref(h), handle))
         self.h = h
         self.handle = bytes(handle)
+        self._group, self._collective = group, False
         if connect:
             self.connect(group)
 
@@ -240,6 +241,7 @@ class Mailbox:
         blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in every)
         check(self._L.slk_mailbox_connect(self.h, blob))
         dist.barrier(group=group)
+        self._group, self._collective = group, True
 
     @staticmethod
     def connect_local(boxes: Sequence["Mailbox"]):
@@ -248,7 +250,13 @@ class Mailbox:
         check(boxes[0]._L.slk_mailbox_connect_local(arr, len(boxes)))
 
     def close(self):
+        """Collective when the mailbox was connected across processes: nobody frees memory a peer has mapped before every
+        rank is through with its last batch (the device-side protocol already guarantees that no store is in flight)."""
         if getattr(self, "h", None):
+            if self._collective and self.world > 1:
+                dist = _dist()
+                if dist.is_initialized():
+                    dist.barrier(group=self._group)
             self._L.slk_mailbox_destroy(self.h)
             self.h = None
 

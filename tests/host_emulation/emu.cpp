@@ -245,3 +245,8 @@ EMU_API void emu_synth_reads(uint64_t gseed, uint64_t rseed, uint64_t n_genomes,
   for (uint64_t r = 0; r < n_reads; r++)
     for (uint32_t j = 0; j < L; j++) out[r * L + j] = slk_synth_read_base(gseed, rseed, n_genomes, genome_len, first + r, L, j);
 }
+EMU_API void emu_synth_mates(uint64_t gseed, uint64_t rseed, uint64_t n_genomes, uint64_t genome_len, uint64_t first,
+                             uint64_t n_reads, uint32_t L, uint32_t mate, uint8_t* out) {
+  for (uint64_t r = 0; r < n_reads; r++)
+    for (uint32_t j = 0; j < L; j++) out[r * L + j] = slk_synth_read_base(gseed, rseed, n_genomes, genome_len, first + r, L, j, mate);
+}

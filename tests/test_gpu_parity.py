@@ -241,6 +241,9 @@ def test_synthetic_generators_match_oracle(gpu):
     out = np.zeros(nr * L, dtype=np.uint8)
     gpu.d2h(out, d)
     assert np.array_equal(out, oracle.synth_reads(42, 43, 5, 100000, 7, nr, L))
+    check(gpu._L.slk_synth_mates_dev(gpu.h, 42, 43, 5, 100000, 7, nr, L, 1, C.c_void_p(d)))
+    gpu.d2h(out, d)
+    assert np.array_equal(out, oracle.synth_reads(42, 43, 5, 100000, 7, nr, L, mate=1))
     gpu.dev_free(d)
 
 

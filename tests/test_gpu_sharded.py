@@ -142,6 +142,22 @@ def test_mailbox_exchange_ranks_on_one_gpu(gpu, world):
         c.close()
 
 
+def test_mailbox_empty_batch_then_full_batch_and_teardown(gpu):
+    """A rank that sends nothing to any owner still consumes every owner's completion flag (so the next batch may reuse the
+    flags and buffers), several epochs in a row, and the mailboxes can be torn down right after the last batch."""
+    world = 3
+    rng, genomes, olib, cls, keep = _mailbox_world([gpu.device] * world)
+    reads = simulate_reads(rng, genomes, 900, (30, 220), n_rate=0.1)
+    for rnd in range(4):
+        share = [reads[r::world] for r in range(world)]
+        share[rnd % world] = []            # this rank has no reads at all in this batch
+        share[(rnd + 1) % world] = [b"N" * 90, b"ACG"]   # ... and this one only reads without a sequence span
+        _mailbox_round(cls, olib, share, 0.0)
+    _mailbox_round(cls, olib, [reads[r::world] for r in range(world)], 0.15)
+    for c in cls:
+        c.close()
+
+
 def test_mailbox_overflow_fails_loudly(gpu):
     from slacken_b200._lib import SLK_E_NOSPACE, SlackenGpuError
     rng, genomes, olib, cls, keep = _mailbox_world([gpu.device] * 2, cap=64)

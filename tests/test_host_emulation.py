@@ -146,6 +146,13 @@ def test_synthetic_generators_agree_with_the_oracle_copy():
     r = np.zeros(3000 * 150, dtype=np.uint8)
     emu.lib().emu_synth_reads(7, 8, 4, 70_000, 11, 3000, 150, emu._p(r))
     assert np.array_equal(r, oracle.synth_reads(7, 8, 4, 70_000, 11, 3000, 150))
+    # mate 2 of a read pair: same genome 250 bases on, opposite strand (the paired leg of bench.py)
+    r2 = np.zeros(3000 * 150, dtype=np.uint8)
+    emu.lib().emu_synth_mates(7, 8, 4, 70_000, 11, 3000, 150, 1, emu._p(r2))
+    assert np.array_equal(r2, oracle.synth_reads(7, 8, 4, 70_000, 11, 3000, 150, mate=1))
+    assert not np.array_equal(r, r2)
+    emu.lib().emu_synth_mates(7, 8, 4, 70_000, 11, 3000, 150, 0, emu._p(r2))
+    assert np.array_equal(r, r2)
 
 
 @pytest.mark.parametrize("read_len", [50, 100])
