@@ -373,6 +373,12 @@ def run_ours(args, w):
     r = timed_device(device_step, args.steps, args.warmup)
     ms, S, H, launches, clocks = r["ms"], r["S"], r["H"], r["launches"], r["clocks"]
     value = world * n * args.steps / (ms / 1e3)
+    if args.quick:   # tuning runs: the device-timed single-end leg only
+        sampler.stop()
+        if rank == 0:
+            print(json.dumps({"quick": True, "so": os.environ.get("SLK_SO", "libslacken_gpu.so"), "kernel": os.environ.get("SLK_KERNEL", "2"),
+                              "value": value, "ms_per_step": ms / args.steps, "lookups_per_s": value * S, "S": S}), flush=True)
+        return
     used = np.zeros(1, dtype=np.uint64)
     ctx.d2h(used, d_used)
     assert int(used[0]) <= hits_cap
@@ -681,6 +687,7 @@ def main():
     ap.add_argument("--genome-len", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="reads in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="tuning: only the device-timed single-end leg, short JSON")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded-library and distributed-build legs")
     ap.add_argument("--paired-confidence", type=float, default=0.15)
     ap.add_argument("--sharded-reads", type=int, default=4_000_000, help="N > 1: reads per GPU per step of the sharded-library leg")

@@ -29,7 +29,7 @@ if os.environ.get("SLK_VARIANT"):
 
 
 def _sources():
-    deps = [os.path.join(CSRC, f) for f in ("slk_core.h", "slk_kernels.cuh", "slk_sort.h", "slk_host.h")]
+    deps = [os.path.join(CSRC, f) for f in ("slk_core.h", "slk_group.h", "slk_kernels.cuh", "slk_sort.h", "slk_host.h")]
     deps.append(os.path.join(HERE, "..", "include", "slacken_gpu.h"))
     units = [("slacken_gpu", os.path.join(CSRC, "slacken_gpu.cu"), []),
              ("slk_sort", os.path.join(CSRC, "slk_sort.cu"), []),
@@ -62,9 +62,17 @@ def _compile(unit, deps, force):
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     units, deps = _sources()
+    # SLK_VARIANT_UNITS=slk_inst_w5[,..]: a variant recompiles only these units with its flags and links the default build's
+    # objects for the rest (the tuning macros only reach the classify kernels)
+    only = [u for u in os.environ.get("SLK_VARIANT_UNITS", "").split(",") if u] if os.environ.get("SLK_VARIANT") else []
+    reuse = []
+    if only:
+        default_obj = os.path.join(HERE, "build")
+        reuse = [os.path.join(default_obj, u[0] + ".o") for u in units if u[0] not in only]
+        units = [u for u in units if u[0] in only]
     with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 4)) as ex:
         results = list(ex.map(lambda u: _compile(u, deps, force), units))
-    objs = [o for o, _ in results]
+    objs = [o for o, _ in results] + reuse
     if verbose:
         for _, log in results:
             sys.stderr.write(log)

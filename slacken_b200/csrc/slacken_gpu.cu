@@ -1039,10 +1039,36 @@ struct mate_dev {
   const uint32_t* mask = nullptr;    // packed only
   const uint32_t* len = nullptr;     // packed only
 };
+// SLK_KERNEL=1 selects the first-generation fused kernel (one fragment per thread, cp.async tiles) for A/B runs;
+// the default is the warp-cooperative kernel of slk_group.h (packed input only: ASCII input is packed first, stage 1)
+static int kernel_generation() {
+  static const int g = [] { const char* e = getenv("SLK_KERNEL"); return (e && atoi(e) == 1) ? 1 : 2; }();
+  return g;
+}
 static void launch_classify(slk_classifier* c, bool hits, bool packed, const slk_classify_opts* o, const mate_dev& m1,
                             const mate_dev& m2, uint32_t n, int32_t* taxon, uint8_t* flags, slk_read_detail* detail,
                             slk_hit* hbase, const unsigned long long* hshift, uint64_t hcap, unsigned long long* cursor) {
   slk_index* idx = c->idx;
+  if (packed && kernel_generation() == 2) {
+    slk_classify2_args a;
+    a.sp = idx->sp; a.tb = idx->table; a.tx = idx->dt.view();
+    a.in1 = slk_group_in{reinterpret_cast<const uint64_t*>(m1.bases), m1.mask, m1.off, m1.len, m1.shift};
+    a.in2 = slk_group_in{reinterpret_cast<const uint64_t*>(m2.bases), m2.mask, m2.off, m2.len, m2.shift};
+    a.paired = m2.bases != nullptr; a.n_reads = n;
+    a.confidence = o->confidence; a.min_hit_groups = o->min_hit_groups; a.hits = hits;
+    a.taxon_out = taxon; a.flags_out = flags; a.detail_out = detail;
+    a.hits_base = hbase; a.hits_shift_ptr = hshift; a.hits_cap = hcap; a.hits_cursor = cursor;
+    a.counts = c->counts ? c->counts->d + (size_t)c->counts_sample * c->counts->n_taxa : nullptr;
+    a.error_flag = c->d_err; a.stats = c->d_stats;
+    switch (idx->sp.w) {
+      case 1: slk_launch_classify2_w1(a, c->s_k); break; case 2: slk_launch_classify2_w2(a, c->s_k); break;
+      case 3: slk_launch_classify2_w3(a, c->s_k); break; case 4: slk_launch_classify2_w4(a, c->s_k); break;
+      case 5: slk_launch_classify2_w5(a, c->s_k); break; case 6: slk_launch_classify2_w6(a, c->s_k); break;
+      case 7: slk_launch_classify2_w7(a, c->s_k); break; default: slk_launch_classify2_w8(a, c->s_k); break;
+    }
+    c->launches++;
+    return;
+  }
   slk_classify_args a;
   a.sp = idx->sp; a.tb = idx->table; a.tx = idx->dt.view();
   a.bases1 = m1.bases; a.off1 = m1.off; a.shift1 = m1.shift; a.mask1 = m1.mask; a.len1 = m1.len;

@@ -38,6 +38,23 @@ void SLK_CAT(slk_launch_classify_w, SLK_W)(const slk_classify_args& a) {
     else SLK_CLS_LAUNCH(false, false, nullptr, nullptr, 0);
   }
 }
+template <bool CANON>
+static void launch_classify2(const slk_classify2_args& a, cudaStream_t stream) {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !done[dev]) {
+    cudaFuncSetAttribute(classify2_kernel<SLK_W, CANON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLK_G_SMEM_BYTES);
+    cudaFuncSetAttribute(classify2_kernel<SLK_W, CANON>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (dev >= 0 && dev < 64) done[dev] = true;
+  }
+  const unsigned grid = (a.n_reads + SLK_G_THREADS - 1) / SLK_G_THREADS;
+  classify2_kernel<SLK_W, CANON><<<grid, SLK_G_THREADS, SLK_G_SMEM_BYTES, stream>>>(a);
+}
+void SLK_CAT(slk_launch_classify2_w, SLK_W)(const slk_classify2_args& a, cudaStream_t stream) {
+  if (a.sp.canonical) launch_classify2<true>(a, stream);
+  else launch_classify2<false>(a, stream);
+}
 void SLK_CAT(slk_launch_emit_w, SLK_W)(const slk_emit_args& a) {
   emit_cells_kernel<SLK_W><<<(unsigned)((a.n_items + 127) / 128), 128, 0, a.stream>>>(
       a.sp, a.bases, a.frag_off, a.off_shift, a.frag_dense, a.item_prefix, a.n_frag, a.n_items, a.out, a.cap, a.cursor);

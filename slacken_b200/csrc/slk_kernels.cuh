@@ -9,6 +9,7 @@
 
 #include "../../include/slacken_gpu.h"
 #include "slk_core.h"
+#include "slk_group.h"
 
 #define BUILD_WPT 96  // k-mer windows scanned per thread of the build-side emit kernel
 
@@ -52,6 +53,7 @@ struct slk_bracken_scan_args {
   cudaStream_t stream;
 };
 #define SLK_DECL_W(w) void slk_launch_classify_w##w(const slk_classify_args&); void slk_launch_emit_w##w(const slk_emit_args&); \
+  void slk_launch_classify2_w##w(const slk_classify2_args&, cudaStream_t); \
   void slk_launch_spans_w##w(const slk_spans_args&); void slk_launch_bracken_scan_w##w(const slk_bracken_scan_args&);
 SLK_DECL_W(1) SLK_DECL_W(2) SLK_DECL_W(3) SLK_DECL_W(4) SLK_DECL_W(5) SLK_DECL_W(6) SLK_DECL_W(7) SLK_DECL_W(8)
 
@@ -414,6 +416,22 @@ __global__ void __launch_bounds__(SLK_CLS_THREADS, SLK_CLS_MINB) classify_kernel
     d.num_distinct = res.num_distinct;
     detail_out[r] = d;
   }
+}
+
+// ---------------------------------------------------------------------------------------------- classify kernel, 2nd generation
+// One warp = 32 fragments (slk_group.h). Four warps per block, four blocks per SM: 16 x 13.6 KB of entry buffers
+// (measured: 14 warps 712, 16 warps 741-750 M reads/s; more warps need fewer than 100 registers, and spilling costs more).
+#ifndef SLK_G_THREADS
+#define SLK_G_THREADS 128
+#endif
+#ifndef SLK_G_MINB
+#define SLK_G_MINB 4
+#endif
+#define SLK_G_SMEM_BYTES ((SLK_G_THREADS / 32u) * SLK_G_WARP_BYTES)
+template <int W, bool CANON>
+__global__ void __launch_bounds__(SLK_G_THREADS, SLK_G_MINB) classify2_kernel(const __grid_constant__ slk_classify2_args a) {
+  extern __shared__ __align__(16) uint8_t slk_smem2[];
+  slk_classify2_thread<W, CANON>(a, slk_smem2);
 }
 
 #endif  // __CUDACC__

@@ -155,6 +155,47 @@ class EmuIndex:
         return res, hit_off, hits[:used]
 
 
+_SO2 = os.path.join(_HERE, "libslk_emu2.so")
+_lib2 = None
+DETAIL_DTYPE = np.dtype([("hit_off", "<u8"), ("hit_cnt", "<u4"), ("len1", "<u4"), ("len2", "<u4"), ("num_distinct", "<u4")])
+
+
+def lib2():
+    """The warp-cooperative classify kernel body (slk_group.h) under the fibre emulation of simt.h."""
+    global _lib2
+    if _lib2 is None:
+        srcs = [os.path.join(_HERE, "emu2.cpp"), os.path.join(_HERE, "simt.h"), _CORE, os.path.join(os.path.dirname(_CORE), "slk_group.h")]
+        if not os.path.exists(_SO2) or os.path.getmtime(_SO2) < max(os.path.getmtime(x) for x in srcs):
+            subprocess.check_call(["/usr/bin/g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-o", _SO2, srcs[0]])
+        _lib2 = C.CDLL(_SO2)
+        _lib2.emu2_classify.restype = C.c_int
+        _lib2.emu2_classify.argtypes = [C.POINTER(ScanParams), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                        C.c_uint32] + [C.c_void_p] * 8 + [C.c_uint32, C.c_double, C.c_int, C.c_int] + [C.c_void_p] * 4 + \
+                                       [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    return _lib2
+
+
+def classify2(ix: "EmuIndex", r1, r2=None, confidence=0.0, min_hit_groups=2, want_hits=True):
+    """r1 / r2: slacken_b200.host.PackedReads. Returns (taxon, flags, detail, hits, probes, merged_hits, counts)."""
+    n = len(r1.len)
+    taxon = np.zeros(n, dtype=np.int32)
+    flags = np.zeros(n, dtype=np.uint8)
+    detail = np.zeros(n, dtype=DETAIL_DTYPE)
+    cap = int(r1.len.sum()) + (int(r2.len.sum()) if r2 is not None else 0) + 5 * n + 8
+    hits = np.zeros(cap, dtype=HIT_DTYPE)
+    used = C.c_uint64(0)
+    stats = np.zeros(2, dtype=np.uint64)
+    counts = np.zeros(int(ix.raw.max()) + 1, dtype=np.uint64)
+    m2 = (r2.codes, r2.mask, r2.boff, r2.len) if r2 is not None else (None, None, None, None)
+    pad = lambda a, dt: np.concatenate([a, np.zeros(4, dtype=dt)])   # the kernel never reads past a read's blocks; be strict anyway
+    rc = lib2().emu2_classify(C.byref(ix.sp), _p(ix.cells), ix.n_buckets, _p(ix.parent), _p(ix.depth), _p(ix.raw), len(ix.raw),
+                              ix.dt.root, _p(r1.codes), _p(r1.mask), _p(r1.boff), _p(r1.len), _p(m2[0]), _p(m2[1]), _p(m2[2]), _p(m2[3]),
+                              n, float(confidence), int(min_hit_groups), 1 if want_hits else 0, _p(taxon), _p(flags), _p(detail),
+                              _p(hits), cap, C.byref(used), _p(stats), _p(counts))
+    assert rc == 0, rc
+    return taxon, flags, detail, hits[:used.value], int(stats[0]), int(stats[1]), counts
+
+
 def bracken_dests(ix: "EmuIndex", seq: bytes, read_len: int) -> np.ndarray:
     """Destination taxon (raw id) of every read of length read_len of one genome fragment."""
     b = np.frombuffer(seq, dtype=np.uint8).copy() if len(seq) else np.zeros(1, dtype=np.uint8)

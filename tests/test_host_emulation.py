@@ -32,6 +32,32 @@ def compare(lib, ix, rb, ro, rb2=None, ro2=None, confidence=0.0, k=35):
     for packed in (False, True):   # both input forms of the ABI must give the same answer
         _compare(lib, ix, rb, ro, rb2, ro2, confidence, k, packed, False)
     _compare(lib, ix, rb, ro, rb2, ro2, confidence, k, False, True)   # ... and so must the split (sharded-library) path
+    _compare2(lib, ix, rb, ro, rb2, ro2, confidence, k)                # ... and the warp-cooperative kernel body (slk_group.h)
+
+
+def _compare2(lib, ix, rb, ro, rb2, ro2, confidence, k):
+    from slacken_b200.host import pack_reads
+    res, _, _, per = lib.classify(rb, ro, rb2, ro2, confidence=confidence)
+    r1 = pack_reads(np.frombuffer(bytes(rb), dtype=np.uint8), np.asarray(ro))
+    r2 = pack_reads(np.frombuffer(bytes(rb2), dtype=np.uint8), np.asarray(ro2)) if rb2 is not None else None
+    taxon, flags, detail, hits, probes, merged, counts = emu.classify2(ix, r1, r2, confidence=confidence)
+    assert np.array_equal(res["taxon"], taxon)
+    assert np.array_equal(res["classified"], flags & 1)
+    assert np.array_equal(res["has_span"], (flags >> 1) & 1)
+    hs = res["has_span"].astype(bool)
+    assert np.array_equal(res["num_distinct"][hs], detail["num_distinct"][hs].astype(np.int32))
+    assert np.array_equal(res["len1"][hs], detail["len1"][hs].astype(np.int32))
+    if rb2 is not None:
+        assert np.array_equal(res["len2"][hs], detail["len2"][hs].astype(np.int32))
+    for i in range(len(per)):
+        h = hits[int(detail["hit_off"][i]):int(detail["hit_off"][i]) + int(detail["hit_cnt"][i])]
+        assert np.array_equal(h["taxon"], per[i]["taxon"]) and np.array_equal(h["count"], per[i]["count"]), i
+    assert merged == sum(len(x) for x in per)
+    rep = np.bincount(res["taxon"][hs], minlength=len(counts))
+    assert np.array_equal(rep, counts.astype(np.int64)[:len(rep)])
+    # without per-read hit lists (the --nodetailed mode): the same taxa
+    t2, f2, _, _, _, _, _ = emu.classify2(ix, r1, r2, confidence=confidence, want_hits=False)
+    assert np.array_equal(t2, taxon) and np.array_equal(f2, flags)
 
 
 def _compare(lib, ix, rb, ro, rb2, ro2, confidence, k, packed, split):
