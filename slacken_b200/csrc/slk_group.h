@@ -31,7 +31,7 @@
 #endif
 #define SLK_G_MAXNE 19        // entries one lane can produce in one step: border + cut run + 16 run ends + the run open at the mate's end
 #ifndef SLK_G_DEPTH
-#define SLK_G_DEPTH 2         // table lookups in flight per lane (measured: 2 -> 707, 4 -> 673, 8 -> 393 M reads/s)
+#define SLK_G_DEPTH 4         // table lookups in flight per lane (measured: 2 -> 762, 3 -> 737, 4 -> 802, 6 -> 624 M reads/s)
 #endif
 #ifndef SLK_G_HIST
 #define SLK_G_HIST 32         // (taxon, k-mers) pairs per lane that fit the idle entry buffer
@@ -60,7 +60,10 @@ struct slk_group_in {   // one mate of the batch, packed form (include/slacken_g
 #if defined(__CUDA_ARCH__)
 #define SLK_G_LDG32(p) __ldg(p)
 __device__ __forceinline__ void slk_g_load_bucket(const uint64_t* p, slk_bucket* o) {
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(o->c0), "=l"(o->c1), "=l"(o->c2), "=l"(o->c3) : "l"(p));
+#ifndef SLK_G_LD
+#define SLK_G_LD "ld.global.nc.L1::no_allocate.v4.u64"
+#endif
+  asm volatile(SLK_G_LD " {%0,%1,%2,%3}, [%4];" : "=l"(o->c0), "=l"(o->c1), "=l"(o->c2), "=l"(o->c3) : "l"(p));
 }
 #else
 #define SLK_G_LDG32(p) (*(p))
@@ -266,6 +269,9 @@ __device__ __forceinline__ void slk_group_classify(uint8_t* sm_warp, const slk_s
   bool l_have_last = false, l_have_cur = false, l_spilled = false, any = false;
   int32_t l_label = 0, l_count = 0;
   uint32_t l_mate = 0, l_k0 = 0, l_k1 = 0, l_nd = 0, l_np = 0, l_nh = 0, nh_spilled = 0;
+  // the usual fragment hits ONE taxon (plus misses): resolveTree is then a comparison, no histogram needed
+  uint32_t l_t1 = 0, l_c1 = 0;
+  bool l_multi = false;
   ov.nk = 0; ov.overflow = false;
 
   // ---- this lane's fragment (no arrays indexed by the mate: they would live in local memory)
@@ -404,6 +410,10 @@ __device__ __forceinline__ void slk_group_classify(uint8_t* sm_warp, const slk_s
           const uint64_t ck = kl & 0xffffffffffffull;
           const uint32_t dense = (uint32_t)(kl >> 48);
           l_nd += (is_seq && (!l_have_last || ck != l_last) && dense != 0) ? 1u : 0u;
+          const bool nz = is_seq && dense != 0;
+          l_t1 = (nz && l_t1 == 0) ? dense : l_t1;
+          l_c1 += (nz && dense == l_t1) ? n : 0u;
+          l_multi = l_multi || (nz && dense != l_t1);
           l_last = is_seq ? ck : l_last;
           l_have_last = l_have_last || is_seq;
           const int32_t label = is_seq ? (int32_t)dense : (is_border ? SLK_MATE_PAIR_BORDER : SLK_AMBIGUOUS_SPAN);
@@ -439,7 +449,7 @@ __device__ __forceinline__ void slk_group_classify(uint8_t* sm_warp, const slk_s
     }
     // ---- the chunk's minimizers, position-parallel (a warp without ambiguous bases takes the version without masks)
     uint64_t V[SLK_G_CHUNK];
-    const bool dirty = __any_sync(0xffffffffu, am != 0);
+    const bool dirty = __any_sync(0xffffffffu, am != 0 || run_val == SLK_V_AMB);   // (an open AMBIGUOUS run counts: its entry needs the type)
     slk_g_chunk<W, CANON>(cw, m, mmask, xor_mask, sig_mask, V);
     if (dirty) slk_g_chunk_ambiguity(am, k, V);
     // ---- run ends (MinSplitter.scala:180-216: consecutive windows with an equal minimizer VALUE are one super-mer).
@@ -498,18 +508,31 @@ __device__ __forceinline__ void slk_group_classify(uint8_t* sm_warp, const slk_s
       S.key(slot) = split_val; S.meta(slot) = (uint8_t)(split_cnt | ((amb ? SLK_G_T_AMB : SLK_G_T_SEQ) << 6)); slot++;
       l_np += amb ? 0u : 1u;
     }
-    {
-      // run end j closes the run whose last window is j - 1: its minimizer is V[j - 1], its length j - (previous run end)
+    // run end j closes the run whose last window is j - 1: its minimizer is V[j - 1], its length j - (previous run end)
+    if (ne) {
+      uint64_t* kp = &S.key(slot);
+      uint8_t* mp = &S.meta(slot);
       int32_t last = -(int32_t)run_cnt;
+      if (!dirty) {   // no ambiguous base in the warp's chunks: every run end is emitted (but a mate's first), all are sequence spans
 #pragma unroll
-      for (int j = 0; j < SLK_G_CHUNK; j++) {
-        if ((emit >> j) & 1u) {
-          S.key(slot) = j == 0 ? run_val : V[j > 0 ? j - 1 : 0];
-          S.meta(slot) = (uint8_t)((uint32_t)(j - last) | (((ambs >> j) & 1u) << 6));   // SLK_G_T_AMB == 1
-          slot++;
+        for (int j = 0; j < SLK_G_CHUNK; j++) {
+          if ((emit >> j) & 1u) {
+            *kp++ = j == 0 ? run_val : V[j > 0 ? j - 1 : 0];
+            *mp++ = (uint8_t)(j - last);
+            last = j;
+          }
         }
-        last = ((ends >> j) & 1u) ? j : last;
+      } else {
+#pragma unroll
+        for (int j = 0; j < SLK_G_CHUNK; j++) {
+          if ((emit >> j) & 1u) {
+            *kp++ = j == 0 ? run_val : V[j > 0 ? j - 1 : 0];
+            *mp++ = (uint8_t)((uint32_t)(j - last) | (((ambs >> j) & 1u) << 6));   // SLK_G_T_AMB == 1
+          }
+          last = ((ends >> j) & 1u) ? j : last;
+        }
       }
+      slot += (uint32_t)__popc(emit);
       l_np += (uint32_t)__popc(emit & ~ambs);
     }
     if (fin_emit) {
@@ -542,7 +565,15 @@ __device__ __forceinline__ void slk_group_classify(uint8_t* sm_warp, const slk_s
   sink.reserve(l_spilled ? 0u : l_nh);
   uint32_t taxon = 0;
   bool fast_done = false;
-  if (!l_spilled) {   // nearly every fragment: the histogram fits the (now idle) key array
+  if (!l_multi) {
+    // One hit taxon t (or none): its root-path score is its own count and every clade on the way up holds exactly that
+    // count, so LowestCommonAncestor.resolveTree (slacken/LowestCommonAncestor.scala:91-146) returns t when the count reaches
+    // ceil(confidence * totalKmers) and NONE otherwise.
+    const double required = ceil(confidence * (double)(int32_t)(l_k0 + l_k1));
+    taxon = (l_t1 != 0 && (double)(int32_t)l_c1 >= required) ? l_t1 : 0u;
+    fast_done = true;
+    if (l_spilled) spill(0);
+  } else if (!l_spilled) {   // the histogram fits the (now idle) key array
     slk_group_fast_hist fh{S, 0u};
     bool fits = true;
     for (uint32_t i = 0; i < l_nh && fits; i++) {
