@@ -851,6 +851,10 @@ struct cls_slot {
   uint8_t *bases1 = nullptr, *bases2 = nullptr;   // ASCII bases, or the uint64 code blocks of packed input
   uint64_t *off1 = nullptr, *off2 = nullptr;
   uint32_t *mask1 = nullptr, *mask2 = nullptr, *len1 = nullptr, *len2 = nullptr;   // packed input only
+  // ASCII input: stage 1 (pack_reads_kernel) writes the chunk's packed form here before the classify kernel runs
+  uint64_t *pk_codes[2] = {nullptr, nullptr}, *pk_boff[2] = {nullptr, nullptr};
+  uint32_t *pk_mask[2] = {nullptr, nullptr}, *pk_len[2] = {nullptr, nullptr};
+  uint64_t* h_boff[2] = {nullptr, nullptr};   // pinned: the chunk's block offsets, computed from the host's offsets
   int32_t* taxon = nullptr; uint8_t* flags = nullptr; slk_read_detail* detail = nullptr;
   slk_hit* hits = nullptr; uint64_t hits_cap = 0;
   unsigned long long* d_range = nullptr;   // [0] = cursor value before the kernel, [1] = after
@@ -865,7 +869,11 @@ struct slk_classifier {
   cudaStream_t s_h2d, s_k, s_d2h;
   cls_slot slot[NSLOT];
   size_t cap_reads = 0, cap_bases = 0;
-  bool cap_paired = false, cap_hits = false, cap_packed = false;
+  bool cap_paired = false, cap_hits = false, cap_packed = false, cap_ascii = false;
+  // device-resident ASCII input (slk_classify_batch_dev): its packed form, grow-only
+  uint64_t *dv_codes[2] = {nullptr, nullptr}, *dv_boff[2] = {nullptr, nullptr};
+  uint32_t *dv_mask[2] = {nullptr, nullptr}, *dv_len[2] = {nullptr, nullptr};
+  uint64_t dv_blocks[2] = {0, 0}, dv_reads[2] = {0, 0};
   unsigned long long* d_cursor = nullptr;
   uint32_t* d_err = nullptr;
   unsigned long long* d_stats = nullptr;  // [0] probes, [1] merged hits, accumulated over launches
@@ -907,6 +915,10 @@ extern "C" int slk_classifier_create(slk_index* idx, slk_classifier** out) {
 static void slot_free(cls_slot& s) {
   cudaFree(s.bases1); cudaFree(s.bases2); cudaFree(s.off1); cudaFree(s.off2); cudaFree(s.taxon); cudaFree(s.flags);
   cudaFree(s.detail); cudaFree(s.hits); cudaFree(s.mask1); cudaFree(s.mask2); cudaFree(s.len1); cudaFree(s.len2);
+  for (int m = 0; m < 2; m++) {
+    cudaFree(s.pk_codes[m]); cudaFree(s.pk_boff[m]); cudaFree(s.pk_mask[m]); cudaFree(s.pk_len[m]); cudaFreeHost(s.h_boff[m]);
+    s.pk_codes[m] = s.pk_boff[m] = nullptr; s.pk_mask[m] = s.pk_len[m] = nullptr; s.h_boff[m] = nullptr;
+  }
   s.bases1 = s.bases2 = nullptr; s.off1 = s.off2 = nullptr; s.taxon = nullptr; s.flags = nullptr; s.detail = nullptr; s.hits = nullptr;
   s.mask1 = s.mask2 = s.len1 = s.len2 = nullptr;
 }
@@ -920,6 +932,7 @@ extern "C" void slk_classifier_destroy(slk_classifier* c) {
     cudaEventDestroy(c->slot[i].h2d_done); cudaEventDestroy(c->slot[i].k_done); cudaEventDestroy(c->slot[i].d2h_done);
   }
   cudaFree(c->d_cursor); cudaFree(c->d_err); cudaFree(c->d_stats);
+  for (int m = 0; m < 2; m++) { cudaFree(c->dv_codes[m]); cudaFree(c->dv_boff[m]); cudaFree(c->dv_mask[m]); cudaFree(c->dv_len[m]); }
   cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_k); cudaStreamDestroy(c->s_d2h);
   delete c;
 }
@@ -1093,9 +1106,51 @@ static int check_error_flag(slk_classifier* c) {
   return SLK_OK;
 }
 
-static int classify_dev_common(slk_classifier* c, const slk_classify_opts* opts, bool packed, const mate_dev& m1,
-                               const mate_dev& m2, uint32_t n_reads, int32_t* taxon_out, uint8_t* flags_out,
+// block counts of a batch of ASCII reads: boff[i] = ceil(len_i / 32), boff[n] = 0 (the exclusive scan follows)
+__global__ void __launch_bounds__(256) block_counts_kernel(const uint64_t* __restrict__ off, uint32_t n, uint64_t* __restrict__ boff) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) boff[i] = (off[i + 1] - off[i] + 31) >> 5;
+  else if (i == n) boff[i] = 0;
+}
+static void launch_pack(const uint8_t* bases, const uint64_t* off, uint32_t n, const uint64_t* boff, uint64_t* codes, uint32_t* mask,
+                        uint32_t* len, cudaStream_t st) {
+  const uint64_t warps = ((uint64_t)n + 31) / 32;   // one warp per 32 reads, 8 warps per block
+  pack_reads_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(bases, off, n, boff, codes, mask, len);
+}
+// Stage 1 for device-resident ASCII input: the batch's packed form in scratch owned by the classifier (grow-only).
+static int pack_device_mate(slk_classifier* c, int m, const mate_dev& in, uint32_t n, mate_dev* out) {
+  uint64_t ends[2];
+  CU(cudaMemcpyAsync(&ends[0], in.off, 8, cudaMemcpyDeviceToHost, c->s_k));
+  CU(cudaMemcpyAsync(&ends[1], in.off + n, 8, cudaMemcpyDeviceToHost, c->s_k));
+  CU(cudaStreamSynchronize(c->s_k));
+  const uint64_t blocks = (ends[1] - ends[0]) / 32 + n + 1;
+  if (blocks > c->dv_blocks[m]) {
+    CU(cudaStreamSynchronize(c->s_k));
+    cudaFree(c->dv_codes[m]); cudaFree(c->dv_mask[m]); c->dv_codes[m] = nullptr; c->dv_mask[m] = nullptr; c->dv_blocks[m] = 0;
+    CU(cudaMalloc(&c->dv_codes[m], blocks * 8));
+    CU(cudaMalloc(&c->dv_mask[m], blocks * 4));
+    c->dv_blocks[m] = blocks;
+  }
+  if (n > c->dv_reads[m]) {
+    CU(cudaStreamSynchronize(c->s_k));
+    cudaFree(c->dv_boff[m]); cudaFree(c->dv_len[m]); c->dv_boff[m] = nullptr; c->dv_len[m] = nullptr; c->dv_reads[m] = 0;
+    CU(cudaMalloc(&c->dv_boff[m], ((size_t)n + 1) * 8));
+    CU(cudaMalloc(&c->dv_len[m], (size_t)n * 4));
+    c->dv_reads[m] = n;
+  }
+  block_counts_kernel<<<(n + 256) / 256, 256, 0, c->s_k>>>(in.off, n, c->dv_boff[m]);
+  if (slk_exclusive_scan_u64(c->dv_boff[m], (uint64_t)n + 1, c->s_k) != 0) return fail(SLK_E_CUDA, "prefix sum of the block counts failed");
+  launch_pack(in.bases - in.shift, in.off, n, c->dv_boff[m], c->dv_codes[m], c->dv_mask[m], c->dv_len[m], c->s_k);
+  c->launches += 2;
+  out->bases = reinterpret_cast<const uint8_t*>(c->dv_codes[m]); out->off = c->dv_boff[m]; out->shift = 0;
+  out->mask = c->dv_mask[m]; out->len = c->dv_len[m];
+  return SLK_OK;
+}
+
+static int classify_dev_common(slk_classifier* c, const slk_classify_opts* opts, bool packed, const mate_dev& m1_in,
+                               const mate_dev& m2_in, uint32_t n_reads, int32_t* taxon_out, uint8_t* flags_out,
                                slk_read_detail* detail_out, slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_used_dev) {
+  mate_dev m1 = m1_in, m2 = m2_in;
   if (!c || !opts || !m1.bases || !m1.off || !taxon_out || !flags_out) return fail(SLK_E_INVALID, "bad arguments");
   if ((m2.bases == nullptr) != (m2.off == nullptr)) return fail(SLK_E_INVALID, "mate 2 needs both its data and its offsets");
   if (packed && (!m1.mask || !m1.len || (m2.bases && (!m2.mask || !m2.len))))
@@ -1104,6 +1159,11 @@ static int classify_dev_common(slk_classifier* c, const slk_classify_opts* opts,
   if (hits && (!detail_out || !hits_used_dev)) return fail(SLK_E_INVALID, "hits_out needs detail_out and hits_used_dev");
   CU(cudaSetDevice(c->ctx->device));
   if (n_reads == 0) return SLK_OK;
+  if (!packed && kernel_generation() == 2) {   // stage 1 as a kernel of its own, then the packed-input classify kernel
+    TRY(pack_device_mate(c, 0, m1_in, n_reads, &m1));
+    if (m2_in.bases) TRY(pack_device_mate(c, 1, m2_in, n_reads, &m2));
+    packed = true;
+  }
   if (hits) CU(cudaMemsetAsync(hits_used_dev, 0, 8, c->s_k));
   launch_classify(c, hits, packed, opts, m1, m2, n_reads, taxon_out, flags_out, detail_out, hits_out, nullptr, hits_cap,
                   reinterpret_cast<unsigned long long*>(hits_used_dev));
@@ -1144,9 +1204,13 @@ extern "C" int slk_pack_reads_dev(slk_ctx* ctx, const uint8_t* bases_dev, const 
 
 static const uint64_t CH_BLOCKS = CH_BASES / 8;   // packed input: the same buffer holds CH_BLOCKS code blocks
 
+static const uint64_t CH_PK_BLOCKS = CH_BASES / 32 + SLK_CH_READS + 1;   // most 32-base blocks a chunk of ASCII reads can have
 static int ensure_slots(slk_classifier* c, bool paired, bool hits, bool packed) {
-  bool need = c->cap_reads == 0 || (paired && !c->cap_paired) || (hits && !c->cap_hits) || (packed && !c->cap_packed);
+  const bool ascii = !packed && kernel_generation() == 2;
+  bool need = c->cap_reads == 0 || (paired && !c->cap_paired) || (hits && !c->cap_hits) || (packed && !c->cap_packed) ||
+              (ascii && !c->cap_ascii);
   paired = paired || c->cap_paired; hits = hits || c->cap_hits; packed = packed || c->cap_packed;
+  const bool want_ascii = ascii || c->cap_ascii;
   if (!need) return SLK_OK;
   CU(cudaDeviceSynchronize());
   for (int i = 0; i < NSLOT; i++) {
@@ -1162,6 +1226,13 @@ static int ensure_slots(slk_classifier* c, bool paired, bool hits, bool packed) 
       CU(cudaMalloc(&s.mask1, CH_BLOCKS * 4)); CU(cudaMalloc(&s.len1, (size_t)CH_READS * 4));
       if (paired) { CU(cudaMalloc(&s.mask2, CH_BLOCKS * 4)); CU(cudaMalloc(&s.len2, (size_t)CH_READS * 4)); }
     }
+    if (want_ascii) {
+      for (int m = 0; m < (paired ? 2 : 1); m++) {
+        CU(cudaMalloc(&s.pk_codes[m], CH_PK_BLOCKS * 8)); CU(cudaMalloc(&s.pk_mask[m], CH_PK_BLOCKS * 4));
+        CU(cudaMalloc(&s.pk_boff[m], ((size_t)CH_READS + 1) * 8)); CU(cudaMalloc(&s.pk_len[m], (size_t)CH_READS * 4));
+        CU(cudaHostAlloc(&s.h_boff[m], ((size_t)CH_READS + 1) * 8, cudaHostAllocDefault));
+      }
+    }
     CU(cudaMalloc(&s.taxon, (size_t)CH_READS * 4));
     CU(cudaMalloc(&s.flags, CH_READS));
     CU(cudaMalloc(&s.detail, (size_t)CH_READS * sizeof(slk_read_detail)));
@@ -1171,6 +1242,7 @@ static int ensure_slots(slk_classifier* c, bool paired, bool hits, bool packed) 
     }
   }
   c->cap_reads = CH_READS; c->cap_bases = CH_BASES; c->cap_paired = paired; c->cap_hits = hits; c->cap_packed = packed;
+  c->cap_ascii = want_ascii;
   return SLK_OK;
 }
 
@@ -1216,6 +1288,7 @@ static int classify_host_common(slk_classifier* c, const slk_classify_opts* opts
   CU(cudaSetDevice(c->ctx->device));
   if (n_reads == 0) return SLK_OK;
   TRY(ensure_slots(c, paired, hits, packed));
+  const bool gen2_ascii = !packed && kernel_generation() == 2;
   CU(cudaMemsetAsync(c->d_cursor, 0, 8, c->s_k));
   const uint64_t unit_cap = packed ? CH_BLOCKS : CH_BASES;   // offsets count blocks or bytes
   uint64_t hits_total = 0;
@@ -1261,14 +1334,32 @@ static int classify_host_common(slk_classifier* c, const slk_classify_opts* opts
         d.mask = dmask; d.len = dlen;
       } else {
         CU(cudaMemcpyAsync(dbases, h.bases + u0, units, cudaMemcpyHostToDevice, c->s_h2d));
+        if (gen2_ascii) {   // the chunk's block offsets, from the host's offsets (the slot's pinned buffer is free: its last use
+          uint64_t* hb = s.h_boff[mt];   // was copied before the slot's d2h_done, which was awaited above)
+          uint64_t acc = 0;
+          for (uint32_t i = 0; i < s.n; i++) { hb[i] = acc; acc += (h.off[r0 + i + 1] - h.off[r0 + i] + 31) >> 5; }
+          hb[s.n] = acc;
+          CU(cudaMemcpyAsync(s.pk_boff[mt], hb, ((size_t)s.n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d));
+        }
       }
       CU(cudaMemcpyAsync(doff, h.off + r0, ((size_t)s.n + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d));
       d.bases = dbases; d.off = doff; d.shift = u0;
     }
     CU(cudaEventRecord(s.h2d_done, c->s_h2d));
     CU(cudaStreamWaitEvent(c->s_k, s.h2d_done, 0));
+    bool chunk_packed = packed;
+    if (gen2_ascii) {   // stage 1 as a kernel of its own: ASCII chunk -> packed chunk
+      for (int mt = 0; mt < (paired ? 2 : 1); mt++) {
+        mate_dev& d = mt ? d2 : d1;
+        launch_pack(d.bases - d.shift, d.off, s.n, s.pk_boff[mt], s.pk_codes[mt], s.pk_mask[mt], s.pk_len[mt], c->s_k);
+        c->launches++;
+        d.bases = reinterpret_cast<const uint8_t*>(s.pk_codes[mt]); d.off = s.pk_boff[mt]; d.shift = 0;
+        d.mask = s.pk_mask[mt]; d.len = s.pk_len[mt];
+      }
+      chunk_packed = true;
+    }
     if (hits) snapshot_kernel<<<1, 1, 0, c->s_k>>>(c->d_cursor, s.d_range);
-    launch_classify(c, hits, packed, opts, d1, d2, s.n, s.taxon, s.flags, s.detail, s.hits, s.d_range, s.hits_cap, c->d_cursor);
+    launch_classify(c, hits, chunk_packed, opts, d1, d2, s.n, s.taxon, s.flags, s.detail, s.hits, s.d_range, s.hits_cap, c->d_cursor);
     CU(cudaGetLastError());
     if (hits) {
       snapshot_kernel<<<1, 1, 0, c->s_k>>>(c->d_cursor, s.d_range + 1);
