@@ -430,8 +430,38 @@ def run_ours(args, w):
     e2e = e2e_line(lambda: cls.classify_packed(hp1, confidence=w.confidence, min_hit_groups=w.min_hit_groups, out=out), hp1.nbytes, True,
                    "slk_classify_batch_packed: pinned HOST buffers holding 2-bit packed reads + ambiguity masks (the host-side "
                    "packing is the Scala driver's batching work and is outside the timed region), per-read hit lists on")
+    # the compact boundary: codes + lengths + sparse ambiguity list in, 16-byte results + hits in read order out
+    from slacken_b200.host import RESULT_DTYPE, CompactBatch, CompactReads
+    nzb = np.nonzero(hp1.mask)[0]
+    nz_read = (np.searchsorted(boff, nzb, side="right") - 1).astype(np.uint32)
+    amb_r, amb_p = [], []
+    for b, rr in zip(nzb, nz_read):
+        mbits = int(hp1.mask[b])
+        for i in range(32):
+            if (mbits >> i) & 1:
+                amb_r.append(int(rr)); amb_p.append(32 * (int(b) - int(boff[rr])) + i)
+    cr1 = CompactReads(hp1.codes, hp1.len, np.array(amb_r, dtype=np.uint32), np.array(amb_p, dtype=np.uint32))
+    cout = CompactBatch(ctx.pinned(n, RESULT_DTYPE), np.zeros((0, n), dtype=np.int32), np.zeros((0, n), dtype=np.uint8),
+                        ctx.pinned(e2e_cap, HIT_DTYPE))
+    cs, ct0, ct1 = timed_e2e(lambda: cls.classify_compact(cr1, None, thresholds=[w.confidence], min_hit_groups=w.min_hit_groups, out=cout))
+    e2e_compact = {"value": world * n * args.steps / cs, "unit": "reads/s", "h2d_bytes_per_step": int(cr1.nbytes),
+                   "d2h_bytes_per_step": int(cout.results.nbytes + cout.hits_used * 8), "ms_per_step": 1e3 * cs / args.steps,
+                   "api": "slk_classify_batch_compact: pinned HOST buffers holding 2-bit codes + lengths + a sparse list of ambiguous "
+                          "positions (no block offsets, no mask words); 16-byte results and the merged hits in read order come back",
+                   "equal_to_packed_entry_point": None, "clocks": ClockSampler.summarize(sampler.window(ct0, ct1))}
     # `out` now holds the single-end results of the whole batch (the CPU leg below checks a sample of them)
     single_out = ClassifiedBatch(out.taxon.copy(), out.flags.copy(), out.detail.copy(), out.hits[:out.hits_used].copy(), out.hits_used)
+    # the compact results against the packed entry point's, all reads: taxon, flags, lengths, and the hit lists in read order
+    cls.classify_compact(cr1, None, thresholds=[w.confidence], min_hit_groups=w.min_hit_groups, out=cout)
+    ccnt = cout.hit_cnt.astype(np.int64)
+    same_c = bool(np.array_equal(cout.taxon, single_out.taxon) and np.array_equal(cout.flags, single_out.flags & 3) and
+                  np.array_equal(cout.results["len1"], single_out.detail["len1"]) and
+                  np.array_equal(ccnt, single_out.detail["hit_cnt"].astype(np.int64)) and cout.hits_used == int(ccnt.sum()))
+    if same_c:
+        within = np.arange(int(ccnt.sum()), dtype=np.int64) - np.repeat(np.cumsum(ccnt) - ccnt, ccnt)
+        gi = np.repeat(single_out.detail["hit_off"].astype(np.int64), ccnt) + within
+        same_c = bool(np.array_equal(cout.hits[:cout.hits_used], single_out.hits[gi]))
+    e2e_compact["equal_to_packed_entry_point"] = same_c
 
     # ================================================================== leg 2: configs[3] shape, paired-end 2 x 150 bp, confidence 0.15
     m2 = Mate(1)
@@ -473,7 +503,7 @@ def run_ours(args, w):
                        "classified_fraction": float((rep.sum() - rep[0]) / max(1, rep.sum())),
                        "reads_counted_in_report": total_reads_counted,
                        "device_report_counters_equal_per_read_results": report_consistent},
-            "probes_per_s": value * S, "clocks": clocks, "e2e": e2e, "e2e_report_only": e2e_report, "e2e_ascii_input": e2e_ascii,
+            "probes_per_s": value * S, "clocks": clocks, "e2e": e2e, "e2e_compact": e2e_compact, "e2e_report_only": e2e_report, "e2e_ascii_input": e2e_ascii,
             "value_ascii_input": {"value": world * n * args.steps / (ms_ascii / 1e3), "unit": "reads/s", "ms_per_step": ms_ascii / args.steps,
                                   "note": "same launch with ASCII reads resident in HBM (stage 1 runs first as its own kernel)"},
             "encode_kernel": {"ms": 1e3 * t_pack, "reads_per_s": n / t_pack, "gbs": (L + 8 + 12.0 * n_blocks / n + 4) * n / t_pack / 1e9,

@@ -86,6 +86,15 @@ typedef struct {
   int32_t reserved;
 } slk_classify_opts;
 
+/* ClassifyParams with several thresholds (ClassifyParams.thresholds, slacken/Classifier.scala:47-63): Slacken keeps the
+ * hits of a read and classifies them once per threshold (Classifier.scala:156-170); so does one call with these options. */
+#define SLK_MAX_THRESHOLDS 8
+typedef struct {
+  uint32_t n_thresholds;  /* 1 .. SLK_MAX_THRESHOLDS */
+  int32_t min_hit_groups;
+  double confidence[SLK_MAX_THRESHOLDS];
+} slk_classify_multi_opts;
+
 SLK_API const char* slk_last_error(void);
 
 /* ---- context ------------------------------------------------------------------------------------------- */
@@ -161,6 +170,33 @@ SLK_API int slk_classify_batch_packed(slk_classifier* c, const slk_classify_opts
                               const uint64_t* codes2, const uint32_t* mask2, const uint64_t* boff2, const uint32_t* len2,
                               uint32_t n_reads, int32_t* taxon_out, uint8_t* flags_out, slk_read_detail* detail_out,
                               slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_used);
+/* The same for several confidence thresholds in one pass: taxon_out and flags_out are [n_thresholds][n_reads] (row t =
+ * threshold t), detail_out and hits_out do not depend on the threshold. One scan and one table lookup per super-mer
+ * whatever the number of thresholds (slacken/Classifier.scala:156-170). */
+SLK_API int slk_classify_batch_packed_multi(slk_classifier* c, const slk_classify_multi_opts* opts,
+                              const uint64_t* codes1, const uint32_t* mask1, const uint64_t* boff1, const uint32_t* len1,
+                              const uint64_t* codes2, const uint32_t* mask2, const uint64_t* boff2, const uint32_t* len2,
+                              uint32_t n_reads, int32_t* taxon_out, uint8_t* flags_out, slk_read_detail* detail_out,
+                              slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_used);
+/* Compact boundary: the fewest bytes across PCIe for the same results (the end-to-end rate of a multi-GPU box is bounded by
+ * the host's memory traffic).
+ *   in:  codes (as above; every read starts a new 32-base block) and len[n]; NO block offsets (a prefix sum the device does
+ *        itself) and NO mask words: ambiguous characters travel as a list sorted by read, one entry per character,
+ *        entry = read_index << 32 | mate << 31 | position (mate 0 / 1, position < len). Code bits at ambiguous positions
+ *        are ignored. 44 bytes per 150-base read instead of 72.
+ *   out: results_out[n] (16 bytes per read, threshold 0); taxon_more / flags_more [n_thresholds - 1][n_reads] for the further
+ *        thresholds (NULL with one threshold); hits_out (may be NULL): the merged hits in READ ORDER, read i's hits right
+ *        after read i - 1's, (hits_flags >> 2) of them each. */
+typedef struct {
+  int32_t taxon;        /* raw taxon id, 0 = unclassified */
+  uint32_t len1;        /* lengthString parts as in slk_read_detail */
+  uint32_t len2;        /* 0xFFFFFFFF for single-end */
+  uint32_t hits_flags;  /* number of merged hits << 2 | SLK_READ_HAS_SPAN | SLK_READ_CLASSIFIED */
+} slk_read_result;
+SLK_API int slk_classify_batch_compact(slk_classifier* c, const slk_classify_multi_opts* opts,
+                              const uint64_t* codes1, const uint32_t* len1, const uint64_t* codes2, const uint32_t* len2,
+                              const uint64_t* ambiguous, uint64_t n_ambiguous, uint32_t n_reads, slk_read_result* results_out,
+                              int32_t* taxon_more, uint8_t* flags_more, slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_used);
 SLK_API int slk_classify_packed_dev(slk_classifier* c, const slk_classify_opts* opts,
                             const uint64_t* codes1, const uint32_t* mask1, const uint64_t* boff1, const uint32_t* len1,
                             const uint64_t* codes2, const uint32_t* mask2, const uint64_t* boff2, const uint32_t* len2,

@@ -23,6 +23,13 @@ class Params(C.Structure):
                 ("toggle_mask", C.c_uint64)]
 
 
+MAX_THRESHOLDS = 8
+
+
+class ClassifyMultiOpts(C.Structure):
+    _fields_ = [("n_thresholds", C.c_uint32), ("min_hit_groups", C.c_int32), ("confidence", C.c_double * MAX_THRESHOLDS)]
+
+
 class ClassifyOpts(C.Structure):
     _fields_ = [("confidence", C.c_double), ("min_hit_groups", C.c_int32), ("reserved", C.c_int32)]
 
@@ -61,6 +68,10 @@ SIGNATURES = {
                                       _VP]),
     "slk_classify_batch_packed": (_INT, [_VP, C.POINTER(ClassifyOpts), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP, _VP,
                                          _VP, _VP, _U64, C.POINTER(_U64)]),
+    "slk_classify_batch_packed_multi": (_INT, [_VP, C.POINTER(ClassifyMultiOpts), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP, _VP,
+                                               _VP, _VP, _U64, C.POINTER(_U64)]),
+    "slk_classify_batch_compact": (_INT, [_VP, C.POINTER(ClassifyMultiOpts), _VP, _VP, _VP, _VP, _VP, _U64, _U32, _VP, _VP, _VP, _VP, _U64,
+                                          C.POINTER(_U64)]),
     "slk_classify_packed_dev": (_INT, [_VP, C.POINTER(ClassifyOpts), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP, _VP,
                                        _VP, _VP, _U64, _VP]),
     "slk_pack_reads_dev": (_INT, [_VP, _VP, _VP, _U32, _VP, _VP, _VP, _VP]),

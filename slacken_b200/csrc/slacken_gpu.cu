@@ -846,7 +846,7 @@ extern "C" int slk_counts_fetch(slk_counts* c, int32_t sample, int64_t* per_taxo
 }
 
 // ---------------------------------------------------------------------------------------------- classifier
-#define NSLOT 3
+#define NSLOT 4
 struct cls_slot {
   uint8_t *bases1 = nullptr, *bases2 = nullptr;   // ASCII bases, or the uint64 code blocks of packed input
   uint64_t *off1 = nullptr, *off2 = nullptr;
@@ -855,11 +855,17 @@ struct cls_slot {
   uint64_t *pk_codes[2] = {nullptr, nullptr}, *pk_boff[2] = {nullptr, nullptr};
   uint32_t *pk_mask[2] = {nullptr, nullptr}, *pk_len[2] = {nullptr, nullptr};
   uint64_t* h_boff[2] = {nullptr, nullptr};   // pinned: the chunk's block offsets, computed from the host's offsets
+  // compact boundary (slk_classify_batch_compact): 16-byte results, hits in read order, the chunk's ambiguity entries
+  slk_read_result* res16 = nullptr; slk_hit* hits_ord = nullptr; uint64_t* hoff = nullptr; uint64_t* scan_scr = nullptr;
+  uint64_t* amb = nullptr;
+  uint64_t* h_amb = nullptr;   // pinned staging of the chunk's ambiguity entries (the caller's list need not be pinned)
+  bool staged = false;
   int32_t* taxon = nullptr; uint8_t* flags = nullptr; slk_read_detail* detail = nullptr;
   slk_hit* hits = nullptr; uint64_t hits_cap = 0;
-  unsigned long long* d_range = nullptr;   // [0] = cursor value before the kernel, [1] = after
+  unsigned long long* d_range = nullptr;   // [0] = cursor value before the kernel, [1] = after, [2] = hits in read order (compact)
   unsigned long long* h_range = nullptr;   // pinned copy
   cudaEvent_t h2d_done, k_done, d2h_done;
+  cudaEvent_t copied_in, post_done;   // compact boundary: copies landed (the prep kernels may run), results ready (the copies back may run)
   bool busy = false;
   uint32_t r0 = 0, n = 0;
 };
@@ -867,9 +873,11 @@ struct slk_classifier {
   slk_index* idx;
   slk_ctx* ctx;
   cudaStream_t s_h2d, s_k, s_d2h;
+  cudaStream_t s_prep, s_post;   // compact boundary: the small kernels in front of / behind a chunk's classify kernel
+  cudaStream_t s_k2;             // compact boundary: odd chunks classify here, so that a kernel's last wave overlaps its successor's first
   cls_slot slot[NSLOT];
   size_t cap_reads = 0, cap_bases = 0;
-  bool cap_paired = false, cap_hits = false, cap_packed = false, cap_ascii = false;
+  bool cap_paired = false, cap_hits = false, cap_packed = false, cap_ascii = false, cap_compact = false;
   // device-resident ASCII input (slk_classify_batch_dev): its packed form, grow-only
   uint64_t *dv_codes[2] = {nullptr, nullptr}, *dv_boff[2] = {nullptr, nullptr};
   uint32_t *dv_mask[2] = {nullptr, nullptr}, *dv_len[2] = {nullptr, nullptr};
@@ -894,15 +902,26 @@ extern "C" int slk_classifier_create(slk_index* idx, slk_classifier** out) {
   slk_classifier* c = new (std::nothrow) slk_classifier;
   if (!c) return fail(SLK_E_NOMEM, "host allocation failed");
   c->idx = idx; c->ctx = ctx;
+  // The small kernels around a chunk's classify kernel (block offsets, ambiguity bits, results in read order) run on two
+  // streams of their own with the higher priority: their few blocks are placed ahead of the thousands of blocks the
+  // neighbouring chunk's classify kernel still has to place. (The copy streams keep the default priority: pending work of
+  // a higher-priority stream, copies included, holds back kernel launches of the lower ones.)
+  int prio_lo = 0, prio_hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   CU(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithPriority(&c->s_prep, cudaStreamNonBlocking, prio_hi));
+  CU(cudaStreamCreateWithPriority(&c->s_post, cudaStreamNonBlocking, prio_hi));
+  CU(cudaStreamCreateWithFlags(&c->s_k2, cudaStreamNonBlocking));
   for (int i = 0; i < NSLOT; i++) {
     CU(cudaEventCreateWithFlags(&c->slot[i].h2d_done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->slot[i].k_done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->slot[i].d2h_done, cudaEventDisableTiming));
-    CU(cudaMalloc(&c->slot[i].d_range, 16));
-    CU(cudaHostAlloc(&c->slot[i].h_range, 16, cudaHostAllocDefault));
+    CU(cudaEventCreateWithFlags(&c->slot[i].copied_in, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->slot[i].post_done, cudaEventDisableTiming));
+    CU(cudaMalloc(&c->slot[i].d_range, 32));
+    CU(cudaHostAlloc(&c->slot[i].h_range, 32, cudaHostAllocDefault));
   }
   CU(cudaMalloc(&c->d_cursor, 8));
   CU(cudaMalloc(&c->d_err, 4));
@@ -915,6 +934,9 @@ extern "C" int slk_classifier_create(slk_index* idx, slk_classifier** out) {
 static void slot_free(cls_slot& s) {
   cudaFree(s.bases1); cudaFree(s.bases2); cudaFree(s.off1); cudaFree(s.off2); cudaFree(s.taxon); cudaFree(s.flags);
   cudaFree(s.detail); cudaFree(s.hits); cudaFree(s.mask1); cudaFree(s.mask2); cudaFree(s.len1); cudaFree(s.len2);
+  cudaFree(s.res16); cudaFree(s.hits_ord); cudaFree(s.hoff); cudaFree(s.scan_scr); cudaFree(s.amb); cudaFreeHost(s.h_amb);
+  s.h_amb = nullptr;
+  s.res16 = nullptr; s.hits_ord = nullptr; s.hoff = nullptr; s.scan_scr = nullptr; s.amb = nullptr;
   for (int m = 0; m < 2; m++) {
     cudaFree(s.pk_codes[m]); cudaFree(s.pk_boff[m]); cudaFree(s.pk_mask[m]); cudaFree(s.pk_len[m]); cudaFreeHost(s.h_boff[m]);
     s.pk_codes[m] = s.pk_boff[m] = nullptr; s.pk_mask[m] = s.pk_len[m] = nullptr; s.h_boff[m] = nullptr;
@@ -930,10 +952,12 @@ extern "C" void slk_classifier_destroy(slk_classifier* c) {
     slot_free(c->slot[i]);
     cudaFree(c->slot[i].d_range); cudaFreeHost(c->slot[i].h_range);
     cudaEventDestroy(c->slot[i].h2d_done); cudaEventDestroy(c->slot[i].k_done); cudaEventDestroy(c->slot[i].d2h_done);
+    cudaEventDestroy(c->slot[i].copied_in); cudaEventDestroy(c->slot[i].post_done);
   }
   cudaFree(c->d_cursor); cudaFree(c->d_err); cudaFree(c->d_stats);
   for (int m = 0; m < 2; m++) { cudaFree(c->dv_codes[m]); cudaFree(c->dv_boff[m]); cudaFree(c->dv_mask[m]); cudaFree(c->dv_len[m]); }
   cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_k); cudaStreamDestroy(c->s_d2h);
+  cudaStreamDestroy(c->s_prep); cudaStreamDestroy(c->s_post); cudaStreamDestroy(c->s_k2);
   delete c;
 }
 extern "C" int slk_classifier_sync(slk_classifier* c) {
@@ -1058,26 +1082,50 @@ static int kernel_generation() {
   static const int g = [] { const char* e = getenv("SLK_KERNEL"); return (e && atoi(e) == 1) ? 1 : 2; }();
   return g;
 }
-static void launch_classify(slk_classifier* c, bool hits, bool packed, const slk_classify_opts* o, const mate_dev& m1,
+// ClassifyParams of one call: the thresholds (row t of taxon / flags starts `stride` elements after row t - 1)
+struct cls_opts {
+  double conf[SLK_MAX_THRESHOLDS];
+  uint32_t n = 1;
+  int32_t mhg = 2;
+  uint64_t stride = 0;
+};
+static int make_opts(const slk_classify_opts* o, uint64_t stride, cls_opts* out) {
+  if (!o) return fail(SLK_E_INVALID, "bad arguments");
+  out->n = 1; out->conf[0] = o->confidence; out->mhg = o->min_hit_groups; out->stride = stride;
+  return SLK_OK;
+}
+static int make_opts(const slk_classify_multi_opts* o, uint64_t stride, cls_opts* out) {
+  if (!o || o->n_thresholds < 1 || o->n_thresholds > SLK_MAX_THRESHOLDS)
+    return fail(SLK_E_INVALID, "1 to %d confidence thresholds per call", SLK_MAX_THRESHOLDS);
+  if (o->n_thresholds > 1 && kernel_generation() != 2) return fail(SLK_E_UNSUPPORTED, "several thresholds need the second-generation kernel");
+  out->n = o->n_thresholds; out->mhg = o->min_hit_groups; out->stride = stride;
+  for (uint32_t t = 0; t < out->n; t++) out->conf[t] = o->confidence[t];
+  return SLK_OK;
+}
+static void launch_classify(slk_classifier* c, bool hits, bool packed, const cls_opts& o, const mate_dev& m1,
                             const mate_dev& m2, uint32_t n, int32_t* taxon, uint8_t* flags, slk_read_detail* detail,
-                            slk_hit* hbase, const unsigned long long* hshift, uint64_t hcap, unsigned long long* cursor) {
+                            slk_hit* hbase, const unsigned long long* hshift, uint64_t hcap, unsigned long long* cursor,
+                            unsigned long long* hits_over = nullptr, cudaStream_t st = nullptr) {
   slk_index* idx = c->idx;
+  if (st == nullptr) st = c->s_k;
   if (packed && kernel_generation() == 2) {
     slk_classify2_args a;
     a.sp = idx->sp; a.tb = idx->table; a.tx = idx->dt.view();
     a.in1 = slk_group_in{reinterpret_cast<const uint64_t*>(m1.bases), m1.mask, m1.off, m1.len, m1.shift};
     a.in2 = slk_group_in{reinterpret_cast<const uint64_t*>(m2.bases), m2.mask, m2.off, m2.len, m2.shift};
     a.paired = m2.bases != nullptr; a.n_reads = n;
-    a.confidence = o->confidence; a.min_hit_groups = o->min_hit_groups; a.hits = hits;
+    a.mt.n = o.n; a.mt.stride = o.stride; a.mt.taxon_out = taxon; a.mt.flags_out = flags;
+    for (uint32_t t = 0; t < o.n; t++) a.mt.confidence[t] = o.conf[t];
+    a.min_hit_groups = o.mhg; a.hits = hits;
     a.taxon_out = taxon; a.flags_out = flags; a.detail_out = detail;
-    a.hits_base = hbase; a.hits_shift_ptr = hshift; a.hits_cap = hcap; a.hits_cursor = cursor;
+    a.hits_base = hbase; a.hits_shift_ptr = hshift; a.hits_cap = hcap; a.hits_cursor = cursor; a.hits_over = hits_over;
     a.counts = c->counts ? c->counts->d + (size_t)c->counts_sample * c->counts->n_taxa : nullptr;
     a.error_flag = c->d_err; a.stats = c->d_stats;
     switch (idx->sp.w) {
-      case 1: slk_launch_classify2_w1(a, c->s_k); break; case 2: slk_launch_classify2_w2(a, c->s_k); break;
-      case 3: slk_launch_classify2_w3(a, c->s_k); break; case 4: slk_launch_classify2_w4(a, c->s_k); break;
-      case 5: slk_launch_classify2_w5(a, c->s_k); break; case 6: slk_launch_classify2_w6(a, c->s_k); break;
-      case 7: slk_launch_classify2_w7(a, c->s_k); break; default: slk_launch_classify2_w8(a, c->s_k); break;
+      case 1: slk_launch_classify2_w1(a, st); break; case 2: slk_launch_classify2_w2(a, st); break;
+      case 3: slk_launch_classify2_w3(a, st); break; case 4: slk_launch_classify2_w4(a, st); break;
+      case 5: slk_launch_classify2_w5(a, st); break; case 6: slk_launch_classify2_w6(a, st); break;
+      case 7: slk_launch_classify2_w7(a, st); break; default: slk_launch_classify2_w8(a, st); break;
     }
     c->launches++;
     return;
@@ -1087,11 +1135,11 @@ static void launch_classify(slk_classifier* c, bool hits, bool packed, const slk
   a.bases1 = m1.bases; a.off1 = m1.off; a.shift1 = m1.shift; a.mask1 = m1.mask; a.len1 = m1.len;
   a.bases2 = m2.bases; a.off2 = m2.off; a.shift2 = m2.shift; a.mask2 = m2.mask; a.len2 = m2.len;
   a.packed = packed; a.n_reads = n;
-  a.confidence = o->confidence; a.min_hit_groups = o->min_hit_groups;
+  a.confidence = o.conf[0]; a.min_hit_groups = o.mhg;
   a.taxon_out = taxon; a.flags_out = flags; a.detail_out = detail;
   a.hits_base = hbase; a.hits_shift_ptr = hshift; a.hits_cap = hcap; a.hits_cursor = cursor;
   a.counts = c->counts ? c->counts->d + (size_t)c->counts_sample * c->counts->n_taxa : nullptr;
-  a.error_flag = c->d_err; a.stats = c->d_stats; a.hits = hits; a.stream = c->s_k;
+  a.error_flag = c->d_err; a.stats = c->d_stats; a.hits = hits; a.stream = st;
   DISPATCH_W(idx->sp.w, slk_launch_classify_w, a);
   c->launches++;
 }
@@ -1147,16 +1195,18 @@ static int pack_device_mate(slk_classifier* c, int m, const mate_dev& in, uint32
   return SLK_OK;
 }
 
-static int classify_dev_common(slk_classifier* c, const slk_classify_opts* opts, bool packed, const mate_dev& m1_in,
+static int classify_dev_common(slk_classifier* c, const slk_classify_opts* opts_in, bool packed, const mate_dev& m1_in,
                                const mate_dev& m2_in, uint32_t n_reads, int32_t* taxon_out, uint8_t* flags_out,
                                slk_read_detail* detail_out, slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_used_dev) {
   mate_dev m1 = m1_in, m2 = m2_in;
-  if (!c || !opts || !m1.bases || !m1.off || !taxon_out || !flags_out) return fail(SLK_E_INVALID, "bad arguments");
+  cls_opts opts;
+  if (!c || !opts_in || !m1.bases || !m1.off || !taxon_out || !flags_out) return fail(SLK_E_INVALID, "bad arguments");
   if ((m2.bases == nullptr) != (m2.off == nullptr)) return fail(SLK_E_INVALID, "mate 2 needs both its data and its offsets");
   if (packed && (!m1.mask || !m1.len || (m2.bases && (!m2.mask || !m2.len))))
     return fail(SLK_E_INVALID, "packed input needs mask and len arrays");
   bool hits = hits_out != nullptr;
   if (hits && (!detail_out || !hits_used_dev)) return fail(SLK_E_INVALID, "hits_out needs detail_out and hits_used_dev");
+  TRY(make_opts(opts_in, n_reads, &opts));
   CU(cudaSetDevice(c->ctx->device));
   if (n_reads == 0) return SLK_OK;
   if (!packed && kernel_generation() == 2) {   // stage 1 as a kernel of its own, then the packed-input classify kernel
@@ -1233,8 +1283,8 @@ static int ensure_slots(slk_classifier* c, bool paired, bool hits, bool packed) 
         CU(cudaHostAlloc(&s.h_boff[m], ((size_t)CH_READS + 1) * 8, cudaHostAllocDefault));
       }
     }
-    CU(cudaMalloc(&s.taxon, (size_t)CH_READS * 4));
-    CU(cudaMalloc(&s.flags, CH_READS));
+    CU(cudaMalloc(&s.taxon, (size_t)CH_READS * 4 * SLK_MAX_THRESHOLDS));   // one row per confidence threshold
+    CU(cudaMalloc(&s.flags, (size_t)CH_READS * SLK_MAX_THRESHOLDS));
     CU(cudaMalloc(&s.detail, (size_t)CH_READS * sizeof(slk_read_detail)));
     if (hits) {
       s.hits_cap = (paired ? 2 : 1) * CH_BASES + 5ull * CH_READS;
@@ -1243,15 +1293,18 @@ static int ensure_slots(slk_classifier* c, bool paired, bool hits, bool packed) 
   }
   c->cap_reads = CH_READS; c->cap_bases = CH_BASES; c->cap_paired = paired; c->cap_hits = hits; c->cap_packed = packed;
   c->cap_ascii = want_ascii;
+  c->cap_compact = false;   // (slot_free released the compact-boundary buffers as well)
   return SLK_OK;
 }
 
 // finish one chunk: wait for its kernel, then copy its results into the caller's arrays
-static int finalize_slot(slk_classifier* c, cls_slot& s, bool hits, int32_t* taxon_out, uint8_t* flags_out,
+static int finalize_slot(slk_classifier* c, cls_slot& s, bool hits, uint32_t n_thr, uint32_t n_reads, int32_t* taxon_out, uint8_t* flags_out,
                          slk_read_detail* detail_out, slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_total, bool* nospace) {
   CU(cudaEventSynchronize(s.k_done));
-  CU(cudaMemcpyAsync(taxon_out + s.r0, s.taxon, (size_t)s.n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
-  CU(cudaMemcpyAsync(flags_out + s.r0, s.flags, s.n, cudaMemcpyDeviceToHost, c->s_d2h));
+  for (uint32_t t = 0; t < n_thr; t++) {   // row t of the caller's [n_thr][n_reads] arrays
+    CU(cudaMemcpyAsync(taxon_out + (size_t)t * n_reads + s.r0, s.taxon + (size_t)t * CH_READS, (size_t)s.n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    CU(cudaMemcpyAsync(flags_out + (size_t)t * n_reads + s.r0, s.flags + (size_t)t * CH_READS, s.n, cudaMemcpyDeviceToHost, c->s_d2h));
+  }
   if (detail_out)
     CU(cudaMemcpyAsync(detail_out + s.r0, s.detail, (size_t)s.n * sizeof(slk_read_detail), cudaMemcpyDeviceToHost, c->s_d2h));
   if (hits) {
@@ -1276,10 +1329,10 @@ struct mate_host {
 };
 
 // The chunked, triple-buffered H2D -> kernel -> D2H pipeline behind both host-buffer entry points.
-static int classify_host_common(slk_classifier* c, const slk_classify_opts* opts, bool packed, const mate_host& h1,
+static int classify_host_common(slk_classifier* c, const cls_opts& opts, bool packed, const mate_host& h1,
                                 const mate_host& h2, uint32_t n_reads, int32_t* taxon_out, uint8_t* flags_out,
                                 slk_read_detail* detail_out, slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_used) {
-  if (!c || !opts || !h1.off || !taxon_out || !flags_out) return fail(SLK_E_INVALID, "bad arguments");
+  if (!c || !h1.off || !taxon_out || !flags_out) return fail(SLK_E_INVALID, "bad arguments");
   const bool paired = h2.off != nullptr, hits = hits_out != nullptr;
   if (packed ? (!h1.codes || !h1.mask || !h1.len || (paired && (!h2.codes || !h2.mask || !h2.len))) : (!h1.bases || (paired && !h2.bases)))
     return fail(SLK_E_INVALID, "missing input arrays");
@@ -1369,16 +1422,255 @@ static int classify_host_common(slk_classifier* c, const slk_classify_opts* opts
     CU(cudaEventRecord(s.k_done, c->s_k));
     s.busy = true;
     if (prev >= 0)
-      TRY(finalize_slot(c, c->slot[prev], hits, taxon_out, flags_out, detail_out, hits_out, hits_cap, &hits_total, &nospace));
+      TRY(finalize_slot(c, c->slot[prev], hits, opts.n, n_reads, taxon_out, flags_out, detail_out, hits_out, hits_cap, &hits_total, &nospace));
     prev = ci % NSLOT;
     ci++;
     r0 = r1;
   }
   if (prev >= 0)
-    TRY(finalize_slot(c, c->slot[prev], hits, taxon_out, flags_out, detail_out, hits_out, hits_cap, &hits_total, &nospace));
+    TRY(finalize_slot(c, c->slot[prev], hits, opts.n, n_reads, taxon_out, flags_out, detail_out, hits_out, hits_cap, &hits_total, &nospace));
   CU(cudaStreamSynchronize(c->s_d2h));
   for (int i = 0; i < NSLOT; i++) c->slot[i].busy = false;
   if (hits_used) *hits_used = hits_total;
+  TRY(check_error_flag(c));
+  if (nospace) return fail(SLK_E_NOSPACE, "hits_out needs room for %llu hits", (unsigned long long)hits_total);
+  return SLK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- compact boundary
+// The same classification with fewer bytes across PCIe ("boundary"): in, 2-bit codes + read lengths + a sparse
+// list of ambiguous positions (44 instead of 72 bytes per 150-base read: the block offsets are a prefix sum the device
+// does itself, and nearly all ambiguity mask words are zero); out, one 16-byte slk_read_result per read and the merged
+// hits in READ ORDER (a read's hits follow its predecessor's, so no offsets travel).
+#define SLK_AMB_CAP (4u << 20)   // ambiguity entries per chunk
+#define SCAN_SCR_WORDS 4096      // >= slk_scan_scratch_words(CH_READS + 1)
+__global__ void __launch_bounds__(256) block_counts_len_kernel(const uint32_t* __restrict__ len, uint32_t n, uint64_t* __restrict__ boff) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) boff[i] = ((uint64_t)len[i] + 31) >> 5;
+  else if (i == n) boff[i] = 0;
+}
+// entry = read << 32 | mate << 31 | position: sets the position's bit in the read's mask words
+__global__ void __launch_bounds__(256) amb_scatter_kernel(const uint64_t* __restrict__ amb, uint32_t n_amb, uint32_t r0, uint32_t n,
+                                                          const uint64_t* __restrict__ boff1, const uint32_t* __restrict__ len1, uint32_t* mask1,
+                                                          const uint64_t* __restrict__ boff2, const uint32_t* __restrict__ len2, uint32_t* mask2,
+                                                          uint32_t* error_flag) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_amb) return;
+  const uint64_t e = amb[i];
+  const uint32_t r = (uint32_t)(e >> 32) - r0, mate = (uint32_t)(e >> 31) & 1u, pos = (uint32_t)e & 0x7fffffffu;
+  const uint64_t* boff = mate ? boff2 : boff1;
+  const uint32_t* len = mate ? len2 : len1;
+  uint32_t* mask = mate ? mask2 : mask1;
+  if (r >= n || boff == nullptr || pos >= len[r]) { atomicExch(error_flag, 2u); return; }
+  atomicOr(&mask[boff[r] + (pos >> 5)], 1u << (pos & 31u));
+}
+__global__ void __launch_bounds__(256) hit_counts_kernel(const slk_read_detail* __restrict__ detail, uint32_t n, uint64_t* __restrict__ hoff) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) hoff[i] = detail[i].hit_cnt;
+  else if (i == n) hoff[i] = 0;
+}
+// results + hits in read order. hits: the chunk's hit block (index = detail.hit_off - *lo), ord: the ordered copy
+__global__ void __launch_bounds__(256) compact_results_kernel(const int32_t* __restrict__ taxon, const uint8_t* __restrict__ flags,
+                                                              const slk_read_detail* __restrict__ detail, uint32_t n,
+                                                              const uint64_t* __restrict__ hoff, const slk_hit* __restrict__ hits,
+                                                              const unsigned long long* __restrict__ lo, uint64_t cap, slk_hit* __restrict__ ord,
+                                                              slk_read_result* __restrict__ res) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const slk_read_detail d = detail[i];
+  slk_read_result r;
+  r.taxon = taxon[i]; r.len1 = d.len1; r.len2 = d.len2; r.hits_flags = (d.hit_cnt << 2) | (flags[i] & 3u);
+  res[i] = r;
+  if (hits != nullptr) {
+    const uint64_t src = d.hit_off - *lo, dst = hoff[i];
+    for (uint32_t j = 0; j < d.hit_cnt; j++)
+      if (src + j < cap && dst + j < cap) ord[dst + j] = hits[src + j];
+  }
+}
+
+extern "C" int slk_classify_batch_compact(slk_classifier* c, const slk_classify_multi_opts* opts_in, const uint64_t* codes1,
+                                          const uint32_t* len1, const uint64_t* codes2, const uint32_t* len2, const uint64_t* ambiguous,
+                                          uint64_t n_ambiguous, uint32_t n_reads, slk_read_result* results_out, int32_t* taxon_more,
+                                          uint8_t* flags_more, slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_used) {
+  if (!c || !opts_in || !codes1 || !len1 || !results_out || (codes2 != nullptr) != (len2 != nullptr) || (n_ambiguous && !ambiguous))
+    return fail(SLK_E_INVALID, "bad arguments");
+  if (kernel_generation() != 2) return fail(SLK_E_UNSUPPORTED, "the compact entry point needs the second-generation kernel");
+  cls_opts opts;
+  TRY(make_opts(opts_in, CH_READS, &opts));
+  if (opts.n > 1 && (!taxon_more || !flags_more)) return fail(SLK_E_INVALID, "several thresholds need taxon_more and flags_more");
+  const bool paired = codes2 != nullptr, hits = hits_out != nullptr;
+  if (hits_used) *hits_used = 0;
+  CU(cudaSetDevice(c->ctx->device));
+  if (n_reads == 0) return SLK_OK;
+  TRY(ensure_slots(c, paired, true, true));
+  if (!c->cap_compact) {
+    CU(cudaDeviceSynchronize());
+    for (int i = 0; i < NSLOT; i++) {
+      cls_slot& s = c->slot[i];
+      CU(cudaMalloc(&s.res16, (size_t)CH_READS * sizeof(slk_read_result)));
+      CU(cudaMalloc(&s.hits_ord, s.hits_cap * sizeof(slk_hit)));
+      CU(cudaMalloc(&s.hoff, ((size_t)CH_READS + 1) * 8));
+      CU(cudaMalloc(&s.scan_scr, 2 * SCAN_SCR_WORDS * 8));   // one half per stream that scans
+      CU(cudaMalloc(&s.amb, (size_t)SLK_AMB_CAP * 8));
+      CU(cudaHostAlloc(&s.h_amb, (size_t)SLK_AMB_CAP * 8, cudaHostAllocDefault));
+    }
+    c->cap_compact = true;
+  }
+  CU(cudaMemsetAsync(c->d_cursor, 0, 8, c->s_k));
+  // SLK_TRACE=1: the device timeline of every chunk (copy in / kernel / copy back) on stderr, for tuning the pipeline
+  static const bool trace = getenv("SLK_TRACE") != nullptr;
+  struct tr_ev { cudaEvent_t h0, h1, k0, k1, d0, d1; uint32_t n; };
+  std::vector<tr_ev> tr;
+  cudaEvent_t tr0 = nullptr;
+  auto tmark = [&](cudaEvent_t* e, cudaStream_t st) { if (trace) { cudaEventCreate(e); cudaEventRecord(*e, st); } };
+  if (trace) { cudaEventCreate(&tr0); cudaEventRecord(tr0, c->s_h2d); }
+  uint64_t hits_total = 0, blk0[2] = {0, 0}, a0 = 0;
+  bool nospace = false;
+  int ci = 0;
+  uint32_t r0 = 0;
+  mate_dev sd1[NSLOT], sd2[NSLOT];
+  // Results and hits in read order are made on the COPY-BACK stream in front of the copies: that work overlaps the classify
+  // kernel of the next chunk. The number of hits is known on the host without another synchronisation: the cursor's advance
+  // minus what spilled fragments reserved in excess.
+  auto finalize = [&](cls_slot& s, int idx) -> int {
+    CU(cudaEventSynchronize(s.k_done));
+    if (trace) tmark(&tr[idx].d0, c->s_post);
+    const uint64_t cnt = hits ? (s.h_range[1] - s.h_range[0]) - s.h_range[2] : 0;
+    if (hits) {
+      hit_counts_kernel<<<(s.n + 256) / 256, 256, 0, c->s_post>>>(s.detail, s.n, s.hoff);
+      if (slk_exclusive_scan_u64_async(s.hoff, (uint64_t)s.n + 1, s.scan_scr + SCAN_SCR_WORDS, c->s_post) != 0) return fail(SLK_E_CUDA, "prefix sum of the hit counts failed");
+    }
+    compact_results_kernel<<<(s.n + 255) / 256, 256, 0, c->s_post>>>(s.taxon, s.flags, s.detail, s.n, s.hoff, hits ? s.hits : nullptr, s.d_range,
+                                                                      s.hits_cap, s.hits_ord, s.res16);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(s.post_done, c->s_post));
+    CU(cudaStreamWaitEvent(c->s_d2h, s.post_done, 0));
+    CU(cudaMemcpyAsync(results_out + s.r0, s.res16, (size_t)s.n * sizeof(slk_read_result), cudaMemcpyDeviceToHost, c->s_d2h));
+    for (uint32_t t = 1; t < opts.n; t++) {
+      CU(cudaMemcpyAsync(taxon_more + (size_t)(t - 1) * n_reads + s.r0, s.taxon + (size_t)t * CH_READS, (size_t)s.n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+      CU(cudaMemcpyAsync(flags_more + (size_t)(t - 1) * n_reads + s.r0, s.flags + (size_t)t * CH_READS, s.n, cudaMemcpyDeviceToHost, c->s_d2h));
+    }
+    if (hits) {
+      uint64_t used = cnt;
+      if (hits_total + used > hits_cap) { nospace = true; used = hits_cap > hits_total ? hits_cap - hits_total : 0; }
+      if (used) CU(cudaMemcpyAsync(hits_out + hits_total, s.hits_ord, (size_t)used * sizeof(slk_hit), cudaMemcpyDeviceToHost, c->s_d2h));
+      hits_total += cnt;
+    }
+    CU(cudaEventRecord(s.d2h_done, c->s_d2h));
+    if (trace) tmark(&tr[idx].d1, c->s_d2h);
+    return SLK_OK;
+  };
+  // Three chunks are in flight: chunk i is copied in and prepared while chunk i - 1 is classified and chunk i - 2 is copied
+  // back, so that a classify kernel always finds its input on the device when its predecessor ends.
+  auto stage_in = [&]() -> int {
+    uint32_t want = CH_READS;
+    if (ci < 3) want = std::max<uint32_t>(CH_READS >> (3 - ci), 32768u);
+    const uint32_t left = n_reads - r0;
+    if (left < 2 * (uint64_t)want) want = std::max<uint32_t>(left / 2, 32768u);
+    uint32_t r1 = (uint32_t)std::min<uint64_t>(n_reads, (uint64_t)r0 + want);
+    uint64_t blocks[2] = {0, 0};
+    auto count = [&](const uint32_t* len, uint32_t a, uint32_t b) { uint64_t t = 0; for (uint32_t i = a; i < b; i++) t += ((uint64_t)len[i] + 31) >> 5; return t; };
+    blocks[0] = count(len1, r0, r1);
+    if (paired) blocks[1] = count(len2, r0, r1);
+    if (blocks[0] > CH_BLOCKS || blocks[1] > CH_BLOCKS) {   // long reads: as many as fit
+      uint64_t b1 = 0, b2 = 0;
+      uint32_t e = r0;
+      for (; e < r1; e++) {
+        const uint64_t n1 = ((uint64_t)len1[e] + 31) >> 5, n2 = paired ? ((uint64_t)len2[e] + 31) >> 5 : 0;
+        if (b1 + n1 > CH_BLOCKS || b2 + n2 > CH_BLOCKS) break;
+        b1 += n1; b2 += n2;
+      }
+      if (e == r0) return fail(SLK_E_UNSUPPORTED, "read %u is longer than %llu bases", r0, (unsigned long long)CH_BASES);
+      r1 = e; blocks[0] = b1; blocks[1] = b2;
+    }
+    uint64_t a1 = a0;   // the chunk's ambiguity entries (the list is sorted by read)
+    while (a1 < n_ambiguous && (ambiguous[a1] >> 32) < r1) a1++;
+    if (a1 - a0 > SLK_AMB_CAP) return fail(SLK_E_UNSUPPORTED, "more than %u ambiguous positions in one chunk: use the mask entry point", SLK_AMB_CAP);
+    if (a1 > a0 && (ambiguous[a0] >> 32) < r0) return fail(SLK_E_INVALID, "the ambiguity list must be sorted by read");
+    cls_slot& s = c->slot[ci % NSLOT];
+    if (s.busy) { CU(cudaEventSynchronize(s.d2h_done)); s.busy = false; }
+    s.r0 = r0; s.n = r1 - r0;
+    if (trace) { tr.push_back(tr_ev{}); tr[ci].n = s.n; tmark(&tr[ci].h0, c->s_h2d); }
+    mate_dev d1, d2;
+    for (int mt = 0; mt < (paired ? 2 : 1); mt++) {
+      mate_dev& d = mt ? d2 : d1;
+      uint8_t* dcodes = mt ? s.bases2 : s.bases1;
+      uint32_t* dlen = mt ? s.len2 : s.len1;
+      CU(cudaMemcpyAsync(dcodes, (mt ? codes2 : codes1) + blk0[mt], blocks[mt] * 8, cudaMemcpyHostToDevice, c->s_h2d));
+      CU(cudaMemcpyAsync(dlen, (mt ? len2 : len1) + r0, (size_t)s.n * 4, cudaMemcpyHostToDevice, c->s_h2d));
+      d.bases = dcodes; d.off = mt ? s.off2 : s.off1; d.shift = 0; d.mask = mt ? s.mask2 : s.mask1; d.len = dlen;
+    }
+    if (a1 > a0) {
+      memcpy(s.h_amb, ambiguous + a0, (size_t)(a1 - a0) * 8);
+      CU(cudaMemcpyAsync(s.amb, s.h_amb, (size_t)(a1 - a0) * 8, cudaMemcpyHostToDevice, c->s_h2d));
+    }
+    // Block offsets, (empty) masks and the ambiguity bits are made on the device, behind the copies on a stream of their
+    // own: that work overlaps the classify kernel of the previous chunk instead of standing in front of this chunk's.
+    CU(cudaEventRecord(s.copied_in, c->s_h2d));
+    CU(cudaStreamWaitEvent(c->s_prep, s.copied_in, 0));
+    for (int mt = 0; mt < (paired ? 2 : 1); mt++) {
+      mate_dev& d = mt ? d2 : d1;
+      CU(cudaMemsetAsync(const_cast<uint32_t*>(d.mask), 0, (blocks[mt] + 1) * 4, c->s_prep));
+      block_counts_len_kernel<<<(s.n + 256) / 256, 256, 0, c->s_prep>>>(d.len, s.n, const_cast<uint64_t*>(d.off));
+      if (slk_exclusive_scan_u64_async(const_cast<uint64_t*>(d.off), (uint64_t)s.n + 1, s.scan_scr, c->s_prep) != 0)
+        return fail(SLK_E_CUDA, "prefix sum of the block counts failed");
+    }
+    if (a1 > a0)
+      amb_scatter_kernel<<<(unsigned)((a1 - a0 + 255) / 256), 256, 0, c->s_prep>>>(s.amb, (uint32_t)(a1 - a0), r0, s.n, d1.off, d1.len,
+                                                                                  const_cast<uint32_t*>(d1.mask), paired ? d2.off : nullptr,
+                                                                                  paired ? d2.len : nullptr, paired ? const_cast<uint32_t*>(d2.mask) : nullptr,
+                                                                                  c->d_err);
+    CU(cudaMemsetAsync(s.d_range, 0, 32, c->s_prep));   // [0] first hit slot of the chunk (0), [2] slots reserved in excess, [3] the cursor
+    CU(cudaEventRecord(s.h2d_done, c->s_prep));
+    if (trace) tmark(&tr[ci].h1, c->s_prep);
+    sd1[ci % NSLOT] = d1; sd2[ci % NSLOT] = d2;
+    ci++;
+    r0 = r1; a0 = a1; blk0[0] += blocks[0]; blk0[1] += blocks[1];
+    return SLK_OK;
+  };
+  // Every chunk allocates its hits from a cursor of its own (d_range[3]) into its slot's hit block, and odd and even chunks
+  // classify on two streams: the first blocks of a chunk's kernel fill the SMs that the last wave of its predecessor frees.
+  auto launch = [&](int idx) -> int {
+    cls_slot& s = c->slot[idx % NSLOT];
+    const mate_dev &d1 = sd1[idx % NSLOT], &d2 = sd2[idx % NSLOT];
+    cudaStream_t st = (idx & 1) ? c->s_k2 : c->s_k;
+    CU(cudaStreamWaitEvent(st, s.h2d_done, 0));
+    if (trace) tmark(&tr[idx].k0, st);
+    launch_classify(c, hits, true, opts, d1, d2, s.n, s.taxon, s.flags, s.detail, s.hits, nullptr, s.hits_cap, s.d_range + 3, s.d_range + 2, st);
+    snapshot_kernel<<<1, 1, 0, st>>>(s.d_range + 3, s.d_range + 1);
+    CU(cudaMemcpyAsync(s.h_range, s.d_range, 24, cudaMemcpyDeviceToHost, st));
+    CU(cudaGetLastError());
+    c->launches += 8;
+    CU(cudaEventRecord(s.k_done, st));
+    if (trace) tmark(&tr[idx].k1, st);
+    s.busy = true;
+    return SLK_OK;
+  };
+  int launched = 0, finalized = 0;
+  for (;;) {
+    const bool more = r0 < n_reads;
+    if (more) TRY(stage_in());
+    if (launched < ci && (launched + 1 < ci || !more)) { TRY(launch(launched)); launched++; }
+    if (finalized < launched && (finalized + 1 < launched || (launched == ci && !more))) { TRY(finalize(c->slot[finalized % NSLOT], finalized)); finalized++; }
+    if (!more && finalized == ci) break;
+  }
+  CU(cudaStreamSynchronize(c->s_d2h));
+  if (trace) {
+    for (size_t i = 0; i < tr.size(); i++) {
+      float t[6];
+      cudaEvent_t ev[6] = {tr[i].h0, tr[i].h1, tr[i].k0, tr[i].k1, tr[i].d0, tr[i].d1};
+      for (int j = 0; j < 6; j++) { cudaEventElapsedTime(&t[j], tr0, ev[j]); cudaEventDestroy(ev[j]); }
+      fprintf(stderr, "[slk trace] chunk %2zu n=%7u  in %7.3f-%7.3f  kernel %7.3f-%7.3f  out %7.3f-%7.3f ms\n", i, tr[i].n, t[0], t[1], t[2], t[3], t[4], t[5]);
+    }
+    cudaEventDestroy(tr0);
+  }
+  for (int i = 0; i < NSLOT; i++) c->slot[i].busy = false;
+  if (hits_used) *hits_used = hits_total;
+  {
+    uint32_t err = 0;
+    CU(cudaMemcpy(&err, c->d_err, 4, cudaMemcpyDeviceToHost));
+    if (err & 2u) { CU(cudaMemset(c->d_err, 0, 4)); return fail(SLK_E_INVALID, "an ambiguity entry names a read or position outside its chunk"); }
+  }
   TRY(check_error_flag(c));
   if (nospace) return fail(SLK_E_NOSPACE, "hits_out needs room for %llu hits", (unsigned long long)hits_total);
   return SLK_OK;
@@ -1391,7 +1683,9 @@ extern "C" int slk_classify_batch(slk_classifier* c, const slk_classify_opts* op
   if ((bases2 == nullptr) != (off2 == nullptr)) return fail(SLK_E_INVALID, "bases2/off2 must both be given or both be NULL");
   mate_host h1, h2;
   h1.bases = bases1; h1.off = off1; h2.bases = bases2; h2.off = off2;
-  return classify_host_common(c, opts, false, h1, h2, n_reads, taxon_out, flags_out, detail_out, hits_out, hits_cap, hits_used);
+  cls_opts o;
+  TRY(make_opts(opts, CH_READS, &o));
+  return classify_host_common(c, o, false, h1, h2, n_reads, taxon_out, flags_out, detail_out, hits_out, hits_cap, hits_used);
 }
 extern "C" int slk_classify_batch_packed(slk_classifier* c, const slk_classify_opts* opts, const uint64_t* codes1,
                                          const uint32_t* mask1, const uint64_t* boff1, const uint32_t* len1,
@@ -1402,5 +1696,22 @@ extern "C" int slk_classify_batch_packed(slk_classifier* c, const slk_classify_o
   mate_host h1, h2;
   h1.codes = codes1; h1.mask = mask1; h1.off = boff1; h1.len = len1;
   h2.codes = codes2; h2.mask = mask2; h2.off = boff2; h2.len = len2;
-  return classify_host_common(c, opts, true, h1, h2, n_reads, taxon_out, flags_out, detail_out, hits_out, hits_cap, hits_used);
+  cls_opts o;
+  TRY(make_opts(opts, CH_READS, &o));
+  return classify_host_common(c, o, true, h1, h2, n_reads, taxon_out, flags_out, detail_out, hits_out, hits_cap, hits_used);
+}
+// Classifier.classify with several thresholds (slacken/Classifier.scala:156-170): the reads are scanned and looked up ONCE,
+// resolveTree runs once per threshold; taxon_out / flags_out are [n_thresholds][n_reads], details and hits are shared.
+extern "C" int slk_classify_batch_packed_multi(slk_classifier* c, const slk_classify_multi_opts* opts, const uint64_t* codes1,
+                                               const uint32_t* mask1, const uint64_t* boff1, const uint32_t* len1,
+                                               const uint64_t* codes2, const uint32_t* mask2, const uint64_t* boff2,
+                                               const uint32_t* len2, uint32_t n_reads, int32_t* taxon_out, uint8_t* flags_out,
+                                               slk_read_detail* detail_out, slk_hit* hits_out, uint64_t hits_cap,
+                                               uint64_t* hits_used) {
+  mate_host h1, h2;
+  h1.codes = codes1; h1.mask = mask1; h1.off = boff1; h1.len = len1;
+  h2.codes = codes2; h2.mask = mask2; h2.off = boff2; h2.len = len2;
+  cls_opts o;
+  TRY(make_opts(opts, CH_READS, &o));
+  return classify_host_common(c, o, true, h1, h2, n_reads, taxon_out, flags_out, detail_out, hits_out, hits_cap, hits_used);
 }

@@ -53,6 +53,15 @@ static_assert(SLK_G_OFF_HITS % 8 == 0, "alignment of the hit slots");
 #define SLK_V_AMB (1ull << 62)    // every base of the window is ambiguous: part of an AMBIGUOUS span
 #define SLK_V_NONE (2ull << 62)   // some but not all bases ambiguous (or no window at all): belongs to no span
 
+#ifndef SLK_MAX_THRESHOLDS
+#define SLK_MAX_THRESHOLDS 8
+#endif
+struct slk_group_thresholds {   // ClassifyParams.thresholds: row t of the outputs (t >= 1) starts at taxon_out + t * stride
+  double confidence[SLK_MAX_THRESHOLDS];
+  uint32_t n;
+  uint64_t stride;
+  int32_t* taxon_out; uint8_t* flags_out;
+};
 struct slk_group_in {   // one mate of the batch, packed form (include/slacken_gpu.h, "Packed input")
   const uint64_t* codes; const uint32_t* mask; const uint64_t* boff; const uint32_t* len; uint64_t shift;
 };
@@ -253,7 +262,7 @@ template <int W, bool CANON, class Sink>
 __device__ __forceinline__ void slk_group_classify(uint8_t* sm_warp, const slk_scan_params& sp, const slk_table_view& tb,
                                                    const slk_tax_view& tx, Sink& sink, slk_group_overflow& ov,
                                                    const slk_group_in& in1, const slk_group_in& in2, bool paired, bool live,
-                                                   uint64_t r, double confidence, int32_t min_hit_groups, slk_frag_result& res) {
+                                                   uint64_t r, const slk_group_thresholds& mt, int32_t min_hit_groups, slk_frag_result& res) {
   const uint32_t lane = threadIdx.x & 31u;
   const slk_group_smem S{sm_warp, lane};
   const uint32_t k = (uint32_t)sp.k, km1 = k - 1;
@@ -563,35 +572,47 @@ __device__ __forceinline__ void slk_group_classify(uint8_t* sm_warp, const slk_s
   // The number of buffered hits is final: their place in the output is reserved now (one atomic per warp, whose latency
   // the resolve step hides). All lanes call it.
   sink.reserve(l_spilled ? 0u : l_nh);
-  uint32_t taxon = 0;
-  bool fast_done = false;
+  // Classifier.classify (slacken/Classifier.scala:156-170) keeps the hits and classifies them once per confidence threshold:
+  // here the histogram is built once and resolveTree runs once per threshold. Threshold 0 goes to `res`, the others
+  // straight to their rows of the outputs.
+  const int32_t total_kmers = (int32_t)(l_k0 + l_k1);
+  int mode = 0;   // 0: one hit taxon at most; 1: histogram in the key array; 2: slow-path histogram
+  slk_group_fast_hist fh{S, 0u};
   if (!l_multi) {
-    // One hit taxon t (or none): its root-path score is its own count and every clade on the way up holds exactly that
-    // count, so LowestCommonAncestor.resolveTree (slacken/LowestCommonAncestor.scala:91-146) returns t when the count reaches
-    // ceil(confidence * totalKmers) and NONE otherwise.
-    const double required = ceil(confidence * (double)(int32_t)(l_k0 + l_k1));
-    taxon = (l_t1 != 0 && (double)(int32_t)l_c1 >= required) ? l_t1 : 0u;
-    fast_done = true;
     if (l_spilled) spill(0);
   } else if (!l_spilled) {   // the histogram fits the (now idle) key array
-    slk_group_fast_hist fh{S, 0u};
     bool fits = true;
     for (uint32_t i = 0; i < l_nh && fits; i++) {
       int32_t l, cc;
       buffered_hit(i, &l, &cc);
       if (l >= 0) fits = fh.add((uint32_t)l, cc);
     }
-    if (fits) { taxon = slk_resolve_tree(fh, tx, confidence, (int32_t)(l_k0 + l_k1)); fast_done = true; }
+    mode = fits ? 1 : 2;
+    if (!fits) slk_group_fold_hits(S, ov, l_nh);
   } else {
-    spill(0);   // a fragment that went to the sink keeps all its hits there
+    spill(0);   // a fragment that went to the sink keeps all its hits there (and folded them into the slow-path histogram)
+    mode = 2;
   }
-  if (!fast_done) {
-    if (!l_spilled) slk_group_fold_hits(S, ov, l_nh);
-    taxon = slk_group_resolve_slow(ov, tx, confidence, (int32_t)(l_k0 + l_k1));
+  for (uint32_t t = 0; t < mt.n; t++) {
+    const double confidence = mt.confidence[t];
+    uint32_t taxon;
+    if (mode == 0) {
+      // One hit taxon (or none): its root-path score is its own count and every clade on the way up holds exactly that
+      // count, so LowestCommonAncestor.resolveTree (slacken/LowestCommonAncestor.scala:91-146) returns it when the count
+      // reaches ceil(confidence * totalKmers) and NONE otherwise.
+      const double required = ceil(confidence * (double)total_kmers);
+      taxon = (l_t1 != 0 && (double)(int32_t)l_c1 >= required) ? l_t1 : 0u;
+    } else if (mode == 1) {
+      taxon = slk_resolve_tree(fh, tx, confidence, total_kmers);
+    } else {
+      taxon = slk_group_resolve_slow(ov, tx, confidence, total_kmers);
+    }
+    const bool classified = taxon != 0 && l_nd >= (uint32_t)min_hit_groups;   // slacken/Classifier.scala:446
+    const int32_t raw = classified ? tx.raw[taxon] : 0;
+    const uint32_t fl = (classified ? SLK_F_CLASSIFIED : 0u) | (any ? SLK_F_HAS_SPAN : 0u) | (ov.overflow ? SLK_F_OVERFLOW : 0u);
+    if (t == 0) { res.taxon = raw; res.flags = fl; }
+    else if (live) { mt.taxon_out[(uint64_t)t * mt.stride + r] = raw; mt.flags_out[(uint64_t)t * mt.stride + r] = (uint8_t)(fl & 3u); }
   }
-  const bool classified = taxon != 0 && l_nd >= (uint32_t)min_hit_groups;   // slacken/Classifier.scala:446
-  res.taxon = classified ? tx.raw[taxon] : 0;
-  res.flags = (classified ? SLK_F_CLASSIFIED : 0u) | (any ? SLK_F_HAS_SPAN : 0u) | (ov.overflow ? SLK_F_OVERFLOW : 0u);
   res.kmers1 = l_k0; res.kmers2 = l_k1;
   res.num_distinct = l_nd; res.n_hits = l_nh + nh_spilled; res.n_probes = l_np;
 }
@@ -616,7 +637,7 @@ __device__ __forceinline__ uint64_t slk_g_warp_alloc(unsigned long long* cursor,
 // kernel from the per-lane buffers. A fragment with more merged hits than the buffers hold takes a worst-case block for
 // itself (one atomic) and appends there.
 struct slk_g_hit_sink {
-  uint32_t n;
+  uint32_t n, alloc;      // hits pushed to the private block, and the block's size
   bool spilled, live, enabled;
   uint64_t goff, reserved;
   slk_hit* gbase;         // indexed by (absolute index - gshift)
@@ -633,7 +654,7 @@ struct slk_g_hit_sink {
   }
   __device__ __forceinline__ void push(int32_t taxon, int32_t count, uint32_t need) {
     if (!enabled) return;
-    if (!spilled) { goff = atomicAdd(cursor, (unsigned long long)need + 2ull); spilled = true; }
+    if (!spilled) { alloc = need + 2u; goff = atomicAdd(cursor, (unsigned long long)alloc); spilled = true; }
     put(goff + n, taxon, count);
     n++;
   }
@@ -642,9 +663,10 @@ struct slk_g_hit_sink {
 struct slk_classify2_args {
   slk_scan_params sp; slk_table_view tb; slk_tax_view tx;
   slk_group_in in1, in2; uint32_t paired; uint32_t n_reads;
-  double confidence; int32_t min_hit_groups; uint32_t hits;
+  slk_group_thresholds mt; int32_t min_hit_groups; uint32_t hits;
   int32_t* taxon_out; uint8_t* flags_out; slk_read_detail* detail_out;
   slk_hit* hits_base; const unsigned long long* hits_shift_ptr; uint64_t hits_cap; unsigned long long* hits_cursor;
+  unsigned long long* hits_over;   // (optional) slots reserved beyond the hits written: cursor advance - *hits_over = merged hits
   unsigned long long* counts; uint32_t* error_flag; unsigned long long* stats;
 };
 
@@ -657,13 +679,13 @@ __device__ __forceinline__ void slk_classify2_thread(const slk_classify2_args& a
   const uint32_t lane = threadIdx.x & 31u;
   uint8_t* sm_warp = smem + (threadIdx.x >> 5) * SLK_G_WARP_BYTES;
   slk_g_hit_sink sink;
-  sink.n = 0; sink.spilled = false; sink.live = live; sink.enabled = want_hits; sink.goff = 0; sink.reserved = 0;
+  sink.n = 0; sink.alloc = 0; sink.spilled = false; sink.live = live; sink.enabled = want_hits; sink.goff = 0; sink.reserved = 0;
   sink.gbase = a.hits_base; sink.gshift = (want_hits && a.hits_shift_ptr) ? *a.hits_shift_ptr : 0ull;
   sink.gcap = a.hits_cap; sink.cursor = a.hits_cursor;
   slk_group_overflow ov;
   slk_frag_result res;
   res.taxon = 0; res.flags = 0; res.kmers1 = 0; res.kmers2 = 0; res.num_distinct = 0; res.n_hits = 0; res.n_probes = 0;
-  slk_group_classify<W, CANON>(sm_warp, a.sp, a.tb, a.tx, sink, ov, a.in1, a.in2, paired, live, r, a.confidence, a.min_hit_groups, res);
+  slk_group_classify<W, CANON>(sm_warp, a.sp, a.tb, a.tx, sink, ov, a.in1, a.in2, paired, live, r, a.mt, a.min_hit_groups, res);
   if (live) {
     a.taxon_out[r] = res.taxon;
     a.flags_out[r] = (uint8_t)(res.flags & 3u);
@@ -699,6 +721,7 @@ __device__ __forceinline__ void slk_classify2_thread(const slk_classify2_args& a
       }
       d.hit_off = sink.spilled ? sink.goff : sink.reserved;
       d.hit_cnt = res.n_hits;
+      if (sink.spilled && a.hits_over != nullptr) atomicAdd(a.hits_over, (unsigned long long)(sink.alloc - sink.n));
     }
     d.len1 = res.kmers1 + (uint32_t)(a.sp.k - 1);
     d.len2 = paired ? res.kmers2 + (uint32_t)(a.sp.k - 1) : 0xFFFFFFFFu;

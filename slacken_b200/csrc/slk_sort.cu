@@ -226,6 +226,18 @@ int slk_sort_cells_by_line(uint64_t* cells, uint64_t* tmp, uint64_t n, cudaStrea
   return sort_impl<true>(cells, tmp, n, 0, 32, stream, sorted);
 }
 
+// the same without allocation or synchronisation: scratch holds slk_scan_scratch_words(n) words
+uint64_t slk_scan_scratch_words(uint64_t n) {
+  uint64_t w = 8;
+  for (uint64_t x = (n + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK; ; x = (x + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK) {
+    w += x;
+    if (x <= 1) break;
+  }
+  return w;
+}
+int slk_exclusive_scan_u64_async(uint64_t* d, uint64_t n, uint64_t* scratch, cudaStream_t stream) {
+  return (int)exclusive_scan_u64(d, n, scratch, stream);
+}
 int slk_exclusive_scan_u64(uint64_t* d, uint64_t n, cudaStream_t stream) {
   if (n == 0) return 0;
   uint64_t scratch_len = 0;

@@ -14,3 +14,6 @@ int slk_sort_cells_by_line(uint64_t* cells, uint64_t* tmp, uint64_t n, cudaStrea
 // In-place exclusive prefix sum of n 64-bit counters on the device (allocates its own scratch; asynchronous on `stream`
 // apart from that allocation). Returns 0 or a non-zero CUDA error code.
 int slk_exclusive_scan_u64(uint64_t* d, uint64_t n, cudaStream_t stream);
+// ... with caller-owned scratch of slk_scan_scratch_words(n) words: no allocation, no synchronisation
+uint64_t slk_scan_scratch_words(uint64_t n);
+int slk_exclusive_scan_u64_async(uint64_t* d, uint64_t n, uint64_t* scratch, cudaStream_t stream);

@@ -9,7 +9,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import ClassifyOpts, Params, check
+from ._lib import ClassifyMultiOpts, ClassifyOpts, Params, check
 
 DEFAULT_TOGGLE_MASK = 0xE37E28C4271B5A2D  # kmers/minimizer/package.scala:32
 NONE, ROOT = 0, 1  # slacken/Taxonomy.scala:30-31
@@ -18,6 +18,7 @@ AMBIGUOUS_SPAN, MATE_PAIR_BORDER = -1, -2  # slacken/package.scala:28-29
 HIT_DTYPE = np.dtype([("taxon", "<i4"), ("count", "<i4")])
 DETAIL_DTYPE = np.dtype([("hit_off", "<u8"), ("hit_cnt", "<u4"), ("len1", "<u4"), ("len2", "<u4"), ("num_distinct", "<u4")])
 assert DETAIL_DTYPE.itemsize == 24
+RESULT_DTYPE = np.dtype([("taxon", "<i4"), ("len1", "<u4"), ("len2", "<u4"), ("hits_flags", "<u4")])   # slk_read_result
 
 
 def _ptr(a) -> Optional[C.c_void_p]:
@@ -398,6 +399,58 @@ class Classifier:
         out.hits_used = int(used.value)
         return out
 
+    @staticmethod
+    def _multi_opts(thresholds, min_hit_groups: int) -> ClassifyMultiOpts:
+        thr = [float(t) for t in thresholds]
+        o = ClassifyMultiOpts()
+        o.n_thresholds, o.min_hit_groups = len(thr), int(min_hit_groups)
+        for i, t in enumerate(thr[:_lib.MAX_THRESHOLDS]):
+            o.confidence[i] = t
+        return o
+
+    def classify_packed_thresholds(self, r1: PackedReads, r2: Optional[PackedReads], thresholds: Sequence[float],
+                                   min_hit_groups: int = 2, per_read_output: bool = True):
+        """Classifier.classify for several confidence thresholds (slacken/Classifier.scala:156-170): the reads are scanned and
+        looked up once. Returns (taxon int32[n_thr, n], flags uint8[n_thr, n], detail, hits, hits_used)."""
+        n, nt = len(r1.len), len(thresholds)
+        taxon, flags = np.zeros((nt, n), dtype=np.int32), np.zeros((nt, n), dtype=np.uint8)
+        detail = np.zeros(n, dtype=DETAIL_DTYPE)
+        hits = None
+        if per_read_output:
+            total = int(r1.len.sum()) + (int(r2.len.sum()) if r2 is not None else 0)
+            hits = np.zeros(self.hits_bound(n, total, r2 is not None), dtype=HIT_DTYPE)
+        o = self._multi_opts(thresholds, min_hit_groups)
+        used = C.c_uint64(0)
+        m2 = (r2.codes, r2.mask, r2.boff, r2.len) if r2 is not None else (None, None, None, None)
+        check(self.ctx._L.slk_classify_batch_packed_multi(self.h, C.byref(o), _ptr(r1.codes), _ptr(r1.mask), _ptr(r1.boff), _ptr(r1.len),
+                                                          _ptr(m2[0]), _ptr(m2[1]), _ptr(m2[2]), _ptr(m2[3]), n, _ptr(taxon), _ptr(flags),
+                                                          _ptr(detail), _ptr(hits), len(hits) if hits is not None else 0, C.byref(used)))
+        return taxon, flags, detail, hits, int(used.value)
+
+    def classify_compact(self, r1: "CompactReads", r2: Optional["CompactReads"] = None, thresholds: Sequence[float] = (0.0,),
+                         min_hit_groups: int = 2, per_read_output: bool = True, out: Optional["CompactBatch"] = None) -> "CompactBatch":
+        """The compact boundary (include/slacken_gpu.h, slk_classify_batch_compact): codes + lengths + a sparse list of
+        ambiguous positions in, 16-byte results + hits in read order out."""
+        n, nt = len(r1.len), len(thresholds)
+        if out is None:
+            hits = None
+            if per_read_output:
+                total = int(r1.len.sum()) + (int(r2.len.sum()) if r2 is not None else 0)
+                hits = np.zeros(self.hits_bound(n, total, r2 is not None), dtype=HIT_DTYPE)
+            out = CompactBatch(np.zeros(n, dtype=RESULT_DTYPE), np.zeros((max(nt - 1, 0), n), dtype=np.int32),
+                               np.zeros((max(nt - 1, 0), n), dtype=np.uint8), hits)
+        amb = merge_ambiguous(r1, r2)
+        o = self._multi_opts(thresholds, min_hit_groups)
+        used = C.c_uint64(0)
+        hits = out.hits if per_read_output else None
+        check(self.ctx._L.slk_classify_batch_compact(self.h, C.byref(o), _ptr(r1.codes), _ptr(r1.len), _ptr(r2.codes) if r2 is not None else None,
+                                                     _ptr(r2.len) if r2 is not None else None, _ptr(amb) if len(amb) else None, len(amb), n,
+                                                     _ptr(out.results), _ptr(out.taxon_more) if nt > 1 else None,
+                                                     _ptr(out.flags_more) if nt > 1 else None, _ptr(hits),
+                                                     len(hits) if hits is not None else 0, C.byref(used)))
+        out.hits_used = int(used.value)
+        return out
+
     def classify_packed_dev(self, codes1: int, mask1: int, boff1: int, len1: int, codes2: int, mask2: int, boff2: int,
                             len2: int, n_reads: int, taxon_out: int, flags_out: int, detail_out: int, hits_out: int,
                             hits_cap: int, hits_used_dev: int, confidence: float = 0.0, min_hit_groups: int = 2):
@@ -459,6 +512,68 @@ class PackedReads:
     @property
     def nbytes(self) -> int:
         return self.codes.nbytes + self.mask.nbytes + self.boff.nbytes + self.len.nbytes
+
+
+@dataclass
+class CompactReads:
+    """One mate of a batch at the compact boundary: 2-bit code blocks, lengths, and the ambiguous positions as
+    (read index, position) pairs sorted by read."""
+    codes: np.ndarray     # uint64[n_blocks]
+    len: np.ndarray       # uint32[n]
+    amb_read: np.ndarray  # uint32[n_amb]
+    amb_pos: np.ndarray   # uint32[n_amb]
+
+    @property
+    def nbytes(self) -> int:
+        return self.codes.nbytes + self.len.nbytes + 8 * len(self.amb_read)
+
+
+@dataclass
+class CompactBatch:
+    results: np.ndarray      # RESULT_DTYPE[n]: threshold 0
+    taxon_more: np.ndarray   # int32[n_thr - 1, n]
+    flags_more: np.ndarray   # uint8[n_thr - 1, n]
+    hits: Optional[np.ndarray]
+    hits_used: int = 0
+
+    @property
+    def taxon(self):
+        return self.results["taxon"]
+
+    @property
+    def flags(self):
+        return (self.results["hits_flags"] & 3).astype(np.uint8)
+
+    @property
+    def hit_cnt(self):
+        return self.results["hits_flags"] >> 2
+
+
+def compact_reads(p: "PackedReads") -> CompactReads:
+    """PackedReads -> CompactReads: drops the block offsets and turns the mask words into a list of positions."""
+    nz = np.nonzero(p.mask)[0]
+    if len(nz) == 0:
+        e = np.zeros(0, dtype=np.uint32)
+        return CompactReads(p.codes, p.len, e, e)
+    blk_read = np.searchsorted(p.boff, nz, side="right") - 1
+    reads, poss = [], []
+    for b, r in zip(nz, blk_read):
+        m = int(p.mask[b])
+        base = 32 * (int(b) - int(p.boff[r]))
+        for i in range(32):
+            if (m >> i) & 1:
+                reads.append(int(r)); poss.append(base + i)
+    return CompactReads(p.codes, p.len, np.array(reads, dtype=np.uint32), np.array(poss, dtype=np.uint32))
+
+
+def merge_ambiguous(r1: CompactReads, r2: Optional[CompactReads]) -> np.ndarray:
+    """The ambiguity list of the ABI: read << 32 | mate << 31 | position, sorted by read."""
+    a = (r1.amb_read.astype(np.uint64) << np.uint64(32)) | r1.amb_pos.astype(np.uint64)
+    if r2 is not None and len(r2.amb_read):
+        b = (r2.amb_read.astype(np.uint64) << np.uint64(32)) | np.uint64(1 << 31) | r2.amb_pos.astype(np.uint64)
+        a = np.concatenate([a, b])
+        a = a[np.argsort(a >> np.uint64(32), kind="stable")]
+    return np.ascontiguousarray(a, dtype=np.uint64)
 
 
 def block_offsets(off: np.ndarray) -> np.ndarray:

@@ -170,16 +170,19 @@ def lib2():
         _lib2 = C.CDLL(_SO2)
         _lib2.emu2_classify.restype = C.c_int
         _lib2.emu2_classify.argtypes = [C.POINTER(ScanParams), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
-                                        C.c_uint32] + [C.c_void_p] * 8 + [C.c_uint32, C.c_double, C.c_int, C.c_int] + [C.c_void_p] * 4 + \
+                                        C.c_uint32] + [C.c_void_p] * 8 + [C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_int] + [C.c_void_p] * 4 + \
                                        [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib2
 
 
 def classify2(ix: "EmuIndex", r1, r2=None, confidence=0.0, min_hit_groups=2, want_hits=True):
-    """r1 / r2: slacken_b200.host.PackedReads. Returns (taxon, flags, detail, hits, probes, merged_hits, counts)."""
+    """r1 / r2: slacken_b200.host.PackedReads. Returns (taxon, flags, detail, hits, probes, merged_hits, counts); with a list
+    of confidences taxon and flags have one row per threshold."""
     n = len(r1.len)
-    taxon = np.zeros(n, dtype=np.int32)
-    flags = np.zeros(n, dtype=np.uint8)
+    multi = not np.isscalar(confidence)
+    conf = np.atleast_1d(np.asarray(confidence, dtype=np.float64)).copy()
+    taxon = np.zeros((len(conf), n), dtype=np.int32)
+    flags = np.zeros((len(conf), n), dtype=np.uint8)
     detail = np.zeros(n, dtype=DETAIL_DTYPE)
     cap = int(r1.len.sum()) + (int(r2.len.sum()) if r2 is not None else 0) + 5 * n + 8
     hits = np.zeros(cap, dtype=HIT_DTYPE)
@@ -190,9 +193,11 @@ def classify2(ix: "EmuIndex", r1, r2=None, confidence=0.0, min_hit_groups=2, wan
     pad = lambda a, dt: np.concatenate([a, np.zeros(4, dtype=dt)])   # the kernel never reads past a read's blocks; be strict anyway
     rc = lib2().emu2_classify(C.byref(ix.sp), _p(ix.cells), ix.n_buckets, _p(ix.parent), _p(ix.depth), _p(ix.raw), len(ix.raw),
                               ix.dt.root, _p(r1.codes), _p(r1.mask), _p(r1.boff), _p(r1.len), _p(m2[0]), _p(m2[1]), _p(m2[2]), _p(m2[3]),
-                              n, float(confidence), int(min_hit_groups), 1 if want_hits else 0, _p(taxon), _p(flags), _p(detail),
+                              n, _p(conf), len(conf), int(min_hit_groups), 1 if want_hits else 0, _p(taxon), _p(flags), _p(detail),
                               _p(hits), cap, C.byref(used), _p(stats), _p(counts))
     assert rc == 0, rc
+    if not multi:
+        taxon, flags = taxon[0], flags[0]
     return taxon, flags, detail, hits[:used.value], int(stats[0]), int(stats[1]), counts
 
 

@@ -35,7 +35,7 @@ static void run_w(const slk_classify2_args& a, uint32_t threads) {
 EMU_API int emu2_classify(const slk_scan_params* sp, uint64_t* cells, uint64_t n_buckets, const uint16_t* parent, const uint8_t* depth,
                           const int32_t* raw, uint32_t n_dense, uint32_t root, const uint64_t* codes1, const uint32_t* mask1,
                           const uint64_t* boff1, const uint32_t* len1, const uint64_t* codes2, const uint32_t* mask2,
-                          const uint64_t* boff2, const uint32_t* len2, uint32_t n, double confidence, int min_hit_groups,
+                          const uint64_t* boff2, const uint32_t* len2, uint32_t n, const double* confidence, uint32_t n_conf, int min_hit_groups,
                           int want_hits, int32_t* taxon_out, uint8_t* flags_out, slk_read_detail* detail_out, slk_hit* hits_out,
                           uint64_t hits_cap, uint64_t* hits_used, uint64_t* stats, uint64_t* counts) {
   slk_classify2_args a;
@@ -44,11 +44,13 @@ EMU_API int emu2_classify(const slk_scan_params* sp, uint64_t* cells, uint64_t n
   a.tx = slk_tax_view{parent, depth, raw, n_dense, root};
   a.in1 = slk_group_in{codes1, mask1, boff1, len1, 0};
   a.in2 = slk_group_in{codes2, mask2, boff2, len2, 0};
-  a.paired = codes2 != nullptr; a.n_reads = n; a.confidence = confidence; a.min_hit_groups = min_hit_groups; a.hits = want_hits != 0;
+  a.paired = codes2 != nullptr; a.n_reads = n; a.min_hit_groups = min_hit_groups; a.hits = want_hits != 0;
+  a.mt.n = n_conf; a.mt.stride = n; a.mt.taxon_out = taxon_out; a.mt.flags_out = flags_out;   // [n_conf][n]
+  for (uint32_t t = 0; t < n_conf; t++) a.mt.confidence[t] = confidence[t];
   a.taxon_out = taxon_out; a.flags_out = flags_out; a.detail_out = detail_out;
   unsigned long long cursor = 0;
   uint32_t err = 0;
-  a.hits_base = hits_out; a.hits_shift_ptr = nullptr; a.hits_cap = hits_cap; a.hits_cursor = &cursor;
+  a.hits_base = hits_out; a.hits_shift_ptr = nullptr; a.hits_cap = hits_cap; a.hits_cursor = &cursor; a.hits_over = nullptr;
   a.counts = reinterpret_cast<unsigned long long*>(counts); a.error_flag = &err; a.stats = reinterpret_cast<unsigned long long*>(stats);
   switch (sp->w) {
     case 1: run_w<1>(a, 64); break; case 2: run_w<2>(a, 64); break; case 3: run_w<3>(a, 64); break; case 4: run_w<4>(a, 64); break;

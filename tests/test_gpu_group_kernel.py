@@ -92,3 +92,58 @@ def test_other_parameters(gpu, k, m, s, canonical):
     _check(cls, olib, reads, conf=0.1, k=k)
     _check(cls, olib, reads, mates, conf=0.0, k=k)
     cls.close(); index.close(); tax.close()
+
+
+def test_several_thresholds_in_one_pass_equal_separate_calls(gpu):
+    """slk_classify_batch_packed_multi (Classifier.scala:156-170): row t == a call with threshold t; hits are shared."""
+    rng, parents, genomes, olib, tax, index = _setup(gpu, 65)
+    cls = Classifier(index)
+    reads = simulate_reads(rng, genomes, 3000, (20, 300), n_rate=0.1)
+    mates = simulate_reads(rng, genomes, 3000, (20, 300), n_rate=0.1)
+    thr = [0.0, 0.05, 0.15, 0.3, 0.6, 1.0]
+    for pk in ([pack_reads(*pack_sequences(reads))], [pack_reads(*pack_sequences(reads)), pack_reads(*pack_sequences(mates))]):
+        r2 = pk[1] if len(pk) > 1 else None
+        taxon, flags, detail, hits, used = cls.classify_packed_thresholds(pk[0], r2, thr)
+        for t, conf in enumerate(thr):
+            one = cls.classify_packed(*pk, confidence=conf)
+            assert np.array_equal(taxon[t], one.taxon) and np.array_equal(flags[t], one.flags), conf
+            assert np.array_equal(detail["hit_cnt"], one.detail["hit_cnt"]) and used == one.hits_used
+    cls.close(); index.close(); tax.close()
+
+
+def test_compact_boundary_equals_the_oracle(gpu):
+    """slk_classify_batch_compact: codes + lengths + sparse ambiguity list in, 16-byte results + hits in read order out."""
+    from slacken_b200.host import compact_reads
+    rng, parents, genomes, olib, tax, index = _setup(gpu, 66)
+    cls = Classifier(index)
+    reads = simulate_reads(rng, genomes, 5000, (1, 400), n_rate=0.2) + [b"", b"N" * 90, genomes[0][:200]] + chimeric_reads(rng, genomes, 50, 120)
+    mates = simulate_reads(rng, genomes, len(reads), (1, 400), n_rate=0.2)
+    for paired in (False, True):
+        rb, ro = pack_sequences(reads)
+        r1 = compact_reads(pack_reads(rb, ro))
+        mb = mo = r2 = None
+        if paired:
+            mb, mo = pack_sequences(mates)
+            r2 = compact_reads(pack_reads(mb, mo))
+        thr = [0.1, 0.0, 0.5]
+        got = cls.classify_compact(r1, r2, thresholds=thr)
+        for t, conf in enumerate(thr):
+            res, _, _, per = olib.classify(rb, ro.astype(np.int64), mb, mo.astype(np.int64) if mo is not None else None, confidence=conf)
+            tx = got.taxon if t == 0 else got.taxon_more[t - 1]
+            fl = got.flags if t == 0 else got.flags_more[t - 1]
+            assert np.array_equal(res["taxon"], tx), conf
+            assert np.array_equal(res["classified"], fl & 1) and np.array_equal(res["has_span"], (fl >> 1) & 1)
+        hs = res["has_span"].astype(bool)
+        assert np.array_equal(res["len1"][hs], got.results["len1"][hs].astype(np.int32))
+        if paired:
+            assert np.array_equal(res["len2"][hs], got.results["len2"][hs].astype(np.int32))
+        # hits in read order: read i's hits follow read i - 1's
+        cnt = got.hit_cnt.astype(np.int64)
+        assert np.array_equal(cnt, res["n_hits"].astype(np.int64)) and got.hits_used == int(cnt.sum())
+        off = np.concatenate([[0], np.cumsum(cnt)])
+        for i in range(len(per)):
+            h = got.hits[off[i]:off[i + 1]]
+            assert np.array_equal(h["taxon"], per[i]["taxon"]) and np.array_equal(h["count"], per[i]["count"]), i
+        lean = cls.classify_compact(r1, r2, thresholds=thr[:1], per_read_output=False)
+        assert np.array_equal(lean.taxon, got.taxon) and np.array_equal(lean.flags, got.flags)
+    cls.close(); index.close(); tax.close()

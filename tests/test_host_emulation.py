@@ -58,6 +58,14 @@ def _compare2(lib, ix, rb, ro, rb2, ro2, confidence, k):
     # without per-read hit lists (the --nodetailed mode): the same taxa
     t2, f2, _, _, _, _, _ = emu.classify2(ix, r1, r2, confidence=confidence, want_hits=False)
     assert np.array_equal(t2, taxon) and np.array_equal(f2, flags)
+    # several thresholds in one pass (Classifier.scala:156-170): row t equals a separate call with threshold t
+    thr = [confidence, 0.05, 0.3, 0.9]
+    tm, fm, dm, hm, _, _, _ = emu.classify2(ix, r1, r2, confidence=thr)
+    assert np.array_equal(tm[0], taxon) and np.array_equal(fm[0], flags) and np.array_equal(hm, hits)
+    for t in range(1, len(thr)):
+        rt, _, _, _ = lib.classify(rb, ro, rb2, ro2, confidence=thr[t])
+        assert np.array_equal(tm[t], rt["taxon"]), thr[t]
+        assert np.array_equal(fm[t] & 1, rt["classified"]) and np.array_equal((fm[t] >> 1) & 1, rt["has_span"])
 
 
 def _compare(lib, ix, rb, ro, rb2, ro2, confidence, k, packed, split):
