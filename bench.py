@@ -702,7 +702,124 @@ def dist_build_leg(args, w0, ctx, tax, params, genome_taxa0, rank, world, dist):
            "workload": f"{w.n_genomes} synthetic genomes x {w.genome_len} bp = {w.total_bases / 1e9:.2f} Gbp, {len(parents)}-node "
                        f"taxonomy, k{w.k}/m{w.m}/s{w.spaces}",
            "records_before_exchange": int(cnt[0]), "library_records": int(cnt[1]), "records_on_rank0": len(shard)}
+    if not args.no_big_classify:
+        res["classify"] = big_sharded_classify(args, w, ctx, tax, params, shard, parents, genome_taxa, rank, world, dist)
     shard.close()
+    return res
+
+
+def big_sharded_classify(args, w, ctx, tax, params, shard, parents, genome_taxa, rank, world, dist):
+    """BASELINE.json configs[4]: classify against the library the distributed build has just left sharded over the GPUs
+    (8.75 Gbp of genomes per GPU: 70 Gbp, 22.9 G records, ~46 GB of table per GPU at N = 8 -- more than fits one GPU
+    replicated), confidence 0.15, keys and taxa through the NVLink mailbox.
+    Checks, on a sample of rank 0's reads: (1) always: the fused classify kernel on a small REPLICATED index that holds the
+    library's records for exactly the sample's minimizers (fetched from the shards with the plain lookup kernel and
+    gathered) must give the same taxon / flags; (2) with --oracle-check: the CPU oracle, on a table that held the sample's
+    minimizers first and was then fed every genome of the library (update-only), must give the same taxon, flags and hits."""
+    import ctypes as C
+    import torch
+    from slacken_b200 import Classifier, KeyValueIndex
+    from slacken_b200._lib import check
+    from slacken_b200.sharded import ShardedClassifier
+    dev = torch.device("cuda", ctx.device)
+    sr, L, conf = args.sharded_reads, w.read_len, args.paired_confidence
+    rseed = 5
+    d_reads = ctx.dev_alloc(sr * L)
+    check(ctx._L.slk_synth_reads_dev(ctx.h, w.gseed, rseed, w.n_genomes, w.genome_len, rank * sr, sr, L, C.c_void_p(d_reads)))
+    off = np.arange(sr + 1, dtype=np.uint64) * np.uint64(L)
+    d_off = ctx.dev_alloc(off.nbytes)
+    ctx.h2d(d_off, off)
+    cap = int(sr * 44 / world * 1.25) + 65536
+    scl = ShardedClassifier(shard, mailbox_cap=cap)
+    d_b = torch.as_tensor(_DevView(d_reads, sr * L, "|u1"), device=dev)
+    d_o = torch.as_tensor(_DevView(d_off, sr + 1, "<i8"), device=dev)
+
+    def run(k, hits=False):
+        out = None
+        for out in scl.classify_pipelined([(d_b, d_o, None, None, sr)] * k, confidence=conf, min_hit_groups=w.min_hit_groups,
+                                          per_read_output=hits):
+            pass
+        return out
+
+    steps = max(2, args.steps // 2)
+    run(2)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    got = run(steps)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    dist.barrier()
+    t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall = float(t.item())
+    got = run(1, hits=True)
+    s_taxon, s_flags = got.taxon.copy(), got.flags.copy()
+    cs = min(sr, args.big_check_reads)
+    s_hits = [got.hits_of(i).copy() for i in range(cs)] if rank == 0 else None
+
+    # ---- check 1: the sample's minimizers, the shards' records for them, a small replicated index, the fused kernel
+    h_reads = np.zeros(cs * L, dtype=np.uint8)
+    ctx.d2h(h_reads, d_reads)
+    sample_off = off[:cs + 1].copy()
+    span_off, spans, n_spans = scl.ops.scan_spans(d_b[:cs * L], d_o[:cs + 1], None, None, cs) if rank == 0 else (None, None, 0)
+    nk = torch.tensor([n_spans], dtype=torch.int64, device=dev)
+    dist.broadcast(nk, 0)
+    n_spans = int(nk.item())
+    keys = ((spans[:n_spans] >> 16) & 0xFFFFFFFFFFFF).contiguous() if rank == 0 else torch.empty(n_spans, dtype=torch.int64, device=dev)
+    dist.broadcast(keys, 0)                       # compressed minimizers (AMBIGUOUS / BORDER spans carry key 0: harmless)
+    taxa = scl.ops.probe(keys)                    # this shard's answer for every key: raw taxon, 0 = not here
+    every = [torch.empty_like(taxa) for _ in range(world)]
+    dist.all_gather(every, taxa)
+    same1 = None
+    if rank == 0:
+        tx = torch.stack(every).max(dim=0).values   # a key lives in exactly one shard
+        have = tx != 0
+        k_have, t_have = keys[have], tx[have]
+        uk, idx = np.unique(k_have.cpu().numpy(), return_index=True)
+        ut = t_have.cpu().numpy()[idx]
+        from slacken_b200.host import expand_keys
+        id1 = expand_keys(params, uk)   # compressed key -> id1 (the left-aligned priority)
+        small = KeyValueIndex.from_records(ctx, tax, params, id1, ut.astype(np.int32))
+        cls = Classifier(small)
+        ref = cls.classify(h_reads, sample_off, confidence=conf, min_hit_groups=w.min_hit_groups)
+        same1 = bool(np.array_equal(ref.taxon, s_taxon[:cs]) and np.array_equal(ref.flags, s_flags[:cs]) and
+                     all(np.array_equal(ref.hits_of(i), s_hits[i]) for i in range(cs)))
+        cls.close()
+        small.close()
+    # ---- check 2 (optional): the CPU oracle fed with every genome of the library
+    oracle_res = "not run (bench.py --oracle-check: the oracle needs about 3 s of CPU per Gbp of library on 32 threads)"
+    if args.oracle_check:
+        oracle_res = None
+        if rank == 0:
+            from oracle import oracle
+            threads = oracle.set_threads(oracle.host_threads())
+            t0 = time.perf_counter()
+            olib = oracle.Library(oracle.params(k=w.k, m=w.m, spaces=w.spaces), parents, 64 * cs)
+            so = sample_off.astype(np.int64)
+            olib.add_sequences(h_reads, so, np.ones(cs, dtype=np.int32))
+            olib.clear_taxa()
+            olib.set_update_only(True)
+            per = max(1, (256 << 20) // w.genome_len)
+            for g0 in range(0, w.n_genomes, per):
+                g1 = min(w.n_genomes, g0 + per)
+                bases = oracle.synth_genome(w.gseed, g0 * w.genome_len, (g1 - g0) * w.genome_len)
+                olib.add_sequences(bases, np.arange(g1 - g0 + 1, dtype=np.int64) * w.genome_len, genome_taxa[g0:g1])
+            res_o, _, _, per_read = olib.classify(h_reads, so, confidence=conf, min_hit_groups=w.min_hit_groups, threads=threads)
+            ok = bool(np.array_equal(res_o["taxon"], s_taxon[:cs]) and np.array_equal(res_o["classified"], s_flags[:cs] & 1) and
+                      np.array_equal(res_o["has_span"], (s_flags[:cs] >> 1) & 1) and
+                      all(np.array_equal(per_read[i]["taxon"], s_hits[i]["taxon"]) and np.array_equal(per_read[i]["count"], s_hits[i]["count"])
+                          for i in range(cs)))
+            oracle_res = {"equal": ok, "sample_reads": cs, "cpu_seconds": time.perf_counter() - t0, "threads": threads,
+                          "what": "CPU oracle on a table holding the sample's minimizers, fed with all genomes of the library"}
+        dist.barrier()
+    res = {"metric": "reads/sec classified (150bp), library sharded by minimizer hash range", "value": world * sr * steps / wall,
+           "unit": "reads/s", "steps": steps, "ms_per_step": 1e3 * wall / steps, "reads_per_gpu_per_step": sr, "confidence": conf,
+           "library_gbp": w.total_bases / 1e9, "records_on_rank0": len(shard),
+           "equal_to_fused_kernel_on_the_shards_records_for_the_sample": same1, "sample_reads": cs, "oracle": oracle_res}
+    scl.close()
+    ctx.dev_free(d_reads); ctx.dev_free(d_off)
+    torch.cuda.empty_cache()
     return res
 
 
@@ -720,6 +837,9 @@ def main():
     ap.add_argument("--quick", action="store_true", help="tuning: only the device-timed single-end leg, short JSON")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded-library and distributed-build legs")
     ap.add_argument("--paired-confidence", type=float, default=0.15)
+    ap.add_argument("--no-big-classify", action="store_true", help="N > 1: skip classifying against the freshly built sharded library")
+    ap.add_argument("--big-check-reads", type=int, default=20_000, help="N > 1: reads of rank 0 checked in the big sharded-library leg")
+    ap.add_argument("--oracle-check", action="store_true", help="N > 1: also check that sample with the CPU oracle (minutes of CPU)")
     ap.add_argument("--sharded-reads", type=int, default=4_000_000, help="N > 1: reads per GPU per step of the sharded-library leg")
     ap.add_argument("--build-gbp-per-gpu", type=float, default=8.75, help="N > 1: genome bases per GPU of the distributed-build leg")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")

@@ -106,6 +106,8 @@ def lib():
         L.slko_synth_reads.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
         L.slko_synth_mates.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
         L.slko_set_threads.argtypes = [C.c_int]
+        L.slko_lib_clear_taxa.argtypes = [C.c_void_p]
+        L.slko_lib_set_update_only.argtypes = [C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -258,6 +260,13 @@ class Library:
         id1 = np.ascontiguousarray(id1).view(np.uint64)
         taxon = np.ascontiguousarray(taxon, dtype=np.int32)
         lib().slko_lib_add_records(self.h, _ptr(self.parents), _ptr(id1), _ptr(taxon), len(id1))
+
+    def clear_taxa(self):
+        lib().slko_lib_clear_taxa(self.h)
+
+    def set_update_only(self, on: bool):
+        """Later add_* calls only update minimizers that are in the table already (see slko_lib_set_update_only)."""
+        lib().slko_lib_set_update_only(self.h, 1 if on else 0)
 
     def __len__(self):
         return int(lib().slko_lib_size(self.h))

@@ -485,6 +485,7 @@ SLKO_API int32_t slko_resolve_tree(const int32_t* parents, const int32_t* taxa, 
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   uint64_t* keys; int32_t* taxa; uint64_t nslots; uint64_t count;
+  int update_only;   /* checking aid (see slko_lib_set_update_only): minimizers that are not in the table yet are skipped */
 } slko_lib;
 #define EMPTY_KEY (~0ull) /* a priority is never all ones for m<=31 (low pad bits are zero) */
 
@@ -514,6 +515,7 @@ static void lib_insert(slko_lib* L, const int32_t* parents, uint64_t key, int32_
   for (;;) {
     uint64_t cur = __atomic_load_n(&L->keys[i], __ATOMIC_ACQUIRE);
     if (cur == EMPTY_KEY) {
+      if (L->update_only) return;
       uint64_t exp = EMPTY_KEY;
       if (__atomic_compare_exchange_n(&L->keys[i], &exp, key, 0, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {
         __atomic_fetch_add(&L->count, 1, __ATOMIC_RELAXED);
@@ -541,6 +543,11 @@ static inline int lib_lookup(const slko_lib* L, uint64_t key, int32_t* taxon) {
   }
 }
 SLKO_API int slko_lib_lookup(const slko_lib* L, uint64_t key, int32_t* taxon) { return lib_lookup(L, key, taxon); }
+/* Checking a sample of reads against a library too large for host memory (the 70 Gbp configuration): insert the minimizers
+ * of the SAMPLE first, clear their taxa, switch the table to update-only and feed it every genome of the library: it then
+ * holds exactly the library's records for the sample's minimizers (taxon 0 = the library does not have it). */
+SLKO_API void slko_lib_clear_taxa(slko_lib* L) { memset(L->taxa, 0, sizeof(int32_t) * L->nslots); }
+SLKO_API void slko_lib_set_update_only(slko_lib* L, int on) { L->update_only = on; }
 
 /* Insert ready-made records (a library loaded from Parquet, KeyValueIndex.loadRecords :150-159). */
 SLKO_API void slko_lib_add_records(slko_lib* L, const int32_t* parents, const uint64_t* id1, const int32_t* taxon, uint64_t n) {

@@ -106,6 +106,35 @@ class IndexParams:
         return p
 
 
+def significant_mask(params: "IndexParams") -> int:
+    """The bits of a minimizer (the left-aligned 64-bit priority word stored in id1) that can be non-zero: the m-mer's bits,
+    without the positions a spaced seed blanks out (SpacedSeed.spaceMask, kmers/minimizer/MinimizerPriorities.scala:287-301)."""
+    m, spaces = params.m, params.spaces
+    full = (1 << 64) - 1
+    r = full
+    if m % 32 != 0:
+        r &= (full << (64 - (m % 32) * 2)) & full
+    if spaces > 0:
+        final_bits = 3 << ((64 - (m % 32) * 2) & 63)
+        for _ in range(spaces):
+            r = ((r << 4) & full) | final_bits
+    return r
+
+
+def expand_keys(params: "IndexParams", ckeys: np.ndarray) -> np.ndarray:
+    """Compressed keys (the significant bits of a minimizer gathered at the low end, as the table cells and the span words of
+    the split path hold them) -> the id1 values of the Parquet column."""
+    mask = significant_mask(params)
+    ck = np.ascontiguousarray(ckeys).astype(np.uint64)
+    out = np.zeros(len(ck), dtype=np.uint64)
+    j = 0
+    for b in range(64):
+        if (mask >> b) & 1:
+            out |= ((ck >> np.uint64(j)) & np.uint64(1)) << np.uint64(b)
+            j += 1
+    return out
+
+
 class Taxonomy:
     """slacken/Taxonomy.scala:159-160: parents[] indexed by raw taxon id (NONE = 0, ROOT = 1), plus the rank titles
     and scientific names the report needs (host only)."""
