@@ -245,7 +245,10 @@ void slk_dense_free(dense_tax& dt) { dense_free(dt); }
 // K4: insert (compressed key << 16 | dense taxon) cells. Equal keys merge by LCA (TaxonLCA.merge,
 // slacken/LowestCommonAncestor.scala:152-170), so the kernel also serves incremental builds.
 // one thread's insert; returns true when the key was new
-__device__ __forceinline__ bool insert_cell(uint64_t cell, const slk_table_view& tb, const slk_tax_view& tx) {
+// Returns true when the key is new. A table without a free cell on the whole probe sequence (an undersized table: cannot
+// happen with table_alloc's sizing, but would silently lose the record) raises bit 63 of *full.
+#define SLK_TABLE_FULL_BIT (1ull << 63)
+__device__ __forceinline__ bool insert_cell(uint64_t cell, const slk_table_view& tb, const slk_tax_view& tx, unsigned long long* full) {
   uint64_t ckey = cell >> 16;
   uint32_t taxon = (uint32_t)(cell & 0xffffu);
   if (taxon == 0) return false;  // a record whose taxon is NONE behaves exactly like a missing record
@@ -273,13 +276,14 @@ __device__ __forceinline__ bool insert_cell(uint64_t cell, const slk_table_view&
     }
     b = slk_next_bucket(b, tries, tb.n_buckets);   // the lookup's probe sequence: own 128-byte line first
   }
+  atomicOr(full, SLK_TABLE_FULL_BIT);
   return false;
 }
 __global__ void __launch_bounds__(256) insert_cells_kernel(const uint64_t* __restrict__ in, uint64_t n,
                                                            slk_table_view tb, slk_tax_view tx,
                                                            unsigned long long* n_new) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool fresh = i < n && insert_cell(in[i], tb, tx);
+  const bool fresh = i < n && insert_cell(in[i], tb, tx, n_new);
   const uint32_t cnt = (uint32_t)__syncthreads_count(fresh);   // one atomic per block on the record counter
   if (threadIdx.x == 0 && cnt) atomicAdd(n_new, (unsigned long long)cnt);
 }
@@ -566,6 +570,7 @@ extern "C" int slk_index_from_records(slk_ctx* ctx, slk_tax* tax, const slk_para
   }
   unsigned long long nn = 0;
   CUX(cudaMemcpy(&nn, d_new, 8, cudaMemcpyDeviceToHost));
+  if (nn & SLK_TABLE_FULL_BIT) { cleanup(); slk_index_destroy(idx); return fail(SLK_E_NOSPACE, "the minimizer table is full: records were not stored"); }
   idx->n_records = nn;
   cleanup();
 #undef CUX
@@ -774,6 +779,7 @@ extern "C" int slk_build_finish(slk_builder* b, slk_index** out) {
     if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
     CUX(cudaMemcpyAsync(&n_unique, d_cur, 8, cudaMemcpyDeviceToHost, ctx->stream));   // distinct keys actually stored
     CUX(cudaStreamSynchronize(ctx->stream));
+    if (n_unique & SLK_TABLE_FULL_BIT) { cleanup(); slk_index_destroy(idx); return fail(SLK_E_NOSPACE, "the minimizer table is full: records were not stored"); }
     b->launches++;
   } else {
     rc = table_alloc(&idx->table, 0);

@@ -302,7 +302,7 @@ SLK_HD uint64_t slk_min64(uint64_t a, uint64_t b) { return a < b ? a : b; }
 // 2^62 are non-negative finite doubles whose order is the order of the integers, so ONE compare on the otherwise idle
 // FP64 pipe replaces the two integer compares; the selects stay.
 SLK_HD uint64_t slk_min62(uint64_t a, uint64_t b) {
-#if defined(__CUDA_ARCH__) && !defined(SLK_INT_MIN)
+#if defined(__CUDA_ARCH__)
   return __longlong_as_double((long long)a) < __longlong_as_double((long long)b) ? a : b;
 #else
   return a < b ? a : b;
@@ -647,117 +647,11 @@ struct slk_frag_classifier {
     //  5. merge pass: every lane walks ITS entries of the previous tile in span order: numDistinct
     //     (slacken/Classifier.scala:94), k-mer totals, TaxonCounts.fromHits.
     // A lane only ever waits for copies it issued itself: slot s is requested and matched by lane s % 32.
-#ifdef SLK_DRIP
-    // Variant: the lookups are plain loads into registers, one in flight per lane, handed out in flat order over the
-    // warp's tiles every few scan steps and matched at the next hand-out (a stream of cp.async gathers that miss to DRAM
-    // blocks the shared-memory path of the whole SM, plain loads do not: profiles/r01_probe_microbench.md section 6).
-    // No staging area, no issue/match pass; a close only finishes the chains and merges.
-    uint32_t iss_cur = 0, iss_prev = 0;   // entries of the two tiles already handed out (warp-uniform)
-    uint32_t np_cur = 0, np_prev = 0;     // lengths of the two pending lists (warp-uniform)
-    uint32_t d_tile = 0, d_slot = 0xffffffffu;   // this lane's lookup in flight: tile handle, slot (none: all ones)
-    uint64_t d_ck = 0;
-    slk_bucket d_bk;
-    d_bk.c0 = 0; d_bk.c1 = 0; d_bk.c2 = 0; d_bk.c3 = 0;
-#if SLK_DRIP >= 2
-    uint32_t y_tile = 0, y_slot = 0xffffffffu;   // the younger of the lane's two lookups in flight
-    uint64_t y_ck = 0;
-    slk_bucket y_bk = d_bk;
-#endif
-    auto drip = [&]() {
-      const uint32_t prev = cur ^ ent_tile0 ^ ent_tile1;
-      SLK_SYNCWARP();   // the entries other lanes appended are visible
-      // the lookup handed out last time has landed: spanToHit's join (slacken/KeyValueIndex.scala:176-185)
-      bool pend = false;
-      if (d_slot != 0xffffffffu) {
-        uint32_t dense;
-        pend = !slk_match_bucket(d_bk, d_ck, &dense);
-        if (!pend) ent.set_key(d_tile, d_slot, d_ck | ((uint64_t)dense << 48));
-      }
-      const bool pend_p = pend && d_tile == prev, pend_c = pend && d_tile != prev;
-      uint32_t bal = SLK_BALLOT(pend_p);
-      if (pend_p) ent.set_pending(prev, np_prev + SLK_POPC(bal & lanes_below), d_slot);
-      np_prev += SLK_POPC(bal);
-      bal = SLK_BALLOT(pend_c);
-      if (pend_c) ent.set_pending(cur, np_cur + SLK_POPC(bal & lanes_below), d_slot);
-      np_cur += SLK_POPC(bal);
-#if SLK_DRIP >= 2
-      // two lookups in flight per lane: the one matched above was handed out two hand-outs ago
-      d_bk = y_bk; d_ck = y_ck; d_tile = y_tile; d_slot = y_slot;
-#define SLK_DRIP_NEW(f) y_##f
-#else
-#define SLK_DRIP_NEW(f) d_##f
-#endif
-      // hand out the next entries: the previous tile's first
-      const bool from_prev = iss_prev < n_prev;
-      const uint32_t tile = from_prev ? prev : cur, lim = from_prev ? n_prev : n_cur;
-      const uint32_t s = (from_prev ? iss_prev : iss_cur) + lane;
-      SLK_DRIP_NEW(slot) = 0xffffffffu;
-      if (s < lim && (ent.meta(tile, s) >> 14) == SLK_E_SEQ) {
-        const uint64_t key = ent.key(tile, s) << fshift;
-        const uint64_t ck = fast ? slk_compress_fast(key) : slk_compress_generic(sp, key);
-        ent.set_key(tile, s, ck);
-        slk_load_bucket(tb, slk_bucket_of(ck, tb.n_buckets), &SLK_DRIP_NEW(bk));
-        SLK_DRIP_NEW(ck) = ck; SLK_DRIP_NEW(tile) = tile; SLK_DRIP_NEW(slot) = s;
-      }
-#undef SLK_DRIP_NEW
-      const uint32_t adv = lim - (from_prev ? iss_prev : iss_cur);
-      if (from_prev) iss_prev += adv < SLK_LANES ? adv : SLK_LANES;
-      else iss_cur += adv < SLK_LANES ? adv : SLK_LANES;
-    };
-#endif
     auto close = [&]() {
       any = any || cnt_cur != 0;
       const uint32_t prev = cur ^ ent_tile0 ^ ent_tile1;
-#ifdef SLK_DRIP
-      while (iss_prev < n_prev) drip();   // normally long done: the hand-outs serve the previous tile first
-#if SLK_DRIP >= 2
-      while (SLK_WARP_ANY((d_slot != 0xffffffffu && d_tile == prev) || (y_slot != 0xffffffffu && y_tile == prev))) drip();
-#else
-      if (SLK_WARP_ANY(d_slot != 0xffffffffu && d_tile == prev)) drip();   // ... and its last lookups are matched
-#endif
-      const uint32_t n_pend = np_prev;
-      SLK_SYNCWARP();
-      for (uint32_t q = lane; q < n_pend; q += SLK_LANES) {
-        const uint32_t s = ent.pending(prev, q);
-        const uint64_t ck = ent.key(prev, s);
-        const uint32_t dense = slk_probe_rest(tb, slk_bucket_of(ck, tb.n_buckets), 1, ck);
-        ent.set_key(prev, s, ck | ((uint64_t)dense << 48));
-      }
-#else
       SLK_SYNCWARP();   // the entries other lanes appended are visible
       uint32_t n_pend = 0;
-#if defined(__CUDA_ARCH__) && defined(SLK_SYNC_FETCH)
-      // Plain loads instead of asynchronous copies: a stream of cp.async gathers that miss to DRAM blocks the SM's
-      // shared-memory path for every other warp (tools/probe_microbench5.cu: shared-memory work next to 33 G/s of
-      // cp.async gathers runs 6-10x slower, next to the same rate of ld.global.nc gathers not at all). Each lane loads
-      // the buckets of SLK_SYNC_FETCH of its entries into registers, then matches them; the warp waits for DRAM once
-      // per batch while the other warps of the SM scan.
-      for (uint32_t s0 = 0; s0 < n_prev; s0 += SLK_SYNC_FETCH * SLK_LANES) {
-        slk_bucket bks[SLK_SYNC_FETCH];
-        uint64_t cks[SLK_SYNC_FETCH];
-        bool sq[SLK_SYNC_FETCH];
-#pragma unroll
-        for (int j = 0; j < SLK_SYNC_FETCH; j++) {
-          const uint32_t s = s0 + (uint32_t)j * SLK_LANES + lane;
-          sq[j] = s < n_prev && (ent.meta(prev, s) >> 14) == SLK_E_SEQ;
-          cks[j] = 0; bks[j].c0 = 0; bks[j].c1 = 0; bks[j].c2 = 0; bks[j].c3 = 0;
-          if (sq[j]) { cks[j] = ent.key(prev, s); slk_load_bucket(tb, slk_bucket_of(cks[j], tb.n_buckets), &bks[j]); }
-        }
-#pragma unroll
-        for (int j = 0; j < SLK_SYNC_FETCH; j++) {
-          const uint32_t s = s0 + (uint32_t)j * SLK_LANES + lane;
-          bool pend = false;
-          if (sq[j]) {
-            uint32_t dense;
-            pend = !slk_match_bucket(bks[j], cks[j], &dense);
-            if (!pend) ent.set_key(prev, s, cks[j] | ((uint64_t)dense << 48));
-          }
-          const uint32_t bal = SLK_BALLOT(pend);
-          if (pend) ent.set_pending(prev, n_pend + SLK_POPC(bal & lanes_below), s);
-          n_pend += SLK_POPC(bal);
-        }
-      }
-#else
       ent.wait_all(n_commits & 1u);
 #pragma unroll 2
       for (uint32_t s0 = 0; s0 < n_prev; s0 += SLK_LANES) {
@@ -775,7 +669,6 @@ struct slk_frag_classifier {
         if (pend) ent.set_pending(prev, n_pend + SLK_POPC(bal & lanes_below), s);
         n_pend += SLK_POPC(bal);
       }
-#endif
       SLK_SYNCWARP();   // the pending list is complete, and nobody reads the staging area any more
       uint32_t n_fetched = 0;
 #pragma unroll 2
@@ -784,15 +677,11 @@ struct slk_frag_classifier {
           const uint64_t key = ent.key(cur, s) << fshift;
           const uint64_t ck = fast ? slk_compress_fast(key) : slk_compress_generic(sp, key);
           ent.set_key(cur, s, ck);
-#if !(defined(__CUDA_ARCH__) && defined(SLK_SYNC_FETCH))
           ent.fetch(s, tb.cells + slk_bucket_of(ck, tb.n_buckets) * 4);
-#endif
           n_fetched++;
         }
       }
-#if !(defined(__CUDA_ARCH__) && defined(SLK_SYNC_FETCH))
       ent.commit(n_fetched);
-#endif
       n_commits++;
       for (uint32_t q = lane; q < n_pend; q += SLK_LANES) {
         const uint32_t s = ent.pending(prev, q);
@@ -800,7 +689,6 @@ struct slk_frag_classifier {
         const uint32_t dense = slk_probe_rest(tb, slk_bucket_of(ck, tb.n_buckets), 1, ck);
         ent.set_key(prev, s, ck | ((uint64_t)dense << 48));
       }
-#endif
       SLK_SYNCWARP();   // all labels of the previous tile are visible to the lanes that own the entries
       uint32_t s = head_prev;
       for (uint32_t q = 0; q < cnt_prev; q++) {
@@ -831,9 +719,6 @@ struct slk_frag_classifier {
       SLK_SYNCWARP();   // nobody appends to the previous tile before everybody has left it
       n_prev = n_cur; head_prev = head_cur; cnt_prev = cnt_cur;
       n_cur = 0; cnt_cur = 0; cur = prev;
-#ifdef SLK_DRIP
-      iss_prev = iss_cur; np_prev = np_cur; iss_cur = 0; np_cur = 0;
-#endif
     };
     // Appends one entry per lane with `emit` set, in lane order. All lanes call it; the tile has room for all of
     // them (n_cur <= pool_limit). The caller closes the tile when the return value says it is full.
@@ -914,9 +799,6 @@ struct slk_frag_classifier {
           bool full = false;
           if (whole) {
             while (i + 4u <= i1w && !full) {   // four bases per round, no per-lane guards
-#ifdef SLK_DRIP
-              drip();
-#endif
               const uint32_t g = (uint32_t)(cw >> (2u * i)) & 0xffu;
               if (fstep(g & 3u, true)) { i += 1u; full = true; continue; }
               if (fstep((g >> 2) & 3u, true)) { i += 2u; full = true; continue; }
@@ -927,16 +809,10 @@ struct slk_frag_classifier {
             while (i < i1w && !full) { full = fstep((uint32_t)(cw >> (2u * i)) & 3u, true); i++; }
           } else if (!dirty) {
             while (i < i1w && !full) {
-#ifdef SLK_DRIP
-              if ((i & 3u) == 0u) drip();
-#endif
               full = fstep((uint32_t)(cw >> (2u * i)) & 3u, i >= i0 && i < i1); i++;
             }
           } else {
             while (i < i1w && !full) {
-#ifdef SLK_DRIP
-              if ((i & 3u) == 0u) drip();
-#endif
               full = step(((uint32_t)(cw >> (2u * i)) & 3u) | (((mw >> i) & 1u) << 2), i >= i0 && i < i1);
               i++;
             }

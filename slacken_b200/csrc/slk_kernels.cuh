@@ -238,11 +238,7 @@ struct dev_store {
     asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(o->c2), "=l"(o->c3) : "r"(d + 16u * SLK_POOL) : "memory");
   }
   __device__ __forceinline__ void commit(uint32_t) const { asm volatile("cp.async.commit_group;" ::: "memory"); }
-#ifdef SLK_UNSAFE_NOWAIT   // timing experiment only: results are wrong
-  __device__ __forceinline__ void wait_all(uint32_t) const {}
-#else
   __device__ __forceinline__ void wait_all(uint32_t) const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-#endif
 
   __device__ __forceinline__ void set_hit(uint32_t i, int32_t label, int32_t count) const {
     asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(sa(hits + i * (8u * SLK_CLS_THREADS))), "r"(label), "r"(count) : "memory");

@@ -147,7 +147,14 @@ def read_library(location: str):
 
 
 def load_taxonomy_dmp(directory: str):
-    """Taxonomy.load (slacken/Taxonomy.scala:116-137): -> (parents int32[], ranks, names)."""
+    """Taxonomy.load (slacken/Taxonomy.scala:116-137): -> (parents int32[], ranks, names). load_taxonomy_primary also
+    returns merged.dmp's secondary -> primary mapping (Taxonomy.primary, slacken/Taxonomy.scala:100-103)."""
+    return load_taxonomy_primary(directory)[:3]
+
+
+def load_taxonomy_primary(directory: str):
+    """-> (parents, ranks, names, primary int32[]): primary[t] = t unless merged.dmp maps the (secondary) id t to its primary id
+    (Taxonomy.primary; Dynamic's gold set and the comparison tools apply it, slacken/Dynamic.scala:287)."""
     nodes = []
     for line in open(os.path.join(directory, "nodes.dmp")):
         x = line.split("|")
@@ -169,8 +176,13 @@ def load_taxonomy_dmp(directory: str):
     for line in open(os.path.join(directory, "names.dmp")):
         x = line.split("|")
         if len(x) > 3 and x[3].strip() == "scientific name":
-            names[int(x[0].strip())] = x[1].strip()
+            t = int(x[0].strip())
+            if 0 <= t < n:   # names of ids that nodes.dmp and merged.dmp do not know are ignored
+                names[t] = x[1].strip()
     names[0] = "unclassified"
     parents[1] = 0
     ranks[0], ranks[1] = "unclassified", "root"
-    return parents, ranks, names
+    primary = np.arange(n, dtype=np.int32)
+    for sec, prim in merged:
+        primary[sec] = prim
+    return parents, ranks, names, primary

@@ -19,13 +19,40 @@ from .host import ClassifiedBatch, Taxonomy
 from .report import KrakenReport, output_line
 
 
+def java_double_to_string(x: float) -> str:
+    """java.lang.Double.toString: the shortest digits that round-trip (as Python's repr finds them), printed in decimal
+    notation for 1e-3 <= |x| < 1e7 and in "computerized scientific notation" (d.dddE[-]n, at least one digit after the point)
+    otherwise."""
+    x = float(x)
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "Infinity" if x > 0 else "-Infinity"
+    if x == 0:
+        return "-0.0" if str(x).startswith("-") else "0.0"
+    from decimal import Decimal
+    d = Decimal(repr(x))
+    sign, digits, exp = d.as_tuple()
+    digits = list(digits)
+    while len(digits) > 1 and digits[-1] == 0:   # normalise: no trailing zeros in the digit string
+        digits.pop(); exp += 1
+    sci_exp = exp + len(digits) - 1              # x = d.ddd * 10^sci_exp
+    ds = "".join(str(v) for v in digits)
+    neg = "-" if sign else ""
+    if -3 <= sci_exp < 7:
+        if sci_exp >= len(ds) - 1:
+            return neg + ds + "0" * (sci_exp - (len(ds) - 1)) + ".0"
+        if sci_exp >= 0:
+            return neg + ds[:sci_exp + 1] + "." + ds[sci_exp + 1:]
+        return neg + "0." + "0" * (-sci_exp - 1) + ds
+    return neg + ds[0] + "." + (ds[1:] or "0") + "E" + str(sci_exp)
+
+
 def threshold_string(threshold: float, thresholds: Sequence[float]) -> str:
-    """`"%.Nf".format(threshold)` with N = the longest decimal part among `thresholds` as printed by Double.toString."""
-    def decimals(x: float) -> int:
-        s = repr(float(x))
-        return len(s.split(".")[1]) if "." in s and "e" not in s.lower() else 1
+    """`"%.Nf".format(threshold)` with N = the longest `num.toString.split("\\.")(1).length` among the thresholds
+    (slacken/Classifier.scala:189-190): for 1.0E-5 that is the length of "0E-5"."""
     from .report import java_fixed
-    return java_fixed(threshold, max(decimals(t) for t in thresholds))
+    return java_fixed(threshold, max(len(java_double_to_string(t).split(".")[1]) for t in thresholds))
 
 
 def sample_ids(titles: Sequence[str], sample_regex: Optional[str]) -> List[str]:

@@ -9,9 +9,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# SLK_EMU_DEFS="-DSLK_DRIP" builds (and loads) the emulation of a kernel variant next to the default one
-_DEFS = os.environ.get("SLK_EMU_DEFS", "").split()
-_SO = os.path.join(_HERE, "libslk_emu" + "".join(d.replace("-D", "_").replace("=", "") for d in _DEFS) + ".so")
+_DEFS = []
+_SO = os.path.join(_HERE, "libslk_emu.so")
 _CORE = os.path.join(_HERE, "..", "..", "slacken_b200", "csrc", "slk_core.h")
 BUILD_WPT = 96
 

@@ -205,18 +205,3 @@ def test_bracken_window_body_matches_the_oracle(read_len):
         want = oracle.bracken_read_classifications(p, parents, lib.lookup, seq, read_len)
         got = emu.bracken_dests(ix, seq, read_len)
         assert list(got) == want, (len(seq), read_len)
-
-
-@pytest.mark.parametrize("defs", ["-DSLK_DRIP=1", "-DSLK_DRIP=2"])
-def test_kernel_variants_stay_bit_exact(defs):
-    """The experimental lookup variants of the classify kernel body (plain loads handed out inside the scan loop, off by
-    default; profiles/r01_probe_microbench.md section 6) against the oracle: the same emulation tests, with the variant
-    compiled in, in a child interpreter (the emulation library is chosen at import time)."""
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, SLK_EMU_DEFS=defs)
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_host_emulation.py", "-x", "-q", "-k", "classify_body"],
-                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

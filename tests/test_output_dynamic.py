@@ -121,3 +121,29 @@ def test_gold_set_promotion_filter_and_comparison():
     assert (st["tp"], st["fp"], st["fn"]) == (1, 1, 4)
     assert d.log[-1].endswith("True Positives: 1, False Positives: 1, False Negatives: 4, Precision: 50.00%, Recall: 20.00%")
     assert format_perc(1 / 3) == "33.33%"
+
+
+def test_threshold_directory_names_follow_java_double_to_string():
+    """Classifier.scala:189-190 takes the decimal count from Double.toString, which switches to scientific notation below 1e-3:
+    1.0E-5 -> "0E-5" -> four decimals."""
+    from slacken_b200.output import java_double_to_string, threshold_string
+    cases = {0.0: "0.0", 0.15: "0.15", 1e-5: "1.0E-5", 1e-4: "1.0E-4", 0.001: "0.001", 1.5e-7: "1.5E-7", 1e7: "1.0E7",
+             1234567.0: "1234567.0", 100.0: "100.0", 12345678.9: "1.23456789E7", 0.05: "0.05"}
+    for x, want in cases.items():
+        assert java_double_to_string(x) == want
+    assert threshold_string(1e-5, [1e-5]) == "0.0000"
+    assert threshold_string(0.0, [0.0, 0.15]) == "0.00" and threshold_string(0.15, [0.0, 0.15]) == "0.15"
+    assert threshold_string(0.1, [0.1, 1e-4]) == "0.1000"
+
+
+def test_taxonomy_loader_returns_the_merged_mapping(tmp_path):
+    from slacken_b200 import library_io as lio
+    d = tmp_path / "tax"
+    d.mkdir()
+    (d / "nodes.dmp").write_text("1\t|\t1\t|\tno rank\t|\n2\t|\t1\t|\tsuperkingdom\t|\n7\t|\t2\t|\tspecies\t|\n")
+    (d / "names.dmp").write_text("1\t|\troot\t|\t\t|\tscientific name\t|\n7\t|\tSeven\t|\t\t|\tscientific name\t|\n99\t|\tGhost\t|\t\t|\tscientific name\t|\n")
+    (d / "merged.dmp").write_text("12\t|\t7\t|\n")
+    parents, ranks, names, primary = lio.load_taxonomy_primary(str(d))
+    assert len(parents) == 13 and parents[7] == 2 and names[7] == "Seven"      # id 99 of names.dmp is unknown: ignored
+    assert primary[12] == 7 and primary[7] == 7 and primary[2] == 2
+    assert lio.load_taxonomy_dmp(str(d))[0].tolist() == parents.tolist()
