@@ -78,7 +78,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-KERNEL_NAME = "classify_kernel<5,true,true>"
+KERNEL_NAME = "classify2_kernel<5,true>"
 
 
 def measured_peak():
@@ -93,10 +93,10 @@ def measured_peak():
 
 def measured_traffic(args, n_reads):
     """dram__bytes_read + dram__bytes_write of ONE launch of the classify kernel, from the committed ncu --set full capture
-    (profiles/r01_traffic.json); None when the run is not the configuration that was profiled."""
+    (profiles/r02_traffic.json); None when the run is not the configuration that was profiled."""
     if args.traffic is not None:
         return args.traffic
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         t = json.load(open(p))
         if int(t["reads_per_launch"]) == int(n_reads):
@@ -449,6 +449,11 @@ def run_ours(args, w):
                    "api": "slk_classify_batch_compact: pinned HOST buffers holding 2-bit codes + lengths + a sparse list of ambiguous "
                           "positions (no block offsets, no mask words); 16-byte results and the merged hits in read order come back",
                    "equal_to_packed_entry_point": None, "clocks": ClockSampler.summarize(sampler.window(ct0, ct1))}
+    cr_s, _, _ = timed_e2e(lambda: cls.classify_compact(cr1, None, thresholds=[w.confidence], min_hit_groups=w.min_hit_groups,
+                                                        per_read_output=False, out=cout))
+    e2e_compact_report = {"value": world * n * args.steps / cr_s, "unit": "reads/s", "h2d_bytes_per_step": int(cr1.nbytes),
+                          "d2h_bytes_per_step": int(cout.results.nbytes), "ms_per_step": 1e3 * cr_s / args.steps,
+                          "api": "slk_classify_batch_compact without hit lists: 16 bytes per read come back"}
     # `out` now holds the single-end results of the whole batch (the CPU leg below checks a sample of them)
     single_out = ClassifiedBatch(out.taxon.copy(), out.flags.copy(), out.detail.copy(), out.hits[:out.hits_used].copy(), out.hits_used)
     # the compact results against the packed entry point's, all reads: taxon, flags, lengths, and the hit lists in read order
@@ -503,7 +508,7 @@ def run_ours(args, w):
                        "classified_fraction": float((rep.sum() - rep[0]) / max(1, rep.sum())),
                        "reads_counted_in_report": total_reads_counted,
                        "device_report_counters_equal_per_read_results": report_consistent},
-            "probes_per_s": value * S, "clocks": clocks, "e2e": e2e, "e2e_compact": e2e_compact, "e2e_report_only": e2e_report, "e2e_ascii_input": e2e_ascii,
+            "probes_per_s": value * S, "clocks": clocks, "e2e": e2e, "e2e_compact": e2e_compact, "e2e_compact_report_only": e2e_compact_report, "e2e_report_only": e2e_report, "e2e_ascii_input": e2e_ascii,
             "value_ascii_input": {"value": world * n * args.steps / (ms_ascii / 1e3), "unit": "reads/s", "ms_per_step": ms_ascii / args.steps,
                                   "note": "same launch with ASCII reads resident in HBM (stage 1 runs first as its own kernel)"},
             "encode_kernel": {"ms": 1e3 * t_pack, "reads_per_s": n / t_pack, "gbs": (L + 8 + 12.0 * n_blocks / n + 4) * n / t_pack / 1e9,
