@@ -597,7 +597,7 @@ def sharded_leg(args, w, ctx, tax, params, index, cls, m1, d_off, n, L, genome_t
     check(ctx._L.slk_index_records_by_owner_dev(index.h, world, C.c_void_p(sid.data_ptr()), C.c_void_p(stx.data_ptr()), nrec, cnt))
     lo = sum(int(c) for c in cnt[:rank])
     mine = int(cnt[rank])
-    shard = ShardedKeyValueIndex(KeyValueIndex.from_records_dev(ctx, tax, params, sid[lo:lo + mine].clone(), stx[lo:lo + mine].clone()), rank, world)
+    shard = ShardedKeyValueIndex(KeyValueIndex.from_records_dev(ctx, tax, params, sid[lo:lo + mine].clone(), stx[lo:lo + mine].clone(), world=world), rank, world)
     del sid, stx
     torch.cuda.empty_cache()
     cap = int(sr * 44 / world * 1.25) + 65536
@@ -681,17 +681,16 @@ def dist_build_leg(args, w0, ctx, tax, params, genome_taxa0, rank, world, dist):
         ctx.h2d(d_off, np.arange(g1 - g0 + 1, dtype=np.uint64) * np.uint64(w.genome_len))
         ctx.h2d(d_tax, genome_taxa[g0:g1])
         b.add_dev(d_bases, d_off, d_tax, g1 - g0, nb)
-    local_index = b.finish()
-    b.close()
     for p in (d_bases, d_off, d_tax):
         ctx.dev_free(p)
     ctx.sync()
     t_local = time.perf_counter() - t0
-    n_local = len(local_index)
-    shard = ShardedKeyValueIndex.from_local(local_index)
+    shard = ShardedKeyValueIndex.from_builder(b)
+    b.close()
     ctx.sync()
     torch.cuda.synchronize()
     t_all = time.perf_counter() - t0
+    n_local = int(sum(ShardedKeyValueIndex.last_build_counts))
     t = torch.tensor([t_local, t_all], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([n_local, len(shard)], dtype=torch.int64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -701,8 +700,8 @@ def dist_build_leg(args, w0, ctx, tax, params, genome_taxa0, rank, world, dist):
            "value": w.total_bases / t_all / 1e9, "unit": "Gbases/s", "seconds": t_all, "scaling": "weak",
            "timing": "host wall clock from the first genome batch to the finished sharded table, genome generation on the device "
                      "included, max over ranks",
-           "phases_s": {"local scan + sort + LCA reduce + local table": t_local,
-                        "records to their owners + insert on the owner": t_all - t_local,
+           "phases_s": {"local scan (minimizers of this rank's genomes -> cells)": t_local,
+                        "sort + LCA reduce, cells to their owners, insert on the owner": t_all - t_local,
                         "exchange_breakdown_rank0": ShardedKeyValueIndex.last_build_times},
            "workload": f"{w.n_genomes} synthetic genomes x {w.genome_len} bp = {w.total_bases / 1e9:.2f} Gbp, {len(parents)}-node "
                        f"taxonomy, k{w.k}/m{w.m}/s{w.spaces}",

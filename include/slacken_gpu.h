@@ -270,7 +270,8 @@ SLK_API int slk_ctx_sync(slk_ctx* ctx);
  * A span word is (compressed minimizer << 16 | type << 14 | k-mer count), type 0 = sequence, 1 = ambiguous, 2 = mate
  * border (slacken/Supermers.scala:49-125). */
 typedef struct slk_resolver slk_resolver;
-/* owner (0 .. world-1) of every record of the Parquet table; host arrays */
+/* owner (0 .. world-1) of every record of the Parquet table; host arrays. Owner d holds the d-th of `world` equal ranges
+ * of the table-line hash of the minimizer. */
 SLK_API int slk_shard_of_records(const slk_params* params, const int64_t* id1, uint64_t n, uint32_t world, uint8_t* shard_out);
 /* the same for records that live in device memory (id1 and shard_out are device pointers) */
 SLK_API int slk_shard_of_records_dev(slk_ctx* ctx, const slk_params* params, const int64_t* id1, uint64_t n, uint32_t world,
@@ -278,6 +279,26 @@ SLK_API int slk_shard_of_records_dev(slk_ctx* ctx, const slk_params* params, con
 /* the records of an index grouped by owner, in DEVICE memory: rows of owner d at [sum(counts_host[0..d)), +counts_host[d]) */
 SLK_API int slk_index_records_by_owner_dev(slk_index* idx, uint32_t world, int64_t* id1_out, int32_t* taxon_out, uint64_t cap,
                                            uint64_t* counts_host);
+/* One shard of a library range-partitioned over `world` GPUs from the records this rank owns (slk_shard_of_records): as
+ * slk_index_from_records, but the table spreads the owner's RANGE of the line hash over all of its lines. An index of a
+ * shard must be created with the `world` it was cut for; world = 1 is slk_index_from_records. */
+SLK_API int slk_index_from_records_shard(slk_ctx* ctx, slk_tax* tax, const slk_params* params, const int64_t* id1,
+                                         const int32_t* taxon, uint64_t n, uint32_t world, slk_index** out);
+/* Distributed build (BASELINE configs[2]; the shuffle of groupBy(idColumns).agg(udafLca), slacken/KeyValueIndex.scala:85-93):
+ *   every rank: slk_build_begin, slk_build_add* (its own genomes), slk_build_reduce (sort + LCA reduce; counts_out[d] =
+ *   cells bound for owner d), slk_build_take_cells (the cells, grouped by owner, into the caller's send buffer) and
+ *   slk_build_dense_taxa (the raw ids behind the 16-bit taxa inside the cells);
+ *   [all-to-all of the cells, all-gather of the taxa lists: the caller's];
+ *   every owner: slk_index_from_cell_runs on what it received: n_runs runs back to back in cells_dev (run r holds
+ *   run_cells[r] cells and uses the run_dense[r] raw ids that follow those of run r-1 in dense_raw_host). The runs are
+ *   ordered by table line, so the insert walks the table front to back; equal minimizers merge by LCA
+ *   (slacken/LowestCommonAncestor.scala:152-170). cells_dev is overwritten. */
+SLK_API int slk_build_reduce(slk_builder* b, uint32_t world, uint64_t* counts_out);
+SLK_API int slk_build_take_cells(slk_builder* b, uint64_t* cells_out_dev, uint64_t cap);
+SLK_API int slk_build_dense_taxa(slk_builder* b, int32_t* raw_out, uint32_t cap, uint32_t* n_out);
+SLK_API int slk_index_from_cell_runs(slk_ctx* ctx, slk_tax* tax, const slk_params* params, uint32_t world, uint32_t n_runs,
+                                     uint64_t* cells_dev, const uint64_t* run_cells, const int32_t* dense_raw_host,
+                                     const uint32_t* run_dense, slk_index** out);
 /* the taxa (raw ids, ancestors included) an index can answer with; out == NULL queries the count */
 SLK_API int slk_index_taxa(slk_index* idx, int32_t* out, uint32_t cap, uint32_t* n_out);
 /* the query side's view of the taxonomy: the union of slk_index_taxa over all shards (any order, duplicates allowed) */

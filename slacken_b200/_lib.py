@@ -100,6 +100,11 @@ SIGNATURES = {
     "slk_memcpy_d2h": (_INT, [_VP, _VP, _VP, C.c_size_t]),
     "slk_debug_sort_u64": (_INT, [_VP, _VP, _U64, _INT, _INT]),
     "slk_debug_min62": (_INT, [_VP, _VP, _VP, _U64, _VP]),
+    "slk_index_from_records_shard": (_INT, [_VP, _VP, _VP, _VP, _VP, _U64, _U32, _VP]),
+    "slk_build_reduce": (_INT, [_VP, _U32, _VP]),
+    "slk_build_take_cells": (_INT, [_VP, _VP, _U64]),
+    "slk_build_dense_taxa": (_INT, [_VP, _VP, _U32, _VP]),
+    "slk_index_from_cell_runs": (_INT, [_VP, _VP, _VP, _U32, _U32, _VP, _VP, _VP, _VP, _VP]),
     "slk_shard_of_records": (_INT, [_VP, _VP, _U64, _U32, _VP]),
     "slk_shard_of_records_dev": (_INT, [_VP, _VP, _VP, _U64, _U32, _VP]),
     "slk_index_records_by_owner_dev": (_INT, [_VP, _U32, _VP, _VP, _U64, _VP]),

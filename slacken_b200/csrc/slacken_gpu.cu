@@ -71,6 +71,10 @@ struct slk_builder {
   unsigned long long* d_count = nullptr;
   uint64_t count = 0;
   uint64_t launches = 0;
+  // slk_build_reduce: the reduced cells of owner r start at red[seg_first[r]] and there are seg_count[r] of them
+  uint64_t* red = nullptr;
+  uint64_t* red_aux = nullptr;
+  std::vector<uint64_t> seg_first, seg_count;
 };
 struct slk_counts {
   slk_ctx* ctx;
@@ -252,7 +256,7 @@ __device__ __forceinline__ bool insert_cell(uint64_t cell, const slk_table_view&
   uint64_t ckey = cell >> 16;
   uint32_t taxon = (uint32_t)(cell & 0xffffu);
   if (taxon == 0) return false;  // a record whose taxon is NONE behaves exactly like a missing record
-  uint64_t b = slk_bucket_of(ckey, tb.n_buckets);
+  uint64_t b = slk_bucket_of(ckey, tb);
   for (uint64_t tries = 1; tries <= tb.n_buckets; tries++) {
     unsigned long long* slot = reinterpret_cast<unsigned long long*>(tb.cells + b * 4);
     for (int j = 0; j < 4; j++) {
@@ -493,9 +497,9 @@ static uint64_t buckets_for(uint64_t n_keys) {
   uint64_t cells = (uint64_t)((double)n_keys / table_load_factor(n_keys)) + 64;
   return ((cells + 15) / 16) * 4;   // whole 128-byte lines of four buckets
 }
-static int table_alloc(slk_table_view* tb, uint64_t n_keys) {
+static int table_alloc(slk_table_view* tb, uint64_t n_keys, uint32_t world = 1) {
   tb->n_buckets = buckets_for(n_keys);
-  tb->prefetch = 0;
+  tb->mix_mul = world;
   tb->pad_ = 0;
   CU(cudaMalloc(&tb->cells, tb->n_buckets * 32));
   CU(cudaMemset(tb->cells, 0, tb->n_buckets * 32));
@@ -510,7 +514,11 @@ static int insert_cells(slk_ctx* ctx, slk_index* idx, const uint64_t* d_cells, u
 
 extern "C" int slk_index_from_records(slk_ctx* ctx, slk_tax* tax, const slk_params* params, const int64_t* id1,
                                       const int32_t* taxon, uint64_t n, slk_index** out) {
-  if (!ctx || !tax || !params || !out || (n && (!id1 || !taxon))) return fail(SLK_E_INVALID, "bad arguments");
+  return slk_index_from_records_shard(ctx, tax, params, id1, taxon, n, 1, out);
+}
+extern "C" int slk_index_from_records_shard(slk_ctx* ctx, slk_tax* tax, const slk_params* params, const int64_t* id1,
+                                            const int32_t* taxon, uint64_t n, uint32_t world, slk_index** out) {
+  if (!ctx || !tax || !params || !out || world < 1 || (n && (!id1 || !taxon))) return fail(SLK_E_INVALID, "bad arguments");
   CU(cudaSetDevice(ctx->device));
   slk_index* idx = new (std::nothrow) slk_index;
   if (!idx) return fail(SLK_E_NOMEM, "host allocation failed");
@@ -520,22 +528,31 @@ extern "C" int slk_index_from_records(slk_ctx* ctx, slk_tax* tax, const slk_para
   dense_init(idx->dt);
   int32_t n_tax = (int32_t)tax->parents.size();
   // 1) which taxa occur: device bitmap over raw ids, records streamed in chunks
-  const uint64_t CH = 1ull << 26;
+  // records already in device memory (the distributed build hands over what it received from its peers) are read in
+  // place, in larger pieces; host records are staged piece by piece
+  cudaPointerAttributes pa_id{}, pa_tx{};
+  const bool on_device = n > 0 && cudaPointerGetAttributes(&pa_id, id1) == cudaSuccess && pa_id.type == cudaMemoryTypeDevice &&
+                         cudaPointerGetAttributes(&pa_tx, taxon) == cudaSuccess && pa_tx.type == cudaMemoryTypeDevice;
+  cudaGetLastError();
+  const uint64_t CH = on_device ? 1ull << 28 : 1ull << 26;
   uint64_t chunk = std::min<uint64_t>(n ? n : 1, CH);
-  int64_t* d_id = nullptr; int32_t* d_tx = nullptr; uint64_t* d_cells = nullptr;
+  int64_t* d_id = nullptr; int32_t* d_tx = nullptr; uint64_t* d_cells = nullptr; uint64_t* d_tmp = nullptr;
   uint32_t *d_bitmap = nullptr, *d_bad = nullptr; uint16_t* d_r2d = nullptr; unsigned long long* d_new = nullptr;
   size_t words = ((size_t)n_tax + 31) / 32;
   auto cleanup = [&]() {
-    cudaFree(d_id); cudaFree(d_tx); cudaFree(d_cells); cudaFree(d_bitmap); cudaFree(d_bad); cudaFree(d_r2d); cudaFree(d_new);
+    if (!on_device) { cudaFree(d_id); cudaFree(d_tx); }
+    cudaFree(d_cells); cudaFree(d_tmp); cudaFree(d_bitmap); cudaFree(d_bad); cudaFree(d_r2d); cudaFree(d_new);
   };
 #define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); slk_index_destroy(idx); \
     return fail(e_ == cudaErrorMemoryAllocation ? SLK_E_NOMEM : SLK_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
-  CUX(cudaMalloc(&d_id, chunk * 8)); CUX(cudaMalloc(&d_tx, chunk * 4)); CUX(cudaMalloc(&d_cells, chunk * 8));
+  if (!on_device) { CUX(cudaMalloc(&d_id, chunk * 8)); CUX(cudaMalloc(&d_tx, chunk * 4)); }
+  CUX(cudaMalloc(&d_cells, chunk * 8)); CUX(cudaMalloc(&d_tmp, chunk * 8));
   CUX(cudaMalloc(&d_bitmap, words * 4)); CUX(cudaMalloc(&d_bad, 4)); CUX(cudaMalloc(&d_new, 8));
   CUX(cudaMemset(d_bitmap, 0, words * 4)); CUX(cudaMemset(d_bad, 0, 4)); CUX(cudaMemset(d_new, 0, 8));
   for (uint64_t s = 0; s < n; s += chunk) {
     uint64_t c = std::min(chunk, n - s);
-    CUX(cudaMemcpyAsync(d_tx, taxon + s, c * 4, cudaMemcpyDefault, ctx->stream));
+    if (on_device) d_tx = const_cast<int32_t*>(taxon + s);
+    else CUX(cudaMemcpyAsync(d_tx, taxon + s, c * 4, cudaMemcpyDefault, ctx->stream));
     mark_taxa_kernel<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(d_tx, c, n_tax, d_bitmap, d_bad);
     CUX(cudaGetLastError());
     CUX(cudaStreamSynchronize(ctx->stream));
@@ -556,15 +573,23 @@ extern "C" int slk_index_from_records(slk_ctx* ctx, slk_tax* tax, const slk_para
   CUX(cudaMalloc(&d_r2d, (size_t)n_tax * 2));
   CUX(cudaMemcpy(d_r2d, r2d.data(), (size_t)n_tax * 2, cudaMemcpyHostToDevice));
   // 2) table + insert
-  rc = table_alloc(&idx->table, n);
+  rc = table_alloc(&idx->table, n, world);
   if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
   for (uint64_t s = 0; s < n; s += chunk) {
     uint64_t c = std::min(chunk, n - s);
-    CUX(cudaMemcpyAsync(d_id, id1 + s, c * 8, cudaMemcpyDefault, ctx->stream));
-    CUX(cudaMemcpyAsync(d_tx, taxon + s, c * 4, cudaMemcpyDefault, ctx->stream));
+    if (on_device) { d_id = const_cast<int64_t*>(id1 + s); d_tx = const_cast<int32_t*>(taxon + s); }
+    else {
+      CUX(cudaMemcpyAsync(d_id, id1 + s, c * 8, cudaMemcpyDefault, ctx->stream));
+      CUX(cudaMemcpyAsync(d_tx, taxon + s, c * 4, cudaMemcpyDefault, ctx->stream));
+    }
     records_to_cells_kernel<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(d_id, d_tx, c, d_r2d, idx->sp, d_cells);
     CUX(cudaGetLastError());
-    rc = insert_cells(ctx, idx, d_cells, c, d_new);
+    // in the order of the table's lines, as in slk_build_finish: each piece walks the table front to back
+    uint64_t* sorted_ptr = nullptr;
+    if (slk_sort_cells_by_line(d_cells, d_tmp, c, ctx->stream, &sorted_ptr) != 0) {
+      cleanup(); slk_index_destroy(idx); return fail(SLK_E_CUDA, "radix sort failed");
+    }
+    rc = insert_cells(ctx, idx, sorted_ptr, c, d_new);
     if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
     CUX(cudaStreamSynchronize(ctx->stream));
   }
@@ -634,6 +659,8 @@ extern "C" void slk_build_destroy(slk_builder* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
   cudaFree(b->cells); cudaFree(b->d_count);
+  if (b->red != b->cells) cudaFree(b->red);
+  if (b->red_aux != b->cells) cudaFree(b->red_aux);
   dense_free(b->dt);
   delete b;
 }
@@ -789,6 +816,166 @@ extern "C" int slk_build_finish(slk_builder* b, slk_index** out) {
   idx->n_records = n_unique;
   cleanup();
   cudaFree(b->cells); b->cells = nullptr; b->cap = 0; b->count = 0;
+  *out = idx;
+  return SLK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- distributed build
+// The build of a library that is range-partitioned over `world` GPUs (slk_shard_of): every rank scans its own genomes
+// (slk_build_add*), slk_build_reduce sorts and LCA-reduces them, the reduced cells -- ordered by the table-line mix and
+// therefore already grouped by owner -- travel to their owners (the caller's all-to-all), and slk_index_from_cell_runs
+// inserts the `world` ordered runs an owner has received front to back. The dense taxon ids inside the cells are the
+// sender's: its dense -> raw list (slk_build_dense_taxa) travels with them.
+// Replaces the shuffle of groupBy(idColumns).agg(udafLca), slacken/KeyValueIndex.scala:85-93; the merge of the runs on
+// the owner is TaxonLCA.merge, slacken/LowestCommonAncestor.scala:152-170.
+__global__ void owner_bounds_kernel(const uint64_t* __restrict__ sorted, uint64_t n, uint32_t world, uint64_t* __restrict__ first) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > world) return;
+  uint64_t lo = 0, hi = n;                       // first index whose owner is >= r
+  while (r < world && lo < hi) {
+    const uint64_t mid = lo + (hi - lo) / 2;
+    if (slk_shard_of(sorted[mid] >> 16, world) < r) lo = mid + 1; else hi = mid;
+  }
+  first[r] = r < world ? lo : n;
+}
+__global__ void __launch_bounds__(256) remap_cells_kernel(uint64_t* __restrict__ cells, uint64_t n, const uint16_t* __restrict__ map) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t c = cells[i];
+  cells[i] = (c & ~0xffffull) | map[c & 0xffffu];
+}
+
+extern "C" int slk_build_reduce(slk_builder* b, uint32_t world, uint64_t* counts_out) {
+  if (!b || world < 1 || world > 255 || !counts_out) return fail(SLK_E_INVALID, "bad arguments");
+  if (b->red || !b->seg_count.empty()) return fail(SLK_E_INVALID, "slk_build_reduce was already called on this builder");
+  slk_ctx* ctx = b->ctx;
+  CU(cudaSetDevice(ctx->device));
+  const uint64_t n = b->count;
+  b->seg_first.assign(world + 1, 0); b->seg_count.assign(world, 0);
+  if (n == 0) { for (uint32_t r = 0; r < world; r++) counts_out[r] = 0; return SLK_OK; }
+  dense_tax dt = b->dt;                           // device copy of the dense taxonomy for the reduce
+  dt.d_parent = nullptr; dt.d_depth = nullptr; dt.d_raw = nullptr;
+  int rc = dense_upload(dt);
+  if (rc != SLK_OK) return rc;
+  uint64_t* d_tmp = nullptr; uint64_t* d_first = nullptr; unsigned long long* d_cur = nullptr;
+  auto cleanup = [&]() { cudaFree(d_tmp); cudaFree(d_first); cudaFree(d_cur); dense_free(dt); };
+#define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
+    return fail(e_ == cudaErrorMemoryAllocation ? SLK_E_NOMEM : SLK_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+  CUX(cudaMalloc(&d_tmp, n * 8));
+  CUX(cudaMalloc(&d_first, ((size_t)world + 1) * 8));
+  CUX(cudaMalloc(&d_cur, (size_t)world * 8));
+  CUX(cudaMemsetAsync(d_cur, 0, (size_t)world * 8, ctx->stream));
+  uint64_t* sorted_ptr = nullptr;
+  if (slk_sort_cells_by_line(b->cells, d_tmp, n, ctx->stream, &sorted_ptr) != 0) { cleanup(); return fail(SLK_E_CUDA, "radix sort failed"); }
+  uint64_t* other = sorted_ptr == d_tmp ? b->cells : d_tmp;
+  owner_bounds_kernel<<<(world + 1 + 63) / 64, 64, 0, ctx->stream>>>(sorted_ptr, n, world, d_first);
+  CUX(cudaGetLastError());
+  CUX(cudaMemcpyAsync(b->seg_first.data(), d_first, ((size_t)world + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUX(cudaStreamSynchronize(ctx->stream));
+  // one reduce per owner's range: its unique cells land at the start of the range (a range never splits a key)
+  for (uint32_t r = 0; r < world; r++) {
+    const uint64_t s0 = b->seg_first[r], sn = b->seg_first[r + 1] - s0;
+    if (sn == 0) continue;
+    reduce_cells_kernel<<<(unsigned)((sn + 255) / 256), 256, 0, ctx->stream>>>(sorted_ptr + s0, sn, dt.view(), other + s0, d_cur + r);
+    CUX(cudaGetLastError());
+  }
+  CUX(cudaMemcpyAsync(b->seg_count.data(), d_cur, (size_t)world * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUX(cudaStreamSynchronize(ctx->stream));
+#undef CUX
+  b->launches += 3 * 4 + 1 + world;
+  b->red = other; b->red_aux = sorted_ptr;
+  d_tmp = nullptr;                                // owned by red / red_aux now (the other of the two is b->cells)
+  cleanup();
+  for (uint32_t r = 0; r < world; r++) counts_out[r] = b->seg_count[r];
+  return SLK_OK;
+}
+
+// Copies the reduced cells, owner after owner without gaps, to cells_out_dev (sum of slk_build_reduce's counts) and
+// releases the builder's cell buffers.
+extern "C" int slk_build_take_cells(slk_builder* b, uint64_t* cells_out_dev, uint64_t cap) {
+  if (!b || b->seg_count.empty()) return fail(SLK_E_INVALID, "slk_build_reduce has not been called");
+  slk_ctx* ctx = b->ctx;
+  CU(cudaSetDevice(ctx->device));
+  uint64_t total = 0;
+  for (uint64_t c : b->seg_count) total += c;
+  if (total > cap || (total && !cells_out_dev)) return fail(SLK_E_NOSPACE, "%llu cells, room for %llu", (unsigned long long)total, (unsigned long long)cap);
+  uint64_t o = 0;
+  for (size_t r = 0; r < b->seg_count.size(); r++) {
+    if (b->seg_count[r])
+      CU(cudaMemcpyAsync(cells_out_dev + o, b->red + b->seg_first[r], b->seg_count[r] * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    o += b->seg_count[r];
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (b->red != b->cells) cudaFree(b->red);
+  if (b->red_aux != b->cells) cudaFree(b->red_aux);
+  cudaFree(b->cells);
+  b->red = nullptr; b->red_aux = nullptr; b->cells = nullptr; b->cap = 0; b->count = 0;
+  return SLK_OK;
+}
+
+// dense -> raw taxon ids of the cells this builder emits (entry 0 = NONE); *n_out = their number, also when cap is too small
+extern "C" int slk_build_dense_taxa(slk_builder* b, int32_t* raw_out, uint32_t cap, uint32_t* n_out) {
+  if (!b || !n_out) return fail(SLK_E_INVALID, "bad arguments");
+  *n_out = (uint32_t)b->dt.raw.size();
+  if (*n_out > cap) return raw_out ? fail(SLK_E_NOSPACE, "%u dense taxa, room for %u", *n_out, cap) : SLK_OK;
+  memcpy(raw_out, b->dt.raw.data(), (size_t)*n_out * 4);
+  return SLK_OK;
+}
+
+extern "C" int slk_index_from_cell_runs(slk_ctx* ctx, slk_tax* tax, const slk_params* params, uint32_t world, uint32_t n_runs,
+                                        uint64_t* cells_dev, const uint64_t* run_cells, const int32_t* dense_raw,
+                                        const uint32_t* run_dense, slk_index** out) {
+  if (!ctx || !tax || !params || !out || world < 1 || !run_cells || !run_dense || (n_runs && !dense_raw))
+    return fail(SLK_E_INVALID, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  slk_index* idx = new (std::nothrow) slk_index;
+  if (!idx) return fail(SLK_E_NOMEM, "host allocation failed");
+  idx->ctx = ctx; idx->tax = tax; idx->params = *params;
+  int rc = make_scan_params(params, &idx->sp);
+  if (rc != SLK_OK) { delete idx; return rc; }
+  dense_init(idx->dt);
+  const int32_t n_tax = (int32_t)tax->parents.size();
+  // this owner's dense taxonomy = the union of the senders' (each is ancestor-closed); one 16-bit map per run
+  uint64_t total = 0, n_dense = 0;
+  for (uint32_t r = 0; r < n_runs; r++) { total += run_cells[r]; n_dense += run_dense[r]; }
+  if (total && !cells_dev) { delete idx; return fail(SLK_E_INVALID, "bad arguments"); }
+  std::vector<uint16_t> maps(n_dense ? n_dense : 1, 0);
+  rc = dense_add(idx->dt, tax, 1, &idx->dt.root);
+  for (uint64_t i = 0, r = 0, left = n_runs ? run_dense[0] : 0; i < n_dense && rc == SLK_OK; i++, left--) {
+    while (left == 0) left = run_dense[++r];
+    const int32_t t = dense_raw[i];
+    if (t < 0 || t >= n_tax) rc = fail(SLK_E_INVALID, "a sender's taxon is outside the taxonomy (0..%d)", n_tax - 1);
+    else if (t != 0) { uint32_t d = 0; rc = dense_add(idx->dt, tax, t, &d); maps[i] = (uint16_t)d; }
+  }
+  if (rc == SLK_OK) rc = dense_upload(idx->dt);
+  if (rc != SLK_OK) { slk_index_destroy(idx); return rc; }
+  uint16_t* d_maps = nullptr; unsigned long long* d_new = nullptr;
+  auto cleanup = [&]() { cudaFree(d_maps); cudaFree(d_new); };
+#define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); slk_index_destroy(idx); \
+    return fail(e_ == cudaErrorMemoryAllocation ? SLK_E_NOMEM : SLK_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+  CUX(cudaMalloc(&d_maps, maps.size() * 2)); CUX(cudaMalloc(&d_new, 8));
+  CUX(cudaMemcpyAsync(d_maps, maps.data(), maps.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+  CUX(cudaMemsetAsync(d_new, 0, 8, ctx->stream));
+  rc = table_alloc(&idx->table, total, world);
+  if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
+  uint64_t co = 0, mo = 0;
+  for (uint32_t r = 0; r < n_runs; r++) {
+    const uint64_t c = run_cells[r];
+    if (c) {
+      remap_cells_kernel<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(cells_dev + co, c, d_maps + mo);
+      CUX(cudaGetLastError());
+      rc = insert_cells(ctx, idx, cells_dev + co, c, d_new);
+      if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
+    }
+    co += c; mo += run_dense[r];
+  }
+  unsigned long long nn = 0;
+  CUX(cudaMemcpyAsync(&nn, d_new, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUX(cudaStreamSynchronize(ctx->stream));
+#undef CUX
+  cleanup();
+  if (nn & SLK_TABLE_FULL_BIT) { slk_index_destroy(idx); return fail(SLK_E_NOSPACE, "the minimizer table is full: records were not stored"); }
+  idx->n_records = nn;
   *out = idx;
   return SLK_OK;
 }

@@ -98,7 +98,7 @@ SLK_HD int slk_make_scan_params(int k, int m, int spaces, uint64_t toggle_mask, 
 struct slk_table_view {
   uint64_t* cells;     // n_buckets * 4 cells of (compressed key << 16 | dense taxon); 0 = empty; 128-byte aligned
   uint64_t n_buckets;  // one bucket = one 32-byte sector; always a multiple of 4 (four buckets = one 128-byte line)
-  uint32_t prefetch;   // unused (kept for layout): the L2 prefetch pass cost more than it hid on B200
+  uint32_t mix_mul;    // 1; `world` for one shard of a table that is range-partitioned over `world` GPUs (slk_shard_of)
   uint32_t pad_;
 };
 
@@ -214,10 +214,13 @@ SLK_HD uint32_t slk_key_mix(uint64_t ckey) {
   x *= 0xC2B2AE35u; x ^= x >> 13;
   return x;
 }
-SLK_HD uint64_t slk_bucket_of(uint64_t ckey, uint64_t n_buckets) {
+// A table range-partitioned over `world` GPUs is one virtual table cut into `world` equal ranges of x: the 64-bit
+// product x * world has the owner in its high word (slk_shard_of) and the position inside the owner's range in its low
+// word, which takes the place of x when the owner picks the line (mix_mul = world; 1 for a whole table).
+SLK_HD uint64_t slk_bucket_of(uint64_t ckey, const slk_table_view& tb) {
   const uint32_t x = slk_key_mix(ckey);
   const uint32_t y = (x ^ (uint32_t)(ckey >> 32)) * 0x27D4EB2Fu;
-  return (uint64_t)slk_mulhi32(x, (uint32_t)(n_buckets >> 2)) * 4u + (y >> 30);
+  return (uint64_t)slk_mulhi32(x * tb.mix_mul, (uint32_t)(tb.n_buckets >> 2)) * 4u + (y >> 30);
 }
 // Probe sequence. B200 answers a random 32-byte sector miss with the whole 128-byte line (measured: 127 B of DRAM
 // traffic per random 32-byte gather, profiles/r01_probe_microbench.md) and is limited by the NUMBER of random
@@ -271,7 +274,7 @@ static SLK_HD_NOINLINE uint32_t slk_probe_rest(const slk_table_view& tb, uint64_
 }
 // Probe: returns the dense taxon of the key, 0 when absent (a left join miss -> Taxonomy.NONE).
 SLK_HD uint32_t slk_probe(const slk_table_view& tb, uint64_t ckey) {
-  const uint64_t b = slk_bucket_of(ckey, tb.n_buckets);
+  const uint64_t b = slk_bucket_of(ckey, tb);
   uint32_t dense;
   if (slk_probe_bucket(tb, b, ckey, &dense)) return dense;
   return slk_probe_rest(tb, b, 1, ckey);
@@ -677,7 +680,7 @@ struct slk_frag_classifier {
           const uint64_t key = ent.key(cur, s) << fshift;
           const uint64_t ck = fast ? slk_compress_fast(key) : slk_compress_generic(sp, key);
           ent.set_key(cur, s, ck);
-          ent.fetch(s, tb.cells + slk_bucket_of(ck, tb.n_buckets) * 4);
+          ent.fetch(s, tb.cells + slk_bucket_of(ck, tb) * 4);
           n_fetched++;
         }
       }
@@ -686,7 +689,7 @@ struct slk_frag_classifier {
       for (uint32_t q = lane; q < n_pend; q += SLK_LANES) {
         const uint32_t s = ent.pending(prev, q);
         const uint64_t ck = ent.key(prev, s);
-        const uint32_t dense = slk_probe_rest(tb, slk_bucket_of(ck, tb.n_buckets), 1, ck);
+        const uint32_t dense = slk_probe_rest(tb, slk_bucket_of(ck, tb), 1, ck);
         ent.set_key(prev, s, ck | ((uint64_t)dense << 48));
       }
       SLK_SYNCWARP();   // all labels of the previous tile are visible to the lanes that own the entries
@@ -1040,14 +1043,11 @@ SLK_HD void slk_resolve_spans(const slk_tax_view& tx, int32_t k, const uint64_t*
   r.kmers1 = k0; r.kmers2 = k1; r.num_distinct = nd; r.n_hits = nh; r.n_probes = np;
 }
 
-// Owner of a compressed key among `world` hash-range shards: a mix independent of the bucket hash, so that every
-// shard's table stays uniformly loaded.
+// Owner of a compressed key among `world` hash-range shards: the range of the table-line mix x the key falls into.
+// The build's cells, ordered by x, are thereby already grouped by owner, and the owner inserts what it receives front
+// to back (slk_bucket_of with mix_mul = world keeps every shard's table uniformly loaded).
 SLK_HD uint32_t slk_shard_of(uint64_t ckey, uint32_t world) {
-  const uint32_t lo = (uint32_t)ckey, hi = (uint32_t)(ckey >> 32);
-  uint32_t x = (lo ^ 0x7F4A7C15u) * 0x2C1B3C6Du;
-  x ^= x >> 16; x += hi * 0x85EBCA77u;
-  x *= 0x297A2D39u; x ^= x >> 15;
-  return slk_mulhi32(x, world);
+  return slk_mulhi32(slk_key_mix(ckey), world);
 }
 
 // ------------------------------------------------------------------------------------------------ Bracken weights

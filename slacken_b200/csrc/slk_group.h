@@ -368,7 +368,7 @@ __device__ __forceinline__ void slk_group_classify(uint8_t* sm_warp, const slk_s
           for (uint32_t q = lane; q < n_pend; q += 32u) {
             const uint32_t s = S.pend(q);
             const uint64_t kq = S.key(s) & 0xffffffffffffull;
-            const uint32_t dense = slk_probe_rest(tb, slk_bucket_of(kq, tb.n_buckets), 1, kq);
+            const uint32_t dense = slk_probe_rest(tb, slk_bucket_of(kq, tb), 1, kq);
             S.key(s) = kq | ((uint64_t)dense << 48);
           }
           __syncwarp();
@@ -398,7 +398,7 @@ __device__ __forceinline__ void slk_group_classify(uint8_t* sm_warp, const slk_s
             if (s < n_buf && (S.meta(s) >> 6) == SLK_G_T_SEQ) {
               const uint64_t kr = S.key(s);   // right-aligned; the left-aligned priority is kr << fshift
               ck[d] = fast ? slk_compress_fast_r2(kr) : slk_compress_generic(sp, kr << fshift);
-              slk_g_load_bucket(tb.cells + slk_bucket_of(ck[d], tb.n_buckets) * 4, &bk[d]);
+              slk_g_load_bucket(tb.cells + slk_bucket_of(ck[d], tb) * 4, &bk[d]);
             }
           }
         }

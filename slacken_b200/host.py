@@ -171,13 +171,17 @@ class KeyValueIndex:
 
     # KeyValueIndex.loadRecords (slacken/KeyValueIndex.scala:150-159)
     @classmethod
-    def from_records(cls, ctx: GpuContext, taxonomy: Taxonomy, params: IndexParams, id1: np.ndarray, taxon: np.ndarray):
+    def from_records(cls, ctx: GpuContext, taxonomy: Taxonomy, params: IndexParams, id1: np.ndarray, taxon: np.ndarray,
+                     world: int = 1):
+        """world > 1: the records are one shard of a library cut for `world` GPUs (sharded.shard_of_records); the table then
+        spreads the shard's range of the line hash over all of its lines."""
         id1 = np.ascontiguousarray(id1).view(np.int64)
         taxon = np.ascontiguousarray(taxon, dtype=np.int32)
         assert len(id1) == len(taxon)
         p = params.c_params()
         h = C.c_void_p()
-        check(ctx._L.slk_index_from_records(ctx.h, taxonomy.h, C.byref(p), _ptr(id1), _ptr(taxon), len(id1), C.byref(h)))
+        check(ctx._L.slk_index_from_records_shard(ctx.h, taxonomy.h, C.byref(p), _ptr(id1), _ptr(taxon), len(id1), int(world),
+                                                  C.byref(h)))
         return cls(ctx, taxonomy, params, h)
 
     # KeyValueIndex.makeRecords (slacken/KeyValueIndex.scala:85-122): genomes -> records, on the GPU
@@ -220,7 +224,7 @@ class KeyValueIndex:
         return id1[:n], taxon[:n]
 
     @classmethod
-    def from_records_dev(cls, ctx: GpuContext, taxonomy: Taxonomy, params: IndexParams, id1, taxon):
+    def from_records_dev(cls, ctx: GpuContext, taxonomy: Taxonomy, params: IndexParams, id1, taxon, world: int = 1):
         """from_records for torch tensors that already live on the context's device."""
         import torch
         id1, taxon = id1.contiguous(), taxon.contiguous()
@@ -228,8 +232,25 @@ class KeyValueIndex:
         torch.cuda.current_stream(id1.device).synchronize()   # torch's stream is not the library's
         p = params.c_params()
         h = C.c_void_p()
-        check(ctx._L.slk_index_from_records(ctx.h, taxonomy.h, C.byref(p), C.c_void_p(id1.data_ptr()),
-                                            C.c_void_p(taxon.data_ptr()), id1.numel(), C.byref(h)))
+        check(ctx._L.slk_index_from_records_shard(ctx.h, taxonomy.h, C.byref(p), C.c_void_p(id1.data_ptr()),
+                                                  C.c_void_p(taxon.data_ptr()), id1.numel(), int(world), C.byref(h)))
+        return cls(ctx, taxonomy, params, h)
+
+    @classmethod
+    def from_cell_runs(cls, ctx: GpuContext, taxonomy: Taxonomy, params: IndexParams, world: int, cells_dev: int,
+                       run_cells: Sequence[int], dense_raw: np.ndarray, run_dense: Sequence[int]):
+        """The owner's half of the distributed build: `cells_dev` holds len(run_cells) runs of reduced cells back to back,
+        run r written with the dense taxa dense_raw[sum(run_dense[:r]) : +run_dense[r]] (LibraryBuilder.dense_taxa of
+        its sender). The cells are overwritten."""
+        n = len(run_cells)
+        rc = (C.c_uint64 * max(n, 1))(*[int(c) for c in run_cells])
+        rd = (C.c_uint32 * max(n, 1))(*[int(c) for c in run_dense])
+        raw = np.ascontiguousarray(dense_raw, dtype=np.int32)
+        assert len(raw) == sum(int(c) for c in run_dense)
+        p = params.c_params()
+        h = C.c_void_p()
+        check(ctx._L.slk_index_from_cell_runs(ctx.h, taxonomy.h, C.byref(p), int(world), n, C.c_void_p(cells_dev), rc,
+                                              _ptr(raw), rd, C.byref(h)))
         return cls(ctx, taxonomy, params, h)
 
     def close(self):
@@ -263,6 +284,23 @@ class LibraryBuilder:
         h = C.c_void_p()
         check(self.ctx._L.slk_build_finish(self.h, C.byref(h)))
         return KeyValueIndex(self.ctx, self.taxonomy, self.params, h)
+
+    # the sending half of the distributed build (include/slacken_gpu.h, "Distributed build")
+    def reduce(self, world: int) -> List[int]:
+        """Sort + LCA reduce; returns the number of reduced cells bound for every owner."""
+        cnt = (C.c_uint64 * world)()
+        check(self.ctx._L.slk_build_reduce(self.h, int(world), cnt))
+        return [int(c) for c in cnt]
+
+    def take_cells(self, cells_out_dev: int, cap: int):
+        check(self.ctx._L.slk_build_take_cells(self.h, C.c_void_p(cells_out_dev), int(cap)))
+
+    def dense_taxa(self) -> np.ndarray:
+        n = C.c_uint32()
+        check(self.ctx._L.slk_build_dense_taxa(self.h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.int32)
+        check(self.ctx._L.slk_build_dense_taxa(self.h, _ptr(out), n.value, C.byref(n)))
+        return out
 
     def close(self):
         if getattr(self, "h", None):

@@ -279,7 +279,7 @@ class ShardedKeyValueIndex:
         world = w if world is None else world
         mine = shard_of_records(params, id1, world) == rank
         return cls(KeyValueIndex.from_records(ctx, taxonomy, params, np.ascontiguousarray(id1)[mine],
-                                              np.ascontiguousarray(taxon)[mine]), rank, world)
+                                              np.ascontiguousarray(taxon)[mine], world=world), rank, world)
 
     @classmethod
     def build(cls, ctx: GpuContext, taxonomy: Taxonomy, params: IndexParams, local_batches, expected_bases: int = 0,
@@ -288,8 +288,69 @@ class ShardedKeyValueIndex:
         LCA-reduces ITS genomes on its GPU, the reduced records travel to the owner of their key (one all-to-all;
         LCA is associative and commutative, slacken/LowestCommonAncestor.scala:152-170), and the owner's insert merges
         records of the same minimizer by LCA again."""
-        local = KeyValueIndex.build(ctx, taxonomy, params, local_batches, expected_bases)
-        return cls.from_local(local, group)
+        from .host import LibraryBuilder
+        b = LibraryBuilder(ctx, taxonomy, params, expected_bases)
+        try:
+            for bases, off, taxa in local_batches:
+                b.add(bases, off, taxa)
+            return cls.from_builder(b, group)
+        finally:
+            b.close()
+
+    @classmethod
+    def from_builder(cls, b, group=None):
+        """The exchange half of the distributed build, from a LibraryBuilder that has been fed this rank's genomes (it is
+        consumed). The owner of a minimizer is a RANGE of the hash that orders the table's lines, and the builder's
+        reduced cells are ordered by that hash: they are already grouped by owner, travel as they are (8 bytes each, one
+        all-to-all), and every owner inserts the `world` ordered runs it receives front to back."""
+        import torch
+        ctx, taxonomy, params = b.ctx, b.taxonomy, b.params
+        rank, world = world_of(group)
+        if world == 1:
+            index = b.finish()
+            cls.last_build_counts = [len(index)]
+            return cls(index, 0, 1)
+        if _dist().get_backend(group) != "nccl":   # CPU tests (gloo): through a local table and host memory
+            return cls.from_local(b.finish(), group)
+        import time
+        tm, t0 = {}, time.perf_counter()
+
+        def lap(name):
+            nonlocal t0
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            tm[name] = now - t0
+            t0 = now
+        dev = torch.device("cuda", ctx.device)
+        counts = b.reduce(world)
+        cls.last_build_counts = counts
+        lap("sort_and_lca_reduce")
+        send = torch.empty(max(sum(counts), 1), dtype=torch.int64, device=dev)
+        b.take_cells(send.data_ptr(), send.numel())
+        send = send[:sum(counts)]
+        raw = b.dense_taxa()
+        lap("group_cells_by_owner")
+        # the senders' dense -> raw lists (at most 65 535 ids each): padded all-gather
+        dist = _dist()
+        n_raw = torch.tensor([len(raw)], dtype=torch.int64, device=dev)
+        all_n = [torch.empty_like(n_raw) for _ in range(world)]
+        dist.all_gather(all_n, n_raw, group=group)
+        run_dense = [int(x) for x in torch.cat(all_n).tolist()]
+        pad = torch.zeros(max(run_dense), dtype=torch.int32, device=dev)
+        pad[:len(raw)] = torch.from_numpy(raw).to(dev)
+        all_raw = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(all_raw, pad, group=group)
+        dense_raw = np.concatenate([t[:n].cpu().numpy() for t, n in zip(all_raw, run_dense)])
+        recv, run_cells = exchange(send, counts, group)
+        del send
+        lap("all_to_all")
+        out = cls(KeyValueIndex.from_cell_runs(ctx, taxonomy, params, world, recv.data_ptr(), run_cells, dense_raw, run_dense),
+                  rank, world)
+        del recv
+        torch.cuda.empty_cache()   # the staging tensors must not keep HBM that the classifier's buffers will want
+        lap("insert_on_owner")
+        cls.last_build_times = tm
+        return out
 
     @classmethod
     def from_local(cls, local: KeyValueIndex, group=None):
@@ -308,7 +369,7 @@ class ShardedKeyValueIndex:
             counts = np.bincount(owner, minlength=world).tolist()
             rid, _ = exchange(torch.from_numpy(id1.view(np.int64)[order]), counts, group)
             rtx, _ = exchange(torch.from_numpy(taxon[order]), counts, group)
-            return cls(KeyValueIndex.from_records(ctx, taxonomy, params, rid.numpy(), rtx.numpy()), rank, world)
+            return cls(KeyValueIndex.from_records(ctx, taxonomy, params, rid.numpy(), rtx.numpy(), world=world), rank, world)
         # the records never leave HBM: dump the local table, group the rows by owner, all-to-all, insert on the owner
         import time
         tm, t0 = {}, time.perf_counter()
@@ -333,7 +394,7 @@ class ShardedKeyValueIndex:
         rtx, _ = exchange(stx, counts, group)
         del sid, stx
         lap("all_to_all")
-        out = cls(KeyValueIndex.from_records_dev(ctx, taxonomy, params, rid, rtx), rank, world)
+        out = cls(KeyValueIndex.from_records_dev(ctx, taxonomy, params, rid, rtx, world=world), rank, world)
         del rid, rtx
         torch.cuda.empty_cache()   # the staging tensors must not keep HBM that the classifier's buffers will want
         lap("insert_on_owner")
@@ -341,6 +402,7 @@ class ShardedKeyValueIndex:
         return out
 
     last_build_times: dict = {}
+    last_build_counts: list = []
 
     def taxa(self) -> np.ndarray:
         n = C.c_uint32(0)

@@ -32,7 +32,8 @@ EMU_API void emu_insert_cells(uint64_t* cells, uint64_t n_buckets, const uint16_
     uint64_t cell = in[i], ckey = cell >> 16;
     uint32_t taxon = (uint32_t)(cell & 0xffff);
     if (!taxon) continue;
-    uint64_t b = slk_bucket_of(ckey, n_buckets);
+    const slk_table_view tbv{cells, n_buckets, 1, 0};
+    uint64_t b = slk_bucket_of(ckey, tbv);
     bool done = false;
     for (uint64_t tries = 1; !done; tries++) {
       for (int j = 0; j < 4 && !done; j++) {
@@ -59,7 +60,7 @@ static int64_t classify_w(const slk_scan_params* sp, uint64_t* cells, uint64_t n
                           const uint8_t* depth, const int32_t* raw, uint32_t n_dense, uint32_t root, const uint8_t* b1,
                           const uint64_t* o1, const uint8_t* b2, const uint64_t* o2, uint32_t n, double confidence,
                           int min_hit_groups, emu_result* res, uint64_t* hit_off, slk_hit* hits_out, uint64_t cap, bool packed) {
-  slk_table_view tb{cells, n_buckets, 0, 0};
+  slk_table_view tb{cells, n_buckets, 1, 0};
   slk_tax_view tx{parent, depth, raw, n_dense, root};
   std::vector<slk_hit> hv;
   uint64_t used = 0;
@@ -127,7 +128,7 @@ static int64_t classify_split_w(const slk_scan_params* sp, uint64_t* cells, uint
                                 const uint8_t* depth, const int32_t* raw, uint32_t n_dense, uint32_t root, const uint8_t* b1,
                                 const uint64_t* o1, const uint8_t* b2, const uint64_t* o2, uint32_t n, double confidence,
                                 int min_hit_groups, emu_result* res, uint64_t* hit_off, slk_hit* hits_out, uint64_t cap) {
-  slk_table_view tb{cells, n_buckets, 0, 0};
+  slk_table_view tb{cells, n_buckets, 1, 0};
   slk_tax_view tx{parent, depth, raw, n_dense, root};
   uint64_t used = 0;
   std::vector<uint64_t> spans;
@@ -182,7 +183,7 @@ EMU_API int64_t emu_scan_spans(const slk_scan_params* sp, const uint8_t* b1, con
   return r;
 }
 EMU_API void emu_probe_keys(uint64_t* cells, uint64_t n_buckets, const int32_t* raw, const uint64_t* keys, uint64_t n, int32_t* taxa) {
-  slk_table_view tb{cells, n_buckets, 0, 0};
+  slk_table_view tb{cells, n_buckets, 1, 0};
   for (uint64_t i = 0; i < n; i++) { uint32_t d = slk_probe(tb, keys[i]); taxa[i] = d ? raw[d] : 0; }
 }
 EMU_API void emu_resolve_spans(const uint16_t* parent, const uint8_t* depth, const int32_t* raw, uint32_t n_dense, uint32_t root,
@@ -204,7 +205,7 @@ template <int W>
 static int64_t bracken_w(const slk_scan_params* sp, uint64_t* cells, uint64_t n_buckets, const uint16_t* parent, const uint8_t* depth,
                          const int32_t* raw, uint32_t n_dense, uint32_t root, const uint8_t* bases, uint32_t len, uint32_t read_len,
                          int32_t* dest_out) {
-  slk_table_view tb{cells, n_buckets, 0, 0};
+  slk_table_view tb{cells, n_buckets, 1, 0};
   slk_tax_view tx{parent, depth, raw, n_dense, root};
   std::vector<slk_bhit> hits;
   slk_bracken_scan<W>(*sp, bases, len, [&](const slk_bhit& h) { hits.push_back(h); });

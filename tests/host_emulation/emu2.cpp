@@ -40,7 +40,7 @@ EMU_API int emu2_classify(const slk_scan_params* sp, uint64_t* cells, uint64_t n
                           uint64_t hits_cap, uint64_t* hits_used, uint64_t* stats, uint64_t* counts) {
   slk_classify2_args a;
   a.sp = *sp;
-  a.tb = slk_table_view{cells, n_buckets, 0, 0};
+  a.tb = slk_table_view{cells, n_buckets, 1, 0};
   a.tx = slk_tax_view{parent, depth, raw, n_dense, root};
   a.in1 = slk_group_in{codes1, mask1, boff1, len1, 0};
   a.in2 = slk_group_in{codes2, mask2, boff2, len2, 0};

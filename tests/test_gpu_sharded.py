@@ -46,7 +46,7 @@ def test_split_path_many_shards_on_one_gpu(gpu, world):
     rng, genomes, olib, id1, tx, tax = _world(gpu, 37)
     params = IndexParams()
     owner = shard_of_records(params, id1, world)
-    shards = [KeyValueIndex.from_records(gpu, tax, params, id1[owner == r], tx[owner == r]) for r in range(world)]
+    shards = [KeyValueIndex.from_records(gpu, tax, params, id1[owner == r], tx[owner == r], world=world) for r in range(world)]
     assert sum(len(s) for s in shards) == len(id1) and all(len(s) > 0 for s in shards)
     union = np.unique(tx)
     ops = [GpuSplitOps(s, union) for s in shards]
@@ -90,7 +90,7 @@ def _mailbox_world(devices, seed=41, n_reads=1800, cap=120000):
     union = np.unique(tx)
     cls = []
     for r, d in enumerate(devices):
-        shard = ShardedKeyValueIndex(KeyValueIndex.from_records(ctxs[d], taxs[d], params, id1[owner == r], tx[owner == r]), r, world)
+        shard = ShardedKeyValueIndex(KeyValueIndex.from_records(ctxs[d], taxs[d], params, id1[owner == r], tx[owner == r], world=world), r, world)
         cls.append(ShardedClassifier(shard, mailbox=Mailbox(ctxs[d], r, world, cap, connect=False), taxa_union=union))
     Mailbox.connect_local([c.mailbox for c in cls])
     return rng, genomes, olib, cls, (ctxs, taxs)
@@ -200,7 +200,7 @@ def test_records_stay_on_the_device(gpu):
     check(gpu._L.slk_shard_of_records_dev(gpu.h, C.byref(p), C.c_void_p(d_id.data_ptr()), d_id.numel(), 3, C.c_void_p(owner.data_ptr())))
     assert np.array_equal(owner.cpu().numpy(), shard_of_records(params, d_id.cpu().numpy(), 3))
     mine = owner == 1
-    part = KeyValueIndex.from_records_dev(gpu, tax, params, d_id[mine], d_tx[mine])
+    part = KeyValueIndex.from_records_dev(gpu, tax, params, d_id[mine], d_tx[mine], world=3)
     pid, ptx = part.records()
     sel = shard_of_records(params, id1, 3) == 1
     assert np.array_equal(pid, id1[sel]) and np.array_equal(ptx, tx[sel])
@@ -280,3 +280,61 @@ def test_span_scan_one_pass_and_two_pass_agree(gpu, monkeypatch):
     res, _, _, per = olib.classify(lb, lo.astype(np.int64), confidence=0.05)
     assert_batch_equal(res, per, got, 35)
     ops.close(); cls.close(); shard.close(); tax.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_build_on_one_gpu(gpu, world):
+    """The distributed build (include/slacken_gpu.h, "Distributed build"; the shuffle of groupBy(idColumns).agg(udafLca),
+    slacken/KeyValueIndex.scala:85-93) with one GPU playing every rank: rank r builds from every world-th genome, reduces,
+    hands over its cells grouped by owner; owner d receives the d-th group of every rank and inserts the runs. The shards'
+    records must be exactly the oracle library's records, each on the rank slk_shard_of_records names, and a sharded
+    classify over them must equal the oracle."""
+    import torch
+    from slacken_b200 import LibraryBuilder
+    rng, parents, ranks, names, genomes, taxa = make_world(53)
+    olib = oracle_lib(oracle.params(), parents, genomes, taxa)
+    id1, tx = olib.records()
+    tax = Taxonomy(gpu, parents, ranks, names)
+    params = IndexParams()
+    dev = torch.device("cuda", gpu.device)
+    sent, counts, dense = [], [], []
+    for r in range(world):
+        b = LibraryBuilder(gpu, tax, params)
+        gb, go = pack_sequences(genomes[r::world])
+        b.add(gb, go, taxa[r::world])
+        cnt = b.reduce(world)
+        buf = torch.empty(max(sum(cnt), 1), dtype=torch.int64, device=dev)
+        b.take_cells(buf.data_ptr(), buf.numel())
+        dense.append(b.dense_taxa())
+        b.close()
+        sent.append(buf[:sum(cnt)]); counts.append(cnt)
+    assert all(d[0] == 0 for d in dense)
+    owner = shard_of_records(params, id1, world)
+    shards = []
+    for d in range(world):
+        runs = [sent[r][sum(counts[r][:d]):sum(counts[r][:d + 1])] for r in range(world)]
+        recv = torch.cat(runs).contiguous()
+        torch.cuda.synchronize()
+        index = KeyValueIndex.from_cell_runs(gpu, tax, params, world, recv.data_ptr(), [c[d] for c in counts],
+                                             np.concatenate(dense), [len(x) for x in dense])
+        sid, stx = index.records()
+        assert np.array_equal(sid, id1[owner == d]) and np.array_equal(stx, tx[owner == d])
+        shards.append(index)
+    union = np.unique(tx)
+    ops = [GpuSplitOps(s, union) for s in shards]
+    reads = simulate_reads(rng, genomes, 800, (30, 260), n_rate=0.1)
+    rb, ro = pack_sequences(reads)
+    q = ops[0]   # rank 0 asks, every shard answers
+    d_b, d_o = q.upload(rb), q.upload(ro.view(np.int64))
+    span_off, spans, n_spans = q.scan_spans(d_b, d_o, None, None, len(reads))
+    keys, idx, kc = q.route(spans, n_spans, world)
+    starts = np.concatenate([[0], np.cumsum(kc)])
+    answers = torch.cat([ops[r].probe(keys[starts[r]:starts[r + 1]].contiguous()) for r in range(world)])
+    got = q.resolve(spans, span_off, n_spans, len(reads), False, idx, answers, 0.1, 2, True)
+    res, _, _, per = olib.classify(rb, ro.astype(np.int64), confidence=0.1)
+    assert_batch_equal(res, per, got, 35)
+    for o in ops:
+        o.close()
+    for s in shards:
+        s.close()
+    tax.close()
