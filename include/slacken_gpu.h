@@ -286,18 +286,18 @@ SLK_API int slk_index_from_records_shard(slk_ctx* ctx, slk_tax* tax, const slk_p
                                          const int32_t* taxon, uint64_t n, uint32_t world, slk_index** out);
 /* Distributed build (BASELINE configs[2]; the shuffle of groupBy(idColumns).agg(udafLca), slacken/KeyValueIndex.scala:85-93):
  *   every rank: slk_build_begin, slk_build_add* (its own genomes), slk_build_reduce (sort + LCA reduce; counts_out[d] =
- *   cells bound for owner d), slk_build_take_cells (the cells, grouped by owner, into the caller's send buffer) and
+ *   cells bound for owner d), slk_build_cells_dev (the cells, grouped by owner: the send buffer, owned by the builder) and
  *   slk_build_dense_taxa (the raw ids behind the 16-bit taxa inside the cells);
  *   [all-to-all of the cells, all-gather of the taxa lists: the caller's];
  *   every owner: slk_index_from_cell_runs on what it received: n_runs runs back to back in cells_dev (run r holds
  *   run_cells[r] cells and uses the run_dense[r] raw ids that follow those of run r-1 in dense_raw_host). The runs are
  *   ordered by table line, so the insert walks the table front to back; equal minimizers merge by LCA
- *   (slacken/LowestCommonAncestor.scala:152-170). cells_dev is overwritten. */
+ *   (slacken/LowestCommonAncestor.scala:152-170). */
 SLK_API int slk_build_reduce(slk_builder* b, uint32_t world, uint64_t* counts_out);
-SLK_API int slk_build_take_cells(slk_builder* b, uint64_t* cells_out_dev, uint64_t cap);
+SLK_API int slk_build_cells_dev(slk_builder* b, const uint64_t** cells_dev, uint64_t* n_out);
 SLK_API int slk_build_dense_taxa(slk_builder* b, int32_t* raw_out, uint32_t cap, uint32_t* n_out);
 SLK_API int slk_index_from_cell_runs(slk_ctx* ctx, slk_tax* tax, const slk_params* params, uint32_t world, uint32_t n_runs,
-                                     uint64_t* cells_dev, const uint64_t* run_cells, const int32_t* dense_raw_host,
+                                     const uint64_t* cells_dev, const uint64_t* run_cells, const int32_t* dense_raw_host,
                                      const uint32_t* run_dense, slk_index** out);
 /* the taxa (raw ids, ancestors included) an index can answer with; out == NULL queries the count */
 SLK_API int slk_index_taxa(slk_index* idx, int32_t* out, uint32_t cap, uint32_t* n_out);

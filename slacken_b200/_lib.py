@@ -102,7 +102,7 @@ SIGNATURES = {
     "slk_debug_min62": (_INT, [_VP, _VP, _VP, _U64, _VP]),
     "slk_index_from_records_shard": (_INT, [_VP, _VP, _VP, _VP, _VP, _U64, _U32, _VP]),
     "slk_build_reduce": (_INT, [_VP, _U32, _VP]),
-    "slk_build_take_cells": (_INT, [_VP, _VP, _U64]),
+    "slk_build_cells_dev": (_INT, [_VP, _VP, _VP]),
     "slk_build_dense_taxa": (_INT, [_VP, _VP, _U32, _VP]),
     "slk_index_from_cell_runs": (_INT, [_VP, _VP, _VP, _U32, _U32, _VP, _VP, _VP, _VP, _VP]),
     "slk_shard_of_records": (_INT, [_VP, _VP, _U64, _U32, _VP]),

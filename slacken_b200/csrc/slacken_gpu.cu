@@ -71,10 +71,10 @@ struct slk_builder {
   unsigned long long* d_count = nullptr;
   uint64_t count = 0;
   uint64_t launches = 0;
-  // slk_build_reduce: the reduced cells of owner r start at red[seg_first[r]] and there are seg_count[r] of them
+  // slk_build_reduce: the reduced cells, owner after owner, seg_count[r] of them for owner r
   uint64_t* red = nullptr;
   uint64_t* red_aux = nullptr;
-  std::vector<uint64_t> seg_first, seg_count;
+  std::vector<uint64_t> seg_count;
 };
 struct slk_counts {
   slk_ctx* ctx;
@@ -283,11 +283,14 @@ __device__ __forceinline__ bool insert_cell(uint64_t cell, const slk_table_view&
   atomicOr(full, SLK_TABLE_FULL_BIT);
   return false;
 }
+// map != NULL: the cells carry the dense taxa of another rank's builder; map[] translates them to this index's
 __global__ void __launch_bounds__(256) insert_cells_kernel(const uint64_t* __restrict__ in, uint64_t n,
                                                            slk_table_view tb, slk_tax_view tx,
-                                                           unsigned long long* n_new) {
+                                                           unsigned long long* n_new, const uint16_t* __restrict__ map) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool fresh = i < n && insert_cell(in[i], tb, tx, n_new);
+  uint64_t cell = i < n ? in[i] : 0;
+  if (map) cell = (cell & ~0xffffull) | map[cell & 0xffffu];
+  const bool fresh = i < n && insert_cell(cell, tb, tx, n_new);
   const uint32_t cnt = (uint32_t)__syncthreads_count(fresh);   // one atomic per block on the record counter
   if (threadIdx.x == 0 && cnt) atomicAdd(n_new, (unsigned long long)cnt);
 }
@@ -505,9 +508,10 @@ static int table_alloc(slk_table_view* tb, uint64_t n_keys, uint32_t world = 1) 
   CU(cudaMemset(tb->cells, 0, tb->n_buckets * 32));
   return SLK_OK;
 }
-static int insert_cells(slk_ctx* ctx, slk_index* idx, const uint64_t* d_cells, uint64_t n, unsigned long long* d_new) {
+static int insert_cells(slk_ctx* ctx, slk_index* idx, const uint64_t* d_cells, uint64_t n, unsigned long long* d_new,
+                        const uint16_t* d_map = nullptr) {
   if (n == 0) return SLK_OK;
-  insert_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_cells, n, idx->table, idx->dt.view(), d_new);
+  insert_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_cells, n, idx->table, idx->dt.view(), d_new, d_map);
   CU(cudaGetLastError());
   return SLK_OK;
 }
@@ -838,78 +842,60 @@ __global__ void owner_bounds_kernel(const uint64_t* __restrict__ sorted, uint64_
   }
   first[r] = r < world ? lo : n;
 }
-__global__ void __launch_bounds__(256) remap_cells_kernel(uint64_t* __restrict__ cells, uint64_t n, const uint16_t* __restrict__ map) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t c = cells[i];
-  cells[i] = (c & ~0xffffull) | map[c & 0xffffu];
-}
-
 extern "C" int slk_build_reduce(slk_builder* b, uint32_t world, uint64_t* counts_out) {
   if (!b || world < 1 || world > 255 || !counts_out) return fail(SLK_E_INVALID, "bad arguments");
   if (b->red || !b->seg_count.empty()) return fail(SLK_E_INVALID, "slk_build_reduce was already called on this builder");
   slk_ctx* ctx = b->ctx;
   CU(cudaSetDevice(ctx->device));
   const uint64_t n = b->count;
-  b->seg_first.assign(world + 1, 0); b->seg_count.assign(world, 0);
+  b->seg_count.assign(world, 0);
   if (n == 0) { for (uint32_t r = 0; r < world; r++) counts_out[r] = 0; return SLK_OK; }
   dense_tax dt = b->dt;                           // device copy of the dense taxonomy for the reduce
   dt.d_parent = nullptr; dt.d_depth = nullptr; dt.d_raw = nullptr;
   int rc = dense_upload(dt);
   if (rc != SLK_OK) return rc;
-  uint64_t* d_tmp = nullptr; uint64_t* d_first = nullptr; unsigned long long* d_cur = nullptr;
-  auto cleanup = [&]() { cudaFree(d_tmp); cudaFree(d_first); cudaFree(d_cur); dense_free(dt); };
+  uint64_t* d_tmp = nullptr; uint64_t* d_first = nullptr;   // d_first: [world + 1] range starts | cursor | [world] cursor snapshots
+  auto cleanup = [&]() { cudaFree(d_tmp); cudaFree(d_first); dense_free(dt); };
 #define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
     return fail(e_ == cudaErrorMemoryAllocation ? SLK_E_NOMEM : SLK_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
   CUX(cudaMalloc(&d_tmp, n * 8));
-  CUX(cudaMalloc(&d_first, ((size_t)world + 1) * 8));
-  CUX(cudaMalloc(&d_cur, (size_t)world * 8));
-  CUX(cudaMemsetAsync(d_cur, 0, (size_t)world * 8, ctx->stream));
+  CUX(cudaMalloc(&d_first, (2 * (size_t)world + 2) * 8));
+  unsigned long long* d_cur = reinterpret_cast<unsigned long long*>(d_first + world + 1);
+  unsigned long long* d_snap = d_cur + 1;
+  CUX(cudaMemsetAsync(d_cur, 0, 8, ctx->stream));
   uint64_t* sorted_ptr = nullptr;
   if (slk_sort_cells_by_line(b->cells, d_tmp, n, ctx->stream, &sorted_ptr) != 0) { cleanup(); return fail(SLK_E_CUDA, "radix sort failed"); }
   uint64_t* other = sorted_ptr == d_tmp ? b->cells : d_tmp;
+  std::vector<uint64_t> first((size_t)world + 1), snap(world);
   owner_bounds_kernel<<<(world + 1 + 63) / 64, 64, 0, ctx->stream>>>(sorted_ptr, n, world, d_first);
   CUX(cudaGetLastError());
-  CUX(cudaMemcpyAsync(b->seg_first.data(), d_first, ((size_t)world + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUX(cudaMemcpyAsync(first.data(), d_first, ((size_t)world + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CUX(cudaStreamSynchronize(ctx->stream));
-  // one reduce per owner's range: its unique cells land at the start of the range (a range never splits a key)
+  // One reduce per owner's range (a range never splits a key), all appending through the same cursor: the launches run
+  // one after the other, so the output is grouped by owner without gaps -- the send buffer of the all-to-all.
   for (uint32_t r = 0; r < world; r++) {
-    const uint64_t s0 = b->seg_first[r], sn = b->seg_first[r + 1] - s0;
-    if (sn == 0) continue;
-    reduce_cells_kernel<<<(unsigned)((sn + 255) / 256), 256, 0, ctx->stream>>>(sorted_ptr + s0, sn, dt.view(), other + s0, d_cur + r);
+    const uint64_t s0 = first[r], sn = first[r + 1] - s0;
+    if (sn) reduce_cells_kernel<<<(unsigned)((sn + 255) / 256), 256, 0, ctx->stream>>>(sorted_ptr + s0, sn, dt.view(), other, d_cur);
+    snapshot_kernel<<<1, 1, 0, ctx->stream>>>(d_cur, d_snap + r);
     CUX(cudaGetLastError());
   }
-  CUX(cudaMemcpyAsync(b->seg_count.data(), d_cur, (size_t)world * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUX(cudaMemcpyAsync(snap.data(), d_snap, (size_t)world * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CUX(cudaStreamSynchronize(ctx->stream));
 #undef CUX
-  b->launches += 3 * 4 + 1 + world;
+  b->launches += 3 * 4 + 1 + 2 * world;
   b->red = other; b->red_aux = sorted_ptr;
   d_tmp = nullptr;                                // owned by red / red_aux now (the other of the two is b->cells)
   cleanup();
-  for (uint32_t r = 0; r < world; r++) counts_out[r] = b->seg_count[r];
+  for (uint32_t r = 0; r < world; r++) counts_out[r] = b->seg_count[r] = snap[r] - (r ? snap[r - 1] : 0);
   return SLK_OK;
 }
 
-// Copies the reduced cells, owner after owner without gaps, to cells_out_dev (sum of slk_build_reduce's counts) and
-// releases the builder's cell buffers.
-extern "C" int slk_build_take_cells(slk_builder* b, uint64_t* cells_out_dev, uint64_t cap) {
-  if (!b || b->seg_count.empty()) return fail(SLK_E_INVALID, "slk_build_reduce has not been called");
-  slk_ctx* ctx = b->ctx;
-  CU(cudaSetDevice(ctx->device));
+// The reduced cells (device memory owned by the builder until slk_build_destroy): owner after owner without gaps.
+extern "C" int slk_build_cells_dev(slk_builder* b, const uint64_t** cells_dev, uint64_t* n_out) {
+  if (!b || !cells_dev || !n_out || b->seg_count.empty()) return fail(SLK_E_INVALID, "slk_build_reduce has not been called");
   uint64_t total = 0;
   for (uint64_t c : b->seg_count) total += c;
-  if (total > cap || (total && !cells_out_dev)) return fail(SLK_E_NOSPACE, "%llu cells, room for %llu", (unsigned long long)total, (unsigned long long)cap);
-  uint64_t o = 0;
-  for (size_t r = 0; r < b->seg_count.size(); r++) {
-    if (b->seg_count[r])
-      CU(cudaMemcpyAsync(cells_out_dev + o, b->red + b->seg_first[r], b->seg_count[r] * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    o += b->seg_count[r];
-  }
-  CU(cudaStreamSynchronize(ctx->stream));
-  if (b->red != b->cells) cudaFree(b->red);
-  if (b->red_aux != b->cells) cudaFree(b->red_aux);
-  cudaFree(b->cells);
-  b->red = nullptr; b->red_aux = nullptr; b->cells = nullptr; b->cap = 0; b->count = 0;
+  *cells_dev = b->red; *n_out = total;
   return SLK_OK;
 }
 
@@ -923,7 +909,7 @@ extern "C" int slk_build_dense_taxa(slk_builder* b, int32_t* raw_out, uint32_t c
 }
 
 extern "C" int slk_index_from_cell_runs(slk_ctx* ctx, slk_tax* tax, const slk_params* params, uint32_t world, uint32_t n_runs,
-                                        uint64_t* cells_dev, const uint64_t* run_cells, const int32_t* dense_raw,
+                                        const uint64_t* cells_dev, const uint64_t* run_cells, const int32_t* dense_raw,
                                         const uint32_t* run_dense, slk_index** out) {
   if (!ctx || !tax || !params || !out || world < 1 || !run_cells || !run_dense || (n_runs && !dense_raw))
     return fail(SLK_E_INVALID, "bad arguments");
@@ -962,9 +948,7 @@ extern "C" int slk_index_from_cell_runs(slk_ctx* ctx, slk_tax* tax, const slk_pa
   for (uint32_t r = 0; r < n_runs; r++) {
     const uint64_t c = run_cells[r];
     if (c) {
-      remap_cells_kernel<<<(unsigned)((c + 255) / 256), 256, 0, ctx->stream>>>(cells_dev + co, c, d_maps + mo);
-      CUX(cudaGetLastError());
-      rc = insert_cells(ctx, idx, cells_dev + co, c, d_new);
+      rc = insert_cells(ctx, idx, cells_dev + co, c, d_new, d_maps + mo);
       if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
     }
     co += c; mo += run_dense[r];

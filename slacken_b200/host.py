@@ -241,7 +241,7 @@ class KeyValueIndex:
                        run_cells: Sequence[int], dense_raw: np.ndarray, run_dense: Sequence[int]):
         """The owner's half of the distributed build: `cells_dev` holds len(run_cells) runs of reduced cells back to back,
         run r written with the dense taxa dense_raw[sum(run_dense[:r]) : +run_dense[r]] (LibraryBuilder.dense_taxa of
-        its sender). The cells are overwritten."""
+        its sender)."""
         n = len(run_cells)
         rc = (C.c_uint64 * max(n, 1))(*[int(c) for c in run_cells])
         rd = (C.c_uint32 * max(n, 1))(*[int(c) for c in run_dense])
@@ -292,8 +292,24 @@ class LibraryBuilder:
         check(self.ctx._L.slk_build_reduce(self.h, int(world), cnt))
         return [int(c) for c in cnt]
 
-    def take_cells(self, cells_out_dev: int, cap: int):
-        check(self.ctx._L.slk_build_take_cells(self.h, C.c_void_p(cells_out_dev), int(cap)))
+    def cells_dev(self):
+        """(device pointer, count) of the reduced cells, grouped by owner; valid until close()."""
+        p, n = C.c_void_p(), C.c_uint64()
+        check(self.ctx._L.slk_build_cells_dev(self.h, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def cells_tensor(self):
+        """The same memory as a torch int64 tensor (no copy; keep the builder open while it is in use)."""
+        import torch
+        ptr, n = self.cells_dev()
+        dev = torch.device("cuda", self.ctx.device)
+        if n == 0:
+            return torch.empty(0, dtype=torch.int64, device=dev)
+
+        class _View:   # the CUDA array interface torch.as_tensor understands
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2, "strides": None}
+        with torch.cuda.device(dev):
+            return torch.as_tensor(_View(), device=dev)
 
     def dense_taxa(self) -> np.ndarray:
         n = C.c_uint32()

@@ -325,11 +325,8 @@ class ShardedKeyValueIndex:
         counts = b.reduce(world)
         cls.last_build_counts = counts
         lap("sort_and_lca_reduce")
-        send = torch.empty(max(sum(counts), 1), dtype=torch.int64, device=dev)
-        b.take_cells(send.data_ptr(), send.numel())
-        send = send[:sum(counts)]
+        send = b.cells_tensor()     # the builder's own buffer: nothing is copied
         raw = b.dense_taxa()
-        lap("group_cells_by_owner")
         # the senders' dense -> raw lists (at most 65 535 ids each): padded all-gather
         dist = _dist()
         n_raw = torch.tensor([len(raw)], dtype=torch.int64, device=dev)
@@ -344,11 +341,15 @@ class ShardedKeyValueIndex:
         recv, run_cells = exchange(send, counts, group)
         del send
         lap("all_to_all")
+        n_recv = int(recv.numel())
+        if torch.cuda.mem_get_info(dev)[0] < 24 * n_recv + (4 << 30):
+            b.close()               # the table needs the room of the builder's buffers; otherwise their release can wait
         out = cls(KeyValueIndex.from_cell_runs(ctx, taxonomy, params, world, recv.data_ptr(), run_cells, dense_raw, run_dense),
                   rank, world)
         del recv
         torch.cuda.empty_cache()   # the staging tensors must not keep HBM that the classifier's buffers will want
         lap("insert_on_owner")
+        b.close()
         cls.last_build_times = tm
         return out
 

@@ -285,7 +285,7 @@ def test_span_scan_one_pass_and_two_pass_agree(gpu, monkeypatch):
 @pytest.mark.parametrize("world", [2, 3])
 def test_distributed_build_on_one_gpu(gpu, world):
     """The distributed build (include/slacken_gpu.h, "Distributed build"; the shuffle of groupBy(idColumns).agg(udafLca),
-    slacken/KeyValueIndex.scala:85-93) with one GPU playing every rank: rank r builds from every world-th genome, reduces,
+    slacken/KeyValueIndex.scala:85-93) with one GPU playing every rank: rank r builds from the r-th block of genomes, reduces,
     hands over its cells grouped by owner; owner d receives the d-th group of every rank and inserts the runs. The shards'
     records must be exactly the oracle library's records, each on the rank slk_shard_of_records names, and a sharded
     classify over them must equal the oracle."""
@@ -300,14 +300,16 @@ def test_distributed_build_on_one_gpu(gpu, world):
     sent, counts, dense = [], [], []
     for r in range(world):
         b = LibraryBuilder(gpu, tax, params)
-        gb, go = pack_sequences(genomes[r::world])
-        b.add(gb, go, taxa[r::world])
+        lo, hi = r * len(genomes) // world, (r + 1) * len(genomes) // world   # a strain and its relative meet on the owner
+        gb, go = pack_sequences(genomes[lo:hi])
+        b.add(gb, go, taxa[lo:hi])
         cnt = b.reduce(world)
-        buf = torch.empty(max(sum(cnt), 1), dtype=torch.int64, device=dev)
-        b.take_cells(buf.data_ptr(), buf.numel())
+        buf = b.cells_tensor()
+        assert buf.numel() == sum(cnt) and buf.is_cuda
         dense.append(b.dense_taxa())
+        sent.append(buf.clone()); counts.append(cnt)
+        del buf
         b.close()
-        sent.append(buf[:sum(cnt)]); counts.append(cnt)
     assert all(d[0] == 0 for d in dense)
     owner = shard_of_records(params, id1, world)
     shards = []
