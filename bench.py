@@ -644,6 +644,8 @@ def sharded_leg(args, w, ctx, tax, params, index, cls, m1, d_off, n, L, genome_t
            "library_records": int(tot.item()), "records_on_rank0": mine, "sum_of_shards_equals_replicated": int(tot.item()) == nrec,
            "equal_to_replicated_fused_kernel": bool(int(same.item()) == 1),
            "checked": f"taxon and flags of all {sr} reads of every rank against classify_kernel on the replicated library"}
+    if getattr(scl, "last_trace", None):
+        res["host_trace_rank0_ms"] = scl.last_trace
     scl.close()
     shard.close()
     torch.cuda.empty_cache()

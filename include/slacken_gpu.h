@@ -357,6 +357,15 @@ SLK_API int slk_mailbox_probe(slk_mailbox* m, slk_index* idx);
 SLK_API int slk_mailbox_resolve(slk_mailbox* m, slk_resolver* r, const slk_classify_opts* opts, const uint64_t* spans,
                                 const uint64_t* span_off, uint64_t n_spans, uint32_t n_reads, int paired, int32_t* taxon_out,
                                 uint8_t* flags_out, slk_read_detail* detail_out, slk_hit* hits_out);
+/* slk_mailbox_resolve in two halves, for a caller that keeps the GPU busy across batches: _async launches the resolve of
+ * batch e and returns; the caller may then issue slk_mailbox_route / slk_mailbox_probe of batch e+1 (they queue behind the
+ * resolve kernels, which is all the protocol needs) and only then calls _wait, which returns when batch e's results are
+ * complete and, when taxon_host / flags_host (pinned) are given, has copied n_reads of them there past the queued work. */
+SLK_API int slk_mailbox_resolve_async(slk_mailbox* m, slk_resolver* r, const slk_classify_opts* opts, const uint64_t* spans,
+                                      const uint64_t* span_off, uint64_t n_spans, uint32_t n_reads, int paired,
+                                      int32_t* taxon_out, uint8_t* flags_out, slk_read_detail* detail_out, slk_hit* hits_out);
+SLK_API int slk_mailbox_resolve_wait(slk_mailbox* m, slk_resolver* r, uint32_t n_reads, const int32_t* taxon_dev,
+                                     const uint8_t* flags_dev, int32_t* taxon_host, uint8_t* flags_host);
 
 /* ---- Bracken weights (slacken/BrackenWeights.scala:312-354) ------------------------------------------------------------------
  * All reads of length read_len of every genome fragment, self-classified against the library with the sliding window of

@@ -126,6 +126,8 @@ SIGNATURES = {
     "slk_mailbox_route": (_INT, [_VP, _VP, _U64]),
     "slk_mailbox_probe": (_INT, [_VP, _VP]),
     "slk_mailbox_resolve": (_INT, [_VP, _VP, _VP, _VP, _VP, _U64, _U32, _INT, _VP, _VP, _VP, _VP]),
+    "slk_mailbox_resolve_async": (_INT, [_VP, _VP, _VP, _VP, _VP, _U64, _U32, _INT, _VP, _VP, _VP, _VP]),
+    "slk_mailbox_resolve_wait": (_INT, [_VP, _VP, _U32, _VP, _VP, _VP, _VP]),
 }
 IPC_HANDLE_BYTES = 64
 

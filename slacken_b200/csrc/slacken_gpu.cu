@@ -75,6 +75,9 @@ struct slk_builder {
   uint64_t* red = nullptr;
   uint64_t* red_aux = nullptr;
   std::vector<uint64_t> seg_count;
+  // per-batch staging, grow-only (a cudaMalloc / cudaFree pair per batch costs more than the batch's copies)
+  uint8_t* st_frag = nullptr; size_t st_frag_bytes = 0;     // dense taxon + item prefix of the batch's fragments
+  uint8_t* st_bases = nullptr; size_t st_bases_bytes = 0;   // slk_build_add: the batch's bases + fragment offsets
 };
 struct slk_counts {
   slk_ctx* ctx;
@@ -665,6 +668,7 @@ extern "C" void slk_build_destroy(slk_builder* b) {
   cudaFree(b->cells); cudaFree(b->d_count);
   if (b->red != b->cells) cudaFree(b->red);
   if (b->red_aux != b->cells) cudaFree(b->red_aux);
+  cudaFree(b->st_frag); cudaFree(b->st_bases);
   dense_free(b->dt);
   delete b;
 }
@@ -714,9 +718,14 @@ static int build_add_impl(slk_builder* b, const uint8_t* d_bases, const uint64_t
   uint64_t n_items = prefix[n_frag];
   if (n_items == 0) return SLK_OK;
   TRY(builder_reserve(b, windows));
-  uint32_t* d_dense = nullptr; uint64_t* d_prefix = nullptr;
-  CU(cudaMalloc(&d_dense, (size_t)n_frag * 4));
-  CU(cudaMalloc(&d_prefix, ((size_t)n_frag + 1) * 8));
+  const size_t prefix_bytes = ((size_t)n_frag + 1) * 8, need = prefix_bytes + (size_t)n_frag * 4;
+  if (need > b->st_frag_bytes) {
+    cudaFree(b->st_frag); b->st_frag = nullptr; b->st_frag_bytes = 0;
+    CU(cudaMalloc(&b->st_frag, need + need / 2));
+    b->st_frag_bytes = need + need / 2;
+  }
+  uint64_t* d_prefix = reinterpret_cast<uint64_t*>(b->st_frag);
+  uint32_t* d_dense = reinterpret_cast<uint32_t*>(b->st_frag + prefix_bytes);
   CU(cudaMemcpyAsync(d_dense, dense.data(), (size_t)n_frag * 4, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(d_prefix, prefix.data(), ((size_t)n_frag + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   slk_emit_args ea;
@@ -730,7 +739,6 @@ static int build_add_impl(slk_builder* b, const uint8_t* d_bases, const uint64_t
   CU(cudaMemcpyAsync(&cnt, b->d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   b->count = cnt;
-  cudaFree(d_dense); cudaFree(d_prefix);
   return SLK_OK;
 }
 
@@ -741,14 +749,18 @@ extern "C" int slk_build_add(slk_builder* b, const uint8_t* bases, const uint64_
   slk_ctx* ctx = b->ctx;
   CU(cudaSetDevice(ctx->device));
   uint64_t s = frag_off[0], total = frag_off[n_frag] - s;
-  uint8_t* d_bases = nullptr; uint64_t* d_off = nullptr;
-  CU(cudaMalloc(&d_bases, total + 16));
-  CU(cudaMalloc(&d_off, ((size_t)n_frag + 1) * 8));
+  const size_t off_bytes = ((size_t)n_frag + 1) * 8, need = off_bytes + total + 16;
+  if (need > b->st_bases_bytes) {
+    cudaFree(b->st_bases); b->st_bases = nullptr; b->st_bases_bytes = 0;
+    CU(cudaMalloc(&b->st_bases, need + need / 4));
+    b->st_bases_bytes = need + need / 4;
+  }
+  uint64_t* d_off = reinterpret_cast<uint64_t*>(b->st_bases);
+  uint8_t* d_bases = b->st_bases + off_bytes;
   CU(cudaMemcpyAsync(d_bases, bases + s, total, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(d_off, frag_off, ((size_t)n_frag + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   int rc = build_add_impl(b, d_bases, d_off, s, frag_off, frag_taxon, n_frag);
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_bases); cudaFree(d_off);
   return rc;
 }
 extern "C" int slk_build_add_dev(slk_builder* b, const uint8_t* bases, const uint64_t* frag_off, const int32_t* frag_taxon,

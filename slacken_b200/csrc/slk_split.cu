@@ -486,6 +486,8 @@ struct slk_mailbox {
   uint32_t epoch = 0;
   uint32_t blocks_per_sm = 8;              // size of the lookup / unroute grids (slk_mailbox_set_blocks_per_sm)
   bool connected = false;
+  cudaStream_t copy_stream = nullptr;      // slk_mailbox_resolve_wait: the results leave here, past whatever the main stream
+  cudaEvent_t ev_resolved = nullptr;       // has queued behind the resolve kernels (the next batch's route and lookups)
 };
 
 __device__ __forceinline__ unsigned long long mbx_ld_flag(const unsigned long long* p) {
@@ -650,6 +652,8 @@ extern "C" int slk_mailbox_create(slk_ctx* ctx, uint32_t rank, uint32_t world, u
   if (e == cudaSuccess) e = cudaMemset(m->d_cursors, 0, (size_t)world * 8);
   if (e == cudaSuccess) e = cudaMalloc(&m->d_err, 4);
   if (e == cudaSuccess) e = cudaMemset(m->d_err, 0, 4);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_resolved, cudaEventDisableTiming);
   if (e == cudaSuccess && handle_out) {
     cudaIpcMemHandle_t h;
     static_assert(sizeof(h) == SLK_IPC_HANDLE_BYTES, "IPC handle size");
@@ -724,6 +728,8 @@ extern "C" void slk_mailbox_destroy(slk_mailbox* m) {
   for (uint32_t r = 0; r < m->world; r++)
     if (m->opened[r] && m->peer[r]) cudaIpcCloseMemHandle(m->peer[r]);
   cudaFree(m->base); cudaFree(m->d_peer); cudaFree(m->d_send_idx); cudaFree(m->d_cursors); cudaFree(m->d_err); cudaFree(m->d_dense);
+  if (m->copy_stream) { cudaStreamSynchronize(m->copy_stream); cudaStreamDestroy(m->copy_stream); }
+  if (m->ev_resolved) cudaEventDestroy(m->ev_resolved);
   delete m;
 }
 // 256-thread blocks per SM of the lookup and unroute kernels (1..8, default 8 = every thread slot). A caller that scans
@@ -761,16 +767,19 @@ extern "C" int slk_mailbox_probe(slk_mailbox* m, slk_index* idx) {
   SLK_CU(cudaGetLastError());
   return SLK_OK;
 }
-// step 3 (returns when the results are complete): slk_resolve_spans_dev on the answers in the reply area
-extern "C" int slk_mailbox_resolve(slk_mailbox* m, slk_resolver* r, const slk_classify_opts* opts, const uint64_t* spans,
-                                   const uint64_t* span_off, uint64_t n_spans, uint32_t n_reads, int paired, int32_t* taxon_out,
-                                   uint8_t* flags_out, slk_read_detail* detail_out, slk_hit* hits_out) {
+// step 3a (asynchronous): slk_resolve_spans_dev on the answers in the reply area. The next batch's slk_mailbox_route /
+// slk_mailbox_probe may be issued right after this call: they queue behind the resolve kernels on the library's stream,
+// which is all the protocol needs (this rank's unroute kernel has consumed every owner's flag before its next route runs).
+extern "C" int slk_mailbox_resolve_async(slk_mailbox* m, slk_resolver* r, const slk_classify_opts* opts, const uint64_t* spans,
+                                         const uint64_t* span_off, uint64_t n_spans, uint32_t n_reads, int paired,
+                                         int32_t* taxon_out, uint8_t* flags_out, slk_read_detail* detail_out, slk_hit* hits_out) {
   if (!m || !m->connected || !r || r->ctx != m->ctx || !opts || !span_off || !taxon_out || !flags_out || (n_spans && !spans))
     return slk_fail(SLK_E_INVALID, "bad arguments (resolver and mailbox must share a context)");
   if (hits_out && !detail_out) return slk_fail(SLK_E_INVALID, "hits_out needs detail_out");
   SLK_CU(cudaSetDevice(m->ctx->device));
   cudaStream_t st = m->ctx->stream;
   if (m->dense_cap < std::max<uint64_t>(n_spans, 1)) {
+    SLK_CU(cudaStreamSynchronize(st));
     cudaFree(m->d_dense); m->d_dense = nullptr; m->dense_cap = 0;
     const uint64_t cap = std::max<uint64_t>(n_spans + n_spans / 8, 1024);
     SLK_CU(cudaMalloc(&m->d_dense, cap * 2));
@@ -784,17 +793,40 @@ extern "C" int slk_mailbox_resolve(slk_mailbox* m, slk_resolver* r, const slk_cl
     resolve_spans_kernel<<<(n_reads + 127) / 128, 128, 0, st>>>(r->dt.view(), r->sp.k, spans, span_off, m->d_dense, n_reads, paired,
                                                                 opts->confidence, opts->min_hit_groups, taxon_out, flags_out,
                                                                 detail_out, hits_out, r->d_err);
+  SLK_CU(cudaGetLastError());
+  SLK_CU(cudaEventRecord(m->ev_resolved, st));
+  return SLK_OK;
+}
+// step 3b: returns when the results of the last slk_mailbox_resolve_async are complete. taxon_host / flags_host (pinned
+// memory, or NULL) receive n_reads results from taxon_dev / flags_dev on a stream of their own, past whatever has been
+// queued behind the resolve kernels meanwhile.
+extern "C" int slk_mailbox_resolve_wait(slk_mailbox* m, slk_resolver* r, uint32_t n_reads, const int32_t* taxon_dev,
+                                        const uint8_t* flags_dev, int32_t* taxon_host, uint8_t* flags_host) {
+  if (!m || !r || ((taxon_host || flags_host) && (!taxon_dev || !flags_dev))) return slk_fail(SLK_E_INVALID, "bad arguments");
+  SLK_CU(cudaSetDevice(m->ctx->device));
+  cudaStream_t st = m->copy_stream;
   uint32_t err = 0, rerr = 0;
-  if (cudaMemcpyAsync(&err, m->d_err, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-      cudaMemcpyAsync(&rerr, r->d_err, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
-    return slk_fail(SLK_E_CUDA, "mailbox resolve failed: %s", cudaGetErrorString(cudaGetLastError()));
+  bool ok = cudaStreamWaitEvent(st, m->ev_resolved, 0) == cudaSuccess;
+  if (ok && taxon_host && n_reads) ok = cudaMemcpyAsync(taxon_host, taxon_dev, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+  if (ok && flags_host && n_reads) ok = cudaMemcpyAsync(flags_host, flags_dev, (size_t)n_reads, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+  ok = ok && cudaMemcpyAsync(&err, m->d_err, 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+       cudaMemcpyAsync(&rerr, r->d_err, 4, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
+  if (!ok) return slk_fail(SLK_E_CUDA, "mailbox resolve failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (err || rerr) {
+    cudaStreamSynchronize(m->ctx->stream);
     cudaMemset(m->d_err, 0, 4); cudaMemset(r->d_err, 0, 4);
     if (err & 2u) return slk_fail(SLK_E_CUDA, "a peer did not deliver its part of the exchange within 10 s");
     if (err & 1u) return slk_fail(SLK_E_NOSPACE, "more than %llu keys for one owner in a batch: create the mailbox with a larger cap", (unsigned long long)m->cap);
     return slk_fail(SLK_E_UNSUPPORTED, "a returned taxon is unknown to the resolver, or a fragment hit more than %d distinct taxa", SLK_KMAX);
   }
   return SLK_OK;
+}
+// step 3 in one call: returns when the results are complete (device memory)
+extern "C" int slk_mailbox_resolve(slk_mailbox* m, slk_resolver* r, const slk_classify_opts* opts, const uint64_t* spans,
+                                   const uint64_t* span_off, uint64_t n_spans, uint32_t n_reads, int paired, int32_t* taxon_out,
+                                   uint8_t* flags_out, slk_read_detail* detail_out, slk_hit* hits_out) {
+  const int rc = slk_mailbox_resolve_async(m, r, opts, spans, span_off, n_spans, n_reads, paired, taxon_out, flags_out, detail_out, hits_out);
+  return rc != SLK_OK ? rc : slk_mailbox_resolve_wait(m, r, n_reads, nullptr, nullptr, nullptr, nullptr);
 }
 
 // owner of every record (id1 = the uncompressed minimizer of the Parquet column), computed on the host

@@ -136,9 +136,8 @@ class GpuSplitOps:
     def _v(t):
         return C.c_void_p(t.data_ptr()) if t is not None else None
 
-    def download(self, name: str, t, dtype, n: int) -> np.ndarray:
-        """Device tensor -> pinned host array (grow-only, one per result kind; pageable copies run at a few GB/s). The
-        returned view is valid until the next download of the same kind."""
+    def pinned_out(self, name: str, dtype, n: int) -> np.ndarray:
+        """The pinned host array of one result kind (grow-only), as n elements of dtype."""
         dtype = np.dtype(dtype)
         nbytes = n * dtype.itemsize
         if not hasattr(self, "_pinned"):
@@ -149,10 +148,15 @@ class GpuSplitOps:
                 self.ctx.free_pinned(buf)
             buf = self.ctx.pinned((max(nbytes + nbytes // 4, 4096),), np.uint8)
             self._pinned[name] = buf
-        out = buf[:nbytes]
-        if nbytes:
-            self.ctx.d2h(out, t.data_ptr())
-        return out.view(dtype)
+        return buf[:nbytes].view(dtype)
+
+    def download(self, name: str, t, dtype, n: int) -> np.ndarray:
+        """Device tensor -> pinned host array (grow-only, one per result kind; pageable copies run at a few GB/s). The
+        returned view is valid until the next download of the same kind."""
+        out = self.pinned_out(name, dtype, n)
+        if out.nbytes:
+            self.ctx.d2h(out.view(np.uint8), t.data_ptr())
+        return out
 
     def _results(self, taxon, flags, detail, hits, n_reads: int, n_spans: int, want_hits: bool) -> ClassifiedBatch:
         """The arrays of the batch live in pinned buffers that the next batch overwrites: copy what must outlive it."""
@@ -503,18 +507,62 @@ class ShardedClassifier:
         assert self.mailbox is not None, "the pipelined path needs the NVLink mailbox"
         ops = self.ops
         check(ops._L.slk_mailbox_set_blocks_per_sm(self.mailbox.h, 4))   # leave half of every SM to the overlapping scan
+        import os
+        import time
+        trace = [] if os.environ.get("SLK_TRACE_SHARDED") else None   # host-side call boundaries of every step (ms since the first)
+        t0 = time.perf_counter()
+
+        def mark(name):
+            if trace is not None:
+                trace.append((name, round((time.perf_counter() - t0) * 1e3, 3)))
         it = iter(batches)
         cur = next(it, None)
-        scanned = ops.scan_spans(*cur) if cur is not None else None
+        if cur is None:
+            return
+        scanned = ops.scan_spans(*cur)
+        self.mailbox_route(scanned[1], scanned[2])
+        self.mailbox_probe()
         while cur is not None:
             span_off, spans, n_spans = scanned
-            self.mailbox_route(spans, n_spans)
-            self.mailbox_probe()
+            mark("scan_next>")
             nxt = next(it, None)
             scanned_next = ops.scan_spans(*nxt) if nxt is not None else None   # overlaps with the exchange of `cur`
-            yield self.mailbox_resolve(spans, span_off, n_spans, cur[4], cur[2] is not None, confidence, min_hit_groups,
-                                       per_read_output)
+            mark("resolve>")
+            pending = self._resolve_async(spans, span_off, n_spans, cur[4], cur[2] is not None, confidence, min_hit_groups,
+                                          per_read_output)
+            if nxt is not None:             # queued behind the resolve kernels: the GPU goes on while the results leave
+                self.mailbox_route(scanned_next[1], scanned_next[2])
+                self.mailbox_probe()
+            mark("wait>")
+            out = self._resolve_wait(pending)
+            mark("done")
+            self.last_trace = trace
+            yield out
             cur, scanned = nxt, scanned_next
+
+    def _resolve_async(self, spans, span_off, n_spans: int, n_reads: int, paired: bool, confidence: float, min_hit_groups: int,
+                       want_hits: bool):
+        ops, t = self.ops, self.ops.torch
+        taxon = t.empty(max(n_reads, 1), dtype=t.int32, device=ops.device)
+        flags = t.empty(max(n_reads, 1), dtype=t.uint8, device=ops.device)
+        detail = t.empty(max(n_reads, 1) * DETAIL_DTYPE.itemsize, dtype=t.uint8, device=ops.device) if want_hits else None
+        hits = t.empty(max(n_spans, 1) * HIT_DTYPE.itemsize, dtype=t.uint8, device=ops.device) if want_hits else None
+        opts = ClassifyOpts(float(confidence), int(min_hit_groups), 0)
+        check(ops._L.slk_mailbox_resolve_async(self.mailbox.h, ops.resolver, C.byref(opts), ops._v(spans), ops._v(span_off), n_spans,
+                                               n_reads, 1 if paired else 0, ops._v(taxon), ops._v(flags), ops._v(detail),
+                                               ops._v(hits)))
+        return (spans, span_off, taxon, flags, detail, hits, n_reads, n_spans, want_hits)
+
+    def _resolve_wait(self, pending) -> ClassifiedBatch:
+        spans, span_off, taxon, flags, detail, hits, n_reads, n_spans, want_hits = pending
+        ops = self.ops
+        h_taxon = ops.pinned_out("taxon", np.int32, n_reads)
+        h_flags = ops.pinned_out("flags", np.uint8, n_reads)
+        check(ops._L.slk_mailbox_resolve_wait(self.mailbox.h, ops.resolver, n_reads, ops._v(taxon), ops._v(flags),
+                                              h_taxon.ctypes.data_as(C.c_void_p), h_flags.ctypes.data_as(C.c_void_p)))
+        d = ops.download("detail", detail, DETAIL_DTYPE, n_reads) if want_hits else None
+        h = ops.download("hits", hits, HIT_DTYPE, n_spans) if want_hits else None
+        return ClassifiedBatch(h_taxon, h_flags, d, h, n_spans if want_hits else 0)
 
     # the three mailbox steps, separately (a single process driving several ranks interleaves them: tests)
     def mailbox_route(self, spans, n_spans: int):
