@@ -7,7 +7,7 @@ from a synthetic genome set over the synthetic 50k-node taxonomy, on 1/2/4/8 GPU
 
 Weak scaling: every rank scans, sorts and LCA-reduces 8.75 Gbp of genomes (70 Gbp on 8 GPUs, the size of the standard
 library) generated in its own HBM, then the reduced records travel to the owner of their minimizer in one all-to-all and
-the owner's insert merges equal minimizers by LCA (slacken_b200/sharded.py, ShardedKeyValueIndex.from_local). The result
+the owner's insert merges equal minimizers by LCA (slacken_b200/sharded.py, ShardedKeyValueIndex.from_builder). The result
 is the library sharded by minimizer hash range, ready for bench_sharded.py's classifier. Prints one JSON line. Not the
 driver's bench (that is bench.py)."""
 from __future__ import annotations
@@ -73,17 +73,16 @@ def main():
         ctx.h2d(d_off, np.arange(g1 - g0 + 1, dtype=np.uint64) * np.uint64(w.genome_len))
         ctx.h2d(d_tax, genome_taxa[g0:g1])
         b.add_dev(d_bases, d_off, d_tax, g1 - g0, n)
-    local_index = b.finish()
-    b.close()
     for p in (d_bases, d_off, d_tax):
         ctx.dev_free(p)
     ctx.sync()
     t_local = time.perf_counter() - t0
-    n_local = len(local_index)
-    shard = ShardedKeyValueIndex.from_local(local_index)
+    shard = ShardedKeyValueIndex.from_builder(b)
+    b.close()
     ctx.sync()
     torch.cuda.synchronize()
     t_all = time.perf_counter() - t0
+    n_local = int(sum(ShardedKeyValueIndex.last_build_counts))
     t = torch.tensor([t_local, t_all], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([n_local, len(shard)], dtype=torch.int64, device="cuda")
     if world > 1:
@@ -96,8 +95,8 @@ def main():
             "value": w.total_bases / t_all / 1e9, "unit": "Gbases/s", "n_gpus": world, "seconds": t_all, "scaling": "weak",
             "timing": "host wall clock from the first genome batch to the finished sharded table, genome generation on the "
                       "device included, max over ranks",
-            "phases_s": {"local scan + sort + LCA reduce + local table": t_local,
-                         "records to their owners (all-to-all) + insert on the owner": t_all - t_local,
+            "phases_s": {"local scan (minimizers of this rank's genomes -> cells)": t_local,
+                         "sort + LCA reduce, cells to their owners (all-to-all), insert on the owner": t_all - t_local,
                          "exchange_breakdown_rank0": ShardedKeyValueIndex.last_build_times},
             "config": {"workload": f"{w.n_genomes} synthetic genomes x {w.genome_len} bp = {w.total_bases / 1e9:.2f} Gbp, "
                                    f"{len(parents)}-node taxonomy, k{w.k}/m{w.m}/s{w.spaces}",
