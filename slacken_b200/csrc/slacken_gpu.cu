@@ -402,28 +402,37 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(const uint8_t* __restri
     if (b >= b_last) continue;
     const uint64_t start = roff + 32 * (b - rb);
     const uint32_t n = (uint32_t)(rend - start < 32 ? rend - start : 32);
-    // 32 bytes from an arbitrary address: nine aligned words, funnel-shifted into place (the buffer is readable up to
-    // the next 16-byte boundary, as everywhere in this library)
+    // 32 bytes from an arbitrary address: three aligned 16-byte words (only those that hold bytes of the read: the buffer
+    // is readable up to the next 16-byte boundary, as everywhere in this library), moved into place by a word select in
+    // two levels and a funnel shift, then coded four bytes at a time (slk_code4)
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(bases + start);
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a0 & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)(a0 & 3) * 8;
-    const uint32_t nw = (n + (uint32_t)(a0 & 3) + 3) >> 2;   // aligned words that hold the n bytes
-    uint32_t w[9];
+    const uint4* vp = reinterpret_cast<const uint4*>(a0 & ~(uintptr_t)15);
+    const uint32_t mis = (uint32_t)(a0 & 15);
+    const uint32_t nv = (n + mis + 15) >> 4;   // aligned 16-byte words that hold the n bytes
+    uint32_t w[12];
 #pragma unroll
-    for (int i = 0; i < 9; i++) w[i] = (uint32_t)i < nw ? __ldg(wp + i) : 0u;
+    for (int i = 0; i < 3; i++) {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if ((uint32_t)i < nv) v = __ldg(vp + i);
+      w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    }
+    const bool q1 = (mis & 4u) != 0, q2 = (mis & 8u) != 0;
+    const uint32_t sh = (mis & 3u) * 8u;
+    uint32_t u[11], t[9];
+#pragma unroll
+    for (int i = 0; i < 11; i++) u[i] = q1 ? w[i + 1] : w[i];
+#pragma unroll
+    for (int i = 0; i < 9; i++) t[i] = q2 ? u[i + 2] : u[i];
     uint64_t cw = 0;
     uint32_t mw = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const uint32_t x = __funnelshift_r(w[i], w[i + 1], sh);
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t pos = 4 * i + j;
-        const uint32_t c = pos < n ? slk_code((x >> (8 * j)) & 0xffu) : 0u;
-        cw |= (uint64_t)(c & 3u) << (2 * pos);
-        mw |= (c >> 2) << pos;
-      }
+      uint32_t c8, i4;
+      slk_code4(__funnelshift_r(t[i], t[i + 1], sh), &c8, &i4);
+      cw |= (uint64_t)c8 << (8 * i);
+      mw |= i4 << (4 * i);
     }
+    if (n < 32) { cw &= (1ull << (2 * n)) - 1ull; mw &= (1u << n) - 1u; }
     codes[b] = cw;
     mask[b] = mw;
   }

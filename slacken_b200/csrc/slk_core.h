@@ -127,6 +127,23 @@ SLK_HD uint32_t slk_code(uint32_t c) {
   return ok ? code : 4u;
 }
 
+// slk_code for the four bytes of a word at once: *code8 = their 2-bit codes (byte 0 in bits 0-1, invalid characters as 0),
+// *inv4 = one bit per byte that is none of A C G T U (either case). Byte-parallel arithmetic: an exact zero-byte test per
+// accepted letter, and two multiplies that gather the per-byte fields (their partial products never overlap).
+SLK_HD void slk_code4(uint32_t x, uint32_t* code8, uint32_t* inv4) {
+  const uint32_t y = x & 0xDFDFDFDFu;   // upper case
+  const uint32_t ta = y ^ 0x41414141u, tc = y ^ 0x43434343u, tg = y ^ 0x47474747u, tt = (y & 0xFEFEFEFEu) ^ 0x54545454u;
+  // bit 7 of a byte of ((t & 0x7f) + 0x7f) | t is clear exactly when the byte of t is zero
+  const uint32_t nz = (((ta & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | ta) & (((tc & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | tc) &
+                      (((tg & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | tg) & (((tt & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | tt);
+  const uint32_t invb = (nz >> 7) & 0x01010101u;
+  uint32_t v = (x >> 1) & 0x03030303u;
+  v ^= (v >> 1) & 0x01010101u;
+  v &= ~(invb * 3u);
+  *code8 = (v * 0x01041040u) >> 24;
+  *inv4 = ((invb * 0x00204081u) >> 21) & 0xFu;
+}
+
 // Calls f(byte) for every byte of [s, s+len) in order. On the device the bytes arrive through 16-byte aligned
 // vector loads (a thread-per-read kernel would otherwise issue one LSU wavefront per base); the buffer must be
 // readable up to the next 16-byte boundary, which every library-owned / cudaMalloc'ed buffer is.

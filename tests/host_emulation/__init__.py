@@ -44,6 +44,8 @@ def lib():
         L.emu_expand.argtypes = [C.POINTER(ScanParams), C.c_uint64]
         L.emu_code.restype = C.c_uint32
         L.emu_code.argtypes = [C.c_uint32]
+        L.emu_code4_mismatches.argtypes = [C.c_void_p, C.c_uint64]
+        L.emu_code4_mismatches.restype = C.c_uint64
         L.emu_buckets_for.restype = C.c_uint64
         L.emu_buckets_for.argtypes = [C.c_uint64]
         L.emu_insert_cells.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]

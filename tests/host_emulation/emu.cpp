@@ -22,6 +22,21 @@ EMU_API int emu_sizeof_scan_params() { return (int)sizeof(slk_scan_params); }
 EMU_API uint64_t emu_compress(const slk_scan_params* sp, uint64_t x) { return slk_compress(*sp, x); }
 EMU_API uint64_t emu_expand(const slk_scan_params* sp, uint64_t x) { return slk_expand(*sp, x); }
 EMU_API uint32_t emu_code(uint32_t c) { return slk_code(c); }
+// number of words among words[0..n) whose slk_code4 differs from four slk_code calls
+EMU_API uint64_t emu_code4_mismatches(const uint32_t* words, uint64_t n) {
+  uint64_t bad = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    uint32_t c8, i4, rc = 0, ri = 0;
+    slk_code4(words[i], &c8, &i4);
+    for (int j = 0; j < 4; j++) {
+      const uint32_t c = slk_code((words[i] >> (8 * j)) & 0xffu);
+      rc |= (c & 3u) << (2 * j);
+      ri |= (c >> 2) << j;
+    }
+    bad += (c8 != rc) || (i4 != ri);
+  }
+  return bad;
+}
 EMU_API uint64_t emu_buckets_for(uint64_t n_keys) { return (((uint64_t)((double)n_keys / 0.70) + 64 + 15) / 16) * 4; }
 
 // sequential twin of insert_cells_kernel (no atomics needed with one "thread")

@@ -205,3 +205,24 @@ def test_bracken_window_body_matches_the_oracle(read_len):
         want = oracle.bracken_read_classifications(p, parents, lib.lookup, seq, read_len)
         got = emu.bracken_dests(ix, seq, read_len)
         assert list(got) == want, (len(seq), read_len)
+
+
+def test_four_bytes_at_a_time_coding_equals_the_scalar_coding():
+    """slk_code4 (the stage-1 pack kernel's byte-parallel coding) against four slk_code calls: every byte value in every
+    lane next to every accepted letter, plus random words."""
+    L = emu.lib()
+    letters = np.frombuffer(b"ACGTUacgtuNn\x00\xff@[`{SsVv", dtype=np.uint8).astype(np.uint32)
+    words = []
+    for lane in range(4):
+        for other in letters:
+            w = np.full(256, 0, dtype=np.uint32)
+            for j in range(4):
+                w |= (np.arange(256, dtype=np.uint32) if j == lane else other) << np.uint32(8 * j)
+            words.append(w)
+    words.append(np.random.default_rng(3).integers(0, 1 << 32, size=200000, dtype=np.uint64).astype(np.uint32))
+    # words made of accepted letters only (the common case)
+    acgt = np.frombuffer(b"ACGTacgtUu", dtype=np.uint8)
+    pick = np.random.default_rng(4).integers(0, len(acgt), size=(50000, 4))
+    words.append((acgt[pick].astype(np.uint32) << (np.arange(4, dtype=np.uint32) * 8)).sum(axis=1).astype(np.uint32))
+    allw = np.ascontiguousarray(np.concatenate(words))
+    assert L.emu_code4_mismatches(allw.ctypes.data, len(allw)) == 0
