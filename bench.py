@@ -421,12 +421,15 @@ def run_ours(args, w):
         return {"value": world * n * args.steps / s, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * s / args.steps, "api": api, "clocks": ClockSampler.summarize(sampler.window(t0, t1))}
 
-    e2e_report = e2e_line(lambda: cls.classify_packed(hp1, confidence=w.confidence, min_hit_groups=w.min_hit_groups, per_read_output=False, out=out),
-                          hp1.nbytes, False,
-                          "slk_classify_batch_packed without per-read hit lists (the reference's --nodetailed mode, "
-                          "slacken/Classifier.scala:259-410): taxon, flags and lengths per read come back, no hits")
-    e2e_ascii = e2e_line(lambda: cls.classify(h_reads, h_off, confidence=w.confidence, min_hit_groups=w.min_hit_groups, out=out),
-                         h_reads.nbytes + h_off.nbytes, True, "slk_classify_batch: pinned HOST buffers holding ASCII reads")
+    quick_e2e = getattr(args, "e2e_quick", False)   # tuning runs: the packed and compact host-buffer legs only
+    e2e_report = e2e_ascii = None
+    if not quick_e2e:
+        e2e_report = e2e_line(lambda: cls.classify_packed(hp1, confidence=w.confidence, min_hit_groups=w.min_hit_groups,
+                                                          per_read_output=False, out=out), hp1.nbytes, False,
+                              "slk_classify_batch_packed without per-read hit lists (the reference's --nodetailed mode, "
+                              "slacken/Classifier.scala:259-410): taxon, flags and lengths per read come back, no hits")
+        e2e_ascii = e2e_line(lambda: cls.classify(h_reads, h_off, confidence=w.confidence, min_hit_groups=w.min_hit_groups, out=out),
+                             h_reads.nbytes + h_off.nbytes, True, "slk_classify_batch: pinned HOST buffers holding ASCII reads")
     e2e = e2e_line(lambda: cls.classify_packed(hp1, confidence=w.confidence, min_hit_groups=w.min_hit_groups, out=out), hp1.nbytes, True,
                    "slk_classify_batch_packed: pinned HOST buffers holding 2-bit packed reads + ambiguity masks (the host-side "
                    "packing is the Scala driver's batching work and is outside the timed region), per-read hit lists on")
@@ -454,6 +457,13 @@ def run_ours(args, w):
     e2e_compact_report = {"value": world * n * args.steps / cr_s, "unit": "reads/s", "h2d_bytes_per_step": int(cr1.nbytes),
                           "d2h_bytes_per_step": int(cout.results.nbytes), "ms_per_step": 1e3 * cr_s / args.steps,
                           "api": "slk_classify_batch_compact without hit lists: 16 bytes per read come back"}
+    if quick_e2e:
+        sampler.stop()
+        if rank == 0:
+            print(json.dumps({"e2e_quick": True, "so": os.environ.get("SLK_SO", "libslacken_gpu.so"), "value": value,
+                              "e2e": e2e["value"], "e2e_compact": e2e_compact["value"],
+                              "e2e_compact_report_only": e2e_compact_report["value"]}), flush=True)
+        return
     # `out` now holds the single-end results of the whole batch (the CPU leg below checks a sample of them)
     single_out = ClassifiedBatch(out.taxon.copy(), out.flags.copy(), out.detail.copy(), out.hits[:out.hits_used].copy(), out.hits_used)
     # the compact results against the packed entry point's, all reads: taxon, flags, lengths, and the hit lists in read order
@@ -841,6 +851,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="reads in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="tuning: only the device-timed single-end leg, short JSON")
+    ap.add_argument("--e2e-quick", action="store_true", help="tuning: the device-timed leg and the packed / compact host-buffer legs, short JSON")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded-library and distributed-build legs")
     ap.add_argument("--paired-confidence", type=float, default=0.15)
     ap.add_argument("--no-big-classify", action="store_true", help="N > 1: skip classifying against the freshly built sharded library")

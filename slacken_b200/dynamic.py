@@ -228,6 +228,79 @@ class Dynamic:
         u, c = np.unique(pairs[0], return_counts=True)
         return [(int(a), int(b)) for a, b in zip(u, c)]
 
+    # ---- IndexStatistics.showTaxonFullCoverageStats (slacken/IndexStatistics.scala:86-112) -----------------------------
+    def minimizer_coverage(self, batch_bases: int = 256 << 20) -> dict:
+        """For every taxon of the genome library: the super-mers of its genomes whose minimizer has a record in the base
+        index, grouped by the depth of the record's (LCA) taxon. Returns {taxon: ([(depth, super-mers)], [(depth, distinct
+        minimizers)])}, depths ascending. The genomes run through the span scan of the split path in batches (one genome
+        = one "read"; a sequence span is a super-mer, MinSplitter.superkmerPositions = kmers/minimizer/MinSplitter.scala:180-216),
+        the lookups through its probe; the (taxon, minimizer) counting is host work, as this is a report, not the hot path."""
+        from .host import pack_sequences
+        from .sharded import GpuSplitOps
+        ops = GpuSplitOps(self.base, np.zeros(0, dtype=np.int32))
+        parts = []   # per batch: unique (genome taxon, key) with the record's taxon and the number of super-mers
+        try:
+            at = 0
+            while at < len(self.genomes):
+                end, size = at, 0
+                while end < len(self.genomes) and (end == at or size + len(self.genomes[end][1]) <= batch_bases):
+                    size += len(self.genomes[end][1]); end += 1
+                gt = np.array([int(t) for t, _ in self.genomes[at:end]], dtype=np.int64)
+                bases, off = pack_sequences([g for _, g in self.genomes[at:end]])
+                d_b = ops.upload(bases if len(bases) else np.zeros(16, np.uint8))
+                d_o = ops.upload(off.astype(np.uint64).view(np.int64))
+                span_off, spans, n_spans = ops.scan_spans(d_b, d_o, None, None, end - at)
+                keys, idx, _ = ops.route(spans, n_spans, 1)
+                taxa = ops.probe(keys).cpu().numpy().astype(np.int64)
+                k = keys.cpu().numpy().view(np.uint64)
+                so = span_off.cpu().numpy().astype(np.int64)
+                genome_of = np.searchsorted(so, idx.cpu().numpy().astype(np.int64), side="right") - 1
+                hit = taxa > 0                      # the join with the records is an inner join
+                g, k, t = gt[genome_of[hit]], k[hit], taxa[hit]
+                order = np.lexsort((k, g))
+                g, k, t = g[order], k[order], t[order]
+                head = np.ones(len(g), dtype=bool)
+                head[1:] = (g[1:] != g[:-1]) | (k[1:] != k[:-1])
+                starts = np.nonzero(head)[0]
+                parts.append((g[head], k[head], t[head], np.diff(np.append(starts, len(g)))))
+                at = end
+        finally:
+            ops.close()
+        if not parts:
+            return {}
+        g, k, t, c = (np.concatenate([p[i] for p in parts]) for i in range(4))
+        order = np.lexsort((k, g))                   # the same (taxon, minimizer) may occur in several batches
+        g, k, t, c = g[order], k[order], t[order], c[order]
+        head = np.ones(len(g), dtype=bool)
+        head[1:] = (g[1:] != g[:-1]) | (k[1:] != k[:-1])
+        count_all = np.add.reduceat(c, np.nonzero(head)[0]) if len(g) else c
+        g, t = g[head], t[head]
+        depth_of = {int(x): self.tree.depth(int(x)) for x in np.unique(t)}
+        d = np.array([depth_of[int(x)] for x in t], dtype=np.int64)
+        out = {}
+        for taxon in np.unique(g):
+            sel = g == taxon
+            depths = np.unique(d[sel])
+            out[int(taxon)] = ([(int(x), int(count_all[sel][d[sel] == x].sum())) for x in depths],
+                               [(int(x), int((d[sel] == x).sum())) for x in depths])
+        return out
+
+    def write_minimizer_coverage(self, output_location: str, coverage: Optional[dict] = None) -> List[str]:
+        """<out>_support_report_minimizerCoverage/ and <out>_support_report_minimizerDistinctCoverage/ (one text part file
+        each; slacken/Dynamic.scala:230-243): "<taxon>  <depth>:<count>|<depth>:<count>..." per taxon of the genome library."""
+        import os
+        cov = self.minimizer_coverage() if coverage is None else coverage
+        written = []
+        for name, which in (("minimizerCoverage", 0), ("minimizerDistinctCoverage", 1)):
+            d = f"{output_location}_support_report_{name}"
+            os.makedirs(d, exist_ok=True)
+            with open(os.path.join(d, "part-00000.txt"), "w") as f:
+                for taxon in sorted(cov):
+                    f.write(f"{taxon}  " + "|".join(f"{a}:{b}" for a, b in cov[taxon][which]) + "\n")
+            open(os.path.join(d, "_SUCCESS"), "w").close()
+            written.append(d)
+        return written
+
     # ---- findTaxonSet + makeRecords (slacken/Dynamic.scala:250-280,362-374) --------------------------------------------
     def find_taxon_set(self, bases1, off1, bases2=None, off2=None, write_location: Optional[str] = None) -> Set[int]:
         c = self.criteria
@@ -255,8 +328,8 @@ class Dynamic:
     def report_dynamic_index_support(self, output_location: str, bases1, off1, bases2=None, off2=None) -> List[str]:
         """<out>_support_report_{totalKmerCount,distinctMinimizerCount,totalMinimizerCount,classifiedReadCount}.txt:
         per taxon at the reclassify rank or below, the k-mers and (distinct) minimizers of the sample's sequence spans that
-        hit it, and the reads classified to it at confidence 0. (The two minimizerCoverage directories of the reference
-        describe the genome library, not the sample, and are not written.)"""
+        hit it, and the reads classified to it at confidence 0; plus the two minimizerCoverage directories, which describe
+        the genome library (write_minimizer_coverage)."""
         from .report import KrakenReport
         t, k, c = self._span_hits(bases1, off1, bases2, off2)
         taxa = np.unique(t)
@@ -277,6 +350,7 @@ class Dynamic:
             with open(path, "w") as f:
                 f.write(KrakenReport(tx.parents, tx.ranks, tx.names, counts).text())
             written.append(path)
+        written += self.write_minimizer_coverage(output_location)
         return written
 
     def make_index(self, bases1, off1, bases2=None, off2=None, write_location: Optional[str] = None,

@@ -107,7 +107,29 @@ def test_gold_set_library_and_support_reports(gpu, tmp_path):
     out = str(tmp_path / "dyn")
     files = dyn2.report_dynamic_index_support(out, rb, ro)
     assert [f[len(out):] for f in files] == ["_support_report_totalKmerCount.txt", "_support_report_distinctMinimizerCount.txt",
-                                             "_support_report_totalMinimizerCount.txt", "_support_report_classifiedReadCount.txt"]
+                                             "_support_report_totalMinimizerCount.txt", "_support_report_classifiedReadCount.txt",
+                                             "_support_report_minimizerCoverage", "_support_report_minimizerDistinctCoverage"]
+    # minimizerCoverage (IndexStatistics.showTaxonFullCoverageStats): super-mers of every library genome per depth of the
+    # record's taxon, from the oracle's superkmerPositions and records
+    cov_all, cov_dist = {}, {}
+    pieces, labels = oracle.remove_invalid(genomes, taxa)
+    seen = set()
+    for piece, t in zip(pieces, labels.tolist()):
+        if len(piece) < p.k:
+            continue
+        for _loc, rank_, _len in oracle.superkmers(p, piece):
+            lca = olib.lookup(rank_)
+            if lca:
+                d = tree.depth(lca)
+                cov_all[(t, d)] = cov_all.get((t, d), 0) + 1
+                if (t, rank_) not in seen:
+                    seen.add((t, rank_))
+                    cov_dist[(t, d)] = cov_dist.get((t, d), 0) + 1
+    for f, cov in zip(files[4:], (cov_all, cov_dist)):
+        want = "".join(f"{t}  " + "|".join(f"{d}:{cov[(tt, d)]}" for tt, d in sorted(cov) if tt == t) + "\n"
+                       for t in sorted({tt for tt, _ in cov}))
+        assert open(f + "/part-00000.txt").read() == want and len(want) > 0, f
+    files = files[:4]
     kmers, mins, dist = {}, {}, {}
     for i in range(len(ro) - 1):
         for minimizer, _distinct, n_kmers, flag in oracle.spans(p, bytes(rb[int(ro[i]):int(ro[i + 1])])):
