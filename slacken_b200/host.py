@@ -691,8 +691,10 @@ def pack_reads(bases: np.ndarray, off: np.ndarray) -> PackedReads:
 
 
 def pack_sequences(seqs):
-    """list of bytes/str -> (uint8 bases, uint64 offsets[n+1]): what the JVM side assembles in a pinned buffer."""
-    bs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in seqs]
+    """list of bytes/str -> (uint8 bases, uint64 offsets[n+1]): what the JVM side assembles in a pinned buffer. Line breaks
+    inside a sequence are dropped here, as the reference's scanner skips them (kmers/minimizer/ShiftScanner.scala:113-120):
+    the device input is one sequence per offset range, without line breaks."""
+    bs = [(s.encode("latin-1") if isinstance(s, str) else bytes(s)).translate(None, b"\n\r") for s in seqs]
     off = np.zeros(len(bs) + 1, dtype=np.uint64)
     if bs:
         off[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)

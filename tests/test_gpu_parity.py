@@ -349,3 +349,35 @@ def test_fp64_pipe_minimum_is_the_integer_minimum(gpu):
     v = lambda z: z.ctypes.data_as(C.c_void_p)
     check(gpu._L.slk_debug_min62(gpu.h, v(a), v(b), len(a), v(out)))
     assert np.array_equal(out, np.minimum(a, b))
+
+
+def test_line_breaks_inside_sequences(gpu):
+    """kmers/minimizer/ShiftScanner.scala:113-120: line breaks inside a sequence (multi-line FASTA records) are skipped by the
+    reference's scanner. The oracle restates that and sees the raw reads and genomes; on this side pack_sequences drops the
+    line breaks while it assembles the device buffers, in the library build as in the classification."""
+    rng, parents, ranks, names, genomes, taxa = make_world(27)
+    p = oracle.params()
+
+    def wrap(s, width):
+        return b"\n".join(s[i:i + width] for i in range(0, len(s), width)) + (b"\r\n" if len(s) % 2 else b"")
+    raw_genomes = [wrap(g, 60) for g in genomes]
+    olib = oracle_lib(p, parents, raw_genomes, taxa)
+    tax = Taxonomy(gpu, parents, ranks, names)
+    gb, go = pack_sequences(raw_genomes)
+    assert int(go[-1]) == sum(len(g) for g in genomes)
+    index = KeyValueIndex.build(gpu, tax, IndexParams(), [(gb, go, taxa)], expected_bases=len(gb))
+    oid, otx = olib.records()
+    gid, gtx = index.records()
+    assert np.array_equal(oid, gid) and np.array_equal(otx, gtx)
+    # no ambiguous stretches in these reads: a line break INSIDE a run of N splits the run for the reference (each part
+    # then counts its own k-mers, and parts shorter than k count none), whereas dropping the line break joins it -- the one
+    # place where the two differ, see DESIGN.md section 9
+    reads = simulate_reads(rng, genomes, 1500, (40, 260), n_rate=0.0)
+    raw_reads = [wrap(r, int(rng.integers(7, 80))) for r in reads]
+    rb, ro = pack_sequences(raw_reads)
+    ob, oo = oracle.pack_sequences(raw_reads)
+    cls = Classifier(index)
+    got = cls.classify(rb, ro, confidence=0.05)
+    res, _, _, per = olib.classify(ob, oo, confidence=0.05)
+    assert_batch_equal(res, per, got, 35)
+    cls.close(); index.close(); tax.close()
