@@ -477,6 +477,14 @@ def run_ours(args, w):
         gi = np.repeat(single_out.detail["hit_off"].astype(np.int64), ccnt) + within
         same_c = bool(np.array_equal(cout.hits[:cout.hits_used], single_out.hits[gi]))
     e2e_compact["equal_to_packed_entry_point"] = same_c
+    # The headline end-to-end figure: the faster of the two host-buffer entry points that deliver the full per-read output
+    # (taxon, flags, lengths, merged hit lists -- checked identical just above). Which one wins depends on what bounds the
+    # box: the packed one on a single GPU (fewer kernels per chunk), the compact one when several GPUs share the host's
+    # memory bandwidth (91 instead of 131 bytes per read across PCIe). Both stay in the line under their own keys.
+    e2e_packed = e2e
+    e2e = dict(e2e_compact if same_c and e2e_compact["value"] > e2e_packed["value"] else e2e_packed)
+    e2e.pop("equal_to_packed_entry_point", None)
+    e2e["chosen_from"] = {"slk_classify_batch_packed": e2e_packed["value"], "slk_classify_batch_compact": e2e_compact["value"]}
 
     # ================================================================== leg 2: configs[3] shape, paired-end 2 x 150 bp, confidence 0.15
     m2 = Mate(1)
@@ -518,7 +526,7 @@ def run_ours(args, w):
                        "classified_fraction": float((rep.sum() - rep[0]) / max(1, rep.sum())),
                        "reads_counted_in_report": total_reads_counted,
                        "device_report_counters_equal_per_read_results": report_consistent},
-            "probes_per_s": value * S, "clocks": clocks, "e2e": e2e, "e2e_compact": e2e_compact, "e2e_compact_report_only": e2e_compact_report, "e2e_report_only": e2e_report, "e2e_ascii_input": e2e_ascii,
+            "probes_per_s": value * S, "clocks": clocks, "e2e": e2e, "e2e_packed": e2e_packed, "e2e_compact": e2e_compact, "e2e_compact_report_only": e2e_compact_report, "e2e_report_only": e2e_report, "e2e_ascii_input": e2e_ascii,
             "value_ascii_input": {"value": world * n * args.steps / (ms_ascii / 1e3), "unit": "reads/s", "ms_per_step": ms_ascii / args.steps,
                                   "note": "same launch with ASCII reads resident in HBM (stage 1 runs first as its own kernel)"},
             "encode_kernel": {"ms": 1e3 * t_pack, "reads_per_s": n / t_pack, "gbs": (L + 8 + 12.0 * n_blocks / n + 4) * n / t_pack / 1e9,
