@@ -457,11 +457,21 @@ def run_ours(args, w):
     e2e_compact_report = {"value": world * n * args.steps / cr_s, "unit": "reads/s", "h2d_bytes_per_step": int(cr1.nbytes),
                           "d2h_bytes_per_step": int(cout.results.nbytes), "ms_per_step": 1e3 * cr_s / args.steps,
                           "api": "slk_classify_batch_compact without hit lists: 16 bytes per read come back"}
+    # the compact boundary with 4-byte hits (label << 16 | k-mers): 76 bytes per read across PCIe instead of 91
+    cout4 = CompactBatch(ctx.pinned(n, RESULT_DTYPE), np.zeros((0, n), dtype=np.int32), np.zeros((0, n), dtype=np.uint8),
+                         ctx.pinned(e2e_cap, np.uint32))
+    c4s, c4t0, c4t1 = timed_e2e(lambda: cls.classify_compact(cr1, None, thresholds=[w.confidence], min_hit_groups=w.min_hit_groups,
+                                                             out=cout4, short_hits=True))
+    e2e_compact_short = {"value": world * n * args.steps / c4s, "unit": "reads/s", "h2d_bytes_per_step": int(cr1.nbytes),
+                         "d2h_bytes_per_step": int(cout4.results.nbytes + cout4.hits_used * 4), "ms_per_step": 1e3 * c4s / args.steps,
+                         "api": "slk_classify_batch_compact_short: as slk_classify_batch_compact, hits as 4-byte words (index into the "
+                                "library's taxon list << 16 | k-mers)",
+                         "equal_to_packed_entry_point": None, "clocks": ClockSampler.summarize(sampler.window(c4t0, c4t1))}
     if quick_e2e:
         sampler.stop()
         if rank == 0:
             print(json.dumps({"e2e_quick": True, "so": os.environ.get("SLK_SO", "libslacken_gpu.so"), "value": value,
-                              "e2e": e2e["value"], "e2e_compact": e2e_compact["value"],
+                              "e2e": e2e["value"], "e2e_compact": e2e_compact["value"], "e2e_compact_short": e2e_compact_short["value"],
                               "e2e_compact_report_only": e2e_compact_report["value"]}), flush=True)
         return
     # `out` now holds the single-end results of the whole batch (the CPU leg below checks a sample of them)
@@ -477,14 +487,24 @@ def run_ours(args, w):
         gi = np.repeat(single_out.detail["hit_off"].astype(np.int64), ccnt) + within
         same_c = bool(np.array_equal(cout.hits[:cout.hits_used], single_out.hits[gi]))
     e2e_compact["equal_to_packed_entry_point"] = same_c
-    # The headline end-to-end figure: the faster of the two host-buffer entry points that deliver the full per-read output
+    dec4 = cout4.decode_short_hits(index.taxa(), w.k)
+    same_c4 = bool(same_c and cout4.hits_used == cout.hits_used and np.array_equal(cout4.results, cout.results) and
+                   np.array_equal(dec4["taxon"], cout.hits[:cout.hits_used]["taxon"]) and
+                   np.array_equal(dec4["count"], cout.hits[:cout.hits_used]["count"]))
+    e2e_compact_short["equal_to_packed_entry_point"] = same_c4
+    # The headline end-to-end figure: the fastest of the host-buffer entry points that deliver the full per-read output
     # (taxon, flags, lengths, merged hit lists -- checked identical just above). Which one wins depends on what bounds the
     # box: the packed one on a single GPU (fewer kernels per chunk), the compact one when several GPUs share the host's
     # memory bandwidth (91 instead of 131 bytes per read across PCIe). Both stay in the line under their own keys.
     e2e_packed = e2e
-    e2e = dict(e2e_compact if same_c and e2e_compact["value"] > e2e_packed["value"] else e2e_packed)
+    e2e = e2e_packed
+    for cand, ok in ((e2e_compact, same_c), (e2e_compact_short, same_c4)):
+        if ok and cand["value"] > e2e["value"]:
+            e2e = cand
+    e2e = dict(e2e)
     e2e.pop("equal_to_packed_entry_point", None)
-    e2e["chosen_from"] = {"slk_classify_batch_packed": e2e_packed["value"], "slk_classify_batch_compact": e2e_compact["value"]}
+    e2e["chosen_from"] = {"slk_classify_batch_packed": e2e_packed["value"], "slk_classify_batch_compact": e2e_compact["value"],
+                          "slk_classify_batch_compact_short": e2e_compact_short["value"]}
 
     # ================================================================== leg 2: configs[3] shape, paired-end 2 x 150 bp, confidence 0.15
     m2 = Mate(1)
@@ -526,7 +546,7 @@ def run_ours(args, w):
                        "classified_fraction": float((rep.sum() - rep[0]) / max(1, rep.sum())),
                        "reads_counted_in_report": total_reads_counted,
                        "device_report_counters_equal_per_read_results": report_consistent},
-            "probes_per_s": value * S, "clocks": clocks, "e2e": e2e, "e2e_packed": e2e_packed, "e2e_compact": e2e_compact, "e2e_compact_report_only": e2e_compact_report, "e2e_report_only": e2e_report, "e2e_ascii_input": e2e_ascii,
+            "probes_per_s": value * S, "clocks": clocks, "e2e": e2e, "e2e_packed": e2e_packed, "e2e_compact": e2e_compact, "e2e_compact_short": e2e_compact_short, "e2e_compact_report_only": e2e_compact_report, "e2e_report_only": e2e_report, "e2e_ascii_input": e2e_ascii,
             "value_ascii_input": {"value": world * n * args.steps / (ms_ascii / 1e3), "unit": "reads/s", "ms_per_step": ms_ascii / args.steps,
                                   "note": "same launch with ASCII reads resident in HBM (stage 1 runs first as its own kernel)"},
             "encode_kernel": {"ms": 1e3 * t_pack, "reads_per_s": n / t_pack, "gbs": (L + 8 + 12.0 * n_blocks / n + 4) * n / t_pack / 1e9,

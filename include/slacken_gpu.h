@@ -197,6 +197,14 @@ SLK_API int slk_classify_batch_compact(slk_classifier* c, const slk_classify_mul
                               const uint64_t* codes1, const uint32_t* len1, const uint64_t* codes2, const uint32_t* len2,
                               const uint64_t* ambiguous, uint64_t n_ambiguous, uint32_t n_reads, slk_read_result* results_out,
                               int32_t* taxon_more, uint8_t* flags_more, slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_used);
+/* The same with 4-byte hits (76 instead of 91 bytes per 150-base read across PCIe): a hit is (label << 16 | k-mers), where
+ * label 0 = no record, 1..65534 = the taxon at position label - 1 of slk_index_taxa's list, 0xFFFF = an ambiguous span;
+ * the word 0xFFFFFFFF is the mate-pair border (whose count is -(k - 1), slacken/Classifier.scala:439-454). A merged hit of
+ * 65 535 or more k-mers does not fit: SLK_E_UNSUPPORTED, use slk_classify_batch_compact for such reads. */
+SLK_API int slk_classify_batch_compact_short(slk_classifier* c, const slk_classify_multi_opts* opts,
+                              const uint64_t* codes1, const uint32_t* len1, const uint64_t* codes2, const uint32_t* len2,
+                              const uint64_t* ambiguous, uint64_t n_ambiguous, uint32_t n_reads, slk_read_result* results_out,
+                              int32_t* taxon_more, uint8_t* flags_more, uint32_t* hits_out, uint64_t hits_cap, uint64_t* hits_used);
 SLK_API int slk_classify_packed_dev(slk_classifier* c, const slk_classify_opts* opts,
                             const uint64_t* codes1, const uint32_t* mask1, const uint64_t* boff1, const uint32_t* len1,
                             const uint64_t* codes2, const uint32_t* mask2, const uint64_t* boff2, const uint32_t* len2,

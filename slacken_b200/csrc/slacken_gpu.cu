@@ -1082,6 +1082,7 @@ struct slk_classifier {
   uint64_t dv_blocks[2] = {0, 0}, dv_reads[2] = {0, 0};
   unsigned long long* d_cursor = nullptr;
   uint32_t* d_err = nullptr;
+  uint16_t* d_r2d = nullptr;   // raw -> dense taxon, for the 4-byte hits of slk_classify_batch_compact_short (made on first use)
   unsigned long long* d_stats = nullptr;  // [0] probes, [1] merged hits, accumulated over launches
   slk_counts* counts = nullptr;
   int32_t counts_sample = 0;
@@ -1152,7 +1153,7 @@ extern "C" void slk_classifier_destroy(slk_classifier* c) {
     cudaEventDestroy(c->slot[i].h2d_done); cudaEventDestroy(c->slot[i].k_done); cudaEventDestroy(c->slot[i].d2h_done);
     cudaEventDestroy(c->slot[i].copied_in); cudaEventDestroy(c->slot[i].post_done);
   }
-  cudaFree(c->d_cursor); cudaFree(c->d_err); cudaFree(c->d_stats);
+  cudaFree(c->d_cursor); cudaFree(c->d_err); cudaFree(c->d_stats); cudaFree(c->d_r2d);
   for (int m = 0; m < 2; m++) { cudaFree(c->dv_codes[m]); cudaFree(c->dv_boff[m]); cudaFree(c->dv_mask[m]); cudaFree(c->dv_len[m]); }
   cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_k); cudaStreamDestroy(c->s_d2h);
   cudaStreamDestroy(c->s_prep); cudaStreamDestroy(c->s_post); cudaStreamDestroy(c->s_k2);
@@ -1672,7 +1673,8 @@ __global__ void __launch_bounds__(256) compact_results_kernel(const int32_t* __r
                                                               const slk_read_detail* __restrict__ detail, uint32_t n,
                                                               const uint64_t* __restrict__ hoff, const slk_hit* __restrict__ hits,
                                                               const unsigned long long* __restrict__ lo, uint64_t cap, slk_hit* __restrict__ ord,
-                                                              slk_read_result* __restrict__ res) {
+                                                              slk_read_result* __restrict__ res, const uint16_t* __restrict__ r2d,
+                                                              uint32_t* __restrict__ err) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const slk_read_detail d = detail[i];
@@ -1681,17 +1683,41 @@ __global__ void __launch_bounds__(256) compact_results_kernel(const int32_t* __r
   res[i] = r;
   if (hits != nullptr) {
     const uint64_t src = d.hit_off - *lo, dst = hoff[i];
-    for (uint32_t j = 0; j < d.hit_cnt; j++)
-      if (src + j < cap && dst + j < cap) ord[dst + j] = hits[src + j];
+    if (r2d == nullptr) {
+      for (uint32_t j = 0; j < d.hit_cnt; j++)
+        if (src + j < cap && dst + j < cap) ord[dst + j] = hits[src + j];
+    } else {   // 4-byte hits (slk_classify_batch_compact_short): dense taxon << 16 | k-mers
+      uint32_t* ord4 = reinterpret_cast<uint32_t*>(ord);
+      for (uint32_t j = 0; j < d.hit_cnt; j++) {
+        if (src + j >= cap || dst + j >= cap) continue;
+        const slk_hit h = hits[src + j];
+        uint32_t wd;
+        if (h.taxon == SLK_MATE_PAIR_BORDER) wd = 0xFFFFFFFFu;
+        else {
+          if ((uint32_t)h.count >= 0xFFFFu) atomicOr(err, 4u);
+          wd = ((h.taxon == SLK_AMBIGUOUS_SPAN ? 0xFFFFu : (uint32_t)r2d[h.taxon]) << 16) | ((uint32_t)h.count & 0xFFFFu);
+        }
+        ord4[dst + j] = wd;
+      }
+    }
   }
 }
 
-extern "C" int slk_classify_batch_compact(slk_classifier* c, const slk_classify_multi_opts* opts_in, const uint64_t* codes1,
-                                          const uint32_t* len1, const uint64_t* codes2, const uint32_t* len2, const uint64_t* ambiguous,
-                                          uint64_t n_ambiguous, uint32_t n_reads, slk_read_result* results_out, int32_t* taxon_more,
-                                          uint8_t* flags_more, slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_used) {
+static int classify_compact_impl(slk_classifier* c, const slk_classify_multi_opts* opts_in, const uint64_t* codes1,
+                                 const uint32_t* len1, const uint64_t* codes2, const uint32_t* len2, const uint64_t* ambiguous,
+                                 uint64_t n_ambiguous, uint32_t n_reads, slk_read_result* results_out, int32_t* taxon_more,
+                                 uint8_t* flags_more, void* hits_out, bool short_hits, uint64_t hits_cap, uint64_t* hits_used) {
   if (!c || !opts_in || !codes1 || !len1 || !results_out || (codes2 != nullptr) != (len2 != nullptr) || (n_ambiguous && !ambiguous))
     return fail(SLK_E_INVALID, "bad arguments");
+  const size_t hit_bytes = short_hits ? 4 : sizeof(slk_hit);
+  if (short_hits && hits_out && !c->d_r2d) {
+    const slk_index* idx = c->idx;
+    std::vector<uint16_t> r2d(idx->tax->parents.size(), 0);
+    for (auto& kv : idx->dt.to_dense) r2d[kv.first] = (uint16_t)kv.second;
+    CU(cudaSetDevice(c->ctx->device));
+    CU(cudaMalloc(&c->d_r2d, r2d.size() * 2));
+    CU(cudaMemcpy(c->d_r2d, r2d.data(), r2d.size() * 2, cudaMemcpyHostToDevice));
+  }
   if (kernel_generation() != 2) return fail(SLK_E_UNSUPPORTED, "the compact entry point needs the second-generation kernel");
   cls_opts opts;
   TRY(make_opts(opts_in, CH_READS, &opts));
@@ -1739,7 +1765,7 @@ extern "C" int slk_classify_batch_compact(slk_classifier* c, const slk_classify_
       if (slk_exclusive_scan_u64_async(s.hoff, (uint64_t)s.n + 1, s.scan_scr + SCAN_SCR_WORDS, c->s_post) != 0) return fail(SLK_E_CUDA, "prefix sum of the hit counts failed");
     }
     compact_results_kernel<<<(s.n + 255) / 256, 256, 0, c->s_post>>>(s.taxon, s.flags, s.detail, s.n, s.hoff, hits ? s.hits : nullptr, s.d_range,
-                                                                      s.hits_cap, s.hits_ord, s.res16);
+                                                                      s.hits_cap, s.hits_ord, s.res16, short_hits ? c->d_r2d : nullptr, c->d_err);
     CU(cudaGetLastError());
     CU(cudaEventRecord(s.post_done, c->s_post));
     CU(cudaStreamWaitEvent(c->s_d2h, s.post_done, 0));
@@ -1751,7 +1777,7 @@ extern "C" int slk_classify_batch_compact(slk_classifier* c, const slk_classify_
     if (hits) {
       uint64_t used = cnt;
       if (hits_total + used > hits_cap) { nospace = true; used = hits_cap > hits_total ? hits_cap - hits_total : 0; }
-      if (used) CU(cudaMemcpyAsync(hits_out + hits_total, s.hits_ord, (size_t)used * sizeof(slk_hit), cudaMemcpyDeviceToHost, c->s_d2h));
+      if (used) CU(cudaMemcpyAsync(static_cast<uint8_t*>(hits_out) + hits_total * hit_bytes, s.hits_ord, (size_t)used * hit_bytes, cudaMemcpyDeviceToHost, c->s_d2h));
       hits_total += cnt;
     }
     CU(cudaEventRecord(s.d2h_done, c->s_d2h));
@@ -1868,10 +1894,26 @@ extern "C" int slk_classify_batch_compact(slk_classifier* c, const slk_classify_
     uint32_t err = 0;
     CU(cudaMemcpy(&err, c->d_err, 4, cudaMemcpyDeviceToHost));
     if (err & 2u) { CU(cudaMemset(c->d_err, 0, 4)); return fail(SLK_E_INVALID, "an ambiguity entry names a read or position outside its chunk"); }
+    if (err & 4u) { CU(cudaMemset(c->d_err, 0, 4)); return fail(SLK_E_UNSUPPORTED, "a merged hit of 65 535 or more k-mers does not fit the 4-byte hit format: use slk_classify_batch_compact"); }
   }
   TRY(check_error_flag(c));
   if (nospace) return fail(SLK_E_NOSPACE, "hits_out needs room for %llu hits", (unsigned long long)hits_total);
   return SLK_OK;
+}
+extern "C" int slk_classify_batch_compact(slk_classifier* c, const slk_classify_multi_opts* opts_in, const uint64_t* codes1,
+                                          const uint32_t* len1, const uint64_t* codes2, const uint32_t* len2, const uint64_t* ambiguous,
+                                          uint64_t n_ambiguous, uint32_t n_reads, slk_read_result* results_out, int32_t* taxon_more,
+                                          uint8_t* flags_more, slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_used) {
+  return classify_compact_impl(c, opts_in, codes1, len1, codes2, len2, ambiguous, n_ambiguous, n_reads, results_out, taxon_more,
+                               flags_more, hits_out, false, hits_cap, hits_used);
+}
+extern "C" int slk_classify_batch_compact_short(slk_classifier* c, const slk_classify_multi_opts* opts_in, const uint64_t* codes1,
+                                                const uint32_t* len1, const uint64_t* codes2, const uint32_t* len2,
+                                                const uint64_t* ambiguous, uint64_t n_ambiguous, uint32_t n_reads,
+                                                slk_read_result* results_out, int32_t* taxon_more, uint8_t* flags_more,
+                                                uint32_t* hits_out, uint64_t hits_cap, uint64_t* hits_used) {
+  return classify_compact_impl(c, opts_in, codes1, len1, codes2, len2, ambiguous, n_ambiguous, n_reads, results_out, taxon_more,
+                               flags_more, hits_out, true, hits_cap, hits_used);
 }
 
 extern "C" int slk_classify_batch(slk_classifier* c, const slk_classify_opts* opts, const uint8_t* bases1, const uint64_t* off1,

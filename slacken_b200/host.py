@@ -199,6 +199,15 @@ class KeyValueIndex:
     def __len__(self) -> int:
         return int(self.ctx._L.slk_index_size(self.h))
 
+    def taxa(self) -> np.ndarray:
+        """The raw taxon ids this index can answer with, ancestors included (slk_index_taxa); position i holds the taxon that
+        the 4-byte hit format calls label i + 1."""
+        n = C.c_uint32()
+        check(self.ctx._L.slk_index_taxa(self.h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.int32)
+        check(self.ctx._L.slk_index_taxa(self.h, _ptr(out), n.value, C.byref(n)))
+        return out
+
     def records(self, sort: bool = True):
         """(id1 uint64[], taxon int32[]) -- the rows KeyValueIndex.writeRecords stores; sorted by id1 on request
         (the table itself has no order)."""
@@ -511,26 +520,31 @@ class Classifier:
         return taxon, flags, detail, hits, int(used.value)
 
     def classify_compact(self, r1: "CompactReads", r2: Optional["CompactReads"] = None, thresholds: Sequence[float] = (0.0,),
-                         min_hit_groups: int = 2, per_read_output: bool = True, out: Optional["CompactBatch"] = None) -> "CompactBatch":
+                         min_hit_groups: int = 2, per_read_output: bool = True, out: Optional["CompactBatch"] = None,
+                         short_hits: bool = False) -> "CompactBatch":
         """The compact boundary (include/slacken_gpu.h, slk_classify_batch_compact): codes + lengths + a sparse list of
-        ambiguous positions in, 16-byte results + hits in read order out."""
+        ambiguous positions in, 16-byte results + hits in read order out. short_hits: 4-byte hits
+        (slk_classify_batch_compact_short; out.hits is then a uint32 array, see CompactBatch.decode_short_hits)."""
         n, nt = len(r1.len), len(thresholds)
         if out is None:
             hits = None
             if per_read_output:
                 total = int(r1.len.sum()) + (int(r2.len.sum()) if r2 is not None else 0)
-                hits = np.zeros(self.hits_bound(n, total, r2 is not None), dtype=HIT_DTYPE)
+                hits = np.zeros(self.hits_bound(n, total, r2 is not None), dtype=np.uint32 if short_hits else HIT_DTYPE)
             out = CompactBatch(np.zeros(n, dtype=RESULT_DTYPE), np.zeros((max(nt - 1, 0), n), dtype=np.int32),
                                np.zeros((max(nt - 1, 0), n), dtype=np.uint8), hits)
         amb = merge_ambiguous(r1, r2)
         o = self._multi_opts(thresholds, min_hit_groups)
         used = C.c_uint64(0)
         hits = out.hits if per_read_output else None
-        check(self.ctx._L.slk_classify_batch_compact(self.h, C.byref(o), _ptr(r1.codes), _ptr(r1.len), _ptr(r2.codes) if r2 is not None else None,
-                                                     _ptr(r2.len) if r2 is not None else None, _ptr(amb) if len(amb) else None, len(amb), n,
-                                                     _ptr(out.results), _ptr(out.taxon_more) if nt > 1 else None,
-                                                     _ptr(out.flags_more) if nt > 1 else None, _ptr(hits),
-                                                     len(hits) if hits is not None else 0, C.byref(used)))
+        if hits is not None:
+            assert hits.dtype == (np.uint32 if short_hits else HIT_DTYPE)
+        fn = self.ctx._L.slk_classify_batch_compact_short if short_hits else self.ctx._L.slk_classify_batch_compact
+        check(fn(self.h, C.byref(o), _ptr(r1.codes), _ptr(r1.len), _ptr(r2.codes) if r2 is not None else None,
+                 _ptr(r2.len) if r2 is not None else None, _ptr(amb) if len(amb) else None, len(amb), n,
+                 _ptr(out.results), _ptr(out.taxon_more) if nt > 1 else None,
+                 _ptr(out.flags_more) if nt > 1 else None, _ptr(hits),
+                 len(hits) if hits is not None else 0, C.byref(used)))
         out.hits_used = int(used.value)
         return out
 
@@ -630,6 +644,18 @@ class CompactBatch:
     @property
     def hit_cnt(self):
         return self.results["hits_flags"] >> 2
+
+    def decode_short_hits(self, index_taxa: np.ndarray, k: int) -> np.ndarray:
+        """4-byte hits (slk_classify_batch_compact_short) -> HIT_DTYPE records: index_taxa = KeyValueIndex.taxa() (the list of
+        slk_index_taxa), k = the k-mer width (the mate-pair border's count is -(k - 1))."""
+        w = self.hits[:self.hits_used].astype(np.uint32)
+        label, count = (w >> 16).astype(np.int64), (w & 0xFFFF).astype(np.int32)
+        raw = np.concatenate([[0], np.asarray(index_taxa, dtype=np.int64), [0]])   # label 0 = no record; the pad is never read
+        out = np.zeros(len(w), dtype=HIT_DTYPE)
+        amb, border = label == 0xFFFF, w == 0xFFFFFFFF
+        out["taxon"] = np.where(border, -2, np.where(amb, -1, raw[np.minimum(label, len(raw) - 1)]))
+        out["count"] = np.where(border, -(k - 1), count)
+        return out
 
 
 def compact_reads(p: "PackedReads") -> CompactReads:

@@ -146,4 +146,12 @@ def test_compact_boundary_equals_the_oracle(gpu):
             assert np.array_equal(h["taxon"], per[i]["taxon"]) and np.array_equal(h["count"], per[i]["count"]), i
         lean = cls.classify_compact(r1, r2, thresholds=thr[:1], per_read_output=False)
         assert np.array_equal(lean.taxon, got.taxon) and np.array_equal(lean.flags, got.flags)
+        # the same with 4-byte hits (slk_classify_batch_compact_short)
+        short = cls.classify_compact(r1, r2, thresholds=thr[:1], short_hits=True)
+        assert short.hits.dtype == np.uint32 and short.hits_used == got.hits_used and np.array_equal(short.results, got.results)
+        dec = short.decode_short_hits(index.taxa(), 35)
+        assert np.array_equal(dec["taxon"], got.hits[:got.hits_used]["taxon"])
+        assert np.array_equal(dec["count"], got.hits[:got.hits_used]["count"])
+        if paired:
+            assert (dec["taxon"] == -2).sum() > 0 and (dec["taxon"] == -1).sum() > 0
     cls.close(); index.close(); tax.close()
