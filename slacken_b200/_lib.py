@@ -71,8 +71,9 @@ SIGNATURES = {
     "slk_classify_batch_packed_multi": (_INT, [_VP, C.POINTER(ClassifyMultiOpts), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP, _VP,
                                                _VP, _VP, _U64, C.POINTER(_U64)]),
     "slk_classify_batch_compact": (_INT, [_VP, C.POINTER(ClassifyMultiOpts), _VP, _VP, _VP, _VP, _VP, _U64, _U32, _VP, _VP, _VP, _VP, _U64,
-    "slk_classify_batch_compact_short": (_INT, [_VP, C.POINTER(ClassifyMultiOpts), _VP, _VP, _VP, _VP, _VP, _U64, _U32, _VP, _VP, _VP, _VP, _U64,
                                           C.POINTER(_U64)]),
+    "slk_classify_batch_compact_short": (_INT, [_VP, C.POINTER(ClassifyMultiOpts), _VP, _VP, _VP, _VP, _VP, _U64, _U32, _VP, _VP, _VP, _VP,
+                                                _U64, C.POINTER(_U64)]),
     "slk_classify_packed_dev": (_INT, [_VP, C.POINTER(ClassifyOpts), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP, _VP,
                                        _VP, _VP, _U64, _VP]),
     "slk_pack_reads_dev": (_INT, [_VP, _VP, _VP, _U32, _VP, _VP, _VP, _VP]),
