@@ -929,6 +929,43 @@ extern "C" int slk_build_dense_taxa(slk_builder* b, int32_t* raw_out, uint32_t c
   return SLK_OK;
 }
 
+// The runs an owner receives are each ordered by table line. Inserted one after the other they would sweep the whole
+// table once per run; cut at the same line boundaries instead (regions of ~64 MB of table, which the L2 holds), region g
+// of every run is inserted before region g + 1 of any: one sweep of the table whatever the number of runs.
+// bounds[r * (R + 1) + g] = first cell of run r whose line is >= g * lines_per_region (the runs are ordered up to the
+// block shuffling of the reduce, which only blurs the cuts).
+__global__ void run_region_bounds_kernel(const uint64_t* __restrict__ cells, const uint64_t* __restrict__ run_first, uint32_t n_runs,
+                                         uint32_t n_regions, uint64_t lines_per_region, slk_table_view tb, uint64_t* __restrict__ bounds) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_runs * (n_regions + 1)) return;
+  const uint32_t r = i / (n_regions + 1), g = i % (n_regions + 1);
+  const uint64_t* run = cells + run_first[r];
+  uint64_t lo = 0, hi = run_first[r + 1] - run_first[r];
+  const uint64_t want = (uint64_t)g * lines_per_region;
+  while (g < n_regions && lo < hi) {
+    const uint64_t mid = lo + (hi - lo) / 2;
+    if ((slk_bucket_of(run[mid] >> 16, tb) >> 2) < want) lo = mid + 1; else hi = mid;
+  }
+  bounds[i] = g < n_regions ? lo : hi;
+}
+// thread i inserts cell number i of the region-major order: seg_first[s] <= i < seg_first[s + 1] names its segment
+__global__ void __launch_bounds__(256) insert_segments_kernel(const uint64_t* __restrict__ cells, uint64_t n, const uint64_t* __restrict__ seg_first,
+                                                              const uint64_t* __restrict__ seg_src, const uint32_t* __restrict__ seg_map,
+                                                              uint32_t n_seg, const uint16_t* __restrict__ maps, slk_table_view tb,
+                                                              slk_tax_view tx, unsigned long long* n_new) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool fresh = false;
+  if (i < n) {
+    uint32_t lo = 0, hi = n_seg;            // last segment with seg_first <= i
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) / 2; if (seg_first[mid] <= i) lo = mid; else hi = mid; }
+    uint64_t cell = cells[seg_src[lo] + (i - seg_first[lo])];
+    cell = (cell & ~0xffffull) | maps[seg_map[lo] + (cell & 0xffffu)];
+    fresh = insert_cell(cell, tb, tx, n_new);
+  }
+  const uint32_t cnt = (uint32_t)__syncthreads_count(fresh);
+  if (threadIdx.x == 0 && cnt) atomicAdd(n_new, (unsigned long long)cnt);
+}
+
 extern "C" int slk_index_from_cell_runs(slk_ctx* ctx, slk_tax* tax, const slk_params* params, uint32_t world, uint32_t n_runs,
                                         const uint64_t* cells_dev, const uint64_t* run_cells, const int32_t* dense_raw,
                                         const uint32_t* run_dense, slk_index** out) {
@@ -965,14 +1002,67 @@ extern "C" int slk_index_from_cell_runs(slk_ctx* ctx, slk_tax* tax, const slk_pa
   CUX(cudaMemsetAsync(d_new, 0, 8, ctx->stream));
   rc = table_alloc(&idx->table, total, world);
   if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
-  uint64_t co = 0, mo = 0;
-  for (uint32_t r = 0; r < n_runs; r++) {
-    const uint64_t c = run_cells[r];
-    if (c) {
-      rc = insert_cells(ctx, idx, cells_dev + co, c, d_new, d_maps + mo);
-      if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
+  const uint64_t n_lines = idx->table.n_buckets >> 2;
+  // SLK_REGION_SHIFT (tests): log2 of the region size in bytes, so that small tables take the interleaved path as well
+  const char* rs_env = getenv("SLK_REGION_SHIFT");
+  const int region_shift = rs_env ? std::min(30, std::max(8, atoi(rs_env))) : 26;
+  const uint32_t n_regions = (uint32_t)std::min<uint64_t>(1024, std::max<uint64_t>(1, (n_lines * 128) >> region_shift));
+  if (n_runs <= 1 || n_regions <= 1 || total == 0) {   // nothing to interleave
+    uint64_t co = 0, mo = 0;
+    for (uint32_t r = 0; r < n_runs; r++) {
+      const uint64_t c = run_cells[r];
+      if (c) {
+        rc = insert_cells(ctx, idx, cells_dev + co, c, d_new, d_maps + mo);
+        if (rc != SLK_OK) { cleanup(); slk_index_destroy(idx); return rc; }
+      }
+      co += c; mo += run_dense[r];
     }
-    co += c; mo += run_dense[r];
+  } else {
+    const uint64_t lines_per_region = (n_lines + n_regions - 1) / n_regions;
+    const uint32_t nb = n_runs * (n_regions + 1), n_seg = n_runs * n_regions;
+    std::vector<uint64_t> run_first(n_runs + 1, 0), bounds(nb), seg_first((size_t)n_seg + 1), seg_src(n_seg);
+    std::vector<uint32_t> seg_map(n_seg), map_off(n_runs, 0);
+    for (uint32_t r = 0; r < n_runs; r++) { run_first[r + 1] = run_first[r] + run_cells[r]; if (r) map_off[r] = map_off[r - 1] + run_dense[r - 1]; }
+    uint64_t* d_seg = nullptr;   // run_first | bounds, then seg_first | seg_src | seg_map
+    const size_t words = std::max<size_t>((size_t)n_runs + 1 + nb, 2 * (size_t)n_seg + 1 + (n_seg + 1) / 2 + 1);
+    auto cleanup2 = [&]() { cudaFree(d_seg); cleanup(); };
+#define CUY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup2(); slk_index_destroy(idx); \
+    return fail(e_ == cudaErrorMemoryAllocation ? SLK_E_NOMEM : SLK_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    CUY(cudaMalloc(&d_seg, words * 8));
+    CUY(cudaMemcpyAsync(d_seg, run_first.data(), ((size_t)n_runs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    run_region_bounds_kernel<<<(nb + 127) / 128, 128, 0, ctx->stream>>>(cells_dev, d_seg, n_runs, n_regions, lines_per_region, idx->table,
+                                                                          d_seg + n_runs + 1);
+    CUY(cudaGetLastError());
+    CUY(cudaMemcpyAsync(bounds.data(), d_seg + n_runs + 1, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUY(cudaStreamSynchronize(ctx->stream));
+    // the runs are ordered only up to the block shuffling of the reduce, so neighbouring searches may cross: make the
+    // cuts of a run monotone (they then partition the run exactly, whatever the searches found)
+    for (uint32_t r = 0; r < n_runs; r++) {
+      uint64_t* b = &bounds[(size_t)r * (n_regions + 1)];
+      b[0] = 0; b[n_regions] = run_cells[r];
+      for (uint32_t g = 1; g < n_regions; g++) b[g] = std::min<uint64_t>(std::max(b[g], b[g - 1]), run_cells[r]);
+    }
+    uint64_t at = 0;
+    for (uint32_t g = 0; g < n_regions; g++)
+      for (uint32_t r = 0; r < n_runs; r++) {
+        const uint32_t sgi = g * n_runs + r;
+        const uint64_t b0 = bounds[(size_t)r * (n_regions + 1) + g], b1 = bounds[(size_t)r * (n_regions + 1) + g + 1];
+        seg_first[sgi] = at; seg_src[sgi] = run_first[r] + b0; seg_map[sgi] = map_off[r];
+        at += b1 > b0 ? b1 - b0 : 0;
+      }
+    seg_first[n_seg] = at;
+    if (at != total) { cleanup2(); slk_index_destroy(idx); return fail(SLK_E_CUDA, "internal: the region cuts lose cells (%llu of %llu)", (unsigned long long)at, (unsigned long long)total); }
+    uint64_t* d_seg_first = d_seg; uint64_t* d_seg_src = d_seg + n_seg + 1;
+    uint32_t* d_seg_map = reinterpret_cast<uint32_t*>(d_seg + 2 * (size_t)n_seg + 1);
+    CUY(cudaMemcpyAsync(d_seg_first, seg_first.data(), ((size_t)n_seg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUY(cudaMemcpyAsync(d_seg_src, seg_src.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUY(cudaMemcpyAsync(d_seg_map, seg_map.data(), (size_t)n_seg * 4, cudaMemcpyHostToDevice, ctx->stream));
+    insert_segments_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(cells_dev, total, d_seg_first, d_seg_src, d_seg_map, n_seg,
+                                                                                      d_maps, idx->table, idx->dt.view(), d_new);
+    CUY(cudaGetLastError());
+    CUY(cudaStreamSynchronize(ctx->stream));
+#undef CUY
+    cudaFree(d_seg);
   }
   unsigned long long nn = 0;
   CUX(cudaMemcpyAsync(&nn, d_new, 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -282,8 +282,8 @@ def test_span_scan_one_pass_and_two_pass_agree(gpu, monkeypatch):
     ops.close(); cls.close(); shard.close(); tax.close()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_distributed_build_on_one_gpu(gpu, world):
+@pytest.mark.parametrize("world,region_shift", [(2, None), (3, None), (3, 10)])
+def test_distributed_build_on_one_gpu(gpu, world, region_shift, monkeypatch):
     """The distributed build (include/slacken_gpu.h, "Distributed build"; the shuffle of groupBy(idColumns).agg(udafLca),
     slacken/KeyValueIndex.scala:85-93) with one GPU playing every rank: rank r builds from the r-th block of genomes, reduces,
     hands over its cells grouped by owner; owner d receives the d-th group of every rank and inserts the runs. The shards'
@@ -291,6 +291,8 @@ def test_distributed_build_on_one_gpu(gpu, world):
     classify over them must equal the oracle."""
     import torch
     from slacken_b200 import LibraryBuilder
+    if region_shift is not None:   # 1 KB regions: the owner interleaves the runs region by region even on this small table
+        monkeypatch.setenv("SLK_REGION_SHIFT", str(region_shift))
     rng, parents, ranks, names, genomes, taxa = make_world(53)
     olib = oracle_lib(oracle.params(), parents, genomes, taxa)
     id1, tx = olib.records()
