@@ -457,15 +457,16 @@ def run_ours(args, w):
     e2e_compact_report = {"value": world * n * args.steps / cr_s, "unit": "reads/s", "h2d_bytes_per_step": int(cr1.nbytes),
                           "d2h_bytes_per_step": int(cout.results.nbytes), "ms_per_step": 1e3 * cr_s / args.steps,
                           "api": "slk_classify_batch_compact without hit lists: 16 bytes per read come back"}
-    # the compact boundary with 4-byte hits (label << 16 | k-mers): 76 bytes per read across PCIe instead of 91
-    cout4 = CompactBatch(ctx.pinned(n, RESULT_DTYPE), np.zeros((0, n), dtype=np.int32), np.zeros((0, n), dtype=np.uint8),
+    # the compact boundary with 4-byte hits (label << 16 | k-mers) and 8-byte results: 68 bytes per read across PCIe instead of 91
+    from slacken_b200.host import RESULT_SHORT_DTYPE
+    cout4 = CompactBatch(ctx.pinned(n, RESULT_SHORT_DTYPE), np.zeros((0, n), dtype=np.int32), np.zeros((0, n), dtype=np.uint8),
                          ctx.pinned(e2e_cap, np.uint32))
     c4s, c4t0, c4t1 = timed_e2e(lambda: cls.classify_compact(cr1, None, thresholds=[w.confidence], min_hit_groups=w.min_hit_groups,
                                                              out=cout4, short_hits=True))
     e2e_compact_short = {"value": world * n * args.steps / c4s, "unit": "reads/s", "h2d_bytes_per_step": int(cr1.nbytes),
                          "d2h_bytes_per_step": int(cout4.results.nbytes + cout4.hits_used * 4), "ms_per_step": 1e3 * c4s / args.steps,
                          "api": "slk_classify_batch_compact_short: as slk_classify_batch_compact, hits as 4-byte words (index into the "
-                                "library's taxon list << 16 | k-mers)",
+                                "library's taxon list << 16 | k-mers), 8-byte results (the lengths are what the hit list sums to)",
                          "equal_to_packed_entry_point": None, "clocks": ClockSampler.summarize(sampler.window(c4t0, c4t1))}
     if quick_e2e:
         sampler.stop()
@@ -488,7 +489,11 @@ def run_ours(args, w):
         same_c = bool(np.array_equal(cout.hits[:cout.hits_used], single_out.hits[gi]))
     e2e_compact["equal_to_packed_entry_point"] = same_c
     dec4 = cout4.decode_short_hits(index.taxa(), w.k)
-    same_c4 = bool(same_c and cout4.hits_used == cout.hits_used and np.array_equal(cout4.results, cout.results) and
+    l1_4, _ = cout4.lengths_from_hits(dec4, w.k, False)
+    hs4 = (cout.results["hits_flags"] & 2) != 0
+    same_c4 = bool(same_c and cout4.hits_used == cout.hits_used and np.array_equal(cout4.results["taxon"], cout.results["taxon"]) and
+                   np.array_equal(cout4.results["hits_flags"], cout.results["hits_flags"]) and
+                   np.array_equal(l1_4[hs4], cout.results["len1"][hs4]) and
                    np.array_equal(dec4["taxon"], cout.hits[:cout.hits_used]["taxon"]) and
                    np.array_equal(dec4["count"], cout.hits[:cout.hits_used]["count"]))
     e2e_compact_short["equal_to_packed_entry_point"] = same_c4

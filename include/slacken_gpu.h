@@ -197,13 +197,19 @@ SLK_API int slk_classify_batch_compact(slk_classifier* c, const slk_classify_mul
                               const uint64_t* codes1, const uint32_t* len1, const uint64_t* codes2, const uint32_t* len2,
                               const uint64_t* ambiguous, uint64_t n_ambiguous, uint32_t n_reads, slk_read_result* results_out,
                               int32_t* taxon_more, uint8_t* flags_more, slk_hit* hits_out, uint64_t hits_cap, uint64_t* hits_used);
-/* The same with 4-byte hits (76 instead of 91 bytes per 150-base read across PCIe): a hit is (label << 16 | k-mers), where
- * label 0 = no record, 1..65534 = the taxon at position label - 1 of slk_index_taxa's list, 0xFFFF = an ambiguous span;
- * the word 0xFFFFFFFF is the mate-pair border (whose count is -(k - 1), slacken/Classifier.scala:439-454). A merged hit of
- * 65 535 or more k-mers does not fit: SLK_E_UNSUPPORTED, use slk_classify_batch_compact for such reads. */
+/* The same with 4-byte hits and 8-byte results (68 instead of 91 bytes per 150-base read across PCIe): a hit is
+ * (label << 16 | k-mers), where label 0 = no record, 1..65534 = the taxon at position label - 1 of slk_index_taxa's list,
+ * 0xFFFF = an ambiguous span; the word 0xFFFFFFFF is the mate-pair border (whose count is -(k - 1),
+ * slacken/Classifier.scala:439-454). A merged hit of 65 535 or more k-mers does not fit: SLK_E_UNSUPPORTED, use
+ * slk_classify_batch_compact for such reads. The results leave the two length fields out: they are what the hit list sums to
+ * (len1 = k-mers of the hits before the border + k - 1, len2 likewise after it; slk_group.h / slacken/Classifier.scala:39-45). */
+typedef struct slk_read_result_short {
+  int32_t taxon;        /* raw taxon id, 0 = unclassified */
+  uint32_t hits_flags;  /* number of merged hits << 2 | SLK_READ_HAS_SPAN | SLK_READ_CLASSIFIED */
+} slk_read_result_short;
 SLK_API int slk_classify_batch_compact_short(slk_classifier* c, const slk_classify_multi_opts* opts,
                               const uint64_t* codes1, const uint32_t* len1, const uint64_t* codes2, const uint32_t* len2,
-                              const uint64_t* ambiguous, uint64_t n_ambiguous, uint32_t n_reads, slk_read_result* results_out,
+                              const uint64_t* ambiguous, uint64_t n_ambiguous, uint32_t n_reads, slk_read_result_short* results_out,
                               int32_t* taxon_more, uint8_t* flags_more, uint32_t* hits_out, uint64_t hits_cap, uint64_t* hits_used);
 SLK_API int slk_classify_packed_dev(slk_classifier* c, const slk_classify_opts* opts,
                             const uint64_t* codes1, const uint32_t* mask1, const uint64_t* boff1, const uint32_t* len1,

@@ -1770,7 +1770,8 @@ __global__ void __launch_bounds__(256) compact_results_kernel(const int32_t* __r
   const slk_read_detail d = detail[i];
   slk_read_result r;
   r.taxon = taxon[i]; r.len1 = d.len1; r.len2 = d.len2; r.hits_flags = (d.hit_cnt << 2) | (flags[i] & 3u);
-  res[i] = r;
+  if (r2d == nullptr) res[i] = r;
+  else reinterpret_cast<uint2*>(res)[i] = make_uint2((uint32_t)r.taxon, r.hits_flags);   // slk_read_result_short
   if (hits != nullptr) {
     const uint64_t src = d.hit_off - *lo, dst = hoff[i];
     if (r2d == nullptr) {
@@ -1795,12 +1796,13 @@ __global__ void __launch_bounds__(256) compact_results_kernel(const int32_t* __r
 
 static int classify_compact_impl(slk_classifier* c, const slk_classify_multi_opts* opts_in, const uint64_t* codes1,
                                  const uint32_t* len1, const uint64_t* codes2, const uint32_t* len2, const uint64_t* ambiguous,
-                                 uint64_t n_ambiguous, uint32_t n_reads, slk_read_result* results_out, int32_t* taxon_more,
+                                 uint64_t n_ambiguous, uint32_t n_reads, void* results_out, int32_t* taxon_more,
                                  uint8_t* flags_more, void* hits_out, bool short_hits, uint64_t hits_cap, uint64_t* hits_used) {
   if (!c || !opts_in || !codes1 || !len1 || !results_out || (codes2 != nullptr) != (len2 != nullptr) || (n_ambiguous && !ambiguous))
     return fail(SLK_E_INVALID, "bad arguments");
   const size_t hit_bytes = short_hits ? 4 : sizeof(slk_hit);
-  if (short_hits && hits_out && !c->d_r2d) {
+  const size_t res_bytes = short_hits ? sizeof(slk_read_result_short) : sizeof(slk_read_result);
+  if (short_hits && !c->d_r2d) {
     const slk_index* idx = c->idx;
     std::vector<uint16_t> r2d(idx->tax->parents.size(), 0);
     for (auto& kv : idx->dt.to_dense) r2d[kv.first] = (uint16_t)kv.second;
@@ -1859,7 +1861,7 @@ static int classify_compact_impl(slk_classifier* c, const slk_classify_multi_opt
     CU(cudaGetLastError());
     CU(cudaEventRecord(s.post_done, c->s_post));
     CU(cudaStreamWaitEvent(c->s_d2h, s.post_done, 0));
-    CU(cudaMemcpyAsync(results_out + s.r0, s.res16, (size_t)s.n * sizeof(slk_read_result), cudaMemcpyDeviceToHost, c->s_d2h));
+    CU(cudaMemcpyAsync(static_cast<uint8_t*>(results_out) + (size_t)s.r0 * res_bytes, s.res16, (size_t)s.n * res_bytes, cudaMemcpyDeviceToHost, c->s_d2h));
     for (uint32_t t = 1; t < opts.n; t++) {
       CU(cudaMemcpyAsync(taxon_more + (size_t)(t - 1) * n_reads + s.r0, s.taxon + (size_t)t * CH_READS, (size_t)s.n * 4, cudaMemcpyDeviceToHost, c->s_d2h));
       CU(cudaMemcpyAsync(flags_more + (size_t)(t - 1) * n_reads + s.r0, s.flags + (size_t)t * CH_READS, s.n, cudaMemcpyDeviceToHost, c->s_d2h));
@@ -2000,7 +2002,7 @@ extern "C" int slk_classify_batch_compact(slk_classifier* c, const slk_classify_
 extern "C" int slk_classify_batch_compact_short(slk_classifier* c, const slk_classify_multi_opts* opts_in, const uint64_t* codes1,
                                                 const uint32_t* len1, const uint64_t* codes2, const uint32_t* len2,
                                                 const uint64_t* ambiguous, uint64_t n_ambiguous, uint32_t n_reads,
-                                                slk_read_result* results_out, int32_t* taxon_more, uint8_t* flags_more,
+                                                slk_read_result_short* results_out, int32_t* taxon_more, uint8_t* flags_more,
                                                 uint32_t* hits_out, uint64_t hits_cap, uint64_t* hits_used) {
   return classify_compact_impl(c, opts_in, codes1, len1, codes2, len2, ambiguous, n_ambiguous, n_reads, results_out, taxon_more,
                                flags_more, hits_out, true, hits_cap, hits_used);

@@ -19,6 +19,7 @@ HIT_DTYPE = np.dtype([("taxon", "<i4"), ("count", "<i4")])
 DETAIL_DTYPE = np.dtype([("hit_off", "<u8"), ("hit_cnt", "<u4"), ("len1", "<u4"), ("len2", "<u4"), ("num_distinct", "<u4")])
 assert DETAIL_DTYPE.itemsize == 24
 RESULT_DTYPE = np.dtype([("taxon", "<i4"), ("len1", "<u4"), ("len2", "<u4"), ("hits_flags", "<u4")])   # slk_read_result
+RESULT_SHORT_DTYPE = np.dtype([("taxon", "<i4"), ("hits_flags", "<u4")])                                # slk_read_result_short
 
 
 def _ptr(a) -> Optional[C.c_void_p]:
@@ -523,20 +524,22 @@ class Classifier:
                          min_hit_groups: int = 2, per_read_output: bool = True, out: Optional["CompactBatch"] = None,
                          short_hits: bool = False) -> "CompactBatch":
         """The compact boundary (include/slacken_gpu.h, slk_classify_batch_compact): codes + lengths + a sparse list of
-        ambiguous positions in, 16-byte results + hits in read order out. short_hits: 4-byte hits
-        (slk_classify_batch_compact_short; out.hits is then a uint32 array, see CompactBatch.decode_short_hits)."""
+        ambiguous positions in, 16-byte results + hits in read order out. short_hits: 4-byte hits and 8-byte results
+        (slk_classify_batch_compact_short; out.hits is then a uint32 array and out.results RESULT_SHORT_DTYPE, see
+        CompactBatch.decode_short_hits / lengths_from_hits)."""
         n, nt = len(r1.len), len(thresholds)
         if out is None:
             hits = None
             if per_read_output:
                 total = int(r1.len.sum()) + (int(r2.len.sum()) if r2 is not None else 0)
                 hits = np.zeros(self.hits_bound(n, total, r2 is not None), dtype=np.uint32 if short_hits else HIT_DTYPE)
-            out = CompactBatch(np.zeros(n, dtype=RESULT_DTYPE), np.zeros((max(nt - 1, 0), n), dtype=np.int32),
+            out = CompactBatch(np.zeros(n, dtype=RESULT_SHORT_DTYPE if short_hits else RESULT_DTYPE), np.zeros((max(nt - 1, 0), n), dtype=np.int32),
                                np.zeros((max(nt - 1, 0), n), dtype=np.uint8), hits)
         amb = merge_ambiguous(r1, r2)
         o = self._multi_opts(thresholds, min_hit_groups)
         used = C.c_uint64(0)
         hits = out.hits if per_read_output else None
+        assert out.results.dtype == (RESULT_SHORT_DTYPE if short_hits else RESULT_DTYPE)
         if hits is not None:
             assert hits.dtype == (np.uint32 if short_hits else HIT_DTYPE)
         fn = self.ctx._L.slk_classify_batch_compact_short if short_hits else self.ctx._L.slk_classify_batch_compact
@@ -656,6 +659,22 @@ class CompactBatch:
         out["taxon"] = np.where(border, -2, np.where(amb, -1, raw[np.minimum(label, len(raw) - 1)]))
         out["count"] = np.where(border, -(k - 1), count)
         return out
+
+    def lengths_from_hits(self, hits: np.ndarray, k: int, paired: bool):
+        """(len1, len2) of every read from its hit list (HIT_DTYPE records in read order): the k-mers of the hits before the
+        mate-pair border + k - 1, likewise after it; len2 = 0xFFFFFFFF for single-end reads (slk_read_result's fields, which
+        the short results leave out)."""
+        cnt = self.hit_cnt.astype(np.int64)
+        read_of = np.repeat(np.arange(len(cnt), dtype=np.int64), cnt)
+        border = hits["taxon"] == -2
+        after = np.cumsum(border) - np.repeat((np.cumsum(np.bincount(read_of, weights=border, minlength=len(cnt))) -
+                                               np.bincount(read_of, weights=border, minlength=len(cnt))).astype(np.int64), cnt)
+        c = np.where(border, 0, hits["count"]).astype(np.int64)
+        k1 = np.bincount(read_of, weights=np.where(after == 0, c, 0), minlength=len(cnt)).astype(np.int64)
+        k2 = np.bincount(read_of, weights=np.where(after > 0, c, 0), minlength=len(cnt)).astype(np.int64)
+        len1 = (k1 + k - 1).astype(np.uint32)
+        len2 = (k2 + k - 1).astype(np.uint32) if paired else np.full(len(cnt), 0xFFFFFFFF, dtype=np.uint32)
+        return len1, len2
 
 
 def compact_reads(p: "PackedReads") -> CompactReads:
