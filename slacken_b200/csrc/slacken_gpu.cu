@@ -1134,7 +1134,7 @@ extern "C" int slk_counts_fetch(slk_counts* c, int32_t sample, int64_t* per_taxo
 }
 
 // ---------------------------------------------------------------------------------------------- classifier
-#define NSLOT 4
+#define NSLOT 6
 struct cls_slot {
   uint8_t *bases1 = nullptr, *bases2 = nullptr;   // ASCII bases, or the uint64 code blocks of packed input
   uint64_t *off1 = nullptr, *off2 = nullptr;
@@ -1967,7 +1967,10 @@ static int classify_compact_impl(slk_classifier* c, const slk_classify_multi_opt
     const bool more = r0 < n_reads;
     if (more) TRY(stage_in());
     if (launched < ci && (launched + 1 < ci || !more)) { TRY(launch(launched)); launched++; }
-    if (finalized < launched && (finalized + 1 < launched || (launched == ci && !more))) { TRY(finalize(c->slot[finalized % NSLOT], finalized)); finalized++; }
+    // finalize waits on the host for its chunk's kernel (it needs the chunk's hit count): keep it two kernels behind the
+    // launches, so that the wait falls on a kernel that has long finished and the next launch is never held up by it
+    // (with one kernel of lag the device idled ~0.3 ms between every pair of chunks: SLK_TRACE=1)
+    if (finalized < launched && (finalized + 2 < launched || (launched == ci && !more))) { TRY(finalize(c->slot[finalized % NSLOT], finalized)); finalized++; }
     if (!more && finalized == ci) break;
   }
   CU(cudaStreamSynchronize(c->s_d2h));
