@@ -656,7 +656,7 @@ def sharded_leg(args, w, ctx, tax, params, index, cls, m1, d_off, n, L, genome_t
         return out
 
     steps = max(2, args.steps // 2)
-    got = run(2)
+    got = run(3)   # warm-up: three batches, so that every buffer the pipeline keeps alive at once exists before the timing
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -791,7 +791,7 @@ def big_sharded_classify(args, w, ctx, tax, params, shard, parents, genome_taxa,
         return out
 
     steps = max(2, args.steps // 2)
-    run(2)
+    run(3)   # warm-up, as in the sharded leg
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()

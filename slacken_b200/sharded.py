@@ -535,6 +535,7 @@ class ShardedClassifier:
                 self.mailbox_probe()
             mark("wait>")
             out = self._resolve_wait(pending)
+            pending = None                  # the batch's device tensors go back to the allocator before the next scan
             mark("done")
             self.last_trace = trace
             yield out
