@@ -66,6 +66,10 @@ def lib():
                                   C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.emu_shard_of.restype = C.c_uint32
         L.emu_shard_of.argtypes = [C.c_uint64, C.c_uint32]
+        L.emu_key_mix.argtypes = [C.c_uint64]
+        L.emu_key_mix.restype = C.c_uint32
+        L.emu_bucket_of.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
+        L.emu_bucket_of.restype = C.c_uint64
         L.emu_emit_cells.restype = C.c_int64
         L.emu_emit_cells.argtypes = [C.POINTER(ScanParams), C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]
         L.emu_synth_genome.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]

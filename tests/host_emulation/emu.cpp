@@ -175,6 +175,12 @@ EMU_API int64_t emu_classify_split(const slk_scan_params* sp, uint64_t* cells, u
   return r;
 }
 EMU_API uint32_t emu_shard_of(uint64_t ckey, uint32_t world) { return slk_shard_of(ckey, world); }
+EMU_API uint32_t emu_key_mix(uint64_t ckey) { return slk_key_mix(ckey); }
+// home bucket of a key in one shard (n_buckets buckets) of a table cut for `world` GPUs
+EMU_API uint64_t emu_bucket_of(uint64_t ckey, uint64_t n_buckets, uint32_t world) {
+  const slk_table_view tb{nullptr, n_buckets, world, 0};
+  return slk_bucket_of(ckey, tb);
+}
 
 // the three device steps of the split path one by one (what tests/test_dist_gloo.py plugs into ShardedClassifier)
 template <int W>

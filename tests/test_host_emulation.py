@@ -226,3 +226,32 @@ def test_four_bytes_at_a_time_coding_equals_the_scalar_coding():
     words.append((acgt[pick].astype(np.uint32) << (np.arange(4, dtype=np.uint32) * 8)).sum(axis=1).astype(np.uint32))
     allw = np.ascontiguousarray(np.concatenate(words))
     assert L.emu_code4_mismatches(allw.ctypes.data, len(allw)) == 0
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_range_partition_is_one_virtual_table_cut_in_equal_ranges(world):
+    """slk_shard_of / slk_bucket_of with mix_mul = world: the owner of a key and its line inside the
+    owner's shard, read as one number (owner * lines + line), must be monotone in the table-line hash of the key -- which is
+    what lets the distributed build ship cells ordered by that hash to their owners and insert them front to back -- and
+    every shard must be used evenly over all of its lines."""
+    L = emu.lib()
+    rng = np.random.default_rng(world)
+    keys = rng.integers(0, 1 << 48, size=20000, dtype=np.uint64)
+    n_buckets = 4 * 1000                                  # 1000 lines per shard, not a power of two
+    x = np.array([L.emu_key_mix(int(k)) for k in keys], dtype=np.int64)
+    owner = np.array([L.emu_shard_of(int(k), world) for k in keys], dtype=np.int64)
+    bucket = np.array([L.emu_bucket_of(int(k), n_buckets, world) for k in keys], dtype=np.int64)
+    line = bucket >> 2
+    assert owner.min() >= 0 and owner.max() < world and line.min() >= 0 and line.max() < 1000
+    order = np.argsort(x, kind="stable")
+    virtual = (owner * 1000 + line)[order]
+    assert (np.diff(virtual) >= 0).all()
+    assert np.array_equal(owner, (x * world) >> 32)
+    # even use: every shard gets about 1/world of the keys, and every tenth of a shard's lines about a tenth of those
+    for r in range(world):
+        mine = line[owner == r]
+        assert abs(len(mine) - len(keys) / world) < 6 * np.sqrt(len(keys) / world)
+        h = np.bincount(mine // 100, minlength=10)
+        assert h.min() > 0.8 * len(mine) / 10 and h.max() < 1.2 * len(mine) / 10
+    # the sub-bucket inside the line does not depend on the cut
+    assert np.array_equal(bucket & 3, np.array([L.emu_bucket_of(int(k), n_buckets, 1) for k in keys], dtype=np.int64) & 3)

@@ -147,3 +147,29 @@ def test_taxonomy_loader_returns_the_merged_mapping(tmp_path):
     assert len(parents) == 13 and parents[7] == 2 and names[7] == "Seven"      # id 99 of names.dmp is unknown: ignored
     assert primary[12] == 7 and primary[7] == 7 and primary[2] == 2
     assert lio.load_taxonomy_dmp(str(d))[0].tolist() == parents.tolist()
+
+
+def test_short_hit_words_and_the_lengths_they_imply():
+    """The 4-byte hit format of slk_classify_batch_compact_short (include/slacken_gpu.h) and the two length fields that its
+    8-byte results leave out: decoded on the host, they must give back the (taxon, count) records and len1 / len2."""
+    import numpy as np
+    from slacken_b200.host import HIT_DTYPE, RESULT_SHORT_DTYPE, CompactBatch
+    k = 35
+    taxa = np.array([1, 7, 12, 40], dtype=np.int32)                     # slk_index_taxa: label i + 1 -> taxa[i]
+    # read 0: single mate; read 1: no hits; read 2: pair with a border; read 3: ambiguous only
+    want = np.zeros(8, dtype=HIT_DTYPE)
+    want["taxon"] = [7, 0, 12, -2, 0, 40, -1, -1]
+    want["count"] = [10, 6, 20, -(k - 1), 3, 4, 2, 65534]
+    words = np.zeros(8, dtype=np.uint32)
+    label = {0: 0, 1: 1, 7: 2, 12: 3, 40: 4, -1: 0xFFFF}
+    for i, (t, c) in enumerate(zip(want["taxon"], want["count"])):
+        words[i] = 0xFFFFFFFF if t == -2 else (label[int(t)] << 16) | int(c)
+    res = np.zeros(4, dtype=RESULT_SHORT_DTYPE)
+    res["hits_flags"] = np.array([2, 0, 4, 2], dtype=np.uint32) << 2
+    b = CompactBatch(res, None, None, words, 8)
+    got = b.decode_short_hits(taxa, k)
+    assert np.array_equal(got["taxon"], want["taxon"]) and np.array_equal(got["count"], want["count"])
+    l1, l2 = b.lengths_from_hits(got, k, True)
+    assert l1.tolist() == [16 + k - 1, k - 1, 20 + k - 1, 65536 + k - 1] and l2.tolist() == [k - 1, k - 1, 7 + k - 1, k - 1]
+    l1s, l2s = b.lengths_from_hits(got, k, False)
+    assert l2s.tolist() == [0xFFFFFFFF] * 4 and l1s.tolist() == l1.tolist()
