@@ -48,7 +48,7 @@ def lib():
         L.emu_code4_mismatches.restype = C.c_uint64
         L.emu_buckets_for.restype = C.c_uint64
         L.emu_buckets_for.argtypes = [C.c_uint64]
-        L.emu_insert_cells.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
+        L.emu_insert_cells.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32]
         L.emu_classify.restype = C.c_int64
         L.emu_classify.argtypes = [C.POINTER(ScanParams), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
@@ -58,7 +58,7 @@ def lib():
         L.emu_scan_spans.restype = C.c_int64
         L.emu_scan_spans.argtypes = [C.POINTER(ScanParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                      C.c_void_p, C.c_void_p, C.c_uint64]
-        L.emu_probe_keys.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.emu_probe_keys.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
         L.emu_resolve_spans.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.emu_bracken.restype = C.c_int64
@@ -126,16 +126,31 @@ class DenseTax:
 
 
 class EmuIndex:
-    def __init__(self, sp: ScanParams, parents: np.ndarray, id1: np.ndarray, taxon: np.ndarray):
-        self.sp = sp
+    def __init__(self, sp: ScanParams, parents: np.ndarray, id1: np.ndarray, taxon: np.ndarray, world: int = 1):
+        """world > 1: the records are one shard of a library cut for `world` ranks (the table then spreads the shard's range
+        of the line hash over all of its lines, as slk_index_from_records_shard does)."""
+        self.sp, self.world = sp, world
         self.dt = DenseTax(parents, taxon)
         self.parent, self.depth, self.raw = self.dt.arrays()
         self.n_buckets = int(lib().emu_buckets_for(len(id1)))
         self.cells = np.zeros(self.n_buckets * 4, dtype=np.uint64)
         cells_in = np.array([(lib().emu_compress(C.byref(sp), int(k)) << 16) | self.dt.to_dense[int(t)]
                              for k, t in zip(id1.view(np.uint64), taxon)], dtype=np.uint64)
+        self.insert(cells_in)
+
+    def insert(self, cells_in: np.ndarray):
+        """(compressed key << 16 | dense taxon of self.dt) cells; equal keys merge by LCA."""
+        cells_in = np.ascontiguousarray(cells_in, dtype=np.uint64)
         lib().emu_insert_cells(_p(self.cells), self.n_buckets, _p(self.parent), _p(self.depth), self.dt.root,
-                               _p(cells_in), len(cells_in))
+                               _p(cells_in), len(cells_in), self.world)
+
+    def records(self):
+        """(id1 uint64[], raw taxon int32[]) of the table, sorted by id1."""
+        c = self.cells[self.cells != 0]
+        id1 = np.array([lib().emu_expand(C.byref(self.sp), int(x) >> 16) for x in c], dtype=np.uint64)
+        tx = np.array([self.raw[int(x) & 0xffff] for x in c], dtype=np.int32)
+        o = np.argsort(id1, kind="stable")
+        return id1[o], tx[o]
 
     def classify(self, bases1, off1, bases2=None, off2=None, confidence=0.0, min_hit_groups=2, packed=False, split=False):
         """split=True: the scan | probe | merge+resolve bodies of the sharded-library path instead of the fused one."""

@@ -40,14 +40,15 @@ EMU_API uint64_t emu_code4_mismatches(const uint32_t* words, uint64_t n) {
 EMU_API uint64_t emu_buckets_for(uint64_t n_keys) { return (((uint64_t)((double)n_keys / 0.70) + 64 + 15) / 16) * 4; }
 
 // sequential twin of insert_cells_kernel (no atomics needed with one "thread")
+// world > 1: the table is one shard of a library cut for `world` ranks (slk_table_view::mix_mul)
 EMU_API void emu_insert_cells(uint64_t* cells, uint64_t n_buckets, const uint16_t* parent, const uint8_t* depth,
-                              uint32_t root, const uint64_t* in, uint64_t n) {
+                              uint32_t root, const uint64_t* in, uint64_t n, uint32_t world) {
   slk_tax_view tx{parent, depth, nullptr, 0, root};
   for (uint64_t i = 0; i < n; i++) {
     uint64_t cell = in[i], ckey = cell >> 16;
     uint32_t taxon = (uint32_t)(cell & 0xffff);
     if (!taxon) continue;
-    const slk_table_view tbv{cells, n_buckets, 1, 0};
+    const slk_table_view tbv{cells, n_buckets, world ? world : 1u, 0};
     uint64_t b = slk_bucket_of(ckey, tbv);
     bool done = false;
     for (uint64_t tries = 1; !done; tries++) {
@@ -203,8 +204,9 @@ EMU_API int64_t emu_scan_spans(const slk_scan_params* sp, const uint8_t* b1, con
   DISPATCH_W(sp->w, r = scan_spans_w<W_>(sp, b1, o1, b2, o2, n, span_off, spans, cap));
   return r;
 }
-EMU_API void emu_probe_keys(uint64_t* cells, uint64_t n_buckets, const int32_t* raw, const uint64_t* keys, uint64_t n, int32_t* taxa) {
-  slk_table_view tb{cells, n_buckets, 1, 0};
+EMU_API void emu_probe_keys(uint64_t* cells, uint64_t n_buckets, const int32_t* raw, const uint64_t* keys, uint64_t n, int32_t* taxa,
+                            uint32_t world) {
+  slk_table_view tb{cells, n_buckets, world ? world : 1u, 0};
   for (uint64_t i = 0; i < n; i++) { uint32_t d = slk_probe(tb, keys[i]); taxa[i] = d ? raw[d] : 0; }
 }
 EMU_API void emu_resolve_spans(const uint16_t* parent, const uint8_t* depth, const int32_t* raw, uint32_t n_dense, uint32_t root,
