@@ -173,3 +173,12 @@ def test_short_hit_words_and_the_lengths_they_imply():
     assert l1.tolist() == [16 + k - 1, k - 1, 20 + k - 1, 65536 + k - 1] and l2.tolist() == [k - 1, k - 1, 7 + k - 1, k - 1]
     l1s, l2s = b.lengths_from_hits(got, k, False)
     assert l2s.tolist() == [0xFFFFFFFF] * 4 and l1s.tolist() == l1.tolist()
+
+
+def test_pack_sequences_drops_line_breaks():
+    """host.pack_sequences assembles the device input: one sequence per offset range, line breaks inside a sequence dropped
+    (the reference's scanner skips them, kmers/minimizer/ShiftScanner.scala:113-120)."""
+    import numpy as np
+    from slacken_b200.host import pack_sequences
+    b, off = pack_sequences([b"ACGT\nACG\r\nT", "NN\nAC", b"", b"\n"])
+    assert bytes(b) == b"ACGTACGTNNAC" and off.tolist() == [0, 8, 12, 12, 12] and off.dtype == np.uint64
